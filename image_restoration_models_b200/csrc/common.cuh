@@ -1,0 +1,121 @@
+// Shared declarations for the sm_100a Restormer / DnCNN forward library.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/irb200.h"
+
+namespace irb {
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing (thread-local message, int status; SURVEY.md §8b "Errors")
+// ---------------------------------------------------------------------------------------------
+void set_error(const std::string& msg);
+int  cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define IRB_CUDA(expr)                                                        \
+  do {                                                                        \
+    cudaError_t _e = (expr);                                                  \
+    if (_e != cudaSuccess) return ::irb::cuda_fail(_e, #expr, __FILE__, __LINE__); \
+  } while (0)
+
+#define IRB_LAUNCH_CHECK() IRB_CUDA(cudaGetLastError())
+
+#define IRB_REQUIRE(cond, msg)                                                \
+  do {                                                                        \
+    if (!(cond)) { ::irb::set_error(std::string("invalid argument: ") + (msg)); return IR_ERR_INVALID; } \
+  } while (0)
+
+#define IRB_TRY(expr)                                                         \
+  do { int _s = (expr); if (_s != IR_OK) return _s; } while (0)
+
+__host__ __device__ static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+static inline long long cdivll(long long a, long long b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ---------------------------------------------------------------------------------------------
+// generic contraction (1x1 conv, 3x3 conv as implicit GEMM) parameter block
+// rows = pixels of image b (row = b*H*W + y*W + x), columns = output channels
+// ---------------------------------------------------------------------------------------------
+enum AMode { A_PLAIN = 0, A_IM2COL_NHWC = 1, A_IM2COL_NCHW = 2 };
+enum OMode { O_NHWC = 0, O_UNSHUFFLE = 1, O_SHUFFLE = 2, O_NCHW = 3 };
+enum LnMode { LN_NONE = 0, LN_BIASFREE = 1, LN_WITHBIAS = 2 };
+
+struct GemmParams {
+  // A operand: source 1 (+ optional concat source 2, plain mode only)
+  const float* a1; int lda1; int k1;      // plain: channels of source 1; im2col: Cin
+  const float* a2; int lda2; int k2;
+  int a_mode;
+  int B, H, W;                            // spatial extent of the rows (conv input == conv output extent)
+  // weights, row-major [N][Kp]; w_bstride != 0 selects per-image weights
+  const float* w; long long w_bstride;
+  int N, K, Kp;
+  const float* bias;                      // [N] or nullptr
+  // LayerNorm prologue over the k1 channels of source 1
+  int ln_mode; const float* ln_w; const float* ln_b;
+  // epilogue: y = (r ? r : 0) + acc_sign * act(acc + bias)
+  int relu;
+  const float* r; int ldr; float acc_sign;
+  float* y; int ldy; int o_mode;
+};
+
+struct DwParams {
+  const float* in; int ldi;
+  float* out; int ldo;
+  const float* w;                         // [9][Cw] tap-major
+  const float* bias;                      // [Cw] or nullptr
+  int Cw;                                 // channel pitch of w / bias
+  int B, H, W;
+  int C;                                  // channels produced
+  int gate;                               // 1: out[c] = gelu(dw(in[c])) * dw(in[c + gate_off])
+  int gate_off;
+};
+
+struct GramParams {
+  const float* qkv; int ld;               // depthwise-convolved qkv [B*HW, 3C]
+  int B, HW, C, heads, nparts;
+  float* s_part;                          // [B][heads][nparts][ch][ch]
+  float* n_part;                          // [B][heads][nparts][2][ch]  (sum q^2, sum k^2)
+};
+
+struct FoldParams {
+  const float* s_part; const float* n_part;
+  int B, C, heads, nparts;
+  const float* temperature;               // [heads]
+  const float* w_proj;                    // [C][C] row-major (project_out)
+  float* w_eff; long long w_eff_bstride;  // [B][C][C] row-major
+};
+
+// launchers (simt_kernels.cu)
+int launch_gemm_simt(const GemmParams& p, cudaStream_t s);
+int launch_dwconv(const DwParams& p, cudaStream_t s);
+int launch_gram(const GramParams& p, cudaStream_t s);
+int launch_fold(const FoldParams& p, cudaStream_t s);
+int launch_copy_channels(const float* src, int lds, float* dst, int ldd, long long rows, int C, cudaStream_t s);
+int launch_nchw_to_nhwc(const float* src, float* dst, int B, int C, int H, int W, cudaStream_t s);
+int launch_nhwc_to_nchw(const float* src, float* dst, int B, int C, int H, int W, cudaStream_t s);
+
+// weight packing (pack.cu)
+struct PackMat {
+  const float* src; float* dst;
+  int kind;            // 0: src[n][k] (1x1 / linear), 1: src[n][cin][3][3] -> k = tap*cin + c
+  int cin;             // kind 1 only
+  int n_src_half, n_dst_half, n_halves;   // row split-pad mapping (GDFN hidden padding)
+  int k_src, k_dst;                        // logical / padded reduction length (kind 0: zero-pad; kind 1: k_src = 9*cin)
+  const float* row_scale;                  // optional per-source-row scale (BatchNorm folding)
+};
+int launch_pack_mat(const PackMat& p, cudaStream_t s);
+// dst[t][map(c)] = src[c][t]  (depthwise 3x3 [C][1][3][3] -> [9][Cdst])
+int launch_pack_dw(const float* src, float* dst, int c_src_half, int c_dst_half, int n_halves, cudaStream_t s);
+// dst[map(i)] = src[i]*scale[i] + shift[i] (scale/shift optional)
+int launch_pack_vec(const float* src, float* dst, int src_half, int dst_half, int n_halves,
+                    const float* scale, const float* shift, cudaStream_t s);
+// BatchNorm eval folding: scale = g/sqrt(var+eps), shift = b - mean*scale
+int launch_bn_fold(const float* g, const float* b, const float* mean, const float* var, float eps,
+                   float* scale, float* shift, int n, cudaStream_t s);
+
+}  // namespace irb

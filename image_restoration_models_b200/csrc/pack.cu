@@ -1,0 +1,101 @@
+// One-time weight packing: PyTorch-layout fp32 parameters -> the layouts the kernels read.
+// (state_dict contract: SURVEY.md Appendix A; BatchNorm eval folding: basicblock.py:69.)
+#include "common.cuh"
+
+namespace irb {
+
+// split-pad index map: destination index -> source index or -1 (zero fill).
+// GDFN's 2h channels are stored as two halves of hp >= h channels each (hp multiple of 8).
+__device__ __forceinline__ int map_src(int i_dst, int src_half, int dst_half) {
+  const int hs = i_dst / dst_half, r = i_dst - hs * dst_half;
+  return r < src_half ? hs * src_half + r : -1;
+}
+
+__global__ void pack_mat_kernel(const PackMat p) {
+  const int n_dst = p.n_dst_half * p.n_halves;
+  const long long total = (long long)n_dst * p.k_dst;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(idx / p.k_dst), k = (int)(idx - (long long)n * p.k_dst);
+    const int ns = map_src(n, p.n_src_half, p.n_dst_half);
+    float v = 0.f;
+    if (ns >= 0 && k < p.k_src) {
+      if (p.kind == 0) {
+        v = p.src[(long long)ns * p.k_src + k];
+      } else {
+        const int tap = k / p.cin, c = k - tap * p.cin;
+        v = p.src[((long long)ns * p.cin + c) * 9 + tap];
+      }
+      if (p.row_scale) v *= p.row_scale[ns];
+    }
+    p.dst[idx] = v;
+  }
+}
+
+int launch_pack_mat(const PackMat& p, cudaStream_t s) {
+  const long long total = (long long)p.n_dst_half * p.n_halves * p.k_dst;
+  const int blocks = (int)(cdivll(total, 256) < 1024 ? cdivll(total, 256) : 1024);
+  pack_mat_kernel<<<blocks > 0 ? blocks : 1, 256, 0, s>>>(p);
+  IRB_LAUNCH_CHECK();
+  return IR_OK;
+}
+
+__global__ void pack_dw_kernel(const float* __restrict__ src, float* __restrict__ dst, int src_half, int dst_half,
+                               int n_halves) {
+  const int cd = dst_half * n_halves;
+  const int total = 9 * cd;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int t = idx / cd, c = idx - t * cd;
+    const int cs = map_src(c, src_half, dst_half);
+    dst[idx] = cs >= 0 ? src[cs * 9 + t] : 0.f;
+  }
+}
+
+int launch_pack_dw(const float* src, float* dst, int c_src_half, int c_dst_half, int n_halves, cudaStream_t s) {
+  const int total = 9 * c_dst_half * n_halves;
+  pack_dw_kernel<<<cdiv(total, 256), 256, 0, s>>>(src, dst, c_src_half, c_dst_half, n_halves);
+  IRB_LAUNCH_CHECK();
+  return IR_OK;
+}
+
+__global__ void pack_vec_kernel(const float* __restrict__ src, float* __restrict__ dst, int src_half, int dst_half,
+                                int n_halves, const float* __restrict__ scale, const float* __restrict__ shift) {
+  const int total = dst_half * n_halves;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int is = map_src(idx, src_half, dst_half);
+    float v = 0.f;
+    if (is >= 0) {
+      v = src ? src[is] : 0.f;
+      if (scale) v *= scale[is];
+      if (shift) v += shift[is];
+    }
+    dst[idx] = v;
+  }
+}
+
+int launch_pack_vec(const float* src, float* dst, int src_half, int dst_half, int n_halves, const float* scale,
+                    const float* shift, cudaStream_t s) {
+  const int total = dst_half * n_halves;
+  pack_vec_kernel<<<cdiv(total, 256), 256, 0, s>>>(src, dst, src_half, dst_half, n_halves, scale, shift);
+  IRB_LAUNCH_CHECK();
+  return IR_OK;
+}
+
+__global__ void bn_fold_kernel(const float* g, const float* b, const float* mean, const float* var, float eps,
+                               float* scale, float* shift, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const float sc = g[i] / sqrtf(var[i] + eps);
+    scale[i] = sc;
+    shift[i] = b[i] - mean[i] * sc;
+  }
+}
+
+int launch_bn_fold(const float* g, const float* b, const float* mean, const float* var, float eps, float* scale,
+                   float* shift, int n, cudaStream_t s) {
+  bn_fold_kernel<<<cdiv(n, 256), 256, 0, s>>>(g, b, mean, var, eps, scale, shift, n);
+  IRB_LAUNCH_CHECK();
+  return IR_OK;
+}
+
+}  // namespace irb

@@ -1,0 +1,58 @@
+// Plan / workspace / launch-sequence declarations shared by restormer.cu, dncnn.cu and api.cu.
+#pragma once
+#include <vector>
+
+#include "common.cuh"
+
+namespace irb {
+
+// One weight-packing step: parameter `param` (state_dict order) -> packed[dst ...].
+struct PackOp {
+  enum Kind { VEC = 0, MAT1 = 1, MAT3 = 2, DW = 3 };
+  int kind;
+  int param;
+  long long dst;       // float offset into the packed buffer
+  int a, b, c;         // src_half, dst_half, n_halves (split-pad row/channel mapping)
+  int k_src, k_dst;    // MAT1/MAT3: logical / padded reduction length
+  int cin;             // MAT3
+};
+
+struct BlockPlan {     // one TransformerBlock (restormer.py:137-150); offsets in floats, -1 = absent
+  int C, heads, h, hp;
+  long long ln1_w, ln1_b, temp, qkv_w, qkv_b, qkvdw_w, qkvdw_b, proj_w, proj_b;
+  long long ln2_w, ln2_b, pin_w, pin_b, ffdw_w, ffdw_b, pout_w, pout_b;
+};
+
+struct ConvPlan { int cout, cin, k, kp; long long w, b; };
+
+struct RestormerPlan {
+  IrRestormerCfg cfg;
+  std::vector<PackOp> ops;
+  int n_params = 0;
+  long long packed_floats = 0;
+  ConvPlan patch_embed, down[3], up[3], reduce[3], skip, output;
+  std::vector<BlockPlan> enc[4], dec[3], refine;
+};
+
+struct BlockScratchNeed { long long qkv = 0, hidden = 0, gated = 0, s_part = 0, n_part = 0, w_eff = 0; };
+struct BlockScratch { float *qkv, *qkv_dw, *hidden, *gated, *s_part, *n_part, *w_eff; };
+struct RestormerWs { float* e[4]; float* e1_in; float* d[3]; float* up_tmp; BlockScratch bs; };
+
+int  block_param_count(int bias, int ln_bias);
+int  build_block_plan(BlockPlan& bp, std::vector<PackOp>& ops, long long& packed_floats, int C, int heads, float ffn,
+                      int bias, int ln_bias);
+int  build_restormer_plan(RestormerPlan& pl, const IrRestormerCfg& cfg);
+long long pack_op_src_numel(const PackOp& op);
+int  run_pack_ops(const std::vector<PackOp>& ops, const float* const* params, float* packed, cudaStream_t s);
+
+size_t block_workspace_bytes(const BlockPlan& bp, int B, int H, int W);
+size_t restormer_workspace_bytes(const RestormerPlan& pl, int B, int H, int W);
+int  run_block(const BlockPlan& bp, const float* packed, const float* x_in, float* x_out, int B, int H, int W,
+               const BlockScratch& bs, int ln_with_bias, cudaStream_t s);
+int  block_forward(const BlockPlan& bp, const float* packed, float* x, int B, int H, int W, void* workspace,
+                   size_t workspace_bytes, int ln_with_bias, cudaStream_t s);
+int  restormer_launch_count(const RestormerPlan& pl);
+int  restormer_forward(const RestormerPlan& pl, const float* packed, const float* x, float* y, int B, int H, int W,
+                       void* workspace, size_t workspace_bytes, cudaStream_t s);
+
+}  // namespace irb

@@ -1,0 +1,475 @@
+// CUDA-core (fp32 FMA) kernels: the memory-bound stages of the forward, plus a plain fp32
+// contraction used as the on-device second oracle of the tcgen05 kernels and for shapes the
+// tensor-core kernels do not cover.  Channels-last activations: a[pixel*ld + c].
+//
+// Reference semantics restated here (paths relative to /root/reference/src):
+//   LayerNorm            restormer/restormer.py:37-39 (BiasFree), :54-57 (WithBias)
+//   depthwise 3x3        restormer/restormer.py:83,106 (groups == channels, zero pad 1)
+//   GELU gate            restormer/restormer.py:90-91 (exact erf GELU)
+//   q/k normalise, temperature, softmax   restormer/restormer.py:121-125
+//   PixelUnshuffle / PixelShuffle          restormer/restormer.py:176,186
+#include "common.cuh"
+
+namespace irb {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ float gelu_erf(float x) {
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+
+// ---------------------------------------------------------------------------------------------
+// generic fp32 contraction: y[pixel, n] = sum_k A(pixel, k) * w[n, k]
+// ---------------------------------------------------------------------------------------------
+template <int BM, int BN, int BK>
+__global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmParams p) {
+  static_assert(BM == 64 && BN == 64 && BK == 16, "thread mapping below assumes 64x64x16");
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Bs[BK][BN + 4];
+  __shared__ float s_mu[BM];
+  __shared__ float s_rstd[BM];
+
+  const int tid = threadIdx.x;
+  const int b = blockIdx.z;
+  const int HW = p.H * p.W;
+  const int p0 = blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+  const long long rowbase = (long long)b * HW;
+  const float* __restrict__ w = p.w + (long long)b * p.w_bstride;
+
+  if (p.ln_mode != LN_NONE) {
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int r = warp; r < BM; r += 8) {
+      const int pix = p0 + r;
+      float mu = 0.f, rstd = 0.f;
+      if (pix < HW) {
+        const float* src = p.a1 + (rowbase + pix) * (long long)p.lda1;
+        float s = 0.f;
+        for (int k = lane; k < p.k1; k += 32) s += src[k];
+        s = warp_sum(s);
+        mu = s / (float)p.k1;
+        float v = 0.f;
+        for (int k = lane; k < p.k1; k += 32) { const float d = src[k] - mu; v += d * d; }
+        v = warp_sum(v);
+        rstd = 1.0f / sqrtf(v / (float)p.k1 + 1e-5f);
+      }
+      if (lane == 0) { s_mu[r] = mu; s_rstd[r] = rstd; }
+    }
+    __syncthreads();
+  }
+
+  const int lrow = tid >> 2;          // 0..63: tile row (A) / tile column (B) this thread stages
+  const int lkq = (tid & 3) * 4;      // 0,4,8,12
+  const int pixA = p0 + lrow;
+  const int py = pixA / p.W, px = pixA - py * p.W;
+
+  const int ty = tid >> 4, tx = tid & 15;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < p.K; k0 += BK) {
+    const int k = k0 + lkq;
+    float av[4] = {0.f, 0.f, 0.f, 0.f};
+    if (pixA < HW && k < p.K) {
+      if (p.a_mode == A_PLAIN) {
+        const float* src = (k < p.k1) ? p.a1 + (rowbase + pixA) * (long long)p.lda1 + k
+                                      : p.a2 + (rowbase + pixA) * (long long)p.lda2 + (k - p.k1);
+        const float4 t = *reinterpret_cast<const float4*>(src);
+        av[0] = t.x; av[1] = t.y; av[2] = t.z; av[3] = t.w;
+        if (p.ln_mode != LN_NONE) {
+          const float mu = (p.ln_mode == LN_WITHBIAS) ? s_mu[lrow] : 0.f;
+          const float rs = s_rstd[lrow];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float v = (av[i] - mu) * rs * p.ln_w[k + i];
+            if (p.ln_mode == LN_WITHBIAS) v += p.ln_b[k + i];
+            av[i] = v;
+          }
+        }
+      } else if (p.a_mode == A_IM2COL_NHWC) {
+        const int tap = k / p.k1, c = k - tap * p.k1;
+        const int yy = py + tap / 3 - 1, xx = px + tap % 3 - 1;
+        if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W) {
+          const float4 t = *reinterpret_cast<const float4*>(
+              p.a1 + (rowbase + (long long)yy * p.W + xx) * (long long)p.lda1 + c);
+          av[0] = t.x; av[1] = t.y; av[2] = t.z; av[3] = t.w;
+        }
+      } else {  // A_IM2COL_NCHW, scalar gathers (tiny channel counts at the image boundary of the net)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int kk = k + i;
+          if (kk < p.K) {
+            const int tap = kk / p.k1, c = kk - tap * p.k1;
+            const int yy = py + tap / 3 - 1, xx = px + tap % 3 - 1;
+            if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W)
+              av[i] = p.a1[(((long long)b * p.k1 + c) * p.H + yy) * p.W + xx];
+          }
+        }
+      }
+    }
+    float wv[4] = {0.f, 0.f, 0.f, 0.f};
+    if (n0 + lrow < p.N && k < p.Kp) {
+      const float4 t = *reinterpret_cast<const float4*>(w + (long long)(n0 + lrow) * p.Kp + k);
+      wv[0] = t.x; wv[1] = t.y; wv[2] = t.z; wv[3] = t.w;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { As[lkq + i][lrow] = av[i]; Bs[lkq + i][lrow] = wv[i]; }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      const float4 bb = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      const float ar[4] = {a.x, a.y, a.z, a.w};
+      const float br[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+  // epilogue
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int pix = p0 + ty * 4 + i;
+    if (pix >= HW) continue;
+    const int y = pix / p.W, x = pix - y * p.W;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= p.N) continue;
+      float v = acc[i][j];
+      if (p.bias) v += p.bias[n];
+      if (p.relu) v = fmaxf(v, 0.f);
+      v *= p.acc_sign;
+      long long oidx;
+      if (p.o_mode == O_NHWC) {
+        oidx = (rowbase + pix) * (long long)p.ldy + n;
+        if (p.r) v += p.r[(rowbase + pix) * (long long)p.ldr + n];
+      } else if (p.o_mode == O_UNSHUFFLE) {
+        // out[b, y/2, x/2, n*4 + (y%2)*2 + (x%2)], out extent (H/2, W/2)
+        const long long opix = ((long long)b * (p.H / 2) + (y >> 1)) * (p.W / 2) + (x >> 1);
+        oidx = opix * p.ldy + n * 4 + (y & 1) * 2 + (x & 1);
+      } else if (p.o_mode == O_SHUFFLE) {
+        // out[b, 2y+i, 2x+j, n/4] with i = (n%4)/2, j = n%2, out extent (2H, 2W)
+        const int q = n & 3;
+        const long long opix = ((long long)b * (2 * p.H) + (2 * y + (q >> 1))) * (2 * p.W) + (2 * x + (q & 1));
+        oidx = opix * p.ldy + (n >> 2);
+      } else {  // O_NCHW
+        oidx = (((long long)b * p.N + n) * p.H + y) * p.W + x;
+        if (p.r) v += p.r[oidx];
+      }
+      p.y[oidx] = v;
+    }
+  }
+}
+
+int launch_gemm_simt(const GemmParams& p, cudaStream_t s) {
+  IRB_REQUIRE(p.Kp % 4 == 0, "gemm: padded K must be a multiple of 4");
+  if (p.a_mode == A_PLAIN) {
+    IRB_REQUIRE(p.k1 % 4 == 0 && p.lda1 % 4 == 0, "gemm: plain source 1 must be float4-addressable");
+    IRB_REQUIRE(p.k2 == 0 || (p.k2 % 4 == 0 && p.lda2 % 4 == 0), "gemm: plain source 2 must be float4-addressable");
+    IRB_REQUIRE(p.K == p.k1 + p.k2, "gemm: K != k1 + k2");
+    IRB_REQUIRE(p.ln_mode == LN_NONE || p.k2 == 0, "gemm: LayerNorm prologue needs a single source");
+  } else if (p.a_mode == A_IM2COL_NHWC) {
+    IRB_REQUIRE(p.k1 % 4 == 0 && p.lda1 % 4 == 0 && p.K == 9 * p.k1, "gemm: im2col NHWC needs Cin % 4 == 0");
+  } else {
+    IRB_REQUIRE(p.K == 9 * p.k1, "gemm: im2col NCHW K != 9*Cin");
+  }
+  if (p.o_mode == O_UNSHUFFLE) IRB_REQUIRE(p.H % 2 == 0 && p.W % 2 == 0, "gemm: unshuffle needs even H, W");
+  if (p.o_mode == O_SHUFFLE) IRB_REQUIRE(p.N % 4 == 0, "gemm: shuffle needs N % 4 == 0");
+  const int HW = p.H * p.W;
+  dim3 grid(cdiv(HW, 64), cdiv(p.N, 64), p.B);
+  gemm_simt_kernel<64, 64, 16><<<grid, 256, 0, s>>>(p);
+  IRB_LAUNCH_CHECK();
+  return IR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// depthwise 3x3 (+ optional GELU gate), one thread per (pixel, 4 channels)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 dw9(const float* __restrict__ in, int ldi, const float* __restrict__ w, int Cw,
+                                      long long imgbase, int y, int x, int H, int W, int c) {
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int dy = -1; dy <= 1; ++dy) {
+    const int yy = y + dy;
+    if (yy < 0 || yy >= H) continue;
+#pragma unroll
+    for (int dx = -1; dx <= 1; ++dx) {
+      const int xx = x + dx;
+      if (xx < 0 || xx >= W) continue;
+      const float4 v = *reinterpret_cast<const float4*>(in + (imgbase + (long long)yy * W + xx) * ldi + c);
+      const float4 k = *reinterpret_cast<const float4*>(w + ((dy + 1) * 3 + (dx + 1)) * Cw + c);
+      acc.x = fmaf(v.x, k.x, acc.x); acc.y = fmaf(v.y, k.y, acc.y);
+      acc.z = fmaf(v.z, k.z, acc.z); acc.w = fmaf(v.w, k.w, acc.w);
+    }
+  }
+  return acc;
+}
+
+__global__ void __launch_bounds__(256) dwconv_kernel(const DwParams p) {
+  const int cq = p.C >> 2;
+  const long long total = (long long)p.B * p.H * p.W * cq;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % cq) * 4;
+    const long long pix = idx / cq;
+    const int HW = p.H * p.W;
+    const int b = (int)(pix / HW);
+    const int pp = (int)(pix - (long long)b * HW);
+    const int y = pp / p.W, x = pp - y * p.W;
+    const long long imgbase = (long long)b * HW;
+    float4 a = dw9(p.in, p.ldi, p.w, p.Cw, imgbase, y, x, p.H, p.W, c);
+    if (p.bias) {
+      const float4 bb = *reinterpret_cast<const float4*>(p.bias + c);
+      a.x += bb.x; a.y += bb.y; a.z += bb.z; a.w += bb.w;
+    }
+    if (p.gate) {
+      float4 g = dw9(p.in, p.ldi, p.w, p.Cw, imgbase, y, x, p.H, p.W, c + p.gate_off);
+      if (p.bias) {
+        const float4 bb = *reinterpret_cast<const float4*>(p.bias + c + p.gate_off);
+        g.x += bb.x; g.y += bb.y; g.z += bb.z; g.w += bb.w;
+      }
+      a.x = gelu_erf(a.x) * g.x; a.y = gelu_erf(a.y) * g.y;
+      a.z = gelu_erf(a.z) * g.z; a.w = gelu_erf(a.w) * g.w;
+    }
+    *reinterpret_cast<float4*>(p.out + pix * p.ldo + c) = a;
+  }
+}
+
+int launch_dwconv(const DwParams& p, cudaStream_t s) {
+  IRB_REQUIRE(p.C % 4 == 0 && p.ldi % 4 == 0 && p.ldo % 4 == 0 && p.Cw % 4 == 0 && p.gate_off % 4 == 0,
+              "dwconv: channel counts must be multiples of 4");
+  const long long total = (long long)p.B * p.H * p.W * (p.C / 4);
+  const int blocks = (int)(cdivll(total, 256) < 148LL * 16 ? cdivll(total, 256) : 148LL * 16);
+  dwconv_kernel<<<blocks > 0 ? blocks : 1, 256, 0, s>>>(p);
+  IRB_LAUNCH_CHECK();
+  return IR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// MDTA Gram partials: S[i][j] = sum_p q[p][i] k[p][j], sum q^2, sum k^2 over a slice of pixels
+// grid (nparts, heads, B); block 256; TI = ch/16 outputs per thread per dimension
+// ---------------------------------------------------------------------------------------------
+template <int TI>
+__global__ void __launch_bounds__(256) gram_kernel(const GramParams p) {
+  constexpr int CH = TI * 16;
+  constexpr int PT = 32;  // pixels staged per step
+  __shared__ float qs[PT][CH + 4];
+  __shared__ float ks[PT][CH + 4];
+  const int part = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
+  const int tid = threadIdx.x;
+  const int ty = tid >> 4, tx = tid & 15;
+  const int per = cdiv(p.HW, p.nparts);
+  const int pbeg = part * per;
+  const int pend = min(p.HW, pbeg + per);
+  const float* base = p.qkv + (long long)b * p.HW * p.ld;
+  const int qoff = head * CH, koff = p.C + head * CH;
+
+  float acc[TI][TI];
+#pragma unroll
+  for (int i = 0; i < TI; ++i)
+#pragma unroll
+    for (int j = 0; j < TI; ++j) acc[i][j] = 0.f;
+  float nrm = 0.f;  // thread tid < CH: sum q[:,tid]^2 ; CH <= tid < 2CH: sum k^2
+
+  for (int ps = pbeg; ps < pend; ps += PT) {
+    // stage PT pixels x CH channels of q and k (float4 granularity)
+    constexpr int V = CH / 4;
+    for (int e = tid; e < PT * V * 2; e += 256) {
+      const int which = e / (PT * V);
+      const int r = (e % (PT * V)) / V;
+      const int c4 = (e % V) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ps + r < pend)
+        v = *reinterpret_cast<const float4*>(base + (long long)(ps + r) * p.ld + (which ? koff : qoff) + c4);
+      float* dst = which ? &ks[r][c4] : &qs[r][c4];
+      dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int r = 0; r < PT; ++r) {
+      float qa[TI], ka[TI];
+#pragma unroll
+      for (int i = 0; i < TI; ++i) { qa[i] = qs[r][ty * TI + i]; ka[i] = ks[r][tx * TI + i]; }
+#pragma unroll
+      for (int i = 0; i < TI; ++i)
+#pragma unroll
+        for (int j = 0; j < TI; ++j) acc[i][j] = fmaf(qa[i], ka[j], acc[i][j]);
+    }
+    if (tid < 2 * CH) {
+      const int c = tid < CH ? tid : tid - CH;
+      for (int r = 0; r < PT; ++r) {
+        const float v = tid < CH ? qs[r][c] : ks[r][c];
+        nrm = fmaf(v, v, nrm);
+      }
+    }
+    __syncthreads();
+  }
+  float* sp = p.s_part + (((long long)b * p.heads + head) * p.nparts + part) * CH * CH;
+#pragma unroll
+  for (int i = 0; i < TI; ++i)
+#pragma unroll
+    for (int j = 0; j < TI; ++j) sp[(ty * TI + i) * CH + tx * TI + j] = acc[i][j];
+  if (tid < 2 * CH) {
+    float* np_ = p.n_part + (((long long)b * p.heads + head) * p.nparts + part) * 2 * CH;
+    np_[tid] = nrm;
+  }
+}
+
+int launch_gram(const GramParams& p, cudaStream_t s) {
+  const int ch = p.C / p.heads;
+  IRB_REQUIRE(p.C % p.heads == 0 && ch % 16 == 0 && ch <= 128 && p.ld % 4 == 0, "gram: head dim must be a multiple of 16, <= 128");
+  dim3 grid(p.nparts, p.heads, p.B);
+  switch (ch / 16) {
+    case 1: gram_kernel<1><<<grid, 256, 0, s>>>(p); break;
+    case 2: gram_kernel<2><<<grid, 256, 0, s>>>(p); break;
+    case 3: gram_kernel<3><<<grid, 256, 0, s>>>(p); break;
+    case 4: gram_kernel<4><<<grid, 256, 0, s>>>(p); break;
+    case 5: gram_kernel<5><<<grid, 256, 0, s>>>(p); break;
+    case 6: gram_kernel<6><<<grid, 256, 0, s>>>(p); break;
+    case 7: gram_kernel<7><<<grid, 256, 0, s>>>(p); break;
+    case 8: gram_kernel<8><<<grid, 256, 0, s>>>(p); break;
+    default: IRB_REQUIRE(false, "gram: unsupported head dim");
+  }
+  IRB_LAUNCH_CHECK();
+  return IR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// reduce Gram partials, L2-normalise, temperature, softmax, fold project_out:
+//   W_eff[b][n][h*ch + j] = sum_i W_proj[n][h*ch + i] * softmax_j(S[i][j] / (|q_i| |k_j|) * T_h)
+// grid (heads, B); dynamic smem: ch*ch + 2*ch floats
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fold_kernel(const FoldParams p) {
+  extern __shared__ float sm[];
+  const int head = blockIdx.x, b = blockIdx.y;
+  const int ch = p.C / p.heads;
+  float* A = sm;                 // [ch][ch]
+  float* nq = sm + ch * ch;      // [ch]
+  float* nk = nq + ch;           // [ch]
+  const int tid = threadIdx.x;
+  const long long pb = ((long long)b * p.heads + head) * p.nparts;
+  for (int e = tid; e < ch * ch; e += blockDim.x) {
+    float s = 0.f;
+    for (int part = 0; part < p.nparts; ++part) s += p.s_part[(pb + part) * ch * ch + e];
+    A[e] = s;
+  }
+  for (int e = tid; e < 2 * ch; e += blockDim.x) {
+    float s = 0.f;
+    for (int part = 0; part < p.nparts; ++part) s += p.n_part[(pb + part) * 2 * ch + e];
+    // F.normalize: x / max(||x||_2, 1e-12)
+    nq[e] = 1.0f / fmaxf(sqrtf(s), 1e-12f);
+  }
+  __syncthreads();
+  const float temp = p.temperature[head];
+  const int warp = tid >> 5, lane = tid & 31, nwarp = blockDim.x >> 5;
+  for (int i = warp; i < ch; i += nwarp) {
+    float m = -INFINITY;
+    for (int j = lane; j < ch; j += 32) {
+      const float v = A[i * ch + j] * nq[i] * nk[j] * temp;
+      A[i * ch + j] = v;
+      m = fmaxf(m, v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float sum = 0.f;
+    for (int j = lane; j < ch; j += 32) {
+      const float e = expf(A[i * ch + j] - m);
+      A[i * ch + j] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    const float inv = 1.0f / sum;
+    for (int j = lane; j < ch; j += 32) A[i * ch + j] *= inv;
+  }
+  __syncthreads();
+  float* we = p.w_eff + (long long)b * p.w_eff_bstride;
+  for (int e = tid; e < p.C * ch; e += blockDim.x) {
+    const int n = e / ch, j = e - n * ch;
+    const float* wrow = p.w_proj + (long long)n * p.C + head * ch;
+    float s = 0.f;
+    for (int i = 0; i < ch; ++i) s = fmaf(wrow[i], A[i * ch + j], s);
+    we[(long long)n * p.C + head * ch + j] = s;
+  }
+}
+
+int launch_fold(const FoldParams& p, cudaStream_t s) {
+  const int ch = p.C / p.heads;
+  const size_t smem = (size_t)(ch * ch + 2 * ch) * sizeof(float);
+  IRB_REQUIRE(smem <= 48 * 1024 + 0u || ch <= 128, "fold: head dim too large");
+  if (smem > 48 * 1024) IRB_CUDA(cudaFuncSetAttribute(fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(p.heads, p.B);
+  fold_kernel<<<grid, 256, smem, s>>>(p);
+  IRB_LAUNCH_CHECK();
+  return IR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// layout helpers
+// ---------------------------------------------------------------------------------------------
+__global__ void copy_channels_kernel(const float* __restrict__ src, int lds, float* __restrict__ dst, int ldd,
+                                     long long rows, int c4) {
+  const long long total = rows * c4;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long r = idx / c4;
+    const int c = (int)(idx - r * c4) * 4;
+    *reinterpret_cast<float4*>(dst + r * ldd + c) = *reinterpret_cast<const float4*>(src + r * lds + c);
+  }
+}
+
+int launch_copy_channels(const float* src, int lds, float* dst, int ldd, long long rows, int C, cudaStream_t s) {
+  IRB_REQUIRE(C % 4 == 0 && lds % 4 == 0 && ldd % 4 == 0, "copy_channels: multiples of 4 required");
+  const long long total = rows * (C / 4);
+  const int blocks = (int)(cdivll(total, 256) < 148LL * 16 ? cdivll(total, 256) : 148LL * 16);
+  copy_channels_kernel<<<blocks > 0 ? blocks : 1, 256, 0, s>>>(src, lds, dst, ldd, rows, C / 4);
+  IRB_LAUNCH_CHECK();
+  return IR_OK;
+}
+
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, float* __restrict__ dst, int B, int C, int HW) {
+  const long long total = (long long)B * C * HW;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % C);
+    const long long pix = idx / C;           // b*HW + p
+    const long long b = pix / HW, pp = pix - b * HW;
+    dst[idx] = src[(b * C + c) * HW + pp];
+  }
+}
+__global__ void nhwc_to_nchw_kernel(const float* __restrict__ src, float* __restrict__ dst, int B, int C, int HW) {
+  const long long total = (long long)B * C * HW;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long pp = idx % HW;
+    const long long bc = idx / HW;
+    const long long b = bc / C, c = bc - b * C;
+    dst[idx] = src[(b * HW + pp) * C + c];
+  }
+}
+int launch_nchw_to_nhwc(const float* src, float* dst, int B, int C, int H, int W, cudaStream_t s) {
+  const long long total = (long long)B * C * H * W;
+  const int blocks = (int)(cdivll(total, 256) < 148LL * 16 ? cdivll(total, 256) : 148LL * 16);
+  nchw_to_nhwc_kernel<<<blocks > 0 ? blocks : 1, 256, 0, s>>>(src, dst, B, C, H * W);
+  IRB_LAUNCH_CHECK();
+  return IR_OK;
+}
+int launch_nhwc_to_nchw(const float* src, float* dst, int B, int C, int H, int W, cudaStream_t s) {
+  const long long total = (long long)B * C * H * W;
+  const int blocks = (int)(cdivll(total, 256) < 148LL * 16 ? cdivll(total, 256) : 148LL * 16);
+  nhwc_to_nchw_kernel<<<blocks > 0 ? blocks : 1, 256, 0, s>>>(src, dst, B, C, H * W);
+  IRB_LAUNCH_CHECK();
+  return IR_OK;
+}
+
+}  // namespace irb

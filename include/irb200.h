@@ -1,0 +1,124 @@
+/*
+ * irb200.h — C ABI of the B200-native Restormer / DnCNN inference forward.
+ *
+ * The reference (leducthanhig/image-restoration-models) has no FFI on this path: its
+ * boundary is the Python nn.Module duck-type (src/restormer/__init__.py:8-20,
+ * src/dncnn/__init__.py:7-15, called from src/utils.py:417).  This header is the C-ABI a
+ * host in any language binds instead; the Python mirror classes in
+ * image_restoration_models_b200/ call it through ctypes.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name starts with `h_`;
+ *   - the library never allocates, frees or retains device memory: the caller owns
+ *     parameters, packed weights, workspace, input and output (SURVEY.md §8b "Ownership");
+ *   - every entry point is asynchronous on `stream` (a cudaStream_t passed as void*),
+ *     re-entrant, and returns 0 on success or a negative IrStatus; ir_last_error() returns
+ *     a thread-local message for the last failure;
+ *   - images are contiguous fp32 NCHW, exactly what the reference's forward(x) takes
+ *     (src/restormer/restormer.py:245, src/dncnn/models/network_dncnn.py:69).
+ */
+#ifndef IRB200_H_
+#define IRB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IRB200_ABI_VERSION 1
+
+typedef enum IrStatus {
+  IR_OK = 0,
+  IR_ERR_INVALID = -1,     /* bad argument / unsupported shape (Python shim raises ValueError) */
+  IR_ERR_WORKSPACE = -2,   /* workspace or packed buffer too small */
+  IR_ERR_CUDA = -3,        /* CUDA runtime error; message carries cudaGetErrorString */
+  IR_ERR_OOM = -4          /* message contains "out of memory" (src/utils.py:91-96 convention) */
+} IrStatus;
+
+/* Arithmetic mode of the tensor-core contractions.  Accumulation is always fp32, and the
+ * residual stream, LayerNorm statistics, softmax and GELU are always fp32. */
+typedef enum IrMode {
+  IR_MODE_FP32 = 0,        /* fp32 activations, tf32 tensor-core operands (fp32 parity mode) */
+  IR_MODE_HALF = 1         /* fp16 intermediates + fp16 operands (same 10-bit mantissa as tf32) */
+} IrMode;
+
+/* Mirrors Restormer.__init__ kwargs (src/restormer/restormer.py:194-205). */
+typedef struct IrRestormerCfg {
+  int32_t inp_channels;
+  int32_t out_channels;
+  int32_t dim;
+  int32_t num_blocks[4];
+  int32_t num_refinement_blocks;
+  int32_t heads[4];
+  float   ffn_expansion_factor;
+  int32_t bias;                 /* conv bias (all shipped YAMLs: 0) */
+  int32_t layernorm_with_bias;  /* 0 = 'BiasFree', 1 = 'WithBias' */
+  int32_t dual_pixel_task;
+} IrRestormerCfg;
+
+/* Mirrors DnCNN.__init__ kwargs (src/dncnn/models/network_dncnn.py:41). */
+typedef struct IrDncnnCfg {
+  int32_t in_nc;
+  int32_t out_nc;
+  int32_t nc;
+  int32_t nb;
+  int32_t has_bn;               /* 1 when act_mode contains 'B' (eval-mode BN folded at pack time) */
+} IrDncnnCfg;
+
+int         ir_abi_version(void);
+const char* ir_last_error(void);
+
+/* ---- Restormer (replaces Restormer.forward, src/restormer/restormer.py:245-284) ---- */
+
+/* Number of tensors in state_dict() order; -1 on invalid cfg. */
+int    ir_restormer_param_count(const IrRestormerCfg* cfg);
+/* Element count of parameter `index` in state_dict() order (for caller-side validation). */
+long long ir_restormer_param_numel(const IrRestormerCfg* cfg, int index);
+size_t ir_restormer_packed_bytes(const IrRestormerCfg* cfg, int mode);
+/* params[i]: device pointer to the i-th state_dict tensor (fp32, PyTorch layout). */
+int    ir_restormer_pack_weights(const IrRestormerCfg* cfg, const float* const* h_params, int n_params,
+                                 void* packed, size_t packed_bytes, int mode, void* stream);
+size_t ir_restormer_workspace_bytes(const IrRestormerCfg* cfg, int B, int H, int W, int mode);
+/* x: [B, inp_channels, H, W] fp32; y: [B, out_channels, H, W] fp32; H, W multiples of 8. */
+int    ir_restormer_forward(const IrRestormerCfg* cfg, const void* packed, const float* x, float* y,
+                            int B, int H, int W, void* workspace, size_t workspace_bytes, int mode,
+                            void* stream);
+/* Number of kernel launches one ir_restormer_forward issues (for bench.py's gpu_launches). */
+int    ir_restormer_launch_count(const IrRestormerCfg* cfg);
+
+/* ---- DnCNN (replaces DnCNN.forward, src/dncnn/models/network_dncnn.py:69-71) ---- */
+int    ir_dncnn_param_count(const IrDncnnCfg* cfg);
+long long ir_dncnn_param_numel(const IrDncnnCfg* cfg, int index);
+size_t ir_dncnn_packed_bytes(const IrDncnnCfg* cfg, int mode);
+int    ir_dncnn_pack_weights(const IrDncnnCfg* cfg, const float* const* h_params, int n_params,
+                             void* packed, size_t packed_bytes, int mode, void* stream);
+size_t ir_dncnn_workspace_bytes(const IrDncnnCfg* cfg, int B, int H, int W, int mode);
+int    ir_dncnn_forward(const IrDncnnCfg* cfg, const void* packed, const float* x, float* y,
+                        int B, int H, int W, void* workspace, size_t workspace_bytes, int mode,
+                        void* stream);
+int    ir_dncnn_launch_count(const IrDncnnCfg* cfg);
+
+/* ---- single-stage entry points (unit tests and ncu hit each kernel in isolation) ----
+ * Activations here are channels-last: a[pixel * ld + channel], pixel = (b*H + y)*W + x.    */
+
+/* One TransformerBlock in place on x[B*H*W, C] (src/restormer/restormer.py:146-150).
+ * h_params: the block's tensors in state_dict order (norm1.., attn.., norm2.., ffn..).     */
+size_t ir_block_workspace_bytes(int C, int heads, float ffn_expansion_factor, int B, int H, int W, int mode);
+size_t ir_block_packed_bytes(int C, int heads, float ffn_expansion_factor, int bias, int ln_with_bias, int mode);
+int    ir_block_pack_weights(int C, int heads, float ffn_expansion_factor, int bias, int ln_with_bias,
+                             const float* const* h_params, int n_params, void* packed, size_t packed_bytes,
+                             int mode, void* stream);
+int    ir_block_forward(int C, int heads, float ffn_expansion_factor, int bias, int ln_with_bias,
+                        const void* packed, float* x_nhwc, int B, int H, int W,
+                        void* workspace, size_t workspace_bytes, int mode, void* stream);
+
+/* Layout helpers used at the boundary of unit tests (NCHW fp32 <-> channels-last fp32). */
+int    ir_nchw_to_nhwc(const float* src, float* dst, int B, int C, int H, int W, void* stream);
+int    ir_nhwc_to_nchw(const float* src, float* dst, int B, int C, int H, int W, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IRB200_H_ */
