@@ -1,0 +1,289 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: Restormer forward, Mpix/s (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host CPU cores
+
+A "step" is one forward over one batch of synthetic images.  Workload at every N: BASELINE config 2,
+"Restormer gray Gaussian denoise (1->1 ch, dim=48, blocks [4,6,6,8]), batch 8 of synthetic 512x512",
+one such batch PER GPU (weak scaling; images are independent, there is no collective on the data path).
+Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+TASK = "gray_denoise"
+BATCH, HEIGHT, WIDTH = 8, 512, 512
+SIGMA = 25.0
+METRIC = "restormer_fwd_mpix_per_s"
+UNIT = "Mpix/s"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            d = json.load(open(path))
+            return float(d["hbm_gbs"]), float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), "measured"
+        except Exception:
+            pass
+    return 6650.0, 1590.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i",
+                 str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def build_model(device):
+    import torch
+    import image_restoration_models_b200 as M
+    import oracle
+    kw = oracle.RESTORMER_TASKS[TASK]
+    model = M.Restormer(**kw, bias=False).eval()
+    model.load_state_dict(oracle.synth_state_dict(oracle.restormer_schema(**kw), 7), strict=True)
+    return model.to(device), kw
+
+
+def cpu_reference_run(steps, warmup, sample_hw=None, budget_s=200.0):
+    """The reference algorithm (oracle port == the same ATen ops the reference modules call) on all host cores."""
+    import torch
+    import oracle
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.set_grad_enabled(False)
+    kw = oracle.RESTORMER_TASKS[TASK]
+    sd = oracle.synth_state_dict(oracle.restormer_schema(**kw), 7)
+    if sample_hw is None:
+        # calibrate on a 64x64 crop, then take the largest square crop of one 512x512 image that keeps the run bounded
+        x = oracle.synth_image((1, kw["inp_channels"], 64, 64), 17, SIGMA)
+        oracle.restormer_forward(sd, x)
+        t0 = time.perf_counter(); oracle.restormer_forward(sd, x); t64 = time.perf_counter() - t0
+        sample_hw = 64
+        for hw in (512, 256, 128):
+            if t64 * (hw / 64.0) ** 2 * 1.3 * (steps + warmup) <= budget_s:
+                sample_hw = hw
+                break
+    x = oracle.synth_image((1, kw["inp_channels"], sample_hw, sample_hw), 17, SIGMA)
+    for _ in range(warmup):
+        oracle.restormer_forward(sd, x)
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        oracle.restormer_forward(sd, x)
+        times.append(time.perf_counter() - t0)
+    mean = sum(times) / len(times)
+    mpix = sample_hw * sample_hw / 1e6 / mean
+    return mpix, mean * 1e3, cores, f"1 image of {sample_hw}x{sample_hw} (crop of one 512x512 batch element), fp32, {steps} timed runs"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="fp32", choices=["fp32", "half"])
+    args = ap.parse_args()
+    warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 0)
+    steps = max(args.steps, 1)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    config = {"workload": "Restormer gray Gaussian denoise (1->1 ch, dim=48, blocks [4,6,6,8]), batch 8 of synthetic "
+                          "512x512 per GPU (BASELINE config 2)",
+              "task": TASK, "batch_per_gpu": BATCH, "height": HEIGHT, "width": WIDTH, "weights": "random-init (seeded)",
+              "partition": "by image, one batch per GPU, no collective",
+              "cache": "working set ~12 GB per step >> 126 MB L2, so every step streams from HBM"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        mpix, ms, cores, sample = cpu_reference_run(steps, args.warmup)
+        line = {"impl": "reference", "metric": METRIC, "value": mpix, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+                "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": mpix, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+                "e2e": {"value": mpix, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    import oracle
+    from image_restoration_models_b200 import _native
+    torch.set_grad_enabled(False)
+    model, kw = build_model(dev)
+    model.set_mode(args.mode)
+    x_host = oracle.synth_image((BATCH, kw["inp_channels"], HEIGHT, WIDTH), 100 + rank, SIGMA).pin_memory()
+    y_host = torch.empty((BATCH, kw["out_channels"], HEIGHT, WIDTH), dtype=torch.float32).pin_memory()
+    x_dev = x_host.to(dev)
+    pix_per_step = BATCH * HEIGHT * WIDTH
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def reduce_max(v):
+        if dist is None:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident throughput ----------------------------------------------------------
+    for _ in range(warmup):
+        y = model(x_dev)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(steps):
+        y = model(x_dev)
+    e1.record()
+    barrier()
+    ms_total = reduce_max(e0.elapsed_time(e1))
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = ms_total / steps
+    value = world * pix_per_step / 1e6 / (ms_step / 1e3)
+
+    # ---- end to end through the public API: pinned host input -> forward -> host output ---------
+    def e2e_step():
+        xd = x_host.to(dev, non_blocking=True)
+        yd = model(xd)
+        y_host.copy_(yd, non_blocking=True)
+    e2e_step()
+    barrier()
+    e0.record()
+    for _ in range(steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    e2e_ms = reduce_max(e0.elapsed_time(e1)) / steps
+    e2e_value = world * pix_per_step / 1e6 / (e2e_ms / 1e3)
+
+    # ---- per-kernel breakdown (separate pass: two events per launch) ------------------------------
+    with _native.kernel_profile() as prof:
+        model(x_dev)
+        torch.cuda.synchronize()
+    rows = sorted(prof.rows, key=lambda r: -r["ms"])
+    hbm_peak, tc_peak, peak_kind = load_peaks()
+    kernels = []
+    for r in rows:
+        gbs = r["bytes"] / 1e9 / (r["ms"] / 1e3) if r["ms"] > 0 else 0.0
+        tfs = r["flops"] / 1e12 / (r["ms"] / 1e3) if r["ms"] > 0 else 0.0
+        kernels.append({"name": r["name"], "launches": r["launches"], "ms": round(r["ms"], 3),
+                        "GBps": round(gbs, 1), "hbm_frac": round(gbs / hbm_peak, 4),
+                        "TFLOPs": round(tfs, 2)})
+    top = rows[0]
+    top_ms_per_launch = top["ms"] / top["launches"]
+    achieved = top["bytes"] / top["launches"] / 1e9 / (top_ms_per_launch / 1e3)
+    roofline = {"kernel": top["name"], "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)",
+                "avg_launch_ms": top_ms_per_launch, "share_of_step": top["ms"] / sum(r["ms"] for r in rows),
+                "algorithmic_bytes_per_launch": top["bytes"] / top["launches"]}
+    step_bytes = sum(r["bytes"] for r in rows)
+    step_flops = sum(r["flops"] for r in rows)
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        mpix, ms, cores, sample = cpu_reference_run(1, 0, sample_hw=256)
+        cpu_baseline = {"value": mpix, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                        "ms_per_sample": ms}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "fp32 (fp32 accumulate)" if args.mode == "fp32" else "fp16 operands, fp32 accumulate",
+            "data": "synthetic", "config": config, "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4,
+                    "d2h_bytes_per_step": y_host.numel() * 4, "ms_per_step": e2e_ms},
+            "gpu_launches": steps * model.launches_per_forward(),
+            "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "step_algorithmic_GB": step_bytes / 1e9, "step_TFLOP": step_flops / 1e12,
+            "step_hbm_frac": step_bytes / 1e9 / (ms_step / 1e3) / hbm_peak,
+            "kernels": kernels}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

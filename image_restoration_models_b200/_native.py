@@ -28,6 +28,11 @@ class IrDncnnCfg(C.Structure):
                 ("has_bn", C.c_int32)]
 
 
+class IrKernelStat(C.Structure):
+    _fields_ = [("tag", C.c_int32), ("launches", C.c_int32), ("ms", C.c_double), ("bytes", C.c_double),
+                ("flops", C.c_double)]
+
+
 _PP = C.POINTER(C.c_void_p)
 
 # name -> (restype, argtypes); must list every symbol include/irb200.h declares
@@ -60,6 +65,9 @@ SIGNATURES = {
                                    C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
     "ir_nchw_to_nhwc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "ir_nhwc_to_nchw": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "ir_profile_begin": (C.c_int, []),
+    "ir_profile_end": (C.c_int, [C.POINTER(IrKernelStat), C.c_int]),
+    "ir_profile_tag_name": (C.c_char_p, [C.c_int]),
 }
 
 _lib = None
@@ -119,3 +127,25 @@ def require_cuda(x, what: str):
                            "no CPU fallback")
     if x.dtype != torch.float32:
         raise ValueError(f"{what}: expected float32, got {x.dtype}")
+
+
+class kernel_profile:
+    """Context manager: per-kernel-family CUDA-event times of every launch issued inside the block.
+
+    >>> with kernel_profile() as prof: model(x)
+    >>> prof.rows   # [{'name', 'launches', 'ms', 'bytes', 'flops'}, ...]
+    """
+
+    def __enter__(self):
+        check(lib().ir_profile_begin())
+        self.rows = []
+        return self
+
+    def __exit__(self, *exc):
+        buf = (IrKernelStat * 64)()
+        n = lib().ir_profile_end(buf, 64)
+        if n < 0:
+            check(n)
+        self.rows = [dict(name=lib().ir_profile_tag_name(buf[i].tag).decode(), launches=buf[i].launches,
+                          ms=buf[i].ms, bytes=buf[i].bytes, flops=buf[i].flops) for i in range(n)]
+        return False

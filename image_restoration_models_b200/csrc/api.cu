@@ -2,6 +2,8 @@
 #include "dncnn.cuh"
 #include "restormer.cuh"
 
+#include <mutex>
+
 namespace irb {
 
 static thread_local std::string g_err;
@@ -16,6 +18,31 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
   if (e == cudaErrorMemoryAllocation) { g_err = std::string("CUDA out of memory: ") + buf; return IR_ERR_OOM; }
   return IR_ERR_CUDA;
 }
+
+// ---- per-launch timing -------------------------------------------------------------------------
+struct ProfRec { int tag; double bytes, flops; cudaEvent_t e0, e1; };
+static std::mutex g_prof_mu;
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+
+ProfScope::ProfScope(int tag, double bytes, double flops, cudaStream_t s) : idx(-1), stream(s) {
+  if (!g_prof_on) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  ProfRec r{tag, bytes, flops, nullptr, nullptr};
+  if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return;
+  cudaEventRecord(r.e0, s);
+  g_prof.push_back(r);
+  idx = (int)g_prof.size() - 1;
+}
+ProfScope::~ProfScope() {
+  if (idx < 0) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (idx < (int)g_prof.size()) cudaEventRecord(g_prof[idx].e1, stream);
+}
+
+static const char* kTagNames[TAG_COUNT] = {
+    "other", "ln_qkv_1x1", "dwconv3x3_qkv", "mdta_gram", "softmax_fold", "attn_out_1x1", "ln_project_in_1x1",
+    "dwconv3x3_gelu_gate", "ffn_project_out_1x1", "conv3x3", "reduce_chan_1x1", "concat_copy"};
 
 static int check_mode(int mode) {
   IRB_REQUIRE(mode == IR_MODE_FP32, "mode: only IR_MODE_FP32 is available in this build");
@@ -189,6 +216,39 @@ int ir_nhwc_to_nchw(const float* src, float* dst, int B, int C, int H, int W, vo
   IRB_REQUIRE(src && dst && B > 0 && C > 0 && H > 0 && W > 0, "layout: bad argument");
   return launch_nhwc_to_nchw(src, dst, B, C, H, W, (cudaStream_t)stream);
 }
+
+int ir_profile_begin(void) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (auto& r : g_prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  g_prof.clear();
+  g_prof_on = true;
+  return IR_OK;
+}
+
+int ir_profile_end(IrKernelStat* h_out, int max_rows) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof_on = false;
+  IrKernelStat agg[TAG_COUNT];
+  for (int t = 0; t < TAG_COUNT; ++t) agg[t] = IrKernelStat{t, 0, 0.0, 0.0, 0.0};
+  int status = IR_OK;
+  for (auto& r : g_prof) {
+    float ms = 0.f;
+    cudaError_t e = cudaEventSynchronize(r.e1);
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, r.e0, r.e1);
+    if (e != cudaSuccess) status = cuda_fail(e, "profile event", __FILE__, __LINE__);
+    const int t = (r.tag >= 0 && r.tag < TAG_COUNT) ? r.tag : TAG_OTHER;
+    agg[t].launches += 1; agg[t].ms += ms; agg[t].bytes += r.bytes; agg[t].flops += r.flops;
+    cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
+  }
+  g_prof.clear();
+  if (status != IR_OK) return status;
+  int n = 0;
+  for (int t = 0; t < TAG_COUNT && n < max_rows; ++t)
+    if (agg[t].launches > 0 && h_out) h_out[n++] = agg[t];
+  return n;
+}
+
+const char* ir_profile_tag_name(int tag) { return (tag >= 0 && tag < TAG_COUNT) ? kTagNames[tag] : "invalid"; }
 
 #pragma GCC visibility pop
 }  // extern "C"

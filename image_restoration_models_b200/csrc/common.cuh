@@ -38,6 +38,19 @@ static inline long long cdivll(long long a, long long b) { return (a + b - 1) / 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // ---------------------------------------------------------------------------------------------
+// optional per-launch device timing (api.cu); tags name the kernel family a launch belongs to
+// ---------------------------------------------------------------------------------------------
+enum KernelTag {
+  TAG_OTHER = 0, TAG_LN_QKV, TAG_DW_QKV, TAG_GRAM, TAG_FOLD, TAG_ATTN_OUT, TAG_LN_PIN, TAG_DW_GATE, TAG_FFN_OUT,
+  TAG_CONV3, TAG_REDUCE, TAG_COPY, TAG_COUNT
+};
+struct ProfScope {
+  ProfScope(int tag, double bytes, double flops, cudaStream_t s);
+  ~ProfScope();
+  int idx; cudaStream_t stream;
+};
+
+// ---------------------------------------------------------------------------------------------
 // generic contraction (1x1 conv, 3x3 conv as implicit GEMM) parameter block
 // rows = pixels of image b (row = b*H*W + y*W + x), columns = output channels
 // ---------------------------------------------------------------------------------------------
@@ -61,6 +74,7 @@ struct GemmParams {
   int relu;
   const float* r; int ldr; float acc_sign;
   float* y; int ldy; int o_mode;
+  int tag;                                // KernelTag for the profiler
 };
 
 struct DwParams {
@@ -73,6 +87,7 @@ struct DwParams {
   int C;                                  // channels produced
   int gate;                               // 1: out[c] = gelu(dw(in[c])) * dw(in[c + gate_off])
   int gate_off;
+  int tag;
 };
 
 struct GramParams {

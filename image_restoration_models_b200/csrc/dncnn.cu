@@ -86,6 +86,7 @@ int dncnn_forward(const DncnnPlan& pl, const float* packed, const float* x, floa
     } else {
       g.relu = 1; g.acc_sign = 1.f; g.r = nullptr; g.y = buf[l & 1]; g.ldy = pl.cfg.nc; g.o_mode = O_NHWC;
     }
+    g.tag = TAG_CONV3;
     IRB_TRY(launch_gemm_simt(g, s));
   }
   return IR_OK;

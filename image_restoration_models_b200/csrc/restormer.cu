@@ -275,14 +275,14 @@ int run_block(const BlockPlan& bp, const float* packed, const float* x_in, float
   g.w = P(bp.qkv_w); g.w_bstride = 0; g.N = 3 * C; g.K = C; g.Kp = C; g.bias = P(bp.qkv_b);
   g.ln_mode = ln; g.ln_w = P(bp.ln1_w); g.ln_b = P(bp.ln1_b);
   g.relu = 0; g.r = nullptr; g.ldr = 0; g.acc_sign = 1.f;
-  g.y = bs.qkv; g.ldy = 3 * C; g.o_mode = O_NHWC;
+  g.y = bs.qkv; g.ldy = 3 * C; g.o_mode = O_NHWC; g.tag = TAG_LN_QKV;
   IRB_TRY(launch_gemm_simt(g, s));
 
   // (2) depthwise 3x3 over the 3C channels (restormer.py:114 qkv_dwconv)
   DwParams dwp{};
   dwp.in = bs.qkv; dwp.ldi = 3 * C; dwp.out = bs.qkv_dw; dwp.ldo = 3 * C;
   dwp.w = P(bp.qkvdw_w); dwp.bias = P(bp.qkvdw_b); dwp.Cw = 3 * C;
-  dwp.B = B; dwp.H = H; dwp.W = W; dwp.C = 3 * C; dwp.gate = 0; dwp.gate_off = 0;
+  dwp.B = B; dwp.H = H; dwp.W = W; dwp.C = 3 * C; dwp.gate = 0; dwp.gate_off = 0; dwp.tag = TAG_DW_QKV;
   IRB_TRY(launch_dwconv(dwp, s));
 
   // (3) Gram q.k^T and row norms per (image, head) (restormer.py:121-124), split over pixel slices
@@ -304,7 +304,7 @@ int run_block(const BlockPlan& bp, const float* packed, const float* x_in, float
   g.B = B; g.H = H; g.W = W;
   g.w = bs.w_eff; g.w_bstride = (long long)C * C; g.N = C; g.K = C; g.Kp = C; g.bias = P(bp.proj_b);
   g.ln_mode = LN_NONE; g.acc_sign = 1.f;
-  g.r = x_in; g.ldr = C; g.y = x_out; g.ldy = C; g.o_mode = O_NHWC;
+  g.r = x_in; g.ldr = C; g.y = x_out; g.ldy = C; g.o_mode = O_NHWC; g.tag = TAG_ATTN_OUT;
   IRB_TRY(launch_gemm_simt(g, s));
 
   // (6) norm2 + project_in 1x1 (:148, :89)
@@ -313,14 +313,14 @@ int run_block(const BlockPlan& bp, const float* packed, const float* x_in, float
   g.B = B; g.H = H; g.W = W;
   g.w = P(bp.pin_w); g.N = 2 * hp; g.K = C; g.Kp = C; g.bias = P(bp.pin_b);
   g.ln_mode = ln; g.ln_w = P(bp.ln2_w); g.ln_b = P(bp.ln2_b); g.acc_sign = 1.f;
-  g.y = bs.hidden; g.ldy = 2 * hp; g.o_mode = O_NHWC;
+  g.y = bs.hidden; g.ldy = 2 * hp; g.o_mode = O_NHWC; g.tag = TAG_LN_PIN;
   IRB_TRY(launch_gemm_simt(g, s));
 
   // (7) depthwise 3x3 + gelu(x1)*x2 (:90-91)
   dwp = DwParams{};
   dwp.in = bs.hidden; dwp.ldi = 2 * hp; dwp.out = bs.gated; dwp.ldo = hp;
   dwp.w = P(bp.ffdw_w); dwp.bias = P(bp.ffdw_b); dwp.Cw = 2 * hp;
-  dwp.B = B; dwp.H = H; dwp.W = W; dwp.C = hp; dwp.gate = 1; dwp.gate_off = hp;
+  dwp.B = B; dwp.H = H; dwp.W = W; dwp.C = hp; dwp.gate = 1; dwp.gate_off = hp; dwp.tag = TAG_DW_GATE;
   IRB_TRY(launch_dwconv(dwp, s));
 
   // (8) x_out += project_out . gated (:92, :148)
@@ -329,7 +329,7 @@ int run_block(const BlockPlan& bp, const float* packed, const float* x_in, float
   g.B = B; g.H = H; g.W = W;
   g.w = P(bp.pout_w); g.N = C; g.K = hp; g.Kp = hp; g.bias = P(bp.pout_b);
   g.ln_mode = LN_NONE; g.acc_sign = 1.f;
-  g.r = x_out; g.ldr = C; g.y = x_out; g.ldy = C; g.o_mode = O_NHWC;
+  g.r = x_out; g.ldr = C; g.y = x_out; g.ldy = C; g.o_mode = O_NHWC; g.tag = TAG_FFN_OUT;
   IRB_TRY(launch_gemm_simt(g, s));
   return IR_OK;
 }
@@ -367,7 +367,7 @@ static int conv3(const ConvPlan& cp, const float* packed, const float* in, int l
   g.B = B; g.H = H; g.W = W;
   g.w = packed + cp.w; g.N = cp.cout; g.K = cp.k; g.Kp = cp.kp; g.bias = cp.b >= 0 ? packed + cp.b : nullptr;
   g.ln_mode = LN_NONE; g.acc_sign = 1.f; g.r = r; g.ldr = 0;
-  g.y = out; g.ldy = ld_out; g.o_mode = o_mode;
+  g.y = out; g.ldy = ld_out; g.o_mode = o_mode; g.tag = TAG_CONV3;
   return launch_gemm_simt(g, s);
 }
 
@@ -414,7 +414,7 @@ int restormer_forward(const RestormerPlan& pl, const float* packed, const float*
     g.B = B; g.H = hi * 2; g.W = wi * 2;
     g.w = packed + pl.reduce[l].w; g.N = C; g.K = 2 * C; g.Kp = 2 * C;
     g.bias = pl.reduce[l].b >= 0 ? packed + pl.reduce[l].b : nullptr;
-    g.ln_mode = LN_NONE; g.acc_sign = 1.f; g.y = ws.d[l]; g.ldy = C; g.o_mode = O_NHWC;
+    g.ln_mode = LN_NONE; g.acc_sign = 1.f; g.y = ws.d[l]; g.ldy = C; g.o_mode = O_NHWC; g.tag = TAG_REDUCE;
     IRB_TRY(launch_gemm_simt(g, s));
     IRB_TRY(run_stage(pl.dec[l], packed, ws.d[l], ws.d[l], B, hi * 2, wi * 2, C, ws.bs, lnb, s));
     below = ws.d[l];
@@ -429,7 +429,7 @@ int restormer_forward(const RestormerPlan& pl, const float* packed, const float*
     GemmParams g{};
     g.a1 = e1_in; g.lda1 = d; g.k1 = d; g.a_mode = A_PLAIN; g.B = B; g.H = H; g.W = W;
     g.w = packed + pl.skip.w; g.N = 2 * d; g.K = d; g.Kp = d; g.bias = pl.skip.b >= 0 ? packed + pl.skip.b : nullptr;
-    g.ln_mode = LN_NONE; g.acc_sign = 1.f; g.r = ws.d[0]; g.ldr = 2 * d; g.y = ws.d[0]; g.ldy = 2 * d; g.o_mode = O_NHWC;
+    g.ln_mode = LN_NONE; g.acc_sign = 1.f; g.r = ws.d[0]; g.ldr = 2 * d; g.y = ws.d[0]; g.ldy = 2 * d; g.o_mode = O_NHWC; g.tag = TAG_REDUCE;
     IRB_TRY(launch_gemm_simt(g, s));
     IRB_TRY(conv3(pl.output, packed, ws.d[0], 2 * d, A_IM2COL_NHWC, B, H, W, y, 0, O_NCHW, nullptr, s));
   } else {

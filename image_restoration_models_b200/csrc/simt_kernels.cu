@@ -188,6 +188,9 @@ int launch_gemm_simt(const GemmParams& p, cudaStream_t s) {
   if (p.o_mode == O_SHUFFLE) IRB_REQUIRE(p.N % 4 == 0, "gemm: shuffle needs N % 4 == 0");
   const int HW = p.H * p.W;
   dim3 grid(cdiv(HW, 64), cdiv(p.N, 64), p.B);
+  const double rows = (double)p.B * HW;
+  const double a_elems = p.a_mode == A_PLAIN ? rows * p.K : rows * p.k1;   // im2col re-reads hit cache, not HBM
+  ProfScope prof(p.tag, 4.0 * (a_elems + rows * p.N * (p.r ? 2.0 : 1.0)), 2.0 * rows * p.N * p.K, s);
   gemm_simt_kernel<64, 64, 16><<<grid, 256, 0, s>>>(p);
   IRB_LAUNCH_CHECK();
   return IR_OK;
@@ -251,6 +254,8 @@ int launch_dwconv(const DwParams& p, cudaStream_t s) {
               "dwconv: channel counts must be multiples of 4");
   const long long total = (long long)p.B * p.H * p.W * (p.C / 4);
   const int blocks = (int)(cdivll(total, 256) < 148LL * 16 ? cdivll(total, 256) : 148LL * 16);
+  const double pix = (double)p.B * p.H * p.W;
+  ProfScope prof(p.tag, 4.0 * pix * p.C * (p.gate ? 3.0 : 2.0), 2.0 * 9.0 * pix * p.C * (p.gate ? 2.0 : 1.0), s);
   dwconv_kernel<<<blocks > 0 ? blocks : 1, 256, 0, s>>>(p);
   IRB_LAUNCH_CHECK();
   return IR_OK;
@@ -330,6 +335,7 @@ int launch_gram(const GramParams& p, cudaStream_t s) {
   const int ch = p.C / p.heads;
   IRB_REQUIRE(p.C % p.heads == 0 && ch % 16 == 0 && ch <= 128 && p.ld % 4 == 0, "gram: head dim must be a multiple of 16, <= 128");
   dim3 grid(p.nparts, p.heads, p.B);
+  ProfScope prof(TAG_GRAM, 4.0 * (double)p.B * p.HW * 2.0 * p.C, 2.0 * (double)p.B * p.HW * p.C * ch, s);
   switch (ch / 16) {
     case 1: gram_kernel<1><<<grid, 256, 0, s>>>(p); break;
     case 2: gram_kernel<2><<<grid, 256, 0, s>>>(p); break;
@@ -409,6 +415,7 @@ int launch_fold(const FoldParams& p, cudaStream_t s) {
   IRB_REQUIRE(smem <= 48 * 1024 + 0u || ch <= 128, "fold: head dim too large");
   if (smem > 48 * 1024) IRB_CUDA(cudaFuncSetAttribute(fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(p.heads, p.B);
+  ProfScope prof(TAG_FOLD, 4.0 * (double)p.B * p.C * p.C, 2.0 * (double)p.B * p.C * p.C * ch, s);
   fold_kernel<<<grid, 256, smem, s>>>(p);
   IRB_LAUNCH_CHECK();
   return IR_OK;
@@ -432,6 +439,7 @@ int launch_copy_channels(const float* src, int lds, float* dst, int ldd, long lo
   IRB_REQUIRE(C % 4 == 0 && lds % 4 == 0 && ldd % 4 == 0, "copy_channels: multiples of 4 required");
   const long long total = rows * (C / 4);
   const int blocks = (int)(cdivll(total, 256) < 148LL * 16 ? cdivll(total, 256) : 148LL * 16);
+  ProfScope prof(TAG_COPY, 8.0 * (double)rows * C, 0.0, s);
   copy_channels_kernel<<<blocks > 0 ? blocks : 1, 256, 0, s>>>(src, lds, dst, ldd, rows, C / 4);
   IRB_LAUNCH_CHECK();
   return IR_OK;

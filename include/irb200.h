@@ -118,6 +118,20 @@ int    ir_block_forward(int C, int heads, float ffn_expansion_factor, int bias, 
 int    ir_nchw_to_nhwc(const float* src, float* dst, int B, int C, int H, int W, void* stream);
 int    ir_nhwc_to_nchw(const float* src, float* dst, int B, int C, int H, int W, void* stream);
 
+/* ---- per-kernel device timing (bench.py roofline; off by default, adds two events per launch) ----
+ * ir_profile_begin() starts recording every launch the calling process issues through this library;
+ * ir_profile_end() synchronises the recorded events and returns one aggregate row per kernel family. */
+typedef struct IrKernelStat {
+  int32_t tag;             /* kernel family id, see ir_profile_tag_name */
+  int32_t launches;
+  double  ms;              /* summed CUDA-event time */
+  double  bytes;           /* summed algorithmic bytes (unique activation reads + writes; weights excluded) */
+  double  flops;           /* summed 2*MAC */
+} IrKernelStat;
+int         ir_profile_begin(void);
+int         ir_profile_end(IrKernelStat* h_out, int max_rows);   /* returns rows written, or < 0 */
+const char* ir_profile_tag_name(int tag);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,207 @@
+"""GPU parity: the CUDA path (through the C-ABI, via the mirror classes) against the committed golden
+outputs of the unmodified reference and against the CPU oracle on fresh seeded inputs.
+
+Tolerance (BASELINE.json north_star): fp32 mode max-abs <= 1e-3 on [0,1] images and |PSNR delta| <= 0.01 dB."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+import torch
+
+import image_restoration_models_b200 as M
+from image_restoration_models_b200 import _native
+import oracle
+from conftest import golden_names, load_golden, record
+
+pytestmark = pytest.mark.gpu
+torch.set_grad_enabled(False)
+
+TOL_MAXABS = 1e-3
+TOL_PSNR_DB = 0.01
+
+
+def psnr(a, b):
+    mse = float(np.mean((a.astype(np.float64) - b.astype(np.float64)) ** 2))
+    return 10.0 * math.log10(1.0 / max(mse, 1e-30))
+
+
+def check_parity(case, y, y_ref, clean):
+    err = float(np.abs(y.astype(np.float64) - y_ref.astype(np.float64)).max())
+    d_psnr = abs(psnr(y, clean) - psnr(y_ref, clean))
+    record(case, max_abs=err, psnr_delta_db=d_psnr, psnr_vs_ref_db=psnr(y, y_ref))
+    assert np.isfinite(y).all(), case
+    assert err <= TOL_MAXABS, (case, err)
+    assert d_psnr <= TOL_PSNR_DB, (case, d_psnr)
+
+
+def build_restormer(kw, wseed):
+    m = M.Restormer(**kw, bias=False).eval()
+    m.load_state_dict(oracle.synth_state_dict(oracle.restormer_schema(**kw), wseed), strict=True)
+    return m.cuda()
+
+
+@pytest.mark.parametrize("name", golden_names("restormer"))
+def test_restormer_vs_reference_golden(name):
+    meta, z = load_golden(name)
+    kw = oracle.RESTORMER_TASKS[meta["task"]]
+    m = build_restormer(kw, meta["wseed"])
+    x = oracle.synth_image(meta["shape"], meta["xseed"], meta["sigma"])
+    clean = oracle.synth_image(meta["shape"], meta["xseed"], None).numpy()
+    y = m(x.cuda()).cpu().numpy()
+    if kw["inp_channels"] != kw["out_channels"]:
+        clean = z["y64"].astype(np.float32)
+    check_parity(name, y, z["y64"], clean[:, : y.shape[1]])
+
+
+@pytest.mark.parametrize("name", golden_names("dncnn"))
+def test_dncnn_vs_reference_golden(name):
+    meta, z = load_golden(name)
+    n = meta["in_nc"]
+    m = M.DnCNN(n, n, 64, meta["nb"], meta["act_mode"]).eval()
+    m.load_state_dict(oracle.synth_state_dict(oracle.dncnn_schema(n, n, 64, meta["nb"], meta["act_mode"]),
+                                              meta["wseed"]), strict=True)
+    m = m.cuda()
+    x = oracle.synth_image(meta["shape"], meta["xseed"], meta["sigma"])
+    clean = oracle.synth_image(meta["shape"], meta["xseed"], None).numpy()
+    y = m(x.cuda()).cpu().numpy()
+    check_parity(name, y, z["y64"], clean)
+
+
+def run_block(meta, sd, x_nchw):
+    """One TransformerBlock through ir_block_* (channels-last in place)."""
+    lib = _native.lib()
+    Cc, heads = meta["C"], meta["heads"]
+    wb = int(meta["LayerNorm_type"] != "BiasFree")
+    B, _, H, W = x_nchw.shape
+    params = [v.cuda().contiguous() for v in sd.values()]
+    nbytes = lib.ir_block_packed_bytes(Cc, heads, 2.66, 0, wb, 0)
+    packed = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    _native.check(lib.ir_block_pack_weights(Cc, heads, 2.66, 0, wb, _native.ptr_array(params), len(params),
+                                            packed.data_ptr(), nbytes, 0, stream))
+    ws = torch.empty(lib.ir_block_workspace_bytes(Cc, heads, 2.66, B, H, W, 0), dtype=torch.uint8, device="cuda")
+    xg = x_nchw.cuda().contiguous()
+    xl = torch.empty(B * H * W * Cc, dtype=torch.float32, device="cuda")
+    _native.check(lib.ir_nchw_to_nhwc(xg.data_ptr(), xl.data_ptr(), B, Cc, H, W, stream))
+    # the layout helper must agree with torch's permute
+    assert torch.equal(xl.view(B, H, W, Cc), xg.permute(0, 2, 3, 1))
+    _native.check(lib.ir_block_forward(Cc, heads, 2.66, 0, wb, packed.data_ptr(), xl.data_ptr(), B, H, W,
+                                       ws.data_ptr(), ws.numel(), 0, stream))
+    out = torch.empty_like(xg)
+    _native.check(lib.ir_nhwc_to_nchw(xl.data_ptr(), out.data_ptr(), B, Cc, H, W, stream))
+    torch.cuda.synchronize()
+    return out.cpu().numpy()
+
+
+@pytest.mark.parametrize("name", golden_names("block"))
+def test_transformer_block_vs_reference_golden(name):
+    meta, z = load_golden(name)
+    wb = meta["LayerNorm_type"] != "BiasFree"
+    sd = oracle.synth_state_dict(oracle.synth._block_schema("blk", meta["C"], meta["heads"], 2.66, False, wb),
+                                 meta["wseed"])
+    x = oracle.synth_tensor(meta["shape"], meta["xseed"], -1.0, 1.0)
+    y = run_block(meta, sd, x)
+    err = float(np.abs(y.astype(np.float64) - z["y64"]).max())
+    record(name, max_abs=err)
+    assert err <= TOL_MAXABS, (name, err)
+
+
+@pytest.mark.parametrize("task,shape,wseed,xseed", [
+    ("color_denoise", (1, 3, 40, 72), 61, 71),
+    ("motion_deblur", (2, 3, 24, 16), 62, 72),
+    ("defocus_dual", (1, 6, 16, 48), 63, 73),
+])
+def test_restormer_vs_oracle_fresh_inputs(task, shape, wseed, xseed):
+    kw = oracle.RESTORMER_TASKS[task]
+    sd = oracle.synth_state_dict(oracle.restormer_schema(**kw), wseed)
+    x = oracle.synth_image(shape, xseed, 25.0)
+    y_ref = oracle.restormer_forward({k: v.double() for k, v in sd.items()}, x.double()).numpy()
+    m = build_restormer(kw, wseed)
+    y = m(x.cuda()).cpu().numpy()
+    clean = y_ref.astype(np.float32) if task == "defocus_dual" else oracle.synth_image(shape, xseed, None).numpy()
+    check_parity(f"oracle_{task}_{shape[2]}x{shape[3]}", y, y_ref, clean)
+
+
+def test_restormer_with_conv_bias_and_custom_widths_vs_oracle():
+    kw = dict(inp_channels=3, out_channels=3, dim=32, num_blocks=[1, 2, 1, 2], num_refinement_blocks=1,
+              heads=[1, 2, 2, 4], ffn_expansion_factor=2.0, bias=True, LayerNorm_type="WithBias")
+    sd = oracle.synth_state_dict(oracle.restormer_schema(**kw), 64)
+    x = oracle.synth_image((2, 3, 32, 24), 74, None)
+    y_ref = oracle.restormer_forward({k: v.double() for k, v in sd.items()}, x.double()).numpy()
+    m = M.Restormer(**kw).eval()
+    m.load_state_dict(sd, strict=True)
+    y = m.cuda()(x.cuda()).cpu().numpy()
+    check_parity("oracle_bias_dim32", y, y_ref, x.numpy())
+
+
+def test_dncnn_vs_oracle_odd_sizes():
+    sd = oracle.synth_state_dict(oracle.dncnn_schema(3, 3, 64, 20, "R"), 65)
+    x = oracle.synth_image((2, 3, 19, 31), 75, 50.0)
+    y_ref = oracle.dncnn_forward({k: v.double() for k, v in sd.items()}, x.double()).numpy()
+    m = M.DnCNN(3, 3, 64, 20, "R").eval()
+    m.load_state_dict(sd, strict=True)
+    y = m.cuda()(x.cuda()).cpu().numpy()
+    check_parity("oracle_dncnn_color_19x31", y, y_ref, oracle.synth_image((2, 3, 19, 31), 75, None).numpy())
+
+
+def test_shape_validation_raises_before_launch():
+    m = build_restormer(oracle.RESTORMER_TASKS["color_denoise"], 1)
+    with pytest.raises(ValueError):
+        m(torch.zeros(1, 3, 60, 64, device="cuda"))
+    with pytest.raises(ValueError):
+        m(torch.zeros(1, 1, 64, 64, device="cuda"))
+    with pytest.raises(ValueError):
+        m(torch.zeros(1, 3, 64, 64, device="cuda", dtype=torch.float16))
+
+
+def test_full_size_properties_config2_gray_denoise():
+    """BASELINE config 2 (batch 8 of 512x512 gray): properties that hold at any size.
+    (a) run-to-run determinism, bit-exact; (b) permuting the batch permutes the output, bit-exact;
+    (c) an image's result does not depend on its batch-mates (only the Gram split differs -> fp32 noise)."""
+    kw = oracle.RESTORMER_TASKS["gray_denoise"]
+    m = build_restormer(kw, 81)
+    x = oracle.synth_image((8, 1, 512, 512), 91, 25.0).cuda()
+    y1 = m(x)
+    y2 = m(x)
+    assert torch.equal(y1, y2)
+    assert torch.isfinite(y1).all()
+    perm = torch.tensor([3, 0, 7, 1, 6, 2, 5, 4], device="cuda")
+    yp = m(x[perm].contiguous())
+    assert torch.equal(yp, y1[perm])
+    ys = m(x[2:3].contiguous())
+    err = float((ys - y1[2:3]).abs().max())
+    record("config2_single_vs_batched", max_abs=err)
+    assert err <= 1e-4
+
+
+def test_full_size_properties_config3_real_denoise_and_oracle_crop():
+    """BASELINE config 3 shape (256x256 colour patches; batch reduced to 4 to bound test time) and a
+    256x256 single image against the CPU oracle (5 s on the host)."""
+    kw = oracle.RESTORMER_TASKS["real_denoise"]
+    m = build_restormer(kw, 82)
+    x = oracle.synth_image((4, 3, 256, 256), 92, None)
+    y = m(x.cuda())
+    assert torch.equal(y, m(x.cuda()))
+    sd = oracle.synth_state_dict(oracle.restormer_schema(**kw), 82)
+    y_ref = oracle.restormer_forward(sd, x[1:2]).numpy()      # fp32 oracle (self-noise ~3e-7)
+    check_parity("config3_image1_vs_oracle", y[1:2].cpu().numpy(), y_ref, x[1:2].numpy())
+
+
+def test_dncnn_config1_full_size():
+    """BASELINE config 1: DnCNN-S gray sigma=25, one 256x256 image, both act modes."""
+    for act, seed in (("BR", 83), ("R", 84)):
+        sd = oracle.synth_state_dict(oracle.dncnn_schema(1, 1, 64, 17, act), seed)
+        x = oracle.synth_image((1, 1, 256, 256), 93, 25.0)
+        y_ref = oracle.dncnn_forward({k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()},
+                                     x.double()).numpy()
+        m = M.DnCNN(1, 1, 64, 17, act).eval()
+        m.load_state_dict(sd, strict=True)
+        y = m.cuda()(x.cuda()).cpu().numpy()
+        check_parity(f"config1_dncnn_{act}", y, y_ref, oracle.synth_image((1, 1, 256, 256), 93, None).numpy())
+
+
+def test_native_library_is_the_loaded_code():
+    """The forward must run from the in-tree .so (no silent PyTorch path)."""
+    maps = open("/proc/self/maps").read()
+    assert "libirb200.so" in maps
