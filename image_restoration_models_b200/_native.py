@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libirb200.so")
 
 IR_OK, IR_ERR_INVALID, IR_ERR_WORKSPACE, IR_ERR_CUDA, IR_ERR_OOM = 0, -1, -2, -3, -4
-MODE_FP32, MODE_HALF = 0, 1
+MODE_FP32, MODE_HALF, MODE_FP32_SIMT = 0, 1, 2
 ABI_VERSION = 1
 
 
@@ -65,6 +65,9 @@ SIGNATURES = {
                                    C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
     "ir_nchw_to_nhwc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "ir_nhwc_to_nchw": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "ir_test_conv1x1": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                  C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                  C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     "ir_profile_begin": (C.c_int, []),
     "ir_profile_end": (C.c_int, [C.POINTER(IrKernelStat), C.c_int]),
     "ir_profile_tag_name": (C.c_char_p, [C.c_int]),

@@ -1,6 +1,7 @@
 // extern "C" boundary (include/irb200.h).  Plain pointers and sizes only; no torch types.
 #include "dncnn.cuh"
 #include "restormer.cuh"
+#include "tc_gemm.cuh"
 
 #include <mutex>
 
@@ -42,12 +43,14 @@ ProfScope::~ProfScope() {
 
 static const char* kTagNames[TAG_COUNT] = {
     "other", "ln_qkv_1x1", "dwconv3x3_qkv", "mdta_gram", "softmax_fold", "attn_out_1x1", "ln_project_in_1x1",
-    "dwconv3x3_gelu_gate", "ffn_project_out_1x1", "conv3x3", "reduce_chan_1x1", "concat_copy"};
+    "dwconv3x3_gelu_gate", "ffn_project_out_1x1", "conv3x3", "reduce_chan_1x1", "concat_copy", "layernorm"};
 
 static int check_mode(int mode) {
-  IRB_REQUIRE(mode == IR_MODE_FP32, "mode: only IR_MODE_FP32 is available in this build");
+  IRB_REQUIRE(mode == IR_MODE_FP32 || mode == IR_MODE_FP32_SIMT,
+              "mode: IR_MODE_FP32 and IR_MODE_FP32_SIMT are available in this build");
   return IR_OK;
 }
+static int engine_of(int mode) { return mode == IR_MODE_FP32_SIMT ? ENGINE_SIMT : ENGINE_TC; }
 
 }  // namespace irb
 
@@ -63,14 +66,14 @@ const char* ir_last_error(void) { return g_err.c_str(); }
 int ir_restormer_param_count(const IrRestormerCfg* cfg) {
   if (!cfg) { set_error("invalid argument: null cfg"); return -1; }
   RestormerPlan pl;
-  if (build_restormer_plan(pl, *cfg) != IR_OK) return -1;
+  if (build_restormer_plan(pl, *cfg, ENGINE_TC) != IR_OK) return -1;
   return pl.n_params;
 }
 
 long long ir_restormer_param_numel(const IrRestormerCfg* cfg, int index) {
   if (!cfg) { set_error("invalid argument: null cfg"); return -1; }
   RestormerPlan pl;
-  if (build_restormer_plan(pl, *cfg) != IR_OK) return -1;
+  if (build_restormer_plan(pl, *cfg, ENGINE_TC) != IR_OK) return -1;
   for (const PackOp& op : pl.ops)
     if (op.param == index) return pack_op_src_numel(op);
   set_error("invalid argument: parameter index out of range");
@@ -80,7 +83,7 @@ long long ir_restormer_param_numel(const IrRestormerCfg* cfg, int index) {
 size_t ir_restormer_packed_bytes(const IrRestormerCfg* cfg, int mode) {
   if (!cfg || check_mode(mode) != IR_OK) return 0;
   RestormerPlan pl;
-  if (build_restormer_plan(pl, *cfg) != IR_OK) return 0;
+  if (build_restormer_plan(pl, *cfg, engine_of(mode)) != IR_OK) return 0;
   return (size_t)pl.packed_floats * sizeof(float);
 }
 
@@ -89,7 +92,7 @@ int ir_restormer_pack_weights(const IrRestormerCfg* cfg, const float* const* h_p
   IRB_REQUIRE(cfg && h_params && packed, "pack: null argument");
   IRB_TRY(check_mode(mode));
   RestormerPlan pl;
-  IRB_TRY(build_restormer_plan(pl, *cfg));
+  IRB_TRY(build_restormer_plan(pl, *cfg, engine_of(mode)));
   IRB_REQUIRE(n_params == pl.n_params, "pack: parameter count does not match the configuration's state_dict");
   if (packed_bytes < (size_t)pl.packed_floats * sizeof(float)) { set_error("packed buffer too small"); return IR_ERR_WORKSPACE; }
   IRB_CUDA(cudaMemsetAsync(packed, 0, (size_t)pl.packed_floats * sizeof(float), (cudaStream_t)stream));
@@ -99,7 +102,7 @@ int ir_restormer_pack_weights(const IrRestormerCfg* cfg, const float* const* h_p
 size_t ir_restormer_workspace_bytes(const IrRestormerCfg* cfg, int B, int H, int W, int mode) {
   if (!cfg || check_mode(mode) != IR_OK || B <= 0 || H <= 0 || W <= 0) return 0;
   RestormerPlan pl;
-  if (build_restormer_plan(pl, *cfg) != IR_OK) return 0;
+  if (build_restormer_plan(pl, *cfg, engine_of(mode)) != IR_OK) return 0;
   return restormer_workspace_bytes(pl, B, H, W);
 }
 
@@ -108,14 +111,14 @@ int ir_restormer_forward(const IrRestormerCfg* cfg, const void* packed, const fl
   IRB_REQUIRE(cfg && packed && x && y && workspace, "forward: null argument");
   IRB_TRY(check_mode(mode));
   RestormerPlan pl;
-  IRB_TRY(build_restormer_plan(pl, *cfg));
+  IRB_TRY(build_restormer_plan(pl, *cfg, engine_of(mode)));
   return restormer_forward(pl, (const float*)packed, x, y, B, H, W, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 int ir_restormer_launch_count(const IrRestormerCfg* cfg) {
   if (!cfg) return -1;
   RestormerPlan pl;
-  if (build_restormer_plan(pl, *cfg) != IR_OK) return -1;
+  if (build_restormer_plan(pl, *cfg, ENGINE_TC) != IR_OK) return -1;
   return restormer_launch_count(pl);
 }
 
@@ -175,14 +178,14 @@ int ir_dncnn_launch_count(const IrDncnnCfg* cfg) { return cfg ? cfg->nb : -1; }
 size_t ir_block_workspace_bytes(int C, int heads, float ffn, int B, int H, int W, int mode) {
   if (check_mode(mode) != IR_OK || B <= 0 || H <= 0 || W <= 0) return 0;
   BlockPlan bp; std::vector<PackOp> ops; long long pf;
-  if (build_block_plan(bp, ops, pf, C, heads, ffn, 0, 0) != IR_OK) return 0;
+  if (build_block_plan(bp, ops, pf, C, heads, ffn, 0, 0, engine_of(mode)) != IR_OK) return 0;
   return block_workspace_bytes(bp, B, H, W);
 }
 
 size_t ir_block_packed_bytes(int C, int heads, float ffn, int bias, int ln_with_bias, int mode) {
   if (check_mode(mode) != IR_OK) return 0;
   BlockPlan bp; std::vector<PackOp> ops; long long pf;
-  if (build_block_plan(bp, ops, pf, C, heads, ffn, bias, ln_with_bias) != IR_OK) return 0;
+  if (build_block_plan(bp, ops, pf, C, heads, ffn, bias, ln_with_bias, engine_of(mode)) != IR_OK) return 0;
   return (size_t)pf * sizeof(float);
 }
 
@@ -191,7 +194,7 @@ int ir_block_pack_weights(int C, int heads, float ffn, int bias, int ln_with_bia
   IRB_REQUIRE(h_params && packed, "pack: null argument");
   IRB_TRY(check_mode(mode));
   BlockPlan bp; std::vector<PackOp> ops; long long pf;
-  IRB_TRY(build_block_plan(bp, ops, pf, C, heads, ffn, bias, ln_with_bias));
+  IRB_TRY(build_block_plan(bp, ops, pf, C, heads, ffn, bias, ln_with_bias, engine_of(mode)));
   IRB_REQUIRE(n_params == block_param_count(bias, ln_with_bias), "pack: wrong parameter count for a TransformerBlock");
   if (packed_bytes < (size_t)pf * sizeof(float)) { set_error("packed buffer too small"); return IR_ERR_WORKSPACE; }
   IRB_CUDA(cudaMemsetAsync(packed, 0, (size_t)pf * sizeof(float), (cudaStream_t)stream));
@@ -203,7 +206,7 @@ int ir_block_forward(int C, int heads, float ffn, int bias, int ln_with_bias, co
   IRB_REQUIRE(packed && x_nhwc && workspace, "forward: null argument");
   IRB_TRY(check_mode(mode));
   BlockPlan bp; std::vector<PackOp> ops; long long pf;
-  IRB_TRY(build_block_plan(bp, ops, pf, C, heads, ffn, bias, ln_with_bias));
+  IRB_TRY(build_block_plan(bp, ops, pf, C, heads, ffn, bias, ln_with_bias, engine_of(mode)));
   return block_forward(bp, (const float*)packed, x_nhwc, B, H, W, workspace, workspace_bytes, ln_with_bias,
                        (cudaStream_t)stream);
 }
@@ -215,6 +218,39 @@ int ir_nchw_to_nhwc(const float* src, float* dst, int B, int C, int H, int W, vo
 int ir_nhwc_to_nchw(const float* src, float* dst, int B, int C, int H, int W, void* stream) {
   IRB_REQUIRE(src && dst && B > 0 && C > 0 && H > 0 && W > 0, "layout: bad argument");
   return launch_nhwc_to_nchw(src, dst, B, C, H, W, (cudaStream_t)stream);
+}
+
+int ir_test_conv1x1(int engine, const float* a1, int lda1, int k1, const float* a2, int lda2, int k2,
+                    const float* w_rowmajor, const float* bias, int ln_mode, const float* ln_w, const float* ln_b,
+                    const float* r, int ldr, float* y, int ldy, int B, int HW, int N, int a_pad, void* scratch,
+                    size_t scratch_bytes, void* stream) {
+  IRB_REQUIRE(a1 && w_rowmajor && y && scratch && B > 0 && HW > 0 && N > 0 && k1 > 0, "test_conv1x1: bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int K = k1 + k2;
+  const long long rows = (long long)B * HW;
+  const size_t need = ((size_t)N * K + (size_t)rows * K) * sizeof(float);
+  if (scratch_bytes < need) { set_error("scratch too small"); return IR_ERR_WORKSPACE; }
+  float* wp = (float*)scratch;
+  float* xhat = wp + (size_t)N * K;
+  PackMat pm{w_rowmajor, wp, 0, 0, N, N, 1, K, K, nullptr, engine == ENGINE_TC ? 1 : 0};
+  IRB_TRY(launch_pack_mat(pm, s));
+  if (engine == ENGINE_SIMT) {
+    GemmParams g{};
+    g.a1 = a1; g.lda1 = lda1; g.k1 = k1; g.a2 = a2; g.lda2 = lda2; g.k2 = k2; g.a_mode = A_PLAIN;
+    g.B = B; g.H = 1; g.W = HW; g.w = wp; g.N = N; g.K = K; g.Kp = K; g.bias = bias;
+    g.ln_mode = ln_mode; g.ln_w = ln_w; g.ln_b = ln_b; g.acc_sign = 1.f; g.r = r; g.ldr = ldr; g.y = y; g.ldy = ldy;
+    g.o_mode = O_NHWC;
+    return launch_gemm_simt(g, s);
+  }
+  TcGemmParams t{};
+  t.a1 = a1; t.lda1 = lda1; t.k1 = k1; t.a2 = a2; t.lda2 = lda2; t.k2 = k2; t.B = B; t.HW = HW;
+  t.w = wp; t.N = N; t.K = K; t.bias = bias; t.ln_mode = ln_mode; t.ln_w = ln_w; t.ln_b = ln_b;
+  t.r = r; t.ldr = ldr; t.y = y; t.ldy = ldy; t.a_pad = a_pad;
+  if (ln_mode != LN_NONE && K > 128) {
+    IRB_TRY(launch_layernorm(a1, lda1, xhat, K, rows, K, ln_mode, ln_w, ln_b, s));
+    t.a1 = xhat; t.lda1 = K; t.ln_mode = LN_NONE;
+  }
+  return launch_gemm_tc(t, s);
 }
 
 int ir_profile_begin(void) {

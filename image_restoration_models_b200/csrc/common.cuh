@@ -42,7 +42,7 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 // ---------------------------------------------------------------------------------------------
 enum KernelTag {
   TAG_OTHER = 0, TAG_LN_QKV, TAG_DW_QKV, TAG_GRAM, TAG_FOLD, TAG_ATTN_OUT, TAG_LN_PIN, TAG_DW_GATE, TAG_FFN_OUT,
-  TAG_CONV3, TAG_REDUCE, TAG_COPY, TAG_COUNT
+  TAG_CONV3, TAG_REDUCE, TAG_COPY, TAG_LAYERNORM, TAG_COUNT
 };
 struct ProfScope {
   ProfScope(int tag, double bytes, double flops, cudaStream_t s);
@@ -102,7 +102,8 @@ struct FoldParams {
   int B, C, heads, nparts;
   const float* temperature;               // [heads]
   const float* w_proj;                    // [C][C] row-major (project_out)
-  float* w_eff; long long w_eff_bstride;  // [B][C][C] row-major
+  float* w_eff; long long w_eff_bstride;  // [B][C][C] row-major (fmt 0) or [B][C/4][C][4] tf32 (fmt 1)
+  int fmt;
 };
 
 // launchers (simt_kernels.cu)
@@ -110,6 +111,9 @@ int launch_gemm_simt(const GemmParams& p, cudaStream_t s);
 int launch_dwconv(const DwParams& p, cudaStream_t s);
 int launch_gram(const GramParams& p, cudaStream_t s);
 int launch_fold(const FoldParams& p, cudaStream_t s);
+// standalone channel LayerNorm (levels whose C does not fit the contraction's register-resident prologue)
+int launch_layernorm(const float* x, int ldx, float* y, int ldy, long long rows, int C, int ln_mode, const float* w,
+                     const float* b, cudaStream_t s);
 int launch_copy_channels(const float* src, int lds, float* dst, int ldd, long long rows, int C, cudaStream_t s);
 int launch_nchw_to_nhwc(const float* src, float* dst, int B, int C, int H, int W, cudaStream_t s);
 int launch_nhwc_to_nchw(const float* src, float* dst, int B, int C, int H, int W, cudaStream_t s);
@@ -122,6 +126,7 @@ struct PackMat {
   int n_src_half, n_dst_half, n_halves;   // row split-pad mapping (GDFN hidden padding)
   int k_src, k_dst;                        // logical / padded reduction length (kind 0: zero-pad; kind 1: k_src = 9*cin)
   const float* row_scale;                  // optional per-source-row scale (BatchNorm folding)
+  int fmt;                                 // 0: dst[n][k] fp32;  1: dst[k/4][n][k%4] rounded to tf32 (tcgen05 operand)
 };
 int launch_pack_mat(const PackMat& p, cudaStream_t s);
 // dst[t][map(c)] = src[c][t]  (depthwise 3x3 [C][1][3][3] -> [9][Cdst])

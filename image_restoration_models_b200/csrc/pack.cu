@@ -28,7 +28,13 @@ __global__ void pack_mat_kernel(const PackMat p) {
       }
       if (p.row_scale) v *= p.row_scale[ns];
     }
-    p.dst[idx] = v;
+    if (p.fmt == 1) {
+      uint32_t u;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+      p.dst[((long long)(k >> 2) * n_dst + n) * 4 + (k & 3)] = __uint_as_float(u);
+    } else {
+      p.dst[idx] = v;
+    }
   }
 }
 

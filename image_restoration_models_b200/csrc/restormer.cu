@@ -4,6 +4,7 @@
 // All activations are channels-last fp32 ([pixels][C]); the NCHW<->channels-last conversion is folded
 // into the first (patch_embed) and last (output) 3x3 convs.
 #include "restormer.cuh"
+#include "tc_gemm.cuh"
 
 #include <algorithm>
 
@@ -14,11 +15,19 @@ static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 // -----------------------------------------------------------------------------------------------
 // plan
 // -----------------------------------------------------------------------------------------------
+bool tc_gemm_supported(int K, int N) {
+  TcGemmParams t{};
+  t.K = K; t.N = N; t.k1 = K; t.k2 = 0; t.ln_mode = LN_NONE; t.a_pad = 1;
+  return tc_gemm_configure(t) != 0;
+}
+
 struct Builder {
   std::vector<PackOp>& ops;
   long long off = 0;       // floats
   int pidx = 0;            // running state_dict index
-  explicit Builder(std::vector<PackOp>& o) : ops(o) {}
+  int engine = ENGINE_TC;
+  Builder(std::vector<PackOp>& o, int e) : ops(o), engine(e) {}
+  bool tc(int K, int N) const { return engine == ENGINE_TC && tc_gemm_supported(K, N); }
   long long alloc(long long n) { const long long o = off; off += (n + 63) / 64 * 64; return o; }
 };
 
@@ -29,48 +38,52 @@ static void plan_block(Builder& bl, BlockPlan& bp, int C, int heads, float ffn, 
   bp.hp = round_up(bp.h, 8);
   auto vec = [&](long long& dst, int n) {
     dst = bl.alloc(n);
-    bl.ops.push_back(PackOp{PackOp::VEC, bl.pidx++, dst, n, n, 1, 0, 0, 0});
+    bl.ops.push_back(PackOp{PackOp::VEC, bl.pidx++, dst, n, n, 1, 0, 0, 0, 0});
   };
   auto vec_split = [&](long long& dst, int src_half, int dst_half, int halves) {
     dst = bl.alloc((long long)dst_half * halves);
-    bl.ops.push_back(PackOp{PackOp::VEC, bl.pidx++, dst, src_half, dst_half, halves, 0, 0, 0});
+    bl.ops.push_back(PackOp{PackOp::VEC, bl.pidx++, dst, src_half, dst_half, halves, 0, 0, 0, 0});
   };
-  auto mat = [&](long long& dst, int n_src_half, int n_dst_half, int halves, int k_src, int k_dst) {
+  auto mat = [&](long long& dst, int n_src_half, int n_dst_half, int halves, int k_src, int k_dst, bool tc) {
     dst = bl.alloc((long long)n_dst_half * halves * k_dst);
-    bl.ops.push_back(PackOp{PackOp::MAT1, bl.pidx++, dst, n_src_half, n_dst_half, halves, k_src, k_dst, 0});
+    bl.ops.push_back(PackOp{PackOp::MAT1, bl.pidx++, dst, n_src_half, n_dst_half, halves, k_src, k_dst, 0, tc ? 1 : 0});
   };
   auto dw = [&](long long& dst, int src_half, int dst_half, int halves) {
     dst = bl.alloc(9LL * dst_half * halves);
-    bl.ops.push_back(PackOp{PackOp::DW, bl.pidx++, dst, src_half, dst_half, halves, 0, 0, 0});
+    bl.ops.push_back(PackOp{PackOp::DW, bl.pidx++, dst, src_half, dst_half, halves, 0, 0, 0, 0});
   };
   bp.ln1_b = bp.qkv_b = bp.qkvdw_b = bp.proj_b = bp.ln2_b = bp.pin_b = bp.ffdw_b = bp.pout_b = -1;
+  bp.tc_qkv = bl.tc(C, 3 * C);
+  bp.tc_attn = bl.tc(C, C);
+  bp.tc_pin = bl.tc(C, 2 * bp.hp);
+  bp.tc_pout = bl.tc(bp.hp, C);
   vec(bp.ln1_w, C);
   if (ln_bias) vec(bp.ln1_b, C);
   vec(bp.temp, heads);
-  mat(bp.qkv_w, 3 * C, 3 * C, 1, C, C);
+  mat(bp.qkv_w, 3 * C, 3 * C, 1, C, C, bp.tc_qkv);
   if (bias) vec(bp.qkv_b, 3 * C);
   dw(bp.qkvdw_w, 3 * C, 3 * C, 1);
   if (bias) vec(bp.qkvdw_b, 3 * C);
-  mat(bp.proj_w, C, C, 1, C, C);
+  mat(bp.proj_w, C, C, 1, C, C, false);   // consumed by the softmax/fold kernel, never a GEMM operand
   if (bias) vec(bp.proj_b, C);
   vec(bp.ln2_w, C);
   if (ln_bias) vec(bp.ln2_b, C);
-  mat(bp.pin_w, bp.h, bp.hp, 2, C, C);
+  mat(bp.pin_w, bp.h, bp.hp, 2, C, C, bp.tc_pin);
   if (bias) vec_split(bp.pin_b, bp.h, bp.hp, 2);
   dw(bp.ffdw_w, bp.h, bp.hp, 2);
   if (bias) vec_split(bp.ffdw_b, bp.h, bp.hp, 2);
-  mat(bp.pout_w, C, C, 1, bp.h, bp.hp);
+  mat(bp.pout_w, C, C, 1, bp.h, bp.hp, bp.tc_pout);
   if (bias) vec(bp.pout_b, C);
 }
 
 int block_param_count(int bias, int ln_bias) { return 9 + (ln_bias ? 2 : 0) + (bias ? 6 : 0); }
 
 int build_block_plan(BlockPlan& bp, std::vector<PackOp>& ops, long long& packed_floats, int C, int heads, float ffn,
-                     int bias, int ln_bias) {
+                     int bias, int ln_bias, int engine) {
   IRB_REQUIRE(C > 0 && heads > 0 && C % heads == 0, "block: C must be divisible by heads");
   IRB_REQUIRE((C / heads) % 16 == 0 && C / heads <= 128, "block: head dim must be a multiple of 16 and <= 128");
   IRB_REQUIRE(ffn > 0.f, "block: ffn_expansion_factor must be positive");
-  Builder bl(ops);
+  Builder bl(ops, engine);
   plan_block(bl, bp, C, heads, ffn, bias, ln_bias);
   packed_floats = bl.off;
   return IR_OK;
@@ -79,25 +92,26 @@ int build_block_plan(BlockPlan& bp, std::vector<PackOp>& ops, long long& packed_
 static void plan_conv3(Builder& bl, ConvPlan& cp, int cout, int cin, int bias) {
   cp.cout = cout; cp.cin = cin; cp.k = 9 * cin; cp.kp = round_up(9 * cin, 4);
   cp.w = bl.alloc((long long)cout * cp.kp);
-  bl.ops.push_back(PackOp{PackOp::MAT3, bl.pidx++, cp.w, cout, cout, 1, 9 * cin, cp.kp, cin});
-  cp.b = -1;
+  bl.ops.push_back(PackOp{PackOp::MAT3, bl.pidx++, cp.w, cout, cout, 1, 9 * cin, cp.kp, cin, 0});
+  cp.b = -1; cp.tc = false;
   if (bias) {
     cp.b = bl.alloc(cout);
-    bl.ops.push_back(PackOp{PackOp::VEC, bl.pidx++, cp.b, cout, cout, 1, 0, 0, 0});
+    bl.ops.push_back(PackOp{PackOp::VEC, bl.pidx++, cp.b, cout, cout, 1, 0, 0, 0, 0});
   }
 }
 static void plan_conv1(Builder& bl, ConvPlan& cp, int cout, int cin, int bias) {
   cp.cout = cout; cp.cin = cin; cp.k = cin; cp.kp = cin;
   cp.w = bl.alloc((long long)cout * cin);
-  bl.ops.push_back(PackOp{PackOp::MAT1, bl.pidx++, cp.w, cout, cout, 1, cin, cin, 0});
+  cp.tc = bl.tc(cin, cout);
+  bl.ops.push_back(PackOp{PackOp::MAT1, bl.pidx++, cp.w, cout, cout, 1, cin, cin, 0, cp.tc ? 1 : 0});
   cp.b = -1;
   if (bias) {
     cp.b = bl.alloc(cout);
-    bl.ops.push_back(PackOp{PackOp::VEC, bl.pidx++, cp.b, cout, cout, 1, 0, 0, 0});
+    bl.ops.push_back(PackOp{PackOp::VEC, bl.pidx++, cp.b, cout, cout, 1, 0, 0, 0, 0});
   }
 }
 
-int build_restormer_plan(RestormerPlan& pl, const IrRestormerCfg& c) {
+int build_restormer_plan(RestormerPlan& pl, const IrRestormerCfg& c, int engine) {
   IRB_REQUIRE(c.inp_channels > 0 && c.out_channels > 0, "restormer: channel counts must be positive");
   IRB_REQUIRE(c.dim > 0 && c.dim % 8 == 0, "restormer: dim must be a multiple of 8");
   for (int i = 0; i < 4; ++i) {
@@ -113,7 +127,7 @@ int build_restormer_plan(RestormerPlan& pl, const IrRestormerCfg& c) {
               "restormer: inp_channels must equal out_channels unless dual_pixel_task (residual add, restormer.py:281)");
   pl.cfg = c;
   pl.ops.clear();
-  Builder bl(pl.ops);
+  Builder bl(pl.ops, engine);
   const int d = c.dim, bias = c.bias, lnb = c.layernorm_with_bias;
   auto stage = [&](std::vector<BlockPlan>& v, int C, int heads, int n) {
     v.resize(n);
@@ -163,12 +177,12 @@ int run_pack_ops(const std::vector<PackOp>& ops, const float* const* params, flo
         IRB_TRY(launch_pack_vec(src, dst, op.a, op.b, op.c, nullptr, nullptr, s));
         break;
       case PackOp::MAT1: {
-        PackMat pm{src, dst, 0, 0, op.a, op.b, op.c, op.k_src, op.k_dst, nullptr};
+        PackMat pm{src, dst, 0, 0, op.a, op.b, op.c, op.k_src, op.k_dst, nullptr, op.fmt};
         IRB_TRY(launch_pack_mat(pm, s));
         break;
       }
       case PackOp::MAT3: {
-        PackMat pm{src, dst, 1, op.cin, op.a, op.b, op.c, op.k_src, op.k_dst, nullptr};
+        PackMat pm{src, dst, 1, op.cin, op.a, op.b, op.c, op.k_src, op.k_dst, nullptr, 0};
         IRB_TRY(launch_pack_mat(pm, s));
         break;
       }
@@ -201,6 +215,7 @@ void block_scratch_need(BlockScratchNeed& n, const BlockPlan& bp, int B, int H, 
   n.s_part = std::max(n.s_part, (long long)B * bp.heads * parts * ch * ch);
   n.n_part = std::max(n.n_part, (long long)B * bp.heads * parts * 2 * ch);
   n.w_eff = std::max(n.w_eff, (long long)B * bp.C * bp.C);
+  if (bp.C > 128) n.xhat = std::max(n.xhat, P * bp.C);
 }
 
 struct Carver {
@@ -222,6 +237,7 @@ void carve_block_scratch(Carver& cv, BlockScratch& bs, const BlockScratchNeed& n
   bs.s_part = cv.take(n.s_part);
   bs.n_part = cv.take(n.n_part);
   bs.w_eff = cv.take(n.w_eff);
+  bs.xhat = cv.take(n.xhat);
 }
 
 size_t block_workspace_bytes(const BlockPlan& bp, int B, int H, int W) {
@@ -260,6 +276,25 @@ size_t restormer_workspace_bytes(const RestormerPlan& pl, int B, int H, int W) {
 }
 
 // -----------------------------------------------------------------------------------------------
+// 1x1 contraction dispatch: tcgen05 kernel when the layer was packed for it, CUDA-core kernel otherwise
+// -----------------------------------------------------------------------------------------------
+static int run_1x1(const GemmParams& g, bool tc, float* xhat, cudaStream_t s) {
+  if (!tc) return launch_gemm_simt(g, s);
+  TcGemmParams t{};
+  t.a1 = g.a1; t.lda1 = g.lda1; t.k1 = g.k1; t.a2 = g.a2; t.lda2 = g.lda2; t.k2 = g.k2;
+  t.B = g.B; t.HW = g.H * g.W;
+  t.w = g.w; t.w_bstride = g.w_bstride; t.N = g.N; t.K = g.K; t.bias = g.bias;
+  t.ln_mode = g.ln_mode; t.ln_w = g.ln_w; t.ln_b = g.ln_b;
+  t.r = g.r; t.ldr = g.ldr; t.y = g.y; t.ldy = g.ldy; t.tag = g.tag; t.a_pad = 1;
+  if (g.ln_mode != LN_NONE && g.K > 128) {
+    // wide levels: normalise once into scratch, then a plain contraction
+    IRB_TRY(launch_layernorm(g.a1, g.lda1, xhat, g.K, (long long)g.B * g.H * g.W, g.K, g.ln_mode, g.ln_w, g.ln_b, s));
+    t.a1 = xhat; t.lda1 = g.K; t.ln_mode = LN_NONE;
+  }
+  return launch_gemm_tc(t, s);
+}
+
+// -----------------------------------------------------------------------------------------------
 // one TransformerBlock: x_out = block(x_in)   (x_in may equal x_out)
 // -----------------------------------------------------------------------------------------------
 int run_block(const BlockPlan& bp, const float* packed, const float* x_in, float* x_out, int B, int H, int W,
@@ -276,7 +311,7 @@ int run_block(const BlockPlan& bp, const float* packed, const float* x_in, float
   g.ln_mode = ln; g.ln_w = P(bp.ln1_w); g.ln_b = P(bp.ln1_b);
   g.relu = 0; g.r = nullptr; g.ldr = 0; g.acc_sign = 1.f;
   g.y = bs.qkv; g.ldy = 3 * C; g.o_mode = O_NHWC; g.tag = TAG_LN_QKV;
-  IRB_TRY(launch_gemm_simt(g, s));
+  IRB_TRY(run_1x1(g, bp.tc_qkv, bs.xhat, s));
 
   // (2) depthwise 3x3 over the 3C channels (restormer.py:114 qkv_dwconv)
   DwParams dwp{};
@@ -296,6 +331,7 @@ int run_block(const BlockPlan& bp, const float* packed, const float* x_in, float
   FoldParams fp{};
   fp.s_part = bs.s_part; fp.n_part = bs.n_part; fp.B = B; fp.C = C; fp.heads = bp.heads; fp.nparts = gp.nparts;
   fp.temperature = P(bp.temp); fp.w_proj = P(bp.proj_w); fp.w_eff = bs.w_eff; fp.w_eff_bstride = (long long)C * C;
+  fp.fmt = bp.tc_attn ? 1 : 0;
   IRB_TRY(launch_fold(fp, s));
 
   // (5) x_out = x_in + W_eff[b] . v  (+ project_out bias)   (:127-131, :147)
@@ -305,7 +341,7 @@ int run_block(const BlockPlan& bp, const float* packed, const float* x_in, float
   g.w = bs.w_eff; g.w_bstride = (long long)C * C; g.N = C; g.K = C; g.Kp = C; g.bias = P(bp.proj_b);
   g.ln_mode = LN_NONE; g.acc_sign = 1.f;
   g.r = x_in; g.ldr = C; g.y = x_out; g.ldy = C; g.o_mode = O_NHWC; g.tag = TAG_ATTN_OUT;
-  IRB_TRY(launch_gemm_simt(g, s));
+  IRB_TRY(run_1x1(g, bp.tc_attn, bs.xhat, s));
 
   // (6) norm2 + project_in 1x1 (:148, :89)
   g = GemmParams{};
@@ -314,7 +350,7 @@ int run_block(const BlockPlan& bp, const float* packed, const float* x_in, float
   g.w = P(bp.pin_w); g.N = 2 * hp; g.K = C; g.Kp = C; g.bias = P(bp.pin_b);
   g.ln_mode = ln; g.ln_w = P(bp.ln2_w); g.ln_b = P(bp.ln2_b); g.acc_sign = 1.f;
   g.y = bs.hidden; g.ldy = 2 * hp; g.o_mode = O_NHWC; g.tag = TAG_LN_PIN;
-  IRB_TRY(launch_gemm_simt(g, s));
+  IRB_TRY(run_1x1(g, bp.tc_pin, bs.xhat, s));
 
   // (7) depthwise 3x3 + gelu(x1)*x2 (:90-91)
   dwp = DwParams{};
@@ -330,7 +366,7 @@ int run_block(const BlockPlan& bp, const float* packed, const float* x_in, float
   g.w = P(bp.pout_w); g.N = C; g.K = hp; g.Kp = hp; g.bias = P(bp.pout_b);
   g.ln_mode = LN_NONE; g.acc_sign = 1.f;
   g.r = x_out; g.ldr = C; g.y = x_out; g.ldy = C; g.o_mode = O_NHWC; g.tag = TAG_FFN_OUT;
-  IRB_TRY(launch_gemm_simt(g, s));
+  IRB_TRY(run_1x1(g, bp.tc_pout, bs.xhat, s));
   return IR_OK;
 }
 
@@ -372,11 +408,18 @@ static int conv3(const ConvPlan& cp, const float* packed, const float* in, int l
 }
 
 int restormer_launch_count(const RestormerPlan& pl) {
-  int nblk = (int)pl.refine.size();
-  for (int l = 0; l < 4; ++l) nblk += (int)pl.enc[l].size();
-  for (int l = 0; l < 3; ++l) nblk += (int)pl.dec[l].size();
+  int n = 0;
+  auto blocks = [&](const std::vector<BlockPlan>& v) {
+    for (const auto& bp : v) {
+      n += 8;
+      if (bp.C > 128) n += (bp.tc_qkv ? 1 : 0) + (bp.tc_pin ? 1 : 0);   // standalone LayerNorm on the wide levels
+    }
+  };
+  for (int l = 0; l < 4; ++l) blocks(pl.enc[l]);
+  for (int l = 0; l < 3; ++l) blocks(pl.dec[l]);
+  blocks(pl.refine);
   // patch_embed, 3 down, 3 up, 2 reduce, 1 concat copy, output (+ skip_conv)
-  return nblk * 8 + 11 + (pl.cfg.dual_pixel_task ? 1 : 0);
+  return n + 11 + (pl.cfg.dual_pixel_task ? 1 : 0);
 }
 
 int restormer_forward(const RestormerPlan& pl, const float* packed, const float* x, float* y, int B, int H, int W,
@@ -415,7 +458,7 @@ int restormer_forward(const RestormerPlan& pl, const float* packed, const float*
     g.w = packed + pl.reduce[l].w; g.N = C; g.K = 2 * C; g.Kp = 2 * C;
     g.bias = pl.reduce[l].b >= 0 ? packed + pl.reduce[l].b : nullptr;
     g.ln_mode = LN_NONE; g.acc_sign = 1.f; g.y = ws.d[l]; g.ldy = C; g.o_mode = O_NHWC; g.tag = TAG_REDUCE;
-    IRB_TRY(launch_gemm_simt(g, s));
+    IRB_TRY(run_1x1(g, pl.reduce[l].tc, nullptr, s));
     IRB_TRY(run_stage(pl.dec[l], packed, ws.d[l], ws.d[l], B, hi * 2, wi * 2, C, ws.bs, lnb, s));
     below = ws.d[l];
   }
@@ -430,7 +473,7 @@ int restormer_forward(const RestormerPlan& pl, const float* packed, const float*
     g.a1 = e1_in; g.lda1 = d; g.k1 = d; g.a_mode = A_PLAIN; g.B = B; g.H = H; g.W = W;
     g.w = packed + pl.skip.w; g.N = 2 * d; g.K = d; g.Kp = d; g.bias = pl.skip.b >= 0 ? packed + pl.skip.b : nullptr;
     g.ln_mode = LN_NONE; g.acc_sign = 1.f; g.r = ws.d[0]; g.ldr = 2 * d; g.y = ws.d[0]; g.ldy = 2 * d; g.o_mode = O_NHWC; g.tag = TAG_REDUCE;
-    IRB_TRY(launch_gemm_simt(g, s));
+    IRB_TRY(run_1x1(g, pl.skip.tc, nullptr, s));
     IRB_TRY(conv3(pl.output, packed, ws.d[0], 2 * d, A_IM2COL_NHWC, B, H, W, y, 0, O_NCHW, nullptr, s));
   } else {
     IRB_TRY(conv3(pl.output, packed, ws.d[0], 2 * d, A_IM2COL_NHWC, B, H, W, y, 0, O_NCHW, x, s));   // :281

@@ -15,15 +15,17 @@ struct PackOp {
   int a, b, c;         // src_half, dst_half, n_halves (split-pad row/channel mapping)
   int k_src, k_dst;    // MAT1/MAT3: logical / padded reduction length
   int cin;             // MAT3
+  int fmt;             // MAT1: 0 row-major fp32, 1 tcgen05 operand layout (PackMat::fmt)
 };
 
 struct BlockPlan {     // one TransformerBlock (restormer.py:137-150); offsets in floats, -1 = absent
   int C, heads, h, hp;
   long long ln1_w, ln1_b, temp, qkv_w, qkv_b, qkvdw_w, qkvdw_b, proj_w, proj_b;
   long long ln2_w, ln2_b, pin_w, pin_b, ffdw_w, ffdw_b, pout_w, pout_b;
+  bool tc_qkv, tc_attn, tc_pin, tc_pout;   // which 1x1 contractions run on the tcgen05 kernel
 };
 
-struct ConvPlan { int cout, cin, k, kp; long long w, b; };
+struct ConvPlan { int cout, cin, k, kp; long long w, b; bool tc; };
 
 struct RestormerPlan {
   IrRestormerCfg cfg;
@@ -34,14 +36,17 @@ struct RestormerPlan {
   std::vector<BlockPlan> enc[4], dec[3], refine;
 };
 
-struct BlockScratchNeed { long long qkv = 0, hidden = 0, gated = 0, s_part = 0, n_part = 0, w_eff = 0; };
-struct BlockScratch { float *qkv, *qkv_dw, *hidden, *gated, *s_part, *n_part, *w_eff; };
+struct BlockScratchNeed { long long qkv = 0, hidden = 0, gated = 0, s_part = 0, n_part = 0, w_eff = 0, xhat = 0; };
+struct BlockScratch { float *qkv, *qkv_dw, *hidden, *gated, *s_part, *n_part, *w_eff, *xhat; };
 struct RestormerWs { float* e[4]; float* e1_in; float* d[3]; float* up_tmp; BlockScratch bs; };
 
 int  block_param_count(int bias, int ln_bias);
+// engine: 0 = tcgen05 contractions (tf32 operands), 1 = CUDA-core fp32 contractions (on-device reference)
+enum Engine { ENGINE_TC = 0, ENGINE_SIMT = 1 };
 int  build_block_plan(BlockPlan& bp, std::vector<PackOp>& ops, long long& packed_floats, int C, int heads, float ffn,
-                      int bias, int ln_bias);
-int  build_restormer_plan(RestormerPlan& pl, const IrRestormerCfg& cfg);
+                      int bias, int ln_bias, int engine);
+int  build_restormer_plan(RestormerPlan& pl, const IrRestormerCfg& cfg, int engine);
+bool tc_gemm_supported(int K, int N);
 long long pack_op_src_numel(const PackOp& op);
 int  run_pack_ops(const std::vector<PackOp>& ops, const float* const* params, float* packed, cudaStream_t s);
 

@@ -405,7 +405,14 @@ __global__ void __launch_bounds__(256) fold_kernel(const FoldParams p) {
     const float* wrow = p.w_proj + (long long)n * p.C + head * ch;
     float s = 0.f;
     for (int i = 0; i < ch; ++i) s = fmaf(wrow[i], A[i * ch + j], s);
-    we[(long long)n * p.C + head * ch + j] = s;
+    const int k = head * ch + j;
+    if (p.fmt == 1) {
+      uint32_t u;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(s));
+      we[((long long)(k >> 2) * p.C + n) * 4 + (k & 3)] = __uint_as_float(u);
+    } else {
+      we[(long long)n * p.C + k] = s;
+    }
   }
 }
 
@@ -417,6 +424,69 @@ int launch_fold(const FoldParams& p, cudaStream_t s) {
   dim3 grid(p.heads, p.B);
   ProfScope prof(TAG_FOLD, 4.0 * (double)p.B * p.C * p.C, 2.0 * (double)p.B * p.C * p.C * ch, s);
   fold_kernel<<<grid, 256, smem, s>>>(p);
+  IRB_LAUNCH_CHECK();
+  return IR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// standalone channel LayerNorm, one warp per pixel (C <= 1024), two-pass statistics in registers
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, int ldx, float* __restrict__ y,
+                                                        int ldy, long long rows, int C, int ln_mode,
+                                                        const float* __restrict__ w, const float* __restrict__ b) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int f4n = C >> 2;
+  for (long long row = warp0; row < rows; row += nwarps) {
+    float4 v[8];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int f = lane + 32 * i;
+      v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (f < f4n) v[i] = *reinterpret_cast<const float4*>(x + row * ldx + 4 * f);
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    s = warp_sum(s);
+    const float mu = s / (float)C;
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (lane + 32 * i < f4n) {
+        const float dx = v[i].x - mu, dy = v[i].y - mu, dz = v[i].z - mu, dw = v[i].w - mu;
+        ss += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+      }
+    }
+    ss = warp_sum(ss);
+    const float rstd = 1.0f / sqrtf(ss / (float)C + 1e-5f);
+    const float sub = ln_mode == LN_WITHBIAS ? mu : 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int f = lane + 32 * i;
+      if (f < f4n) {
+        const float4 g = *reinterpret_cast<const float4*>(w + 4 * f);
+        float4 o;
+        o.x = (v[i].x - sub) * rstd * g.x; o.y = (v[i].y - sub) * rstd * g.y;
+        o.z = (v[i].z - sub) * rstd * g.z; o.w = (v[i].w - sub) * rstd * g.w;
+        if (ln_mode == LN_WITHBIAS) {
+          const float4 bb = *reinterpret_cast<const float4*>(b + 4 * f);
+          o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+        }
+        *reinterpret_cast<float4*>(y + row * ldy + 4 * f) = o;
+      }
+    }
+  }
+}
+
+int launch_layernorm(const float* x, int ldx, float* y, int ldy, long long rows, int C, int ln_mode, const float* w,
+                     const float* b, cudaStream_t s) {
+  IRB_REQUIRE(C % 4 == 0 && C <= 1024 && ldx % 4 == 0 && ldy % 4 == 0, "layernorm: C must be a multiple of 4, <= 1024");
+  IRB_REQUIRE(ln_mode == LN_BIASFREE || ln_mode == LN_WITHBIAS, "layernorm: bad mode");
+  const long long blocks_needed = cdivll(rows, 8);
+  const int blocks = (int)(blocks_needed < 148LL * 8 ? blocks_needed : 148LL * 8);
+  ProfScope prof(TAG_LAYERNORM, 8.0 * (double)rows * C, 0.0, s);
+  layernorm_kernel<<<blocks > 0 ? blocks : 1, 256, 0, s>>>(x, ldx, y, ldy, rows, C, ln_mode, w, b);
   IRB_LAUNCH_CHECK();
   return IR_OK;
 }

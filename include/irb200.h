@@ -41,7 +41,9 @@ typedef enum IrStatus {
  * residual stream, LayerNorm statistics, softmax and GELU are always fp32. */
 typedef enum IrMode {
   IR_MODE_FP32 = 0,        /* fp32 activations, tf32 tensor-core operands (fp32 parity mode) */
-  IR_MODE_HALF = 1         /* fp16 intermediates + fp16 operands (same 10-bit mantissa as tf32) */
+  IR_MODE_HALF = 1,        /* fp16 intermediates + fp16 operands (same 10-bit mantissa as tf32) */
+  IR_MODE_FP32_SIMT = 2    /* every contraction on CUDA cores in exact fp32: the on-device second oracle of the
+                              tensor-core kernels (tests / bisecting only; several times slower) */
 } IrMode;
 
 /* Mirrors Restormer.__init__ kwargs (src/restormer/restormer.py:194-205). */
@@ -113,6 +115,14 @@ int    ir_block_pack_weights(int C, int heads, float ffn_expansion_factor, int b
 int    ir_block_forward(int C, int heads, float ffn_expansion_factor, int bias, int ln_with_bias,
                         const void* packed, float* x_nhwc, int B, int H, int W,
                         void* workspace, size_t workspace_bytes, int mode, void* stream);
+
+/* One 1x1 convolution y[pix, n] = sum_k LN?(a)[pix, k] * w[n, k] (+bias) (+r) on channels-last rows, with the
+ * reference's row-major weight [N][K] (K = k1 + k2, second source = channel concat).  engine 0 = tcgen05
+ * kernel, 1 = CUDA-core fp32 kernel.  ln_mode: 0 none, 1 BiasFree, 2 WithBias.  scratch >= (N*K + B*HW*K)*4 bytes. */
+int    ir_test_conv1x1(int engine, const float* a1, int lda1, int k1, const float* a2, int lda2, int k2,
+                       const float* w_rowmajor, const float* bias, int ln_mode, const float* ln_w, const float* ln_b,
+                       const float* r, int ldr, float* y, int ldy, int B, int HW, int N, int a_pad,
+                       void* scratch, size_t scratch_bytes, void* stream);
 
 /* Layout helpers used at the boundary of unit tests (NCHW fp32 <-> channels-last fp32). */
 int    ir_nchw_to_nhwc(const float* src, float* dst, int B, int C, int H, int W, void* stream);

@@ -5,8 +5,12 @@ TAG=${1:-r1}
 OUT=gpurun_out
 mkdir -p $OUT
 nvidia-smi --query-gpu=name,driver_version,memory.total,clocks.max.sm --format=csv > $OUT/gpu_$TAG.txt 2>&1
-echo "== pytest -m gpu" | tee $OUT/status_$TAG.txt
-timeout 1200 python -m pytest tests -m gpu -x -q --timeout 600 > $OUT/pytest_$TAG.log 2>&1
+echo "== tc_unit" | tee $OUT/status_$TAG.txt
+timeout 1500 python scripts/tc_unit.py > $OUT/tc_unit_$TAG.log 2>&1
+echo "tc_unit exit $?" | tee -a $OUT/status_$TAG.txt
+tail -30 $OUT/tc_unit_$TAG.log
+echo "== pytest -m gpu" | tee -a $OUT/status_$TAG.txt
+timeout 1500 python -m pytest tests -m gpu -q --timeout 600 > $OUT/pytest_$TAG.log 2>&1
 echo "pytest exit $?" | tee -a $OUT/status_$TAG.txt
 tail -15 $OUT/pytest_$TAG.log
 echo "== smoke" | tee -a $OUT/status_$TAG.txt

@@ -1,0 +1,84 @@
+"""Shared case list + runner for the tcgen05 1x1-contraction unit tests (GPU)."""
+import numpy as np
+import torch
+
+from image_restoration_models_b200 import _native
+
+# (k1, k2, N, B, HW, ln_mode, bias, residual, a_pad)
+CASES = [
+    # the shapes of the Restormer block at dim=48
+    (48, 0, 144, 1, 256, 1, False, False, 1),     # K1 enc1: LN(BiasFree)+qkv, one 16-column tail
+    (48, 0, 144, 1, 256, 1, False, False, 0),     # same, unpadded A slabs
+    (48, 0, 144, 2, 200, 2, True, False, 1),      # WithBias LN, conv bias, ragged tiles (200 = 128 + 72), batch 2
+    (48, 0, 256, 1, 384, 1, False, False, 1),     # K5 enc1: LN + project_in (2*hp = 256)
+    (128, 0, 48, 1, 300, 0, False, True, 1),      # K6 enc1: project_out K=hp=128 + residual in place
+    (48, 0, 48, 3, 130, 0, False, True, 1),       # K4 enc1 shape (shared weights here)
+    (96, 0, 288, 1, 512, 1, False, False, 1),     # K1 level 2 / dec1: N split in chunks
+    (96, 0, 288, 1, 512, 2, False, False, 0),
+    (96, 0, 512, 2, 256, 1, False, False, 1),     # K5 level 2
+    (256, 0, 96, 1, 256, 0, True, True, 1),       # K6 level 2: K chunked (4 x 64)
+    (96, 0, 96, 1, 128, 0, False, True, 1),       # K4 level 2
+    (192, 0, 576, 1, 256, 2, False, False, 1),    # K1 level 3: standalone LN + chunked K
+    (192, 0, 1024, 1, 128, 1, False, False, 1),   # K5 level 3
+    (512, 0, 192, 1, 200, 0, False, True, 1),     # K6 level 3
+    (384, 0, 1152, 2, 64, 1, False, False, 1),    # K1 latent
+    (384, 0, 2048, 1, 64, 2, True, False, 1),     # K5 latent
+    (1024, 0, 384, 1, 96, 0, False, True, 1),     # K6 latent
+    (192, 192, 192, 1, 256, 0, False, False, 1),  # reduce_chan_level3: concat of two sources
+    (96, 96, 96, 2, 144, 0, True, False, 1),      # reduce_chan_level2 (chunk straddles the two sources)
+    (48, 0, 96, 1, 64, 0, False, True, 1),        # skip_conv
+    (32, 0, 96, 1, 100, 1, False, False, 1),      # dim=32 family
+    (64, 0, 128, 1, 1, 2, False, False, 1),       # single pixel (latent of an 8x8 image)
+    (88, 0, 32, 1, 77, 0, False, False, 1),       # odd multiple-of-8 K
+]
+
+
+def run_case(case, engine, seed=0):
+    """Returns (y, y_ref64) as numpy arrays; y from the C-ABI test entry on the given engine (0 tc, 1 simt)."""
+    k1, k2, N, B, HW, ln_mode, bias, resid, a_pad = case
+    g = torch.Generator().manual_seed(1000 + seed)
+    K = k1 + k2
+    rows = B * HW
+    lda1, lda2, ldy = k1 + 8, (k2 + 4 if k2 else 0), N + 12      # non-trivial leading dimensions
+    a1 = torch.randn(rows, lda1, generator=g) * 1.5 + 0.3
+    a2 = torch.randn(rows, lda2, generator=g) if k2 else None
+    w = (torch.rand(N, K, generator=g) * 2 - 1) / np.sqrt(K)
+    bvec = (torch.rand(N, generator=g) - 0.5) if bias else None
+    lw = torch.rand(k1, generator=g) + 0.5
+    lb = (torch.rand(k1, generator=g) - 0.5) * 0.2
+    r = torch.randn(rows, ldy, generator=g) if resid else None
+
+    # fp64 reference
+    x = a1[:, :k1].double()
+    if ln_mode:
+        var = x.var(dim=1, keepdim=True, unbiased=False)
+        if ln_mode == 1:
+            x = x / torch.sqrt(var + 1e-5) * lw.double()
+        else:
+            x = (x - x.mean(dim=1, keepdim=True)) / torch.sqrt(var + 1e-5) * lw.double() + lb.double()
+    if k2:
+        x = torch.cat([x, a2[:, :k2].double()], 1)
+    y_ref = x @ w.double().t()
+    if bias:
+        y_ref = y_ref + bvec.double()
+    if resid:
+        y_ref = y_ref + r[:, :N].double()
+
+    dev = "cuda"
+    lib = _native.lib()
+    d = lambda t: None if t is None else t.to(dev).contiguous()
+    a1d, a2d, wd, bd, lwd, lbd = d(a1), d(a2), d(w), d(bvec), d(lw), d(lb)
+    y = d(r) if resid else torch.full((rows, ldy), float("nan"), device=dev)
+    scratch = torch.empty((N * K + rows * K) * 4 + 1024, dtype=torch.uint8, device=dev)
+    P = lambda t: 0 if t is None else t.data_ptr()
+    stream = torch.cuda.current_stream().cuda_stream
+    st = lib.ir_test_conv1x1(engine, P(a1d), lda1, k1, P(a2d), lda2, k2, P(wd), P(bd), ln_mode, P(lwd), P(lbd),
+                             P(y) if resid else 0, ldy, P(y), ldy, B, HW, N, a_pad, P(scratch), scratch.numel(), stream)
+    _native.check(st)
+    torch.cuda.synchronize()
+    return y[:, :N].cpu().numpy(), y_ref.numpy()
+
+
+def tolerance(case, y_ref):
+    """tf32 operands (10-bit mantissa, RN) with fp32 accumulation: relative 2^-11 per operand."""
+    return 4e-3 * float(np.abs(y_ref).max()) + 1e-5

@@ -1,0 +1,21 @@
+"""GPU: the tcgen05 1x1 contraction against an fp64 torch reference and against the CUDA-core fp32 kernel."""
+import numpy as np
+import pytest
+
+from conftest import record
+from tc_cases import CASES, run_case, tolerance
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("idx", range(len(CASES)))
+def test_tc_conv1x1_matches_reference(idx):
+    case = CASES[idx]
+    y_tc, y_ref = run_case(case, 0, seed=idx)
+    y_simt, _ = run_case(case, 1, seed=idx)
+    e_tc = float(np.abs(y_tc - y_ref).max())
+    e_simt = float(np.abs(y_simt - y_ref).max())
+    record(f"tc_conv1x1_{idx}", case=str(case), err_tc=e_tc, err_simt=e_simt, tol=tolerance(case, y_ref))
+    assert np.isfinite(y_tc).all()
+    assert e_simt <= 2e-5 * max(1.0, float(np.abs(y_ref).max()))
+    assert e_tc <= tolerance(case, y_ref), (case, e_tc)
