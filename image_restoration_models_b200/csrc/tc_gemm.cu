@@ -8,17 +8,21 @@
 // FeedForward.project_out :86 with the residual add :148, reduce_chan_level{2,3} :223,228 with the channel
 // concat :260,:265 as a two-source K loop, and skip_conv :240.
 //
-// Data movement.  Everything on this path is HBM-bound (K is 48..384), so the kernel is organised around
-// streaming, not around the MMA:
-//   * persistent CTAs; each owns one N-chunk of the weights, which it stages ONCE into shared memory in the
-//     UMMA canonical K-major no-swizzle layout [K/4][NC][4 x tf32] (the weights are pre-packed in HBM in exactly
-//     that order, tf32-rounded), and a contiguous range of 128-pixel tiles;
-//   * the A tile is read with coalesced 16-byte loads, normalised (LayerNorm statistics in registers via
-//     shuffles), rounded to tf32 and written to shared memory as [K/4][128][4 x tf32];
-//   * one thread issues tcgen05.mma (kind::tf32, M=128, N=NC, K=8 per instruction); completion is signalled
-//     with tcgen05.commit on an mbarrier;
-//   * each warp drains its 32 TMEM lanes with tcgen05.ld, transposes through a private padded smem tile and
-//     writes 128-byte-coalesced rows (bias / residual fused).
+// Everything on this path is HBM-bound (K is 48..384, arithmetic intensity 8..40 FLOP/B), so the kernel is a
+// streaming pipeline with a tensor-core stage in the middle.  One persistent CTA per SM, 13 warps, three roles:
+//
+//   producers (8 warps)  coalesced 16-byte global loads of the A rows with several passes in flight, LayerNorm
+//                        statistics in registers (two-pass, shuffles), rounding to the operand type, stores into
+//                        a ring of smem stages in the UMMA canonical K-major no-swizzle layout
+//                        [K/epc][128 (+1 pad row)][16 bytes]; full[s] mbarrier <- all producer threads
+//   MMA (1 warp)         one lane issues tcgen05.mma (M=128, N=NC, K=32 bytes per instruction) from the stage and
+//                        the CTA-resident weight chunk (staged once, same canonical layout, pre-packed in HBM);
+//                        tcgen05.commit -> empty[s] (stage reusable) and tmem_full[a] (tile accumulated)
+//   epilogue (4 warps)   tcgen05.ld of the warp's 32 TMEM lanes, transpose through a private padded smem tile,
+//                        128-byte-coalesced stores with bias / residual fused; arrive tmem_empty[a]
+//
+// The accumulator is double buffered in TMEM (2 x NC columns), so the epilogue of tile t overlaps the loads and
+// MMAs of tile t+1.
 #include "common.cuh"
 #include "tc_gemm.cuh"
 
@@ -27,9 +31,14 @@ namespace irb {
 namespace {
 
 constexpr int TM = 128;                 // pixels per tile == UMMA M
-constexpr int NTHREADS = 128;
+constexpr int EPI_WARPS = 4;
+constexpr int PROD_WARPS = 8;
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+constexpr int PROD_THREADS = PROD_WARPS * 32;
+constexpr int NTHREADS = EPI_THREADS + PROD_THREADS + 32;
+constexpr int MAX_STAGES = 4;
 constexpr int STG_LD = 36;              // floats per staging row (32 + 4 pad -> conflict-free)
-constexpr int STG_BYTES = 4 * 32 * STG_LD * 4;
+constexpr int STG_BYTES = EPI_WARPS * 32 * STG_LD * 4;
 constexpr int HDR_BYTES = 128;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -43,7 +52,9 @@ __device__ __forceinline__ float to_tf32(float x) {
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
+}
 // Spin on an mbarrier phase.  A wrong phase would hang the GPU box, so the spin is bounded and traps.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
@@ -55,7 +66,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "=r"(done)
         : "r"(bar), "r"(parity)
         : "memory");
-    if (it > (1u << 24)) __trap();
+    if (it > (1u << 26)) __trap();
   }
 }
 
@@ -70,19 +81,32 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t lbo_b
   return d;
 }
 
-__device__ __forceinline__ uint32_t make_idesc_tf32(int n) {
-  // c_format F32 (bits 4-5 = 1), a/b format TF32 (= 2), both K-major, N>>3 at bit 17, M>>4 at bit 24
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+template <typename TOp>
+__device__ __forceinline__ uint32_t make_idesc(int n) {
+  // c_format F32 (bits 4-5 = 1); a/b format at bits 7-9 / 10-12: TF32 = 2, F16 = 0; both K-major;
+  // N>>3 at bit 17, M>>4 at bit 24
+  const uint32_t fmt = sizeof(TOp) == 4 ? 2u : 0u;
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
 }
 
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
+template <typename TOp>
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                     uint32_t accumulate) {
+  if constexpr (sizeof(TOp) == 4) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
 }
 
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -120,98 +144,181 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 struct Header {           // first HDR_BYTES of dynamic shared memory
-  unsigned long long bar; // mbarrier: MMA group complete
+  unsigned long long full[MAX_STAGES];
+  unsigned long long empty[MAX_STAGES];
+  unsigned long long tmem_full[2];
+  unsigned long long tmem_empty[2];
   uint32_t tmem_base;
 };
+static_assert(sizeof(Header) <= HDR_BYTES, "header too large");
+
+// ---- element traits: TA = element type of A in global memory, TOp = tensor-core operand type in smem ---------
+template <typename TA> struct GVec;      // one 16-byte global vector
+template <> struct GVec<float> { static constexpr int N = 4; };
+template <> struct GVec<__half> { static constexpr int N = 8; };
+
+template <typename TA>
+__device__ __forceinline__ void load_vec(const TA* src, float* out);
+template <>
+__device__ __forceinline__ void load_vec<float>(const float* src, float* out) {
+  const float4 t = __ldg(reinterpret_cast<const float4*>(src));
+  out[0] = t.x; out[1] = t.y; out[2] = t.z; out[3] = t.w;
+}
+template <>
+__device__ __forceinline__ void load_vec<__half>(const __half* src, float* out) {
+  const uint4 t = __ldg(reinterpret_cast<const uint4*>(src));
+  const __half2* h = reinterpret_cast<const __half2*>(&t);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(h[i]); out[2 * i] = f.x; out[2 * i + 1] = f.y; }
+}
+
+// store EPC = 16/sizeof(TOp) consecutive K elements of one row as one 16-byte smem chunk
+template <typename TOp>
+__device__ __forceinline__ void store_chunk(uint8_t* dst, const float* v);
+template <>
+__device__ __forceinline__ void store_chunk<float>(uint8_t* dst, const float* v) {
+  *reinterpret_cast<float4*>(dst) = make_float4(to_tf32(v[0]), to_tf32(v[1]), to_tf32(v[2]), to_tf32(v[3]));
+}
+template <>
+__device__ __forceinline__ void store_chunk<__half>(uint8_t* dst, const float* v) {
+  uint4 t;
+  __half2* h = reinterpret_cast<__half2*>(&t);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+  *reinterpret_cast<uint4*>(dst) = t;
+}
 
 // ---------------------------------------------------------------------------------------------------
-// A-tile producer: rows [p0, p0+128) of image b, channels [k0, k0+kc) -> smem [kc/4][128 (+pad)][4] tf32.
-// LPP lanes cooperate on one pixel row (LPP consecutive lanes), each holding VPL float4.
+// Producer: rows [p0, p0+128) of image b, channels [k0, k0+kc) -> one smem stage [kc/EPC][a_rows_ld][16 B].
+// LPP consecutive lanes cooperate on one pixel row; each lane owns UPL "units" (one unit = one smem chunk =
+// EPC channels).  UNR row-passes are loaded before any is consumed, to keep enough bytes in flight.
 // ---------------------------------------------------------------------------------------------------
-template <int VPL>
-__device__ __forceinline__ void load_a_tile(const TcGemmParams& p, float* __restrict__ sA, int a_rows_ld,
-                                            long long rowbase, int p0, int valid, int k0, int kc, int lpp, bool do_ln) {
-  const int tid = threadIdx.x;
-  const int q = tid % lpp;
-  const int rsub = tid / lpp;
-  const int pp = NTHREADS / lpp;        // pixels per pass
-  const int f4n = kc >> 2;              // float4 per row in this chunk
-  for (int r0 = 0; r0 < TM; r0 += pp) {
-    const int r = r0 + rsub;
-    const bool live = r < valid;
-    float4 v[VPL];
+template <typename TA, typename TOp, int UPL, int UNR>
+__device__ __forceinline__ void produce_stage(const TcGemmParams& p, uint8_t* __restrict__ sA, int a_rows_ld,
+                                              long long rowbase, int p0, int valid, int k0, int kc, int lpp,
+                                              bool do_ln) {
+  constexpr int EPC = 16 / (int)sizeof(TOp);            // elements per smem chunk
+  constexpr int VPU = EPC / GVec<TA>::N;                // global vectors per unit (1 or 2)
+  static_assert(VPU >= 1, "operand type must not be wider than the global type");
+  const TA* a1 = reinterpret_cast<const TA*>(p.a1);
+  const TA* a2 = reinterpret_cast<const TA*>(p.a2);
+  const int ptid = threadIdx.x - EPI_THREADS;
+  const int q = ptid % lpp;
+  const int rsub = ptid / lpp;
+  const int pp = PROD_THREADS / lpp;                    // pixel rows per pass
+  const int units = kc / EPC;                           // units per row in this chunk
+  for (int r0 = 0; r0 < TM; r0 += pp * UNR) {
+    float v[UNR][UPL][EPC];
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-      const int f = q + i * lpp;
-      v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (live && f < f4n) {
-        const int k = k0 + 4 * f;
-        const float* src = (k < p.k1) ? p.a1 + (rowbase + p0 + r) * (long long)p.lda1 + k
-                                      : p.a2 + (rowbase + p0 + r) * (long long)p.lda2 + (k - p.k1);
-        v[i] = __ldg(reinterpret_cast<const float4*>(src));
-      }
-    }
-    if (do_ln) {
-      // population variance about the mean, eps inside the sqrt (restormer.py:38,55-56); two-pass in registers
-      float s = 0.f;
+    for (int u = 0; u < UNR; ++u) {
+      const int r = r0 + u * pp + rsub;
+      const bool live = r < valid;                      // valid <= TM
 #pragma unroll
-      for (int i = 0; i < VPL; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-      for (int o = lpp >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      const float mu = s / (float)kc;
-      float ss = 0.f;
+      for (int i = 0; i < UPL; ++i) {
+        const int unit = q + i * lpp;
 #pragma unroll
-      for (int i = 0; i < VPL; ++i) {
-        if (q + i * lpp < f4n) {
-          const float dx = v[i].x - mu, dy = v[i].y - mu, dz = v[i].z - mu, dw = v[i].w - mu;
-          ss += (dx * dx + dy * dy) + (dz * dz + dw * dw);
-        }
-      }
-      for (int o = lpp >> 1; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-      const float rstd = 1.0f / sqrtf(ss / (float)kc + 1e-5f);
-      const float sub = (p.ln_mode == LN_WITHBIAS) ? mu : 0.f;
+        for (int e = 0; e < EPC; ++e) v[u][i][e] = 0.f;
+        if (live && unit < units) {
 #pragma unroll
-      for (int i = 0; i < VPL; ++i) {
-        const int f = q + i * lpp;
-        if (f < f4n) {
-          const float4 g = __ldg(reinterpret_cast<const float4*>(p.ln_w + 4 * f));
-          float4 o4;
-          o4.x = (v[i].x - sub) * rstd * g.x; o4.y = (v[i].y - sub) * rstd * g.y;
-          o4.z = (v[i].z - sub) * rstd * g.z; o4.w = (v[i].w - sub) * rstd * g.w;
-          if (p.ln_mode == LN_WITHBIAS) {
-            const float4 bb = __ldg(reinterpret_cast<const float4*>(p.ln_b + 4 * f));
-            o4.x += bb.x; o4.y += bb.y; o4.z += bb.z; o4.w += bb.w;
+          for (int g = 0; g < VPU; ++g) {
+            const int k = k0 + unit * EPC + g * GVec<TA>::N;
+            const TA* src = (k < p.k1) ? a1 + (rowbase + p0 + r) * (long long)p.lda1 + k
+                                       : a2 + (rowbase + p0 + r) * (long long)p.lda2 + (k - p.k1);
+            load_vec<TA>(src, &v[u][i][g * GVec<TA>::N]);
           }
-          v[i] = o4;
         }
       }
     }
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-      const int f = q + i * lpp;
-      if (f < f4n) {
-        float4 o4;
-        o4.x = to_tf32(v[i].x); o4.y = to_tf32(v[i].y); o4.z = to_tf32(v[i].z); o4.w = to_tf32(v[i].w);
-        *reinterpret_cast<float4*>(sA + ((size_t)f * a_rows_ld + r) * 4) = o4;
+    for (int u = 0; u < UNR; ++u) {
+      const int r = r0 + u * pp + rsub;
+      if (do_ln) {
+        // population variance about the mean, eps inside the sqrt (restormer.py:38,55-56); two-pass in registers
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < UPL; ++i)
+#pragma unroll
+          for (int e = 0; e < EPC; ++e) s += v[u][i][e];
+        for (int o = lpp >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const float mu = s / (float)kc;
+        float ss = 0.f;
+#pragma unroll
+        for (int i = 0; i < UPL; ++i) {
+          if (q + i * lpp < units) {
+#pragma unroll
+            for (int e = 0; e < EPC; ++e) { const float d = v[u][i][e] - mu; ss = fmaf(d, d, ss); }
+          }
+        }
+        for (int o = lpp >> 1; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        const float rstd = 1.0f / sqrtf(ss / (float)kc + 1e-5f);
+        const float sub = (p.ln_mode == LN_WITHBIAS) ? mu : 0.f;
+#pragma unroll
+        for (int i = 0; i < UPL; ++i) {
+          const int unit = q + i * lpp;
+          if (unit < units) {
+#pragma unroll
+            for (int e4 = 0; e4 < EPC; e4 += 4) {
+              const float4 g = __ldg(reinterpret_cast<const float4*>(p.ln_w + unit * EPC + e4));
+              v[u][i][e4 + 0] = (v[u][i][e4 + 0] - sub) * rstd * g.x;
+              v[u][i][e4 + 1] = (v[u][i][e4 + 1] - sub) * rstd * g.y;
+              v[u][i][e4 + 2] = (v[u][i][e4 + 2] - sub) * rstd * g.z;
+              v[u][i][e4 + 3] = (v[u][i][e4 + 3] - sub) * rstd * g.w;
+              if (p.ln_mode == LN_WITHBIAS) {
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(p.ln_b + unit * EPC + e4));
+                v[u][i][e4 + 0] += bb.x; v[u][i][e4 + 1] += bb.y; v[u][i][e4 + 2] += bb.z; v[u][i][e4 + 3] += bb.w;
+              }
+            }
+          }
+        }
+      }
+      if (r < TM) {
+#pragma unroll
+        for (int i = 0; i < UPL; ++i) {
+          const int unit = q + i * lpp;
+          if (unit < units) store_chunk<TOp>(sA + ((size_t)unit * a_rows_ld + r) * 16, v[u][i]);
+        }
       }
     }
   }
 }
 
-__global__ void __launch_bounds__(NTHREADS) tc_gemm_kernel(const TcGemmParams p) {
+template <typename TY>
+__device__ __forceinline__ void store_out4(TY* dst, const float4& o);
+template <>
+__device__ __forceinline__ void store_out4<float>(float* dst, const float4& o) { *reinterpret_cast<float4*>(dst) = o; }
+template <>
+__device__ __forceinline__ void store_out4<__half>(__half* dst, const float4& o) {
+  uint2 t;
+  __half2* h = reinterpret_cast<__half2*>(&t);
+  h[0] = __floats2half2_rn(o.x, o.y);
+  h[1] = __floats2half2_rn(o.z, o.w);
+  *reinterpret_cast<uint2*>(dst) = t;
+}
+
+template <typename TA, typename TOp, typename TY>
+__global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const TcGemmParams p) {
+  constexpr int EPC = 16 / (int)sizeof(TOp);
   extern __shared__ __align__(128) uint8_t smem[];
   Header* hdr = reinterpret_cast<Header*>(smem);
   float* stg = reinterpret_cast<float*>(smem + HDR_BYTES);
-  float* sA = reinterpret_cast<float*>(smem + HDR_BYTES + STG_BYTES);
+  uint8_t* sW = smem + HDR_BYTES + STG_BYTES;
   const int a_rows_ld = TM + p.a_pad;                       // rows per 16-byte K-chunk slab of A (pad breaks conflicts)
-  float* sW = sA + (size_t)(p.KC >> 2) * a_rows_ld * 4;
+  const size_t stage_bytes = (size_t)(p.KC / EPC) * a_rows_ld * 16;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n0 = blockIdx.y * p.NC;
   const int nc = min(p.NC, p.N - n0);
-  const uint32_t bar = smem_u32(&hdr->bar);
+  uint8_t* sA0 = sW + (size_t)p.NC * p.K * sizeof(TOp);
 
   if (tid == 0) {
-    mbar_init(bar, 1);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(smem_u32(&hdr->full[s]), PROD_THREADS);
+      mbar_init(smem_u32(&hdr->empty[s]), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(smem_u32(&hdr->tmem_full[a]), 1);
+      mbar_init(smem_u32(&hdr->tmem_empty[a]), EPI_THREADS);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -226,100 +333,141 @@ __global__ void __launch_bounds__(NTHREADS) tc_gemm_kernel(const TcGemmParams p)
   tc_fence_after();
   const uint32_t tmem_base = hdr->tmem_base;
 
-  const long long t_begin = (long long)p.ntiles * blockIdx.x / gridDim.x;
-  const long long t_end = (long long)p.ntiles * (blockIdx.x + 1) / gridDim.x;
-  const uint32_t idesc = make_idesc_tf32(nc);
+  // tile range of this CTA: contiguous; per-image weights -> the CTA stays inside image blockIdx.z
+  long long t_begin, t_end;
+  if (p.w_bstride != 0) {
+    t_begin = (long long)blockIdx.z * p.tiles_per_img + (long long)p.tiles_per_img * blockIdx.x / gridDim.x;
+    t_end = (long long)blockIdx.z * p.tiles_per_img + (long long)p.tiles_per_img * (blockIdx.x + 1) / gridDim.x;
+  } else {
+    t_begin = (long long)p.ntiles * blockIdx.x / gridDim.x;
+    t_end = (long long)p.ntiles * (blockIdx.x + 1) / gridDim.x;
+  }
+  const int nchunks = (p.K + p.KC - 1) / p.KC;
   const uint32_t a_lbo = (uint32_t)a_rows_ld * 16u;
   const uint32_t w_lbo = (uint32_t)nc * 16u;
-  const int nchunks = (p.K + p.KC - 1) / p.KC;
-  const bool do_ln = p.ln_mode != LN_NONE;
-  uint32_t phase = 0;
-  int loaded_b = -1;
 
-  for (long long tile = t_begin; tile < t_end; ++tile) {
-    const int b = (int)(tile / p.tiles_per_img);
-    const int p0 = (int)(tile - (long long)b * p.tiles_per_img) * TM;
-    const int valid = min(TM, p.HW - p0);
-    const long long rowbase = (long long)b * p.HW;
-
-    if (loaded_b < 0 || (p.w_bstride != 0 && b != loaded_b)) {
-      // stage this CTA's weight chunk: global [K/4][N][4] (+ image stride) -> smem [K/4][nc][4]
-      const float4* wg = reinterpret_cast<const float4*>(p.w + (long long)b * p.w_bstride);
-      float4* ws = reinterpret_cast<float4*>(sW);
-      const int total = (p.K >> 2) * nc;
-      for (int idx = tid; idx < total; idx += NTHREADS) {
+  if (warp >= EPI_WARPS && warp < EPI_WARPS + PROD_WARPS) {
+    // =============================== producers ===============================
+    const int ptid = tid - EPI_THREADS;
+    {
+      // stage this CTA's weight chunk once: global [K/EPC][N][16 B] (+ image stride) -> smem [K/EPC][nc][16 B]
+      const uint4* wg = reinterpret_cast<const uint4*>(reinterpret_cast<const TOp*>(p.w) +
+                                                       (long long)blockIdx.z * p.w_bstride);
+      uint4* ws = reinterpret_cast<uint4*>(sW);
+      const int total = (p.K / EPC) * nc;
+      for (int idx = ptid; idx < total; idx += PROD_THREADS) {
         const int kq = idx / nc, n = idx - kq * nc;
         ws[idx] = __ldg(wg + (size_t)kq * p.N + n0 + n);
       }
-      loaded_b = b;
     }
-
-    for (int ch = 0; ch < nchunks; ++ch) {
-      const int k0 = ch * p.KC;
-      const int kc = min(p.KC, p.K - k0);
-      if (ch > 0) {                       // previous chunk's MMAs must have finished reading sA
-        mbar_wait(bar, phase);
-        phase ^= 1;
+    const bool do_ln = p.ln_mode != LN_NONE;
+    uint32_t item = 0;
+    for (long long tile = t_begin; tile < t_end; ++tile) {
+      const int b = (int)(tile / p.tiles_per_img);
+      const int p0 = (int)(tile - (long long)b * p.tiles_per_img) * TM;
+      const int valid = min(TM, p.HW - p0);
+      const long long rowbase = (long long)b * p.HW;
+      for (int ch = 0; ch < nchunks; ++ch, ++item) {
+        const int s = item % p.stages;
+        const uint32_t ph = (item / p.stages) & 1u;
+        mbar_wait(smem_u32(&hdr->empty[s]), ph ^ 1u);
+        uint8_t* sA = sA0 + (size_t)s * stage_bytes;
+        const int k0 = ch * p.KC, kc = min(p.KC, p.K - k0);
+        if (p.upl <= 2) {
+          if (p.unr >= 4)      produce_stage<TA, TOp, 2, 4>(p, sA, a_rows_ld, rowbase, p0, valid, k0, kc, p.lpp, do_ln);
+          else if (p.unr == 2) produce_stage<TA, TOp, 2, 2>(p, sA, a_rows_ld, rowbase, p0, valid, k0, kc, p.lpp, do_ln);
+          else                 produce_stage<TA, TOp, 2, 1>(p, sA, a_rows_ld, rowbase, p0, valid, k0, kc, p.lpp, do_ln);
+        } else {
+          if (p.unr >= 4)      produce_stage<TA, TOp, 3, 4>(p, sA, a_rows_ld, rowbase, p0, valid, k0, kc, p.lpp, do_ln);
+          else if (p.unr == 2) produce_stage<TA, TOp, 3, 2>(p, sA, a_rows_ld, rowbase, p0, valid, k0, kc, p.lpp, do_ln);
+          else                 produce_stage<TA, TOp, 3, 1>(p, sA, a_rows_ld, rowbase, p0, valid, k0, kc, p.lpp, do_ln);
+        }
+        fence_async_smem();               // generic-proxy smem writes -> visible to the tensor core (async proxy)
+        mbar_arrive(smem_u32(&hdr->full[s]));
       }
-      if (p.vpl <= 3) load_a_tile<3>(p, sA, a_rows_ld, rowbase, p0, valid, k0, kc, p.lpp, do_ln);
-      else            load_a_tile<4>(p, sA, a_rows_ld, rowbase, p0, valid, k0, kc, p.lpp, do_ln);
-      fence_async_smem();                 // generic-proxy smem writes -> visible to the tensor core (async proxy)
-      tc_fence_before();
-      __syncthreads();
-      if (tid == 0) {
+    }
+  } else if (warp == EPI_WARPS + PROD_WARPS) {
+    // =============================== MMA issuer ===============================
+    const uint32_t idesc = make_idesc<TOp>(nc);
+    uint32_t item = 0, j = 0;
+    for (long long tile = t_begin; tile < t_end; ++tile, ++j) {
+      const uint32_t a = j & 1u;
+      mbar_wait(smem_u32(&hdr->tmem_empty[a]), ((j >> 1) & 1u) ^ 1u);
+      tc_fence_after();
+      for (int ch = 0; ch < nchunks; ++ch, ++item) {
+        const int s = item % p.stages;
+        mbar_wait(smem_u32(&hdr->full[s]), (item / p.stages) & 1u);
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(sA);
-        const uint32_t w_addr = smem_u32(sW) + (uint32_t)(k0 >> 2) * w_lbo;
-        for (int ks = 0; ks < (kc >> 3); ++ks) {
-          const uint64_t adesc = make_smem_desc(a_addr + (uint32_t)(2 * ks) * a_lbo, a_lbo, 128);
-          const uint64_t bdesc = make_smem_desc(w_addr + (uint32_t)(2 * ks) * w_lbo, w_lbo, 128);
-          umma_tf32(tmem_base, adesc, bdesc, idesc, (ch > 0 || ks > 0) ? 1u : 0u);
+        if (lane == 0) {
+          const int k0 = ch * p.KC, kc = min(p.KC, p.K - k0);
+          const uint32_t a_addr = smem_u32(sA0 + (size_t)s * stage_bytes);
+          const uint32_t w_addr = smem_u32(sW) + (uint32_t)(k0 / EPC) * w_lbo;
+          const uint32_t d_addr = tmem_base + a * (uint32_t)p.acc_stride;
+          for (int ks = 0; ks < kc / (2 * EPC); ++ks) {
+            const uint64_t adesc = make_smem_desc(a_addr + (uint32_t)(2 * ks) * a_lbo, a_lbo, 128);
+            const uint64_t bdesc = make_smem_desc(w_addr + (uint32_t)(2 * ks) * w_lbo, w_lbo, 128);
+            umma<TOp>(d_addr, adesc, bdesc, idesc, (ch > 0 || ks > 0) ? 1u : 0u);
+          }
+          umma_commit(smem_u32(&hdr->empty[s]));
+          if (ch == nchunks - 1) umma_commit(smem_u32(&hdr->tmem_full[a]));
         }
-        umma_commit(bar);
+        __syncwarp();
       }
     }
-    mbar_wait(bar, phase);
-    phase ^= 1;
-    tc_fence_after();
-
-    // epilogue: warp w owns TMEM lanes [32w, 32w+32) == tile rows
+  } else {
+    // =============================== epilogue ===============================
+    // warp e owns TMEM lane quarter e (hardware restriction: warp id % 4) == tile rows [32e, 32e+32)
+    const int quarter = warp & 3;
     float* mystg = stg + warp * 32 * STG_LD;
-    for (int c0 = 0; c0 < nc; c0 += 32) {
-      const int ncols = min(32, nc - c0);     // 32 or 16
-      float v[32];
-      __syncwarp();                           // tcgen05.ld is .sync.aligned: the warp must be converged
-      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
-      if (ncols == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
-      tmem_ld_wait();
+    TY* yout = reinterpret_cast<TY*>(p.y);
+    uint32_t j = 0;
+    for (long long tile = t_begin; tile < t_end; ++tile, ++j) {
+      const int b = (int)(tile / p.tiles_per_img);
+      const int p0 = (int)(tile - (long long)b * p.tiles_per_img) * TM;
+      const int valid = min(TM, p.HW - p0);
+      const long long rowbase = (long long)b * p.HW;
+      const uint32_t a = j & 1u;
+      mbar_wait(smem_u32(&hdr->tmem_full[a]), (j >> 1) & 1u);
+      tc_fence_after();
+      for (int c0 = 0; c0 < nc; c0 += 32) {
+        const int ncols = min(32, nc - c0);     // 32 or 16
+        float v[32];
+        __syncwarp();                           // tcgen05.ld is .sync.aligned: the warp must be converged
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + a * (uint32_t)p.acc_stride + (uint32_t)c0;
+        if (ncols == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
+        tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (j * 4 < ncols)
-          *reinterpret_cast<float4*>(mystg + lane * STG_LD + j * 4) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-      __syncwarp();
-      const int cpr = ncols >> 2;             // float4 per row
-      const int rpi = 32 / cpr;               // rows per iteration
-      for (int it = 0; it < cpr; ++it) {
-        const int row = it * rpi + lane / cpr;
-        const int c4 = (lane % cpr) * 4;
-        const int prow = warp * 32 + row;
-        if (prow < valid) {
-          float4 o = *reinterpret_cast<const float4*>(mystg + row * STG_LD + c4);
-          const int n = n0 + c0 + c4;
-          if (p.bias) {
-            const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-            o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+        for (int jj = 0; jj < 8; ++jj)
+          if (jj * 4 < ncols)
+            *reinterpret_cast<float4*>(mystg + lane * STG_LD + jj * 4) =
+                make_float4(v[4 * jj], v[4 * jj + 1], v[4 * jj + 2], v[4 * jj + 3]);
+        __syncwarp();
+        const int cpr = ncols >> 2;             // float4 per row
+        const int rpi = 32 / cpr;               // rows per iteration
+        for (int it = 0; it < cpr; ++it) {
+          const int row = it * rpi + lane / cpr;
+          const int c4 = (lane % cpr) * 4;
+          const int prow = quarter * 32 + row;
+          if (prow < valid) {
+            float4 o = *reinterpret_cast<const float4*>(mystg + row * STG_LD + c4);
+            const int n = n0 + c0 + c4;
+            if (p.bias) {
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+              o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+            }
+            const long long grow = rowbase + p0 + prow;
+            if (p.r) {
+              const float4 rr = *reinterpret_cast<const float4*>(p.r + grow * p.ldr + n);
+              o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+            }
+            store_out4<TY>(yout + grow * p.ldy + n, o);
           }
-          const long long grow = rowbase + p0 + prow;
-          if (p.r) {
-            const float4 rr = *reinterpret_cast<const float4*>(p.r + grow * p.ldr + n);
-            o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
-          }
-          *reinterpret_cast<float4*>(p.y + grow * p.ldy + n) = o;
         }
+        __syncwarp();
       }
-      __syncwarp();
+      tc_fence_before();
+      mbar_arrive(smem_u32(&hdr->tmem_empty[a]));
     }
-    tc_fence_before();      // TMEM reads of this tile are ordered before the next tile's MMA (after the next bar.sync)
   }
 
   tc_fence_before();
@@ -334,67 +482,91 @@ __global__ void __launch_bounds__(NTHREADS) tc_gemm_kernel(const TcGemmParams p)
 
 static int next_pow2_cols(int n) { int c = 32; while (c < n) c <<= 1; return c; }
 
-// Choose the N-chunk, K-chunk and lane mapping; returns dynamic shared memory bytes (0 if unsupported).
+// Choose the N-chunk, K-chunk, stage count and lane mapping; returns dynamic shared memory bytes (0 if unsupported).
 size_t tc_gemm_configure(TcGemmParams& p) {
-  if (p.K % 8 != 0 || p.N % 16 != 0 || p.K <= 0 || p.N <= 0) return 0;
-  if (p.k1 % 4 != 0 || (p.k2 != 0 && p.k2 % 4 != 0) || p.k1 + p.k2 != p.K) return 0;
-  p.KC = p.K <= 128 ? p.K : 64;
-  if (p.ln_mode != LN_NONE && (p.KC != p.K || p.k2 != 0)) return 0;    // LayerNorm needs the whole row in registers
-  const int f4 = p.KC / 4;
+  const int a_es = p.a_half ? 2 : 4;                    // bytes per A element in global memory
+  const int op_es = p.op_half ? 2 : 4;                  // bytes per tensor-core operand element
+  if (op_es > a_es) return 0;
+  const int epc = 16 / op_es;
+  if (p.K <= 0 || p.N <= 0 || p.K % (2 * epc) != 0 || p.N % 16 != 0) return 0;
+  if (p.k1 % (16 / a_es) != 0 || (p.k2 != 0 && p.k2 % (16 / a_es) != 0) || p.k1 + p.k2 != p.K) return 0;
+  if (p.k2 != 0 && p.k1 % epc != 0) return 0;           // a smem chunk must not straddle the two sources
+  const int kc_max = 512 / op_es;                       // K elements per stage: 128 (tf32) / 256 (f16) = 64 KB of A
+  p.KC = p.K <= kc_max ? p.K : kc_max / 2;
+  if (p.ln_mode != LN_NONE && (p.KC != p.K || p.k2 != 0 || p.a_half)) return 0;   // LayerNorm needs the whole fp32 row
+  const int units = p.KC / epc;
   int lpp = 1;
-  while (lpp < 32 && (f4 + lpp - 1) / lpp > 3) lpp <<= 1;              // <= 3 float4 per lane when possible
-  if ((f4 + lpp - 1) / lpp > 4) return 0;
+  while (lpp < 32 && (units + lpp - 1) / lpp > (epc == 4 ? 3 : 2)) lpp <<= 1;
+  if ((units + lpp - 1) / lpp > 3) return 0;
   p.lpp = lpp;
-  p.vpl = (f4 + lpp - 1) / lpp;
-  const size_t fixed = HDR_BYTES + STG_BYTES + (size_t)(p.KC / 4) * (TM + p.a_pad) * 16;
-  const size_t budget2 = 113 * 1024, budget1 = 227 * 1024;
-  // fewest N-chunks whose weights fit next to the A tile; two resident CTAs per SM are preferred unless that
-  // more than doubles the number of chunks (every chunk re-reads the A tile through L2)
-  int nc_for[2] = {0, 0}, chunks_for[2] = {0, 0};
-  for (int pass = 0; pass < 2; ++pass) {
-    const size_t budget = pass == 0 ? budget2 : budget1;
-    for (int chunks = 1; chunks <= p.N / 16; ++chunks) {
-      int nc = ((p.N + chunks - 1) / chunks + 15) / 16 * 16;
-      if (nc > 256) continue;
-      if (fixed + (size_t)nc * p.K * 4 <= budget) { nc_for[pass] = nc; chunks_for[pass] = chunks; break; }
-    }
-  }
+  p.upl = (units + lpp - 1) / lpp;
+  const int pp = PROD_THREADS / lpp;
+  p.unr = pp >= TM ? 1 : (TM / pp >= 4 ? 4 : TM / pp);
+  if (epc == 8 && p.upl > 2) return 0;
+  if (epc == 8 && p.unr == 4 && p.upl == 2) p.unr = 2;  // register budget: unr * upl * epc floats in flight
+  const size_t stage_bytes = (size_t)units * (TM + p.a_pad) * 16;
+  const size_t fixed = HDR_BYTES + STG_BYTES;
+  const size_t budget = 227 * 1024;
+  // fewest N-chunks such that the weights and at least two A stages fit
   int best = 0;
-  if (nc_for[0] && (!nc_for[1] || chunks_for[0] <= 2 * chunks_for[1])) best = nc_for[0];
-  else best = nc_for[1];
+  for (int chunks = 1; chunks <= p.N / 16; ++chunks) {
+    int nc = ((p.N + chunks - 1) / chunks + 15) / 16 * 16;
+    if (nc > 256) continue;
+    if (fixed + (size_t)nc * p.K * op_es + 2 * stage_bytes <= budget) { best = nc; break; }
+  }
   if (!best) return 0;
   p.NC = best;
-  p.tmem_cols = next_pow2_cols(best);
-  return fixed + (size_t)best * p.K * 4;
+  int stages = (int)((budget - fixed - (size_t)best * p.K * op_es) / stage_bytes);
+  p.stages = std::min(stages, MAX_STAGES);
+  p.acc_stride = (best + 31) / 32 * 32;
+  p.tmem_cols = next_pow2_cols(2 * p.acc_stride);
+  if (p.tmem_cols > 512) return 0;
+  return fixed + (size_t)best * p.K * op_es + (size_t)p.stages * stage_bytes;
+}
+
+template <typename TA, typename TOp, typename TY>
+static int launch_typed(const TcGemmParams& p, dim3 grid, size_t smem, cudaStream_t s) {
+  static bool configured = false;
+  if (!configured) {
+    IRB_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<TA, TOp, TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
+  }
+  tc_gemm_kernel<TA, TOp, TY><<<grid, NTHREADS, smem, s>>>(p);
+  IRB_LAUNCH_CHECK();
+  return IR_OK;
 }
 
 int launch_gemm_tc(TcGemmParams p, cudaStream_t s) {
   size_t smem = tc_gemm_configure(p);
   IRB_REQUIRE(smem != 0, "tc_gemm: unsupported shape");
-  IRB_REQUIRE(p.lda1 % 4 == 0 && (p.k2 == 0 || p.lda2 % 4 == 0) && p.ldy % 4 == 0 && (p.r == nullptr || p.ldr % 4 == 0),
-              "tc_gemm: leading dimensions must be multiples of 4");
+  const int a_vec = p.a_half ? 8 : 4;
+  IRB_REQUIRE(p.lda1 % a_vec == 0 && (p.k2 == 0 || p.lda2 % a_vec == 0) && p.ldy % 4 == 0 &&
+                  (p.r == nullptr || p.ldr % 4 == 0),
+              "tc_gemm: leading dimensions must keep 16-byte (A) / 4-element (y, r) alignment");
   p.tiles_per_img = cdiv(p.HW, TM);
   p.ntiles = p.tiles_per_img * p.B;
   const int nchunks_n = cdiv(p.N, p.NC);
-  // occupancy: TMEM columns (512 per SM) and shared memory; pad smem so the hardware cannot over-subscribe TMEM
-  int occ_tmem = 512 / p.tmem_cols;
-  int occ = (int)std::min<size_t>((size_t)occ_tmem, (228 * 1024) / (smem + 1024));
-  if (occ < 1) occ = 1;
-  if (occ > 4) occ = 4;
-  const size_t min_smem = (228 * 1024) / (occ + 1) + 1;    // more than occ CTAs can no longer fit
-  if (smem < min_smem) smem = std::min<size_t>(min_smem, 227 * 1024);
-  static size_t configured = 0;
-  if (smem > configured) {
-    IRB_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = 227 * 1024;
+  // one CTA per SM (TMEM: two accumulators of up to 256 columns): pad smem so that two can never co-reside
+  smem = std::max<size_t>(smem, 116 * 1024);
+  dim3 grid;
+  if (p.w_bstride != 0) {
+    int gx = std::max(1, 148 / (nchunks_n * p.B));
+    gx = std::min(gx, p.tiles_per_img);
+    grid = dim3(gx, nchunks_n, p.B);
+  } else {
+    int gx = std::max(1, 148 / nchunks_n);
+    gx = std::min(gx, p.ntiles);
+    grid = dim3(gx, nchunks_n, 1);
   }
-  int gx = std::max(1, (148 * occ) / nchunks_n);
-  if (gx > p.ntiles) gx = p.ntiles;
-  dim3 grid(gx, nchunks_n);
   const double rows = (double)p.B * p.HW;
-  ProfScope prof(p.tag, 4.0 * rows * (p.K + p.N * (p.r ? 2.0 : 1.0)), 2.0 * rows * p.N * p.K, s);
-  tc_gemm_kernel<<<grid, NTHREADS, smem, s>>>(p);
-  IRB_LAUNCH_CHECK();
+  const double a_es = p.a_half ? 2.0 : 4.0, y_es = p.y_half ? 2.0 : 4.0;
+  ProfScope prof(p.tag, rows * (p.K * a_es + p.N * (y_es + (p.r ? 4.0 : 0.0))), 2.0 * rows * p.N * p.K, s);
+  if (!p.a_half && !p.op_half && !p.y_half) return launch_typed<float, float, float>(p, grid, smem, s);
+  if (!p.a_half && p.op_half && p.y_half) return launch_typed<float, __half, __half>(p, grid, smem, s);
+  if (!p.a_half && p.op_half && !p.y_half) return launch_typed<float, __half, float>(p, grid, smem, s);
+  if (p.a_half && p.op_half && !p.y_half) return launch_typed<__half, __half, float>(p, grid, smem, s);
+  if (p.a_half && p.op_half && p.y_half) return launch_typed<__half, __half, __half>(p, grid, smem, s);
+  IRB_REQUIRE(false, "tc_gemm: unsupported type combination");
   return IR_OK;
 }
 

@@ -8,20 +8,23 @@ namespace irb {
 
 struct TcGemmParams {
   // A operand: rows = pixels, source 1 channels [0,k1) then optional source 2 channels [k1, k1+k2) (channel concat)
-  const float* a1; int lda1; int k1;
-  const float* a2; int lda2; int k2;
+  // (element type: fp32, or fp16 when a_half)
+  const void* a1; int lda1; int k1;
+  const void* a2; int lda2; int k2;
   int B, HW;
-  // weights packed [K/4][N][4] tf32-rounded fp32 (pack.cu, fold kernel); w_bstride != 0: one matrix per image
-  const float* w; long long w_bstride;
+  // weights packed [K/epc][N][epc] (epc = 4 tf32-rounded fp32, or 8 fp16 when op_half; pack.cu, fold kernel);
+  // w_bstride != 0 (in elements): one matrix per image
+  const void* w; long long w_bstride;
   int N, K;
   const float* bias;
   int ln_mode; const float* ln_w; const float* ln_b;     // LayerNorm prologue (K <= 128, single source)
   const float* r; int ldr;                               // residual added in the epilogue (may alias y)
-  float* y; int ldy;
+  void* y; int ldy;                                      // fp32, or fp16 when y_half
   int tag;
   int a_pad;                                             // 0/1: extra row per K-chunk slab of A in smem
+  int a_half, op_half, y_half;                           // element types (0 = fp32 / tf32 operand, 1 = fp16)
   // filled by tc_gemm_configure / launch_gemm_tc
-  int NC, KC, lpp, vpl, tmem_cols, tiles_per_img, ntiles;
+  int NC, KC, lpp, upl, unr, stages, acc_stride, tmem_cols, tiles_per_img, ntiles;
 };
 
 size_t tc_gemm_configure(TcGemmParams& p);

@@ -52,7 +52,7 @@ _REPORT = {}
 
 def record(case, **kv):
     """Parity numbers land in gpurun_out/parity.json so a GPU run can be read back here."""
-    _REPORT.setdefault(case, {}).update({k: (float(v) if hasattr(v, "__float__") else v) for k, v in kv.items()})
+    _REPORT.setdefault(case, {}).update({k: (v if isinstance(v, str) else float(v)) for k, v in kv.items()})
 
 
 def pytest_sessionfinish(session, exitstatus):

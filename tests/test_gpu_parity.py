@@ -157,7 +157,8 @@ def test_shape_validation_raises_before_launch():
 def test_full_size_properties_config2_gray_denoise():
     """BASELINE config 2 (batch 8 of 512x512 gray): properties that hold at any size.
     (a) run-to-run determinism, bit-exact; (b) permuting the batch permutes the output, bit-exact;
-    (c) an image's result does not depend on its batch-mates (only the Gram split differs -> fp32 noise)."""
+    (c) an image's result does not depend on its batch-mates: only the pixel split of the Gram reduction differs,
+        which moves the folded attention matrix by fp32 noise before its tf32 rounding -> within the parity bar."""
     kw = oracle.RESTORMER_TASKS["gray_denoise"]
     m = build_restormer(kw, 81)
     x = oracle.synth_image((8, 1, 512, 512), 91, 25.0).cuda()
@@ -171,7 +172,7 @@ def test_full_size_properties_config2_gray_denoise():
     ys = m(x[2:3].contiguous())
     err = float((ys - y1[2:3]).abs().max())
     record("config2_single_vs_batched", max_abs=err)
-    assert err <= 1e-4
+    assert err <= TOL_MAXABS
 
 
 def test_full_size_properties_config3_real_denoise_and_oracle_crop():

@@ -15,7 +15,7 @@ def test_tc_conv1x1_matches_reference(idx):
     y_simt, _ = run_case(case, 1, seed=idx)
     e_tc = float(np.abs(y_tc - y_ref).max())
     e_simt = float(np.abs(y_simt - y_ref).max())
-    record(f"tc_conv1x1_{idx}", case=str(case), err_tc=e_tc, err_simt=e_simt, tol=tolerance(case, y_ref))
+    record(f"tc_conv1x1_{idx}", cfg=str(case), err_tc=e_tc, err_simt=e_simt, tol=tolerance(case, y_ref))
     assert np.isfinite(y_tc).all()
     assert e_simt <= 2e-5 * max(1.0, float(np.abs(y_ref).max()))
     assert e_tc <= tolerance(case, y_ref), (case, e_tc)
