@@ -88,6 +88,7 @@ struct DwParams {
   int gate;                               // 1: out[c] = gelu(dw(in[c])) * dw(in[c + gate_off])
   int gate_off;
   int tag;
+  int in_half, out_half;                  // element types of in / out (0 = fp32, 1 = fp16); in/out are then __half*
 };
 
 struct GramParams {
@@ -108,7 +109,8 @@ struct FoldParams {
 
 // launchers (simt_kernels.cu)
 int launch_gemm_simt(const GemmParams& p, cudaStream_t s);
-int launch_dwconv(const DwParams& p, cudaStream_t s);
+int launch_dwconv(const DwParams& p, cudaStream_t s);       // dwconv.cu: rolling-window kernel
+int launch_dwconv_ref(const DwParams& p, cudaStream_t s);   // simt_kernels.cu: one thread per output vector (reference)
 int launch_gram(const GramParams& p, cudaStream_t s);
 int launch_fold(const FoldParams& p, cudaStream_t s);
 // standalone channel LayerNorm (levels whose C does not fit the contraction's register-resident prologue)

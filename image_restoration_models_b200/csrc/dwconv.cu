@@ -1,0 +1,179 @@
+// Depthwise 3x3 convolution on channels-last activations (zero padding 1, cross-correlation), optionally fused
+// with the GDFN gate gelu(x1) * x2.  Replaces Attention.qkv_dwconv (restormer.py:106) and FeedForward.dwconv +
+// gating (restormer.py:83,90-91).  Purely HBM-bound (18..36 FLOP per 16..24 bytes), so the kernel is built to
+// touch every input vector once per band instead of nine times:
+//
+//   * a thread owns 4 consecutive channels x WT consecutive pixels of a row and walks down a band of R rows;
+//   * for each input row it loads WT+2 16-byte vectors (8-byte for fp16) and scatters them into three rolling
+//     accumulator rows (the output rows above / at / below), so each loaded vector is used for 9 FMAs per
+//     channel and re-read only by the neighbouring x-tile (L1) and the neighbouring band (L2);
+//   * consecutive lanes own consecutive channel vectors of the same pixels -> fully coalesced 512-byte segments;
+//   * the 3x3 weights of the block's channel slice live in shared memory.
+#include "common.cuh"
+
+namespace irb {
+
+namespace {
+
+__device__ __forceinline__ float gelu_erf(float x) {
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));   // exact erf GELU (F.gelu default)
+}
+
+template <typename T> __device__ __forceinline__ float4 ld4(const T* p);
+template <> __device__ __forceinline__ float4 ld4<float>(const float* p) {
+  return __ldg(reinterpret_cast<const float4*>(p));
+}
+template <> __device__ __forceinline__ float4 ld4<__half>(const __half* p) {
+  const uint2 t = __ldg(reinterpret_cast<const uint2*>(p));
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&t.x));
+  const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&t.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+template <typename T> __device__ __forceinline__ void st4(T* p, const float4& v);
+template <> __device__ __forceinline__ void st4<float>(float* p, const float4& v) {
+  *reinterpret_cast<float4*>(p) = v;
+}
+template <> __device__ __forceinline__ void st4<__half>(__half* p, const float4& v) {
+  uint2 t;
+  *reinterpret_cast<__half2*>(&t.x) = __floats2half2_rn(v.x, v.y);
+  *reinterpret_cast<__half2*>(&t.y) = __floats2half2_rn(v.z, v.w);
+  *reinterpret_cast<uint2*>(p) = t;
+}
+
+__device__ __forceinline__ void fma4(float4& acc, const float4& w, const float4& x) {
+  acc.x = fmaf(w.x, x.x, acc.x); acc.y = fmaf(w.y, x.y, acc.y);
+  acc.z = fmaf(w.z, x.z, acc.z); acc.w = fmaf(w.w, x.w, acc.w);
+}
+
+struct DwGeom { int cvb, xb, rows; };   // channel vectors per block, x-tiles per block, band height
+
+template <typename TI, typename TO, int WT, bool GATE>
+__global__ void __launch_bounds__(256) dw_roll_kernel(const DwParams p, const DwGeom g) {
+  constexpr int NS = GATE ? 2 : 1;
+  extern __shared__ float4 wsm[];                      // [NS][9][cvb]
+  const TI* __restrict__ in = reinterpret_cast<const TI*>(p.in);
+  TO* __restrict__ out = reinterpret_cast<TO*>(p.out);
+  const int tid = threadIdx.x;
+  const int cv_total = p.C >> 2;
+  const int cv0 = blockIdx.x * g.cvb;
+  const int ncv = min(g.cvb, cv_total - cv0);
+
+  for (int idx = tid; idx < NS * 9 * g.cvb; idx += 256) {
+    const int cvl = idx % g.cvb, tap = (idx / g.cvb) % 9, set = idx / (9 * g.cvb);
+    float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (cvl < ncv) w = *reinterpret_cast<const float4*>(p.w + tap * p.Cw + set * p.gate_off + (cv0 + cvl) * 4);
+    wsm[idx] = w;
+  }
+  __syncthreads();
+
+  const int xl = tid / g.cvb, cvl = tid - xl * g.cvb;
+  const int x0 = (blockIdx.y * g.xb + xl) * WT;
+  if (xl >= g.xb || cvl >= ncv || x0 >= p.W) return;
+  const int nbands = (p.H + g.rows - 1) / g.rows;
+  const int b = blockIdx.z / nbands, band = blockIdx.z - b * nbands;
+  const int y0 = band * g.rows, y1 = min(p.H, y0 + g.rows);
+  const int c = (cv0 + cvl) * 4;
+  const long long img = (long long)b * p.H * p.W;
+
+  float4 bias[NS];
+#pragma unroll
+  for (int s = 0; s < NS; ++s)
+    bias[s] = p.bias ? *reinterpret_cast<const float4*>(p.bias + s * p.gate_off + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+
+  float4 acc[NS][3][WT];
+#pragma unroll
+  for (int s = 0; s < NS; ++s)
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int i = 0; i < WT; ++i) acc[s][r][i] = bias[s];
+
+  for (int yy = y0 - 1; yy <= y1; ++yy) {
+    if (yy >= 0 && yy < p.H) {
+      float4 v[NS][WT + 2];
+      const TI* rowp = in + (img + (long long)yy * p.W) * p.ldi + c;
+#pragma unroll
+      for (int s = 0; s < NS; ++s)
+#pragma unroll
+        for (int i = 0; i < WT + 2; ++i) {
+          const int x = x0 - 1 + i;
+          v[s][i] = (x >= 0 && x < p.W) ? ld4<TI>(rowp + (long long)x * p.ldi + s * p.gate_off)
+                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      // input row yy feeds output rows yy-1 (tap row 2), yy (tap row 1), yy+1 (tap row 0)
+#pragma unroll
+      for (int s = 0; s < NS; ++s)
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx) {
+            const float4 w = wsm[(s * 9 + (2 - r) * 3 + dx) * g.cvb + cvl];
+#pragma unroll
+            for (int i = 0; i < WT; ++i) fma4(acc[s][r][i], w, v[s][i + dx]);
+          }
+    }
+    const int yo = yy - 1;
+    if (yo >= y0 && yo < y1) {
+      TO* orow = out + (img + (long long)yo * p.W) * p.ldo + c;
+#pragma unroll
+      for (int i = 0; i < WT; ++i) {
+        if (x0 + i < p.W) {
+          float4 o = acc[0][0][i];
+          if (GATE) {
+            const float4 gt = acc[NS - 1][0][i];
+            o.x = gelu_erf(o.x) * gt.x; o.y = gelu_erf(o.y) * gt.y;
+            o.z = gelu_erf(o.z) * gt.z; o.w = gelu_erf(o.w) * gt.w;
+          }
+          st4<TO>(orow + (long long)(x0 + i) * p.ldo, o);
+        }
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+#pragma unroll
+      for (int i = 0; i < WT; ++i) {
+        acc[s][0][i] = acc[s][1][i];
+        acc[s][1][i] = acc[s][2][i];
+        acc[s][2][i] = bias[s];
+      }
+  }
+}
+
+template <typename TI, typename TO>
+int launch_typed(const DwParams& p, cudaStream_t s) {
+  const int cv = p.C / 4;
+  DwGeom g;
+  if (cv <= 64) {
+    g.cvb = cv;
+  } else {
+    g.cvb = 32;
+    for (int d = 64; d >= 16; --d)
+      if (cv % d == 0) { g.cvb = d; break; }
+  }
+  g.xb = 256 / g.cvb;
+  g.rows = 16;
+  const int wt = p.gate ? 2 : 4;
+  dim3 grid(cdiv(cv, g.cvb), cdiv(p.W, g.xb * wt), p.B * cdiv(p.H, g.rows));
+  const size_t smem = (size_t)(p.gate ? 2 : 1) * 9 * g.cvb * sizeof(float4);
+  if (p.gate) dw_roll_kernel<TI, TO, 2, true><<<grid, 256, smem, s>>>(p, g);
+  else        dw_roll_kernel<TI, TO, 4, false><<<grid, 256, smem, s>>>(p, g);
+  IRB_LAUNCH_CHECK();
+  return IR_OK;
+}
+
+}  // namespace
+
+int launch_dwconv(const DwParams& p, cudaStream_t s) {
+  IRB_REQUIRE(p.C % 4 == 0 && p.ldi % 4 == 0 && p.ldo % 4 == 0 && p.Cw % 4 == 0 && p.gate_off % 4 == 0,
+              "dwconv: channel counts must be multiples of 4");
+  IRB_REQUIRE((long long)p.B * cdiv(p.H, 16) <= 65535, "dwconv: too many row bands for one launch");
+  const double pix = (double)p.B * p.H * p.W;
+  const double ies = p.in_half ? 2.0 : 4.0, oes = p.out_half ? 2.0 : 4.0;
+  ProfScope prof(p.tag, pix * p.C * ((p.gate ? 2.0 : 1.0) * ies + oes), 2.0 * 9.0 * pix * p.C * (p.gate ? 2.0 : 1.0), s);
+  if (!p.in_half && !p.out_half) return launch_typed<float, float>(p, s);
+  if (p.in_half && p.out_half) return launch_typed<__half, __half>(p, s);
+  IRB_REQUIRE(false, "dwconv: unsupported type combination");
+  return IR_OK;
+}
+
+}  // namespace irb

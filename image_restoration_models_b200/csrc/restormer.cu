@@ -53,6 +53,7 @@ static void plan_block(Builder& bl, BlockPlan& bp, int C, int heads, float ffn, 
     bl.ops.push_back(PackOp{PackOp::DW, bl.pidx++, dst, src_half, dst_half, halves, 0, 0, 0, 0});
   };
   bp.ln1_b = bp.qkv_b = bp.qkvdw_b = bp.proj_b = bp.ln2_b = bp.pin_b = bp.ffdw_b = bp.pout_b = -1;
+  bp.ref_kernels = bl.engine == ENGINE_SIMT;
   bp.tc_qkv = bl.tc(C, 3 * C);
   bp.tc_attn = bl.tc(C, C);
   bp.tc_pin = bl.tc(C, 2 * bp.hp);
@@ -318,7 +319,7 @@ int run_block(const BlockPlan& bp, const float* packed, const float* x_in, float
   dwp.in = bs.qkv; dwp.ldi = 3 * C; dwp.out = bs.qkv_dw; dwp.ldo = 3 * C;
   dwp.w = P(bp.qkvdw_w); dwp.bias = P(bp.qkvdw_b); dwp.Cw = 3 * C;
   dwp.B = B; dwp.H = H; dwp.W = W; dwp.C = 3 * C; dwp.gate = 0; dwp.gate_off = 0; dwp.tag = TAG_DW_QKV;
-  IRB_TRY(launch_dwconv(dwp, s));
+  IRB_TRY(bp.ref_kernels ? launch_dwconv_ref(dwp, s) : launch_dwconv(dwp, s));
 
   // (3) Gram q.k^T and row norms per (image, head) (restormer.py:121-124), split over pixel slices
   GramParams gp{};
@@ -357,7 +358,7 @@ int run_block(const BlockPlan& bp, const float* packed, const float* x_in, float
   dwp.in = bs.hidden; dwp.ldi = 2 * hp; dwp.out = bs.gated; dwp.ldo = hp;
   dwp.w = P(bp.ffdw_w); dwp.bias = P(bp.ffdw_b); dwp.Cw = 2 * hp;
   dwp.B = B; dwp.H = H; dwp.W = W; dwp.C = hp; dwp.gate = 1; dwp.gate_off = hp; dwp.tag = TAG_DW_GATE;
-  IRB_TRY(launch_dwconv(dwp, s));
+  IRB_TRY(bp.ref_kernels ? launch_dwconv_ref(dwp, s) : launch_dwconv(dwp, s));
 
   // (8) x_out += project_out . gated (:92, :148)
   g = GemmParams{};

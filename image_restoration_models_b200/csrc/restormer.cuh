@@ -23,6 +23,7 @@ struct BlockPlan {     // one TransformerBlock (restormer.py:137-150); offsets i
   long long ln1_w, ln1_b, temp, qkv_w, qkv_b, qkvdw_w, qkvdw_b, proj_w, proj_b;
   long long ln2_w, ln2_b, pin_w, pin_b, ffdw_w, ffdw_b, pout_w, pout_b;
   bool tc_qkv, tc_attn, tc_pin, tc_pout;   // which 1x1 contractions run on the tcgen05 kernel
+  bool ref_kernels;                        // ENGINE_SIMT: reference CUDA-core kernels everywhere
 };
 
 struct ConvPlan { int cout, cin, k, kp; long long w, b; bool tc; };

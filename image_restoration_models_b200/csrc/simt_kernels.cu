@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const DwParams p) {
   }
 }
 
-int launch_dwconv(const DwParams& p, cudaStream_t s) {
+int launch_dwconv_ref(const DwParams& p, cudaStream_t s) {
   IRB_REQUIRE(p.C % 4 == 0 && p.ldi % 4 == 0 && p.ldo % 4 == 0 && p.Cw % 4 == 0 && p.gate_off % 4 == 0,
               "dwconv: channel counts must be multiples of 4");
   const long long total = (long long)p.B * p.H * p.W * (p.C / 4);

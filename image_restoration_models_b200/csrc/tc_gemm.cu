@@ -429,6 +429,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const TcGemmParams
       const uint32_t a = j & 1u;
       mbar_wait(smem_u32(&hdr->tmem_full[a]), (j >> 1) & 1u);
       tc_fence_after();
+      // Residual rows are fetched one column group ahead of their use (8 x 16 B per lane in flight), so the
+      // epilogue never stalls on a dependent global load.
+      float4 rr[8];
+      auto fetch_residual = [&](int c0) {
+        const int ncols = min(32, nc - c0);
+        const int cpr = ncols >> 2, rpi = 32 / cpr;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          rr[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (it < cpr) {
+            const int prow = quarter * 32 + it * rpi + lane / cpr;
+            if (prow < valid)
+              rr[it] = *reinterpret_cast<const float4*>(p.r + (rowbase + p0 + prow) * p.ldr + n0 + c0 + (lane % cpr) * 4);
+          }
+        }
+      };
+      if (p.r) fetch_residual(0);
       for (int c0 = 0; c0 < nc; c0 += 32) {
         const int ncols = min(32, nc - c0);     // 32 or 16
         float v[32];
@@ -444,23 +461,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const TcGemmParams
         __syncwarp();
         const int cpr = ncols >> 2;             // float4 per row
         const int rpi = 32 / cpr;               // rows per iteration
-        for (int it = 0; it < cpr; ++it) {
-          const int row = it * rpi + lane / cpr;
-          const int c4 = (lane % cpr) * 4;
-          const int prow = quarter * 32 + row;
-          if (prow < valid) {
-            float4 o = *reinterpret_cast<const float4*>(mystg + row * STG_LD + c4);
-            const int n = n0 + c0 + c4;
-            if (p.bias) {
-              const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-              o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+        float4 o[8];
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          if (it < cpr) {
+            const int row = it * rpi + lane / cpr;
+            o[it] = *reinterpret_cast<const float4*>(mystg + row * STG_LD + (lane % cpr) * 4);
+            if (p.r) { o[it].x += rr[it].x; o[it].y += rr[it].y; o[it].z += rr[it].z; o[it].w += rr[it].w; }
+          }
+        }
+        if (p.r && c0 + 32 < nc) fetch_residual(c0 + 32);     // next group's residual in flight during the stores
+        float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias) bb = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + (lane % cpr) * 4));
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          if (it < cpr) {
+            const int prow = quarter * 32 + it * rpi + lane / cpr;
+            if (prow < valid) {
+              o[it].x += bb.x; o[it].y += bb.y; o[it].z += bb.z; o[it].w += bb.w;
+              store_out4<TY>(yout + (rowbase + p0 + prow) * p.ldy + n0 + c0 + (lane % cpr) * 4, o[it]);
             }
-            const long long grow = rowbase + p0 + prow;
-            if (p.r) {
-              const float4 rr = *reinterpret_cast<const float4*>(p.r + grow * p.ldr + n);
-              o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
-            }
-            store_out4<TY>(yout + grow * p.ldy + n, o);
           }
         }
         __syncwarp();
