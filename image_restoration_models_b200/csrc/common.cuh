@@ -96,6 +96,7 @@ struct GramParams {
   int B, HW, C, heads, nparts;
   float* s_part;                          // [B][heads][nparts][ch][ch]
   float* n_part;                          // [B][heads][nparts][2][ch]  (sum q^2, sum k^2)
+  int in_half;                            // qkv element type: 0 fp32, 1 fp16 (qkv is then a __half*)
 };
 
 struct FoldParams {
@@ -111,7 +112,8 @@ struct FoldParams {
 int launch_gemm_simt(const GemmParams& p, cudaStream_t s);
 int launch_dwconv(const DwParams& p, cudaStream_t s);       // dwconv.cu: rolling-window kernel
 int launch_dwconv_ref(const DwParams& p, cudaStream_t s);   // simt_kernels.cu: one thread per output vector (reference)
-int launch_gram(const GramParams& p, cudaStream_t s);
+int launch_gram(const GramParams& p, cudaStream_t s);         // gram.cu: mma.sync tensor-core kernel
+int launch_gram_ref(const GramParams& p, cudaStream_t s);     // simt_kernels.cu: CUDA-core reference
 int launch_fold(const FoldParams& p, cudaStream_t s);
 // standalone channel LayerNorm (levels whose C does not fit the contraction's register-resident prologue)
 int launch_layernorm(const float* x, int ldx, float* y, int ldy, long long rows, int C, int ln_mode, const float* w,

@@ -48,7 +48,7 @@ __device__ __forceinline__ void fma4(float4& acc, const float4& w, const float4&
 struct DwGeom { int cvb, xb, rows; };   // channel vectors per block, x-tiles per block, band height
 
 template <typename TI, typename TO, int WT, bool GATE>
-__global__ void __launch_bounds__(256) dw_roll_kernel(const DwParams p, const DwGeom g) {
+__global__ void __launch_bounds__(256, 2) dw_roll_kernel(const DwParams p, const DwGeom g) {
   constexpr int NS = GATE ? 2 : 1;
   extern __shared__ float4 wsm[];                      // [NS][9][cvb]
   const TI* __restrict__ in = reinterpret_cast<const TI*>(p.in);

@@ -326,7 +326,7 @@ int run_block(const BlockPlan& bp, const float* packed, const float* x_in, float
   gp.qkv = bs.qkv_dw; gp.ld = 3 * C; gp.B = B; gp.HW = H * W; gp.C = C; gp.heads = bp.heads;
   gp.nparts = gram_parts(B, bp.heads, H * W);
   gp.s_part = bs.s_part; gp.n_part = bs.n_part;
-  IRB_TRY(launch_gram(gp, s));
+  IRB_TRY(bp.ref_kernels ? launch_gram_ref(gp, s) : launch_gram(gp, s));
 
   // (4) normalise, temperature, softmax; fold project_out into a per-image C x C matrix (:124-131)
   FoldParams fp{};

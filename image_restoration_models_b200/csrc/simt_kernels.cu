@@ -331,11 +331,10 @@ __global__ void __launch_bounds__(256) gram_kernel(const GramParams p) {
   }
 }
 
-int launch_gram(const GramParams& p, cudaStream_t s) {
+int launch_gram_ref(const GramParams& p, cudaStream_t s) {
   const int ch = p.C / p.heads;
   IRB_REQUIRE(p.C % p.heads == 0 && ch % 16 == 0 && ch <= 128 && p.ld % 4 == 0, "gram: head dim must be a multiple of 16, <= 128");
   dim3 grid(p.nparts, p.heads, p.B);
-  ProfScope prof(TAG_GRAM, 4.0 * (double)p.B * p.HW * 2.0 * p.C, 2.0 * (double)p.B * p.HW * p.C * ch, s);
   switch (ch / 16) {
     case 1: gram_kernel<1><<<grid, 256, 0, s>>>(p); break;
     case 2: gram_kernel<2><<<grid, 256, 0, s>>>(p); break;

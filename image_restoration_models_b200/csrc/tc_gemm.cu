@@ -240,7 +240,8 @@ __device__ __forceinline__ void produce_stage(const TcGemmParams& p, uint8_t* __
 #pragma unroll
           for (int e = 0; e < EPC; ++e) s += v[u][i][e];
         for (int o = lpp >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        const float mu = s / (float)kc;
+        const float inv_k = 1.0f / (float)kc;
+        const float mu = s * inv_k;
         float ss = 0.f;
 #pragma unroll
         for (int i = 0; i < UPL; ++i) {
@@ -250,7 +251,7 @@ __device__ __forceinline__ void produce_stage(const TcGemmParams& p, uint8_t* __
           }
         }
         for (int o = lpp >> 1; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-        const float rstd = 1.0f / sqrtf(ss / (float)kc + 1e-5f);
+        const float rstd = rsqrtf(ss * inv_k + 1e-5f);
         const float sub = (p.ln_mode == LN_WITHBIAS) ? mu : 0.f;
 #pragma unroll
         for (int i = 0; i < UPL; ++i) {
@@ -293,6 +294,61 @@ __device__ __forceinline__ void store_out4<__half>(__half* dst, const float4& o)
   h[0] = __floats2half2_rn(o.x, o.y);
   h[1] = __floats2half2_rn(o.z, o.w);
   *reinterpret_cast<uint2*>(dst) = t;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Epilogue helpers.  One warp drains 32 rows x NCOLS columns: TMEM -> registers -> padded smem tile (transpose)
+// -> rows of NCOLS*4 contiguous bytes in global memory.  All lane/row arithmetic is compile-time (shifts).
+// ---------------------------------------------------------------------------------------------------
+template <typename TY>
+struct EpiCtx {
+  const float* r; int ldr;
+  TY* y; int ldy;
+  const float* bias;
+  long long row0;        // global row of this warp's first TMEM lane
+  int rows_valid;        // rows of this warp inside the image (may be <= 0)
+  int lane;
+  float* stg;            // this warp's private staging tile [32][STG_LD]
+};
+
+// residual of the column group starting at global column n, fetched ahead of use
+template <int NCOLS, typename TY>
+__device__ __forceinline__ void fetch_residual(const EpiCtx<TY>& ec, int n, float4* rr) {
+  constexpr int CPR = NCOLS / 4, RPI = 32 / CPR;
+  const int rsub = ec.lane / CPR, c4 = (ec.lane % CPR) * 4;     // CPR is a power of two: shifts
+#pragma unroll
+  for (int it = 0; it < CPR; ++it) {
+    const int row = it * RPI + rsub;
+    rr[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row < ec.rows_valid) rr[it] = *reinterpret_cast<const float4*>(ec.r + (ec.row0 + row) * ec.ldr + n + c4);
+  }
+}
+
+template <typename TY, int NCOLS, bool HAS_R>
+__device__ __forceinline__ void epi_group(const EpiCtx<TY>& ec, uint32_t taddr, int n, const float4* rr) {
+  constexpr int CPR = NCOLS / 4, RPI = 32 / CPR;
+  float v[32];
+  __syncwarp();                           // tcgen05.ld is .sync.aligned: the warp must be converged
+  if (NCOLS == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
+  tmem_ld_wait();
+#pragma unroll
+  for (int jj = 0; jj < CPR; ++jj)
+    *reinterpret_cast<float4*>(ec.stg + ec.lane * STG_LD + jj * 4) =
+        make_float4(v[4 * jj], v[4 * jj + 1], v[4 * jj + 2], v[4 * jj + 3]);
+  __syncwarp();
+  const int rsub = ec.lane / CPR, c4 = (ec.lane % CPR) * 4;
+  float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (ec.bias) bb = __ldg(reinterpret_cast<const float4*>(ec.bias + n + c4));
+  TY* ybase = ec.y + (ec.row0 + rsub) * ec.ldy + n + c4;
+  const float* sbase = ec.stg + rsub * STG_LD + c4;
+#pragma unroll
+  for (int it = 0; it < CPR; ++it) {
+    float4 o = *reinterpret_cast<const float4*>(sbase + it * RPI * STG_LD);
+    if (HAS_R) { o.x += rr[it].x; o.y += rr[it].y; o.z += rr[it].z; o.w += rr[it].w; }
+    o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+    if (it * RPI + rsub < ec.rows_valid) store_out4<TY>(ybase + (long long)it * RPI * ec.ldy, o);
+  }
+  __syncwarp();
 }
 
 template <typename TA, typename TOp, typename TY>
@@ -373,7 +429,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const TcGemmParams
         mbar_wait(smem_u32(&hdr->empty[s]), ph ^ 1u);
         uint8_t* sA = sA0 + (size_t)s * stage_bytes;
         const int k0 = ch * p.KC, kc = min(p.KC, p.K - k0);
-        if (p.upl <= 2) {
+        if constexpr (EPC == 8) {
+          // 8-element chunks: at most 2 units per lane and 2 row passes in flight (register budget)
+          if (p.unr >= 2) produce_stage<TA, TOp, 2, 2>(p, sA, a_rows_ld, rowbase, p0, valid, k0, kc, p.lpp, do_ln);
+          else            produce_stage<TA, TOp, 2, 1>(p, sA, a_rows_ld, rowbase, p0, valid, k0, kc, p.lpp, do_ln);
+        } else if (p.upl <= 2) {
           if (p.unr >= 4)      produce_stage<TA, TOp, 2, 4>(p, sA, a_rows_ld, rowbase, p0, valid, k0, kc, p.lpp, do_ln);
           else if (p.unr == 2) produce_stage<TA, TOp, 2, 2>(p, sA, a_rows_ld, rowbase, p0, valid, k0, kc, p.lpp, do_ln);
           else                 produce_stage<TA, TOp, 2, 1>(p, sA, a_rows_ld, rowbase, p0, valid, k0, kc, p.lpp, do_ln);
@@ -429,61 +489,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const TcGemmParams
       const uint32_t a = j & 1u;
       mbar_wait(smem_u32(&hdr->tmem_full[a]), (j >> 1) & 1u);
       tc_fence_after();
-      // Residual rows are fetched one column group ahead of their use (8 x 16 B per lane in flight), so the
-      // epilogue never stalls on a dependent global load.
+      EpiCtx<TY> ec;
+      ec.r = p.r; ec.ldr = p.ldr; ec.y = yout; ec.ldy = p.ldy; ec.bias = p.bias;
+      ec.row0 = rowbase + p0 + quarter * 32; ec.rows_valid = valid - quarter * 32; ec.lane = lane; ec.stg = mystg;
+      const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + a * (uint32_t)p.acc_stride;
+      const int n32 = nc >> 5;
+      const bool tail16 = (nc & 31) != 0;
       float4 rr[8];
-      auto fetch_residual = [&](int c0) {
-        const int ncols = min(32, nc - c0);
-        const int cpr = ncols >> 2, rpi = 32 / cpr;
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          rr[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (it < cpr) {
-            const int prow = quarter * 32 + it * rpi + lane / cpr;
-            if (prow < valid)
-              rr[it] = *reinterpret_cast<const float4*>(p.r + (rowbase + p0 + prow) * p.ldr + n0 + c0 + (lane % cpr) * 4);
-          }
+      if (p.r) { if (n32 > 0) fetch_residual<32>(ec, n0, rr); else fetch_residual<16>(ec, n0, rr); }
+      for (int g = 0; g < n32; ++g) {
+        const int c0 = g * 32;
+        if (p.r) {
+          epi_group<TY, 32, true>(ec, tbase + (uint32_t)c0, n0 + c0, rr);
+          if (g + 1 < n32) fetch_residual<32>(ec, n0 + c0 + 32, rr);
+          else if (tail16) fetch_residual<16>(ec, n0 + c0 + 32, rr);
+        } else {
+          epi_group<TY, 32, false>(ec, tbase + (uint32_t)c0, n0 + c0, rr);
         }
-      };
-      if (p.r) fetch_residual(0);
-      for (int c0 = 0; c0 < nc; c0 += 32) {
-        const int ncols = min(32, nc - c0);     // 32 or 16
-        float v[32];
-        __syncwarp();                           // tcgen05.ld is .sync.aligned: the warp must be converged
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + a * (uint32_t)p.acc_stride + (uint32_t)c0;
-        if (ncols == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int jj = 0; jj < 8; ++jj)
-          if (jj * 4 < ncols)
-            *reinterpret_cast<float4*>(mystg + lane * STG_LD + jj * 4) =
-                make_float4(v[4 * jj], v[4 * jj + 1], v[4 * jj + 2], v[4 * jj + 3]);
-        __syncwarp();
-        const int cpr = ncols >> 2;             // float4 per row
-        const int rpi = 32 / cpr;               // rows per iteration
-        float4 o[8];
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          if (it < cpr) {
-            const int row = it * rpi + lane / cpr;
-            o[it] = *reinterpret_cast<const float4*>(mystg + row * STG_LD + (lane % cpr) * 4);
-            if (p.r) { o[it].x += rr[it].x; o[it].y += rr[it].y; o[it].z += rr[it].z; o[it].w += rr[it].w; }
-          }
-        }
-        if (p.r && c0 + 32 < nc) fetch_residual(c0 + 32);     // next group's residual in flight during the stores
-        float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.bias) bb = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + (lane % cpr) * 4));
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          if (it < cpr) {
-            const int prow = quarter * 32 + it * rpi + lane / cpr;
-            if (prow < valid) {
-              o[it].x += bb.x; o[it].y += bb.y; o[it].z += bb.z; o[it].w += bb.w;
-              store_out4<TY>(yout + (rowbase + p0 + prow) * p.ldy + n0 + c0 + (lane % cpr) * 4, o[it]);
-            }
-          }
-        }
-        __syncwarp();
+      }
+      if (tail16) {
+        const int c0 = n32 * 32;
+        if (p.r) epi_group<TY, 16, true>(ec, tbase + (uint32_t)c0, n0 + c0, rr);
+        else     epi_group<TY, 16, false>(ec, tbase + (uint32_t)c0, n0 + c0, rr);
       }
       tc_fence_before();
       mbar_arrive(smem_u32(&hdr->tmem_empty[a]));
@@ -523,7 +550,7 @@ size_t tc_gemm_configure(TcGemmParams& p) {
   const int pp = PROD_THREADS / lpp;
   p.unr = pp >= TM ? 1 : (TM / pp >= 4 ? 4 : TM / pp);
   if (epc == 8 && p.upl > 2) return 0;
-  if (epc == 8 && p.unr == 4 && p.upl == 2) p.unr = 2;  // register budget: unr * upl * epc floats in flight
+  if (epc == 8 && p.unr > 2) p.unr = 2;                 // register budget: unr * upl * epc floats in flight
   const size_t stage_bytes = (size_t)units * (TM + p.a_pad) * 16;
   const size_t fixed = HDR_BYTES + STG_BYTES;
   const size_t budget = 227 * 1024;
