@@ -67,7 +67,8 @@ SIGNATURES = {
     "ir_nhwc_to_nchw": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "ir_test_conv1x1": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
                                   C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
-                                  C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
+                                  C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t,
+                                  C.c_void_p]),
     "ir_profile_begin": (C.c_int, []),
     "ir_profile_end": (C.c_int, [C.POINTER(IrKernelStat), C.c_int]),
     "ir_profile_tag_name": (C.c_char_p, [C.c_int]),

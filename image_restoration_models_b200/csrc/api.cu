@@ -46,11 +46,10 @@ static const char* kTagNames[TAG_COUNT] = {
     "dwconv3x3_gelu_gate", "ffn_project_out_1x1", "conv3x3", "reduce_chan_1x1", "concat_copy", "layernorm"};
 
 static int check_mode(int mode) {
-  IRB_REQUIRE(mode == IR_MODE_FP32 || mode == IR_MODE_FP32_SIMT,
-              "mode: IR_MODE_FP32 and IR_MODE_FP32_SIMT are available in this build");
+  IRB_REQUIRE(mode == IR_MODE_FP32 || mode == IR_MODE_HALF || mode == IR_MODE_FP32_SIMT, "mode: unknown IrMode");
   return IR_OK;
 }
-static int engine_of(int mode) { return mode == IR_MODE_FP32_SIMT ? ENGINE_SIMT : ENGINE_TC; }
+static int engine_of(int mode) { return engine_of_mode(mode); }
 
 }  // namespace irb
 
@@ -220,10 +219,11 @@ int ir_nhwc_to_nchw(const float* src, float* dst, int B, int C, int H, int W, vo
   return launch_nhwc_to_nchw(src, dst, B, C, H, W, (cudaStream_t)stream);
 }
 
-int ir_test_conv1x1(int engine, const float* a1, int lda1, int k1, const float* a2, int lda2, int k2,
+int ir_test_conv1x1(int engine, const void* a1v, int lda1, int k1, const void* a2v, int lda2, int k2,
                     const float* w_rowmajor, const float* bias, int ln_mode, const float* ln_w, const float* ln_b,
-                    const float* r, int ldr, float* y, int ldy, int B, int HW, int N, int a_pad, void* scratch,
-                    size_t scratch_bytes, void* stream) {
+                    const float* r, int ldr, void* y, int ldy, int B, int HW, int N, int a_pad, int a_half,
+                    int op_half, int y_half, void* scratch, size_t scratch_bytes, void* stream) {
+  const float* a1 = (const float*)a1v; const float* a2 = (const float*)a2v;
   IRB_REQUIRE(a1 && w_rowmajor && y && scratch && B > 0 && HW > 0 && N > 0 && k1 > 0, "test_conv1x1: bad argument");
   cudaStream_t s = (cudaStream_t)stream;
   const int K = k1 + k2;
@@ -232,13 +232,14 @@ int ir_test_conv1x1(int engine, const float* a1, int lda1, int k1, const float* 
   if (scratch_bytes < need) { set_error("scratch too small"); return IR_ERR_WORKSPACE; }
   float* wp = (float*)scratch;
   float* xhat = wp + (size_t)N * K;
-  PackMat pm{w_rowmajor, wp, 0, 0, N, N, 1, K, K, nullptr, engine == ENGINE_TC ? 1 : 0};
+  PackMat pm{w_rowmajor, wp, 0, 0, N, N, 1, K, K, nullptr, engine != ENGINE_TC ? 0 : op_half ? 2 : 1};
   IRB_TRY(launch_pack_mat(pm, s));
   if (engine == ENGINE_SIMT) {
+    IRB_REQUIRE(!a_half && !op_half && !y_half, "test_conv1x1: the CUDA-core engine is fp32 only");
     GemmParams g{};
     g.a1 = a1; g.lda1 = lda1; g.k1 = k1; g.a2 = a2; g.lda2 = lda2; g.k2 = k2; g.a_mode = A_PLAIN;
     g.B = B; g.H = 1; g.W = HW; g.w = wp; g.N = N; g.K = K; g.Kp = K; g.bias = bias;
-    g.ln_mode = ln_mode; g.ln_w = ln_w; g.ln_b = ln_b; g.acc_sign = 1.f; g.r = r; g.ldr = ldr; g.y = y; g.ldy = ldy;
+    g.ln_mode = ln_mode; g.ln_w = ln_w; g.ln_b = ln_b; g.acc_sign = 1.f; g.r = r; g.ldr = ldr; g.y = (float*)y; g.ldy = ldy;
     g.o_mode = O_NHWC;
     return launch_gemm_simt(g, s);
   }
@@ -246,9 +247,14 @@ int ir_test_conv1x1(int engine, const float* a1, int lda1, int k1, const float* 
   t.a1 = a1; t.lda1 = lda1; t.k1 = k1; t.a2 = a2; t.lda2 = lda2; t.k2 = k2; t.B = B; t.HW = HW;
   t.w = wp; t.N = N; t.K = K; t.bias = bias; t.ln_mode = ln_mode; t.ln_w = ln_w; t.ln_b = ln_b;
   t.r = r; t.ldr = ldr; t.y = y; t.ldy = ldy; t.a_pad = a_pad;
-  if (ln_mode != LN_NONE && K > 128) {
-    IRB_TRY(launch_layernorm(a1, lda1, xhat, K, rows, K, ln_mode, ln_w, ln_b, s));
-    t.a1 = xhat; t.lda1 = K; t.ln_mode = LN_NONE;
+  t.a_half = a_half; t.op_half = op_half; t.y_half = y_half;
+  if (ln_mode != LN_NONE) {
+    TcGemmParams probe = t;
+    if (tc_gemm_configure(probe) == 0) {
+      IRB_REQUIRE(!a_half, "test_conv1x1: LayerNorm needs an fp32 source");
+      IRB_TRY(launch_layernorm(a1, lda1, xhat, K, op_half, rows, K, ln_mode, ln_w, ln_b, s));
+      t.a1 = xhat; t.lda1 = K; t.ln_mode = LN_NONE; t.a_half = op_half;
+    }
   }
   return launch_gemm_tc(t, s);
 }

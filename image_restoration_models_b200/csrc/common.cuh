@@ -104,7 +104,8 @@ struct FoldParams {
   int B, C, heads, nparts;
   const float* temperature;               // [heads]
   const float* w_proj;                    // [C][C] row-major (project_out)
-  float* w_eff; long long w_eff_bstride;  // [B][C][C] row-major (fmt 0) or [B][C/4][C][4] tf32 (fmt 1)
+  float* w_eff; long long w_eff_bstride;  // [B][C][C] row-major (fmt 0), [B][C/4][C][4] tf32 (fmt 1), [B][C/8][C][8] fp16 (fmt 2);
+                                          // stride in elements of the output type
   int fmt;
 };
 
@@ -116,8 +117,8 @@ int launch_gram(const GramParams& p, cudaStream_t s);         // gram.cu: mma.sy
 int launch_gram_ref(const GramParams& p, cudaStream_t s);     // simt_kernels.cu: CUDA-core reference
 int launch_fold(const FoldParams& p, cudaStream_t s);
 // standalone channel LayerNorm (levels whose C does not fit the contraction's register-resident prologue)
-int launch_layernorm(const float* x, int ldx, float* y, int ldy, long long rows, int C, int ln_mode, const float* w,
-                     const float* b, cudaStream_t s);
+int launch_layernorm(const float* x, int ldx, void* y, int ldy, int y_half, long long rows, int C, int ln_mode,
+                     const float* w, const float* b, cudaStream_t s);
 int launch_copy_channels(const float* src, int lds, float* dst, int ldd, long long rows, int C, cudaStream_t s);
 int launch_nchw_to_nhwc(const float* src, float* dst, int B, int C, int H, int W, cudaStream_t s);
 int launch_nhwc_to_nchw(const float* src, float* dst, int B, int C, int H, int W, cudaStream_t s);
@@ -130,7 +131,8 @@ struct PackMat {
   int n_src_half, n_dst_half, n_halves;   // row split-pad mapping (GDFN hidden padding)
   int k_src, k_dst;                        // logical / padded reduction length (kind 0: zero-pad; kind 1: k_src = 9*cin)
   const float* row_scale;                  // optional per-source-row scale (BatchNorm folding)
-  int fmt;                                 // 0: dst[n][k] fp32;  1: dst[k/4][n][k%4] rounded to tf32 (tcgen05 operand)
+  int fmt;                                 // 0: dst[n][k] fp32;  1: dst[k/4][n][k%4] rounded to tf32;  2: dst[k/8][n][k%8] fp16
+                                           // (1, 2: tcgen05 operand layouts)
 };
 int launch_pack_mat(const PackMat& p, cudaStream_t s);
 // dst[t][map(c)] = src[c][t]  (depthwise 3x3 [C][1][3][3] -> [9][Cdst])

@@ -32,6 +32,8 @@ __global__ void pack_mat_kernel(const PackMat p) {
       uint32_t u;
       asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
       p.dst[((long long)(k >> 2) * n_dst + n) * 4 + (k & 3)] = __uint_as_float(u);
+    } else if (p.fmt == 2) {
+      reinterpret_cast<__half*>(p.dst)[((long long)(k >> 3) * n_dst + n) * 8 + (k & 7)] = __float2half_rn(v);
     } else {
       p.dst[idx] = v;
     }

@@ -15,10 +15,15 @@ static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 // -----------------------------------------------------------------------------------------------
 // plan
 // -----------------------------------------------------------------------------------------------
-bool tc_gemm_supported(int K, int N) {
+bool tc_gemm_supported(int K, int N, bool half) {
   TcGemmParams t{};
   t.K = K; t.N = N; t.k1 = K; t.k2 = 0; t.ln_mode = LN_NONE; t.a_pad = 1;
+  t.a_half = half; t.op_half = half; t.y_half = 0;
   return tc_gemm_configure(t) != 0;
+}
+
+int engine_of_mode(int mode) {
+  return mode == IR_MODE_FP32_SIMT ? ENGINE_SIMT : mode == IR_MODE_HALF ? ENGINE_TC_HALF : ENGINE_TC;
 }
 
 struct Builder {
@@ -27,7 +32,9 @@ struct Builder {
   int pidx = 0;            // running state_dict index
   int engine = ENGINE_TC;
   Builder(std::vector<PackOp>& o, int e) : ops(o), engine(e) {}
-  bool tc(int K, int N) const { return engine == ENGINE_TC && tc_gemm_supported(K, N); }
+  bool half() const { return engine == ENGINE_TC_HALF; }
+  bool tc(int K, int N) const { return engine != ENGINE_SIMT && tc_gemm_supported(K, N, half()); }
+  int fmt(bool tc_layer) const { return !tc_layer ? 0 : half() ? 2 : 1; }
   long long alloc(long long n) { const long long o = off; off += (n + 63) / 64 * 64; return o; }
 };
 
@@ -35,7 +42,7 @@ static void plan_block(Builder& bl, BlockPlan& bp, int C, int heads, float ffn, 
   bp.C = C; bp.heads = heads;
   bp.h = (int)(C * (double)ffn);   // int(dim*ffn_expansion_factor), restormer.py:80
   // python: int(48*2.66)=127, int(96*2.66)=255, int(192*2.66)=510, int(384*2.66)=1021
-  bp.hp = round_up(bp.h, 8);
+  bp.hp = round_up(bp.h, 16);
   auto vec = [&](long long& dst, int n) {
     dst = bl.alloc(n);
     bl.ops.push_back(PackOp{PackOp::VEC, bl.pidx++, dst, n, n, 1, 0, 0, 0, 0});
@@ -46,7 +53,7 @@ static void plan_block(Builder& bl, BlockPlan& bp, int C, int heads, float ffn, 
   };
   auto mat = [&](long long& dst, int n_src_half, int n_dst_half, int halves, int k_src, int k_dst, bool tc) {
     dst = bl.alloc((long long)n_dst_half * halves * k_dst);
-    bl.ops.push_back(PackOp{PackOp::MAT1, bl.pidx++, dst, n_src_half, n_dst_half, halves, k_src, k_dst, 0, tc ? 1 : 0});
+    bl.ops.push_back(PackOp{PackOp::MAT1, bl.pidx++, dst, n_src_half, n_dst_half, halves, k_src, k_dst, 0, bl.fmt(tc)});
   };
   auto dw = [&](long long& dst, int src_half, int dst_half, int halves) {
     dst = bl.alloc(9LL * dst_half * halves);
@@ -54,6 +61,7 @@ static void plan_block(Builder& bl, BlockPlan& bp, int C, int heads, float ffn, 
   };
   bp.ln1_b = bp.qkv_b = bp.qkvdw_b = bp.proj_b = bp.ln2_b = bp.pin_b = bp.ffdw_b = bp.pout_b = -1;
   bp.ref_kernels = bl.engine == ENGINE_SIMT;
+  bp.half = bl.half();
   bp.tc_qkv = bl.tc(C, 3 * C);
   bp.tc_attn = bl.tc(C, C);
   bp.tc_pin = bl.tc(C, 2 * bp.hp);
@@ -87,6 +95,8 @@ int build_block_plan(BlockPlan& bp, std::vector<PackOp>& ops, long long& packed_
   Builder bl(ops, engine);
   plan_block(bl, bp, C, heads, ffn, bias, ln_bias);
   packed_floats = bl.off;
+  IRB_REQUIRE(!bp.half || (bp.tc_qkv && bp.tc_attn && bp.tc_pin && bp.tc_pout),
+              "half mode: channel widths must be multiples of 16 (tensor-core operand granularity)");
   return IR_OK;
 }
 
@@ -104,7 +114,7 @@ static void plan_conv1(Builder& bl, ConvPlan& cp, int cout, int cin, int bias) {
   cp.cout = cout; cp.cin = cin; cp.k = cin; cp.kp = cin;
   cp.w = bl.alloc((long long)cout * cin);
   cp.tc = bl.tc(cin, cout);
-  bl.ops.push_back(PackOp{PackOp::MAT1, bl.pidx++, cp.w, cout, cout, 1, cin, cin, 0, cp.tc ? 1 : 0});
+  bl.ops.push_back(PackOp{PackOp::MAT1, bl.pidx++, cp.w, cout, cout, 1, cin, cin, 0, bl.fmt(cp.tc)});
   cp.b = -1;
   if (bias) {
     cp.b = bl.alloc(cout);
@@ -127,6 +137,7 @@ int build_restormer_plan(RestormerPlan& pl, const IrRestormerCfg& c, int engine)
   IRB_REQUIRE(c.dual_pixel_task || c.inp_channels == c.out_channels,
               "restormer: inp_channels must equal out_channels unless dual_pixel_task (residual add, restormer.py:281)");
   pl.cfg = c;
+  pl.half = engine == ENGINE_TC_HALF;
   pl.ops.clear();
   Builder bl(pl.ops, engine);
   const int d = c.dim, bias = c.bias, lnb = c.layernorm_with_bias;
@@ -155,6 +166,16 @@ int build_restormer_plan(RestormerPlan& pl, const IrRestormerCfg& c, int engine)
   plan_conv3(bl, pl.output, c.out_channels, 2 * d, bias);
   pl.n_params = bl.pidx;
   pl.packed_floats = bl.off;
+  if (engine == ENGINE_TC_HALF) {
+    auto ok = [](const std::vector<BlockPlan>& v) {
+      for (const auto& bp : v) if (!(bp.tc_qkv && bp.tc_attn && bp.tc_pin && bp.tc_pout)) return false;
+      return true;
+    };
+    bool all = ok(pl.refine);
+    for (int l = 0; l < 4; ++l) all = all && ok(pl.enc[l]);
+    for (int l = 0; l < 3; ++l) all = all && ok(pl.dec[l]);
+    IRB_REQUIRE(all, "half mode: channel widths must be multiples of 16 (tensor-core operand granularity)");
+  }
   return IR_OK;
 }
 
@@ -217,6 +238,7 @@ void block_scratch_need(BlockScratchNeed& n, const BlockPlan& bp, int B, int H, 
   n.n_part = std::max(n.n_part, (long long)B * bp.heads * parts * 2 * ch);
   n.w_eff = std::max(n.w_eff, (long long)B * bp.C * bp.C);
   if (bp.C > 128) n.xhat = std::max(n.xhat, P * bp.C);
+  n.es = bp.half ? 2 : 4;
 }
 
 struct Carver {
@@ -231,14 +253,16 @@ struct Carver {
 };
 
 void carve_block_scratch(Carver& cv, BlockScratch& bs, const BlockScratchNeed& n) {
-  bs.qkv = cv.take(n.qkv);
-  bs.qkv_dw = cv.take(n.qkv);
-  bs.hidden = cv.take(n.hidden);
-  bs.gated = cv.take(n.gated);
+  // intermediates are fp32 or fp16 (n.es bytes per element); take() counts in floats
+  auto elems = [&](long long e) { return (e * n.es + 3) / 4; };
+  bs.qkv = cv.take(elems(n.qkv));
+  bs.qkv_dw = cv.take(elems(n.qkv));
+  bs.hidden = cv.take(elems(n.hidden));
+  bs.gated = cv.take(elems(n.gated));
   bs.s_part = cv.take(n.s_part);
   bs.n_part = cv.take(n.n_part);
-  bs.w_eff = cv.take(n.w_eff);
-  bs.xhat = cv.take(n.xhat);
+  bs.w_eff = cv.take(elems(n.w_eff));
+  bs.xhat = cv.take(elems(n.xhat));
 }
 
 size_t block_workspace_bytes(const BlockPlan& bp, int B, int H, int W) {
@@ -279,7 +303,9 @@ size_t restormer_workspace_bytes(const RestormerPlan& pl, int B, int H, int W) {
 // -----------------------------------------------------------------------------------------------
 // 1x1 contraction dispatch: tcgen05 kernel when the layer was packed for it, CUDA-core kernel otherwise
 // -----------------------------------------------------------------------------------------------
-static int run_1x1(const GemmParams& g, bool tc, float* xhat, cudaStream_t s) {
+// Element types in half mode: a_half / y_half say whether the A source / the output are fp16 buffers (the
+// GemmParams pointers are then reinterpreted); weights were packed as fp16 operands at plan time.
+static int run_1x1(const GemmParams& g, bool tc, bool half, bool a_half, bool y_half, void* xhat, cudaStream_t s) {
   if (!tc) return launch_gemm_simt(g, s);
   TcGemmParams t{};
   t.a1 = g.a1; t.lda1 = g.lda1; t.k1 = g.k1; t.a2 = g.a2; t.lda2 = g.lda2; t.k2 = g.k2;
@@ -287,10 +313,15 @@ static int run_1x1(const GemmParams& g, bool tc, float* xhat, cudaStream_t s) {
   t.w = g.w; t.w_bstride = g.w_bstride; t.N = g.N; t.K = g.K; t.bias = g.bias;
   t.ln_mode = g.ln_mode; t.ln_w = g.ln_w; t.ln_b = g.ln_b;
   t.r = g.r; t.ldr = g.ldr; t.y = g.y; t.ldy = g.ldy; t.tag = g.tag; t.a_pad = 1;
-  if (g.ln_mode != LN_NONE && g.K > 128) {
-    // wide levels: normalise once into scratch, then a plain contraction
-    IRB_TRY(launch_layernorm(g.a1, g.lda1, xhat, g.K, (long long)g.B * g.H * g.W, g.K, g.ln_mode, g.ln_w, g.ln_b, s));
-    t.a1 = xhat; t.lda1 = g.K; t.ln_mode = LN_NONE;
+  t.a_half = a_half; t.op_half = half; t.y_half = y_half;
+  if (g.ln_mode != LN_NONE) {
+    TcGemmParams probe = t;
+    if (tc_gemm_configure(probe) == 0) {
+      // wide levels: the row does not fit the register-resident prologue -> normalise once into scratch
+      IRB_TRY(launch_layernorm(g.a1, g.lda1, xhat, g.K, half ? 1 : 0, (long long)g.B * g.H * g.W, g.K, g.ln_mode,
+                               g.ln_w, g.ln_b, s));
+      t.a1 = xhat; t.lda1 = g.K; t.ln_mode = LN_NONE; t.a_half = half;
+    }
   }
   return launch_gemm_tc(t, s);
 }
@@ -302,6 +333,8 @@ int run_block(const BlockPlan& bp, const float* packed, const float* x_in, float
               const BlockScratch& bs, int ln_with_bias, cudaStream_t s) {
   const int C = bp.C, hp = bp.hp;
   const int ln = ln_with_bias ? LN_WITHBIAS : LN_BIASFREE;
+  const bool hf = bp.half;                 // fp16 intermediates: qkv, qkv_dw (v), hidden, gated, W_eff
+  const size_t es = hf ? 2 : 4;
   auto P = [&](long long off) -> const float* { return off >= 0 ? packed + off : nullptr; };
 
   // (1) norm1 + qkv 1x1   (restormer.py:147 norm1, :114 qkv)
@@ -311,19 +344,21 @@ int run_block(const BlockPlan& bp, const float* packed, const float* x_in, float
   g.w = P(bp.qkv_w); g.w_bstride = 0; g.N = 3 * C; g.K = C; g.Kp = C; g.bias = P(bp.qkv_b);
   g.ln_mode = ln; g.ln_w = P(bp.ln1_w); g.ln_b = P(bp.ln1_b);
   g.relu = 0; g.r = nullptr; g.ldr = 0; g.acc_sign = 1.f;
-  g.y = bs.qkv; g.ldy = 3 * C; g.o_mode = O_NHWC; g.tag = TAG_LN_QKV;
-  IRB_TRY(run_1x1(g, bp.tc_qkv, bs.xhat, s));
+  g.y = (float*)bs.qkv; g.ldy = 3 * C; g.o_mode = O_NHWC; g.tag = TAG_LN_QKV;
+  IRB_TRY(run_1x1(g, bp.tc_qkv, hf, false, hf, bs.xhat, s));
 
   // (2) depthwise 3x3 over the 3C channels (restormer.py:114 qkv_dwconv)
   DwParams dwp{};
-  dwp.in = bs.qkv; dwp.ldi = 3 * C; dwp.out = bs.qkv_dw; dwp.ldo = 3 * C;
+  dwp.in = (const float*)bs.qkv; dwp.ldi = 3 * C; dwp.out = (float*)bs.qkv_dw; dwp.ldo = 3 * C;
+  dwp.in_half = hf; dwp.out_half = hf;
   dwp.w = P(bp.qkvdw_w); dwp.bias = P(bp.qkvdw_b); dwp.Cw = 3 * C;
   dwp.B = B; dwp.H = H; dwp.W = W; dwp.C = 3 * C; dwp.gate = 0; dwp.gate_off = 0; dwp.tag = TAG_DW_QKV;
   IRB_TRY(bp.ref_kernels ? launch_dwconv_ref(dwp, s) : launch_dwconv(dwp, s));
 
   // (3) Gram q.k^T and row norms per (image, head) (restormer.py:121-124), split over pixel slices
   GramParams gp{};
-  gp.qkv = bs.qkv_dw; gp.ld = 3 * C; gp.B = B; gp.HW = H * W; gp.C = C; gp.heads = bp.heads;
+  gp.qkv = (const float*)bs.qkv_dw; gp.ld = 3 * C; gp.B = B; gp.HW = H * W; gp.C = C; gp.heads = bp.heads;
+  gp.in_half = hf;
   gp.nparts = gram_parts(B, bp.heads, H * W);
   gp.s_part = bs.s_part; gp.n_part = bs.n_part;
   IRB_TRY(bp.ref_kernels ? launch_gram_ref(gp, s) : launch_gram(gp, s));
@@ -331,18 +366,18 @@ int run_block(const BlockPlan& bp, const float* packed, const float* x_in, float
   // (4) normalise, temperature, softmax; fold project_out into a per-image C x C matrix (:124-131)
   FoldParams fp{};
   fp.s_part = bs.s_part; fp.n_part = bs.n_part; fp.B = B; fp.C = C; fp.heads = bp.heads; fp.nparts = gp.nparts;
-  fp.temperature = P(bp.temp); fp.w_proj = P(bp.proj_w); fp.w_eff = bs.w_eff; fp.w_eff_bstride = (long long)C * C;
-  fp.fmt = bp.tc_attn ? 1 : 0;
+  fp.temperature = P(bp.temp); fp.w_proj = P(bp.proj_w); fp.w_eff = (float*)bs.w_eff; fp.w_eff_bstride = (long long)C * C;
+  fp.fmt = !bp.tc_attn ? 0 : hf ? 2 : 1;
   IRB_TRY(launch_fold(fp, s));
 
   // (5) x_out = x_in + W_eff[b] . v  (+ project_out bias)   (:127-131, :147)
   g = GemmParams{};
-  g.a1 = bs.qkv_dw + 2 * C; g.lda1 = 3 * C; g.k1 = C; g.a_mode = A_PLAIN;
+  g.a1 = (const float*)((const char*)bs.qkv_dw + (size_t)2 * C * es); g.lda1 = 3 * C; g.k1 = C; g.a_mode = A_PLAIN;
   g.B = B; g.H = H; g.W = W;
-  g.w = bs.w_eff; g.w_bstride = (long long)C * C; g.N = C; g.K = C; g.Kp = C; g.bias = P(bp.proj_b);
+  g.w = (const float*)bs.w_eff; g.w_bstride = (long long)C * C; g.N = C; g.K = C; g.Kp = C; g.bias = P(bp.proj_b);
   g.ln_mode = LN_NONE; g.acc_sign = 1.f;
   g.r = x_in; g.ldr = C; g.y = x_out; g.ldy = C; g.o_mode = O_NHWC; g.tag = TAG_ATTN_OUT;
-  IRB_TRY(run_1x1(g, bp.tc_attn, bs.xhat, s));
+  IRB_TRY(run_1x1(g, bp.tc_attn, hf, hf, false, bs.xhat, s));
 
   // (6) norm2 + project_in 1x1 (:148, :89)
   g = GemmParams{};
@@ -350,24 +385,25 @@ int run_block(const BlockPlan& bp, const float* packed, const float* x_in, float
   g.B = B; g.H = H; g.W = W;
   g.w = P(bp.pin_w); g.N = 2 * hp; g.K = C; g.Kp = C; g.bias = P(bp.pin_b);
   g.ln_mode = ln; g.ln_w = P(bp.ln2_w); g.ln_b = P(bp.ln2_b); g.acc_sign = 1.f;
-  g.y = bs.hidden; g.ldy = 2 * hp; g.o_mode = O_NHWC; g.tag = TAG_LN_PIN;
-  IRB_TRY(run_1x1(g, bp.tc_pin, bs.xhat, s));
+  g.y = (float*)bs.hidden; g.ldy = 2 * hp; g.o_mode = O_NHWC; g.tag = TAG_LN_PIN;
+  IRB_TRY(run_1x1(g, bp.tc_pin, hf, false, hf, bs.xhat, s));
 
   // (7) depthwise 3x3 + gelu(x1)*x2 (:90-91)
   dwp = DwParams{};
-  dwp.in = bs.hidden; dwp.ldi = 2 * hp; dwp.out = bs.gated; dwp.ldo = hp;
+  dwp.in = (const float*)bs.hidden; dwp.ldi = 2 * hp; dwp.out = (float*)bs.gated; dwp.ldo = hp;
+  dwp.in_half = hf; dwp.out_half = hf;
   dwp.w = P(bp.ffdw_w); dwp.bias = P(bp.ffdw_b); dwp.Cw = 2 * hp;
   dwp.B = B; dwp.H = H; dwp.W = W; dwp.C = hp; dwp.gate = 1; dwp.gate_off = hp; dwp.tag = TAG_DW_GATE;
   IRB_TRY(bp.ref_kernels ? launch_dwconv_ref(dwp, s) : launch_dwconv(dwp, s));
 
   // (8) x_out += project_out . gated (:92, :148)
   g = GemmParams{};
-  g.a1 = bs.gated; g.lda1 = hp; g.k1 = hp; g.a_mode = A_PLAIN;
+  g.a1 = (const float*)bs.gated; g.lda1 = hp; g.k1 = hp; g.a_mode = A_PLAIN;
   g.B = B; g.H = H; g.W = W;
   g.w = P(bp.pout_w); g.N = C; g.K = hp; g.Kp = hp; g.bias = P(bp.pout_b);
   g.ln_mode = LN_NONE; g.acc_sign = 1.f;
   g.r = x_out; g.ldr = C; g.y = x_out; g.ldy = C; g.o_mode = O_NHWC; g.tag = TAG_FFN_OUT;
-  IRB_TRY(run_1x1(g, bp.tc_pout, bs.xhat, s));
+  IRB_TRY(run_1x1(g, bp.tc_pout, hf, hf, false, bs.xhat, s));
   return IR_OK;
 }
 
@@ -459,7 +495,7 @@ int restormer_forward(const RestormerPlan& pl, const float* packed, const float*
     g.w = packed + pl.reduce[l].w; g.N = C; g.K = 2 * C; g.Kp = 2 * C;
     g.bias = pl.reduce[l].b >= 0 ? packed + pl.reduce[l].b : nullptr;
     g.ln_mode = LN_NONE; g.acc_sign = 1.f; g.y = ws.d[l]; g.ldy = C; g.o_mode = O_NHWC; g.tag = TAG_REDUCE;
-    IRB_TRY(run_1x1(g, pl.reduce[l].tc, nullptr, s));
+    IRB_TRY(run_1x1(g, pl.reduce[l].tc, pl.half, false, false, nullptr, s));
     IRB_TRY(run_stage(pl.dec[l], packed, ws.d[l], ws.d[l], B, hi * 2, wi * 2, C, ws.bs, lnb, s));
     below = ws.d[l];
   }
@@ -474,7 +510,7 @@ int restormer_forward(const RestormerPlan& pl, const float* packed, const float*
     g.a1 = e1_in; g.lda1 = d; g.k1 = d; g.a_mode = A_PLAIN; g.B = B; g.H = H; g.W = W;
     g.w = packed + pl.skip.w; g.N = 2 * d; g.K = d; g.Kp = d; g.bias = pl.skip.b >= 0 ? packed + pl.skip.b : nullptr;
     g.ln_mode = LN_NONE; g.acc_sign = 1.f; g.r = ws.d[0]; g.ldr = 2 * d; g.y = ws.d[0]; g.ldy = 2 * d; g.o_mode = O_NHWC; g.tag = TAG_REDUCE;
-    IRB_TRY(run_1x1(g, pl.skip.tc, nullptr, s));
+    IRB_TRY(run_1x1(g, pl.skip.tc, pl.half, false, false, nullptr, s));
     IRB_TRY(conv3(pl.output, packed, ws.d[0], 2 * d, A_IM2COL_NHWC, B, H, W, y, 0, O_NCHW, nullptr, s));
   } else {
     IRB_TRY(conv3(pl.output, packed, ws.d[0], 2 * d, A_IM2COL_NHWC, B, H, W, y, 0, O_NCHW, x, s));   // :281

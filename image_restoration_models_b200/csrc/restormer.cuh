@@ -24,12 +24,14 @@ struct BlockPlan {     // one TransformerBlock (restormer.py:137-150); offsets i
   long long ln2_w, ln2_b, pin_w, pin_b, ffdw_w, ffdw_b, pout_w, pout_b;
   bool tc_qkv, tc_attn, tc_pin, tc_pout;   // which 1x1 contractions run on the tcgen05 kernel
   bool ref_kernels;                        // ENGINE_SIMT: reference CUDA-core kernels everywhere
+  bool half;                               // ENGINE_TC_HALF: fp16 intermediates (qkv, v, hidden, gated) and fp16 operands
 };
 
 struct ConvPlan { int cout, cin, k, kp; long long w, b; bool tc; };
 
 struct RestormerPlan {
   IrRestormerCfg cfg;
+  bool half = false;
   std::vector<PackOp> ops;
   int n_params = 0;
   long long packed_floats = 0;
@@ -37,21 +39,24 @@ struct RestormerPlan {
   std::vector<BlockPlan> enc[4], dec[3], refine;
 };
 
-struct BlockScratchNeed { long long qkv = 0, hidden = 0, gated = 0, s_part = 0, n_part = 0, w_eff = 0, xhat = 0; };
-struct BlockScratch { float *qkv, *qkv_dw, *hidden, *gated, *s_part, *n_part, *w_eff, *xhat; };
+struct BlockScratchNeed { long long qkv = 0, hidden = 0, gated = 0, s_part = 0, n_part = 0, w_eff = 0, xhat = 0; int es = 4; };
+struct BlockScratch { void *qkv, *qkv_dw, *hidden, *gated; float *s_part, *n_part; void *w_eff, *xhat; };
 struct RestormerWs { float* e[4]; float* e1_in; float* d[3]; float* up_tmp; BlockScratch bs; };
 
 int  block_param_count(int bias, int ln_bias);
-// engine: 0 = tcgen05 contractions (tf32 operands), 1 = CUDA-core fp32 contractions (on-device reference)
-enum Engine { ENGINE_TC = 0, ENGINE_SIMT = 1 };
+// engine: 0 = tcgen05 contractions with tf32 operands and fp32 intermediates; 1 = CUDA-core fp32 contractions and
+// reference kernels (on-device second oracle); 2 = tcgen05 contractions with fp16 operands and fp16 intermediates
+// (the residual stream, LayerNorm statistics, Gram accumulation, softmax and GELU stay fp32)
+enum Engine { ENGINE_TC = 0, ENGINE_SIMT = 1, ENGINE_TC_HALF = 2 };
 int  build_block_plan(BlockPlan& bp, std::vector<PackOp>& ops, long long& packed_floats, int C, int heads, float ffn,
                       int bias, int ln_bias, int engine);
 int  build_restormer_plan(RestormerPlan& pl, const IrRestormerCfg& cfg, int engine);
-bool tc_gemm_supported(int K, int N);
+bool tc_gemm_supported(int K, int N, bool half);
 long long pack_op_src_numel(const PackOp& op);
 int  run_pack_ops(const std::vector<PackOp>& ops, const float* const* params, float* packed, cudaStream_t s);
 
 size_t block_workspace_bytes(const BlockPlan& bp, int B, int H, int W);
+int  engine_of_mode(int mode);
 size_t restormer_workspace_bytes(const RestormerPlan& pl, int B, int H, int W);
 int  run_block(const BlockPlan& bp, const float* packed, const float* x_in, float* x_out, int B, int H, int W,
                const BlockScratch& bs, int ln_with_bias, cudaStream_t s);

@@ -409,6 +409,9 @@ __global__ void __launch_bounds__(256) fold_kernel(const FoldParams p) {
       uint32_t u;
       asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(s));
       we[((long long)(k >> 2) * p.C + n) * 4 + (k & 3)] = __uint_as_float(u);
+    } else if (p.fmt == 2) {
+      __half* wh = reinterpret_cast<__half*>(p.w_eff) + (long long)b * p.w_eff_bstride;
+      wh[((long long)(k >> 3) * p.C + n) * 8 + (k & 7)] = __float2half_rn(s);
     } else {
       we[(long long)n * p.C + k] = s;
     }
@@ -430,7 +433,8 @@ int launch_fold(const FoldParams& p, cudaStream_t s) {
 // ---------------------------------------------------------------------------------------------
 // standalone channel LayerNorm, one warp per pixel (C <= 1024), two-pass statistics in registers
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, int ldx, float* __restrict__ y,
+template <typename TY>
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, int ldx, TY* __restrict__ y,
                                                         int ldy, long long rows, int C, int ln_mode,
                                                         const float* __restrict__ w, const float* __restrict__ b) {
   const int lane = threadIdx.x & 31;
@@ -472,20 +476,28 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
           const float4 bb = *reinterpret_cast<const float4*>(b + 4 * f);
           o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
         }
-        *reinterpret_cast<float4*>(y + row * ldy + 4 * f) = o;
+        if constexpr (sizeof(TY) == 4) {
+          *reinterpret_cast<float4*>(y + row * ldy + 4 * f) = o;
+        } else {
+          uint2 t;
+          *reinterpret_cast<__half2*>(&t.x) = __floats2half2_rn(o.x, o.y);
+          *reinterpret_cast<__half2*>(&t.y) = __floats2half2_rn(o.z, o.w);
+          *reinterpret_cast<uint2*>(y + row * ldy + 4 * f) = t;
+        }
       }
     }
   }
 }
 
-int launch_layernorm(const float* x, int ldx, float* y, int ldy, long long rows, int C, int ln_mode, const float* w,
-                     const float* b, cudaStream_t s) {
+int launch_layernorm(const float* x, int ldx, void* y, int ldy, int y_half, long long rows, int C, int ln_mode,
+                     const float* w, const float* b, cudaStream_t s) {
   IRB_REQUIRE(C % 4 == 0 && C <= 1024 && ldx % 4 == 0 && ldy % 4 == 0, "layernorm: C must be a multiple of 4, <= 1024");
   IRB_REQUIRE(ln_mode == LN_BIASFREE || ln_mode == LN_WITHBIAS, "layernorm: bad mode");
   const long long blocks_needed = cdivll(rows, 8);
   const int blocks = (int)(blocks_needed < 148LL * 8 ? blocks_needed : 148LL * 8);
-  ProfScope prof(TAG_LAYERNORM, 8.0 * (double)rows * C, 0.0, s);
-  layernorm_kernel<<<blocks > 0 ? blocks : 1, 256, 0, s>>>(x, ldx, y, ldy, rows, C, ln_mode, w, b);
+  ProfScope prof(TAG_LAYERNORM, (y_half ? 6.0 : 8.0) * (double)rows * C, 0.0, s);
+  if (y_half) layernorm_kernel<__half><<<blocks > 0 ? blocks : 1, 256, 0, s>>>(x, ldx, (__half*)y, ldy, rows, C, ln_mode, w, b);
+  else        layernorm_kernel<float><<<blocks > 0 ? blocks : 1, 256, 0, s>>>(x, ldx, (float*)y, ldy, rows, C, ln_mode, w, b);
   IRB_LAUNCH_CHECK();
   return IR_OK;
 }

@@ -15,7 +15,7 @@ import torch.nn as nn
 from .. import _native
 from .._params import AffineParams, ConvParams, Holder, ordered_tensors
 
-_MODES = {"fp32": _native.MODE_FP32, "fp32_simt": _native.MODE_FP32_SIMT}
+_MODES = {"fp32": _native.MODE_FP32, "half": _native.MODE_HALF, "fp32_simt": _native.MODE_FP32_SIMT}
 
 
 def _transformer_block(dim, num_heads, ffn_expansion_factor, bias, LayerNorm_type):
@@ -102,8 +102,9 @@ class Restormer(nn.Module):
 
     # ------------------------------------------------------------------ packed-weight lifetime
     def set_mode(self, mode: str):
-        """'fp32' (tf32 tensor-core operands, fp32 everything else) or 'fp32_simt' (every contraction on CUDA
-        cores in exact fp32: the on-device reference used by the tests)."""
+        """'fp32': tf32 tensor-core operands, fp32 intermediates.  'half': fp16 tensor-core operands and fp16
+        intermediates (same 10-bit mantissa as tf32; residual stream, statistics and accumulation stay fp32).
+        'fp32_simt': every contraction on CUDA cores in exact fp32 (the on-device reference used by the tests)."""
         if mode not in _MODES:
             raise ValueError(f"mode must be one of {sorted(_MODES)}")
         self._mode = mode

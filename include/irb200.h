@@ -119,9 +119,10 @@ int    ir_block_forward(int C, int heads, float ffn_expansion_factor, int bias, 
 /* One 1x1 convolution y[pix, n] = sum_k LN?(a)[pix, k] * w[n, k] (+bias) (+r) on channels-last rows, with the
  * reference's row-major weight [N][K] (K = k1 + k2, second source = channel concat).  engine 0 = tcgen05
  * kernel, 1 = CUDA-core fp32 kernel.  ln_mode: 0 none, 1 BiasFree, 2 WithBias.  scratch >= (N*K + B*HW*K)*4 bytes. */
-int    ir_test_conv1x1(int engine, const float* a1, int lda1, int k1, const float* a2, int lda2, int k2,
+int    ir_test_conv1x1(int engine, const void* a1, int lda1, int k1, const void* a2, int lda2, int k2,
                        const float* w_rowmajor, const float* bias, int ln_mode, const float* ln_w, const float* ln_b,
-                       const float* r, int ldr, float* y, int ldy, int B, int HW, int N, int a_pad,
+                       const float* r, int ldr, void* y, int ldy, int B, int HW, int N, int a_pad,
+                       int a_half, int op_half, int y_half,   /* element types: a1/a2, tensor-core operands, y */
                        void* scratch, size_t scratch_bytes, void* stream);
 
 /* Layout helpers used at the boundary of unit tests (NCHW fp32 <-> channels-last fp32). */

@@ -21,7 +21,10 @@ echo "== bench" | tee -a $OUT/status_$TAG.txt
 timeout 900 python bench.py --steps 5 --warmup 3 > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err
 BENCH_RC=$?
 echo "bench exit $BENCH_RC" | tee -a $OUT/status_$TAG.txt
-tail -c 3000 $OUT/bench_$TAG.json; tail -5 $OUT/bench_$TAG.err
+tail -c 1500 $OUT/bench_$TAG.json; tail -5 $OUT/bench_$TAG.err
+timeout 900 python bench.py --steps 5 --warmup 3 --mode half --no-cpu-baseline > $OUT/bench_half_$TAG.json 2> $OUT/bench_half_$TAG.err
+echo "bench half exit $?" | tee -a $OUT/status_$TAG.txt
+tail -c 1500 $OUT/bench_half_$TAG.json; tail -5 $OUT/bench_half_$TAG.err
 if [ "$BENCH_RC" = "0" ] && [ "${SKIP_NCU:-0}" = "0" ]; then
   echo "== ncu launch list" | tee -a $OUT/status_$TAG.txt
   timeout 900 python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/plain_$TAG.log 2>&1 &&

@@ -14,7 +14,8 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 def child(start):
     import numpy as np
-    from tc_cases import CASES, run_case, tolerance
+    from tc_cases import CASES, HALF_CASES, run_case, tolerance
+    CASES = CASES + HALF_CASES
     for i in range(start, len(CASES)):
         print(json.dumps({"begin": i}), flush=True)
         y, y_ref = run_case(CASES[i], 0, seed=i)
@@ -38,7 +39,8 @@ def main():
     if len(sys.argv) > 2 and sys.argv[1] == "--from":
         child(int(sys.argv[2]))
         return 0
-    from tc_cases import CASES
+    from tc_cases import CASES, HALF_CASES
+    CASES = CASES + HALF_CASES
     results, start = [], 0
     while start < len(CASES):
         p = subprocess.Popen([sys.executable, os.path.abspath(__file__), "--from", str(start)], stdout=subprocess.PIPE,

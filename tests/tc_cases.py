@@ -33,8 +33,29 @@ CASES = [
 ]
 
 
+# fp16-operand variants: (k1, k2, N, B, HW, ln_mode, bias, residual, a_pad, a_half, y_half)
+HALF_CASES = [
+    (48, 0, 144, 1, 256, 1, False, False, 1, 0, 1),     # K1: fp32 x -> LN -> fp16 operands -> fp16 qkv
+    (96, 0, 288, 2, 200, 2, True, False, 1, 0, 1),      # K1 level 2: two 144-column sub-chunks
+    (96, 0, 512, 1, 300, 1, False, False, 1, 0, 1),     # K5 level 2
+    (192, 0, 576, 1, 128, 2, False, False, 1, 0, 1),    # K1 level 3: LN fused up to K = 256 in fp16 mode
+    (384, 0, 1152, 1, 64, 1, False, False, 1, 0, 1),    # K1 latent: standalone LN (fp16 xhat) + chunked K
+    (48, 0, 48, 2, 130, 0, False, True, 1, 1, 0),       # K4: fp16 v -> fp32 residual stream
+    (128, 0, 48, 1, 256, 0, False, True, 1, 1, 0),      # K6 level 1: fp16 gated hidden
+    (256, 0, 96, 1, 384, 0, True, True, 1, 1, 0),       # K6 level 2
+    (1024, 0, 384, 1, 96, 0, False, True, 1, 1, 0),     # K6 latent: 4 K-chunks of 256
+    (192, 192, 192, 1, 256, 0, False, False, 1, 0, 0),  # reduce_chan: fp32 sources, fp16 operands, fp32 out
+    (48, 0, 96, 1, 64, 0, False, True, 1, 0, 0),        # skip_conv
+]
+
+
 def run_case(case, engine, seed=0):
     """Returns (y, y_ref64) as numpy arrays; y from the C-ABI test entry on the given engine (0 tc, 1 simt)."""
+    a_half = y_half = op_half = 0
+    if len(case) == 11:
+        a_half, y_half = case[9], case[10]
+        op_half = 1
+        case = case[:9]
     k1, k2, N, B, HW, ln_mode, bias, resid, a_pad = case
     g = torch.Generator().manual_seed(1000 + seed)
     K = k1 + k2
@@ -42,6 +63,9 @@ def run_case(case, engine, seed=0):
     lda1, lda2, ldy = k1 + 8, (k2 + 4 if k2 else 0), N + 12      # non-trivial leading dimensions
     a1 = torch.randn(rows, lda1, generator=g) * 1.5 + 0.3
     a2 = torch.randn(rows, lda2, generator=g) if k2 else None
+    if a_half:      # the source tensor itself is fp16: the reference sees the same rounded values
+        a1 = a1.half().float()
+        a2 = a2.half().float() if k2 else None
     w = (torch.rand(N, K, generator=g) * 2 - 1) / np.sqrt(K)
     bvec = (torch.rand(N, generator=g) - 0.5) if bias else None
     lw = torch.rand(k1, generator=g) + 0.5
@@ -68,17 +92,24 @@ def run_case(case, engine, seed=0):
     lib = _native.lib()
     d = lambda t: None if t is None else t.to(dev).contiguous()
     a1d, a2d, wd, bd, lwd, lbd = d(a1), d(a2), d(w), d(bvec), d(lw), d(lb)
+    if a_half:
+        a1d = a1d.half()
+        a2d = a2d.half() if k2 else None
     y = d(r) if resid else torch.full((rows, ldy), float("nan"), device=dev)
+    if y_half:
+        y = y.half()
     scratch = torch.empty((N * K + rows * K) * 4 + 1024, dtype=torch.uint8, device=dev)
     P = lambda t: 0 if t is None else t.data_ptr()
     stream = torch.cuda.current_stream().cuda_stream
     st = lib.ir_test_conv1x1(engine, P(a1d), lda1, k1, P(a2d), lda2, k2, P(wd), P(bd), ln_mode, P(lwd), P(lbd),
-                             P(y) if resid else 0, ldy, P(y), ldy, B, HW, N, a_pad, P(scratch), scratch.numel(), stream)
+                             P(y) if resid else 0, ldy, P(y), ldy, B, HW, N, a_pad, a_half, op_half, y_half,
+                             P(scratch), scratch.numel(), stream)
     _native.check(st)
     torch.cuda.synchronize()
-    return y[:, :N].cpu().numpy(), y_ref.numpy()
+    return y[:, :N].float().cpu().numpy(), y_ref.numpy()
 
 
 def tolerance(case, y_ref):
-    """tf32 operands (10-bit mantissa, RN) with fp32 accumulation: relative 2^-11 per operand."""
-    return 4e-3 * float(np.abs(y_ref).max()) + 1e-5
+    """tf32 / fp16 operands (10-bit mantissa, RN) with fp32 accumulation: relative 2^-11 per operand
+    (+ 2^-11 output rounding when y is fp16)."""
+    return (5e-3 if len(case) == 11 else 4e-3) * float(np.abs(y_ref).max()) + 1e-5

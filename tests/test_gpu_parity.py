@@ -35,17 +35,22 @@ def check_parity(case, y, y_ref, clean):
     assert d_psnr <= TOL_PSNR_DB, (case, d_psnr)
 
 
-def build_restormer(kw, wseed):
+MODES = ["fp32", "half"]   # tf32 operands + fp32 intermediates / fp16 operands + fp16 intermediates: same parity bar
+
+
+def build_restormer(kw, wseed, mode="fp32"):
     m = M.Restormer(**kw, bias=False).eval()
     m.load_state_dict(oracle.synth_state_dict(oracle.restormer_schema(**kw), wseed), strict=True)
-    return m.cuda()
+    return m.cuda().set_mode(mode)
 
 
+@pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("name", golden_names("restormer"))
-def test_restormer_vs_reference_golden(name):
+def test_restormer_vs_reference_golden(name, mode):
     meta, z = load_golden(name)
     kw = oracle.RESTORMER_TASKS[meta["task"]]
-    m = build_restormer(kw, meta["wseed"])
+    m = build_restormer(kw, meta["wseed"], mode)
+    name = f"{name}[{mode}]"
     x = oracle.synth_image(meta["shape"], meta["xseed"], meta["sigma"])
     clean = oracle.synth_image(meta["shape"], meta["xseed"], None).numpy()
     y = m(x.cuda()).cpu().numpy()
@@ -67,59 +72,61 @@ def test_dncnn_vs_reference_golden(name):
     check_parity(name, y, z["y64"], clean)
 
 
-def run_block(meta, sd, x_nchw):
+def run_block(meta, sd, x_nchw, mode=0):
     """One TransformerBlock through ir_block_* (channels-last in place)."""
     lib = _native.lib()
     Cc, heads = meta["C"], meta["heads"]
     wb = int(meta["LayerNorm_type"] != "BiasFree")
     B, _, H, W = x_nchw.shape
     params = [v.cuda().contiguous() for v in sd.values()]
-    nbytes = lib.ir_block_packed_bytes(Cc, heads, 2.66, 0, wb, 0)
+    nbytes = lib.ir_block_packed_bytes(Cc, heads, 2.66, 0, wb, mode)
     packed = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
     stream = torch.cuda.current_stream().cuda_stream
     _native.check(lib.ir_block_pack_weights(Cc, heads, 2.66, 0, wb, _native.ptr_array(params), len(params),
-                                            packed.data_ptr(), nbytes, 0, stream))
-    ws = torch.empty(lib.ir_block_workspace_bytes(Cc, heads, 2.66, B, H, W, 0), dtype=torch.uint8, device="cuda")
+                                            packed.data_ptr(), nbytes, mode, stream))
+    ws = torch.empty(lib.ir_block_workspace_bytes(Cc, heads, 2.66, B, H, W, mode), dtype=torch.uint8, device="cuda")
     xg = x_nchw.cuda().contiguous()
     xl = torch.empty(B * H * W * Cc, dtype=torch.float32, device="cuda")
     _native.check(lib.ir_nchw_to_nhwc(xg.data_ptr(), xl.data_ptr(), B, Cc, H, W, stream))
     # the layout helper must agree with torch's permute
     assert torch.equal(xl.view(B, H, W, Cc), xg.permute(0, 2, 3, 1))
     _native.check(lib.ir_block_forward(Cc, heads, 2.66, 0, wb, packed.data_ptr(), xl.data_ptr(), B, H, W,
-                                       ws.data_ptr(), ws.numel(), 0, stream))
+                                       ws.data_ptr(), ws.numel(), mode, stream))
     out = torch.empty_like(xg)
     _native.check(lib.ir_nhwc_to_nchw(xl.data_ptr(), out.data_ptr(), B, Cc, H, W, stream))
     torch.cuda.synchronize()
     return out.cpu().numpy()
 
 
+@pytest.mark.parametrize("mode", [0, 1, 2])      # IR_MODE_FP32 (tf32), IR_MODE_HALF, IR_MODE_FP32_SIMT (exact fp32)
 @pytest.mark.parametrize("name", golden_names("block"))
-def test_transformer_block_vs_reference_golden(name):
+def test_transformer_block_vs_reference_golden(name, mode):
     meta, z = load_golden(name)
     wb = meta["LayerNorm_type"] != "BiasFree"
     sd = oracle.synth_state_dict(oracle.synth._block_schema("blk", meta["C"], meta["heads"], 2.66, False, wb),
                                  meta["wseed"])
     x = oracle.synth_tensor(meta["shape"], meta["xseed"], -1.0, 1.0)
-    y = run_block(meta, sd, x)
+    y = run_block(meta, sd, x, mode)
     err = float(np.abs(y.astype(np.float64) - z["y64"]).max())
-    record(name, max_abs=err)
-    assert err <= TOL_MAXABS, (name, err)
+    record(f"{name}[mode{mode}]", max_abs=err)
+    assert err <= (2e-5 if mode == 2 else TOL_MAXABS), (name, err)
 
 
+@pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("task,shape,wseed,xseed", [
     ("color_denoise", (1, 3, 40, 72), 61, 71),
     ("motion_deblur", (2, 3, 24, 16), 62, 72),
     ("defocus_dual", (1, 6, 16, 48), 63, 73),
 ])
-def test_restormer_vs_oracle_fresh_inputs(task, shape, wseed, xseed):
+def test_restormer_vs_oracle_fresh_inputs(task, shape, wseed, xseed, mode):
     kw = oracle.RESTORMER_TASKS[task]
     sd = oracle.synth_state_dict(oracle.restormer_schema(**kw), wseed)
     x = oracle.synth_image(shape, xseed, 25.0)
     y_ref = oracle.restormer_forward({k: v.double() for k, v in sd.items()}, x.double()).numpy()
-    m = build_restormer(kw, wseed)
+    m = build_restormer(kw, wseed, mode)
     y = m(x.cuda()).cpu().numpy()
     clean = oracle.synth_image(shape, xseed, None).numpy()[:, : y.shape[1]]
-    check_parity(f"oracle_{task}_{shape[2]}x{shape[3]}", y, y_ref, clean)
+    check_parity(f"oracle_{task}_{shape[2]}x{shape[3]}[{mode}]", y, y_ref, clean)
 
 
 def test_restormer_with_conv_bias_and_custom_widths_vs_oracle():
@@ -154,13 +161,14 @@ def test_shape_validation_raises_before_launch():
         m(torch.zeros(1, 3, 64, 64, device="cuda", dtype=torch.float16))
 
 
-def test_full_size_properties_config2_gray_denoise():
+@pytest.mark.parametrize("mode", MODES)
+def test_full_size_properties_config2_gray_denoise(mode):
     """BASELINE config 2 (batch 8 of 512x512 gray): properties that hold at any size.
     (a) run-to-run determinism, bit-exact; (b) permuting the batch permutes the output, bit-exact;
     (c) an image's result does not depend on its batch-mates: only the pixel split of the Gram reduction differs,
         which moves the folded attention matrix by fp32 noise before its tf32 rounding -> within the parity bar."""
     kw = oracle.RESTORMER_TASKS["gray_denoise"]
-    m = build_restormer(kw, 81)
+    m = build_restormer(kw, 81, mode)
     x = oracle.synth_image((8, 1, 512, 512), 91, 25.0).cuda()
     y1 = m(x)
     y2 = m(x)
@@ -171,21 +179,22 @@ def test_full_size_properties_config2_gray_denoise():
     assert torch.equal(yp, y1[perm])
     ys = m(x[2:3].contiguous())
     err = float((ys - y1[2:3]).abs().max())
-    record("config2_single_vs_batched", max_abs=err)
+    record(f"config2_single_vs_batched[{mode}]", max_abs=err)
     assert err <= TOL_MAXABS
 
 
-def test_full_size_properties_config3_real_denoise_and_oracle_crop():
+@pytest.mark.parametrize("mode", MODES)
+def test_full_size_properties_config3_real_denoise_and_oracle_crop(mode):
     """BASELINE config 3 shape (256x256 colour patches; batch reduced to 4 to bound test time) and a
     256x256 single image against the CPU oracle (5 s on the host)."""
     kw = oracle.RESTORMER_TASKS["real_denoise"]
-    m = build_restormer(kw, 82)
+    m = build_restormer(kw, 82, mode)
     x = oracle.synth_image((4, 3, 256, 256), 92, None)
     y = m(x.cuda())
     assert torch.equal(y, m(x.cuda()))
     sd = oracle.synth_state_dict(oracle.restormer_schema(**kw), 82)
     y_ref = oracle.restormer_forward(sd, x[1:2]).numpy()      # fp32 oracle (self-noise ~3e-7)
-    check_parity("config3_image1_vs_oracle", y[1:2].cpu().numpy(), y_ref, x[1:2].numpy())
+    check_parity(f"config3_image1_vs_oracle[{mode}]", y[1:2].cpu().numpy(), y_ref, x[1:2].numpy())
 
 
 def test_dncnn_config1_full_size():

@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 
 from conftest import record
-from tc_cases import CASES, run_case, tolerance
+from tc_cases import CASES, HALF_CASES, run_case, tolerance
 
 pytestmark = pytest.mark.gpu
 
@@ -18,4 +18,14 @@ def test_tc_conv1x1_matches_reference(idx):
     record(f"tc_conv1x1_{idx}", cfg=str(case), err_tc=e_tc, err_simt=e_simt, tol=tolerance(case, y_ref))
     assert np.isfinite(y_tc).all()
     assert e_simt <= 2e-5 * max(1.0, float(np.abs(y_ref).max()))
+    assert e_tc <= tolerance(case, y_ref), (case, e_tc)
+
+
+@pytest.mark.parametrize("idx", range(len(HALF_CASES)))
+def test_tc_conv1x1_fp16_operands_match_reference(idx):
+    case = HALF_CASES[idx]
+    y_tc, y_ref = run_case(case, 0, seed=100 + idx)
+    e_tc = float(np.abs(y_tc - y_ref).max())
+    record(f"tc_conv1x1_half_{idx}", cfg=str(case), err_tc=e_tc, tol=tolerance(case, y_ref))
+    assert np.isfinite(y_tc).all()
     assert e_tc <= tolerance(case, y_ref), (case, e_tc)
