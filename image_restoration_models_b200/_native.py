@@ -69,6 +69,9 @@ SIGNATURES = {
                                   C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
                                   C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t,
                                   C.c_void_p]),
+    "ir_test_conv3x3": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                  C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                  C.c_size_t, C.c_void_p]),
     "ir_profile_begin": (C.c_int, []),
     "ir_profile_end": (C.c_int, [C.POINTER(IrKernelStat), C.c_int]),
     "ir_profile_tag_name": (C.c_char_p, [C.c_int]),

@@ -125,21 +125,21 @@ int ir_restormer_launch_count(const IrRestormerCfg* cfg) {
 int ir_dncnn_param_count(const IrDncnnCfg* cfg) {
   if (!cfg) { set_error("invalid argument: null cfg"); return -1; }
   DncnnPlan pl;
-  if (build_dncnn_plan(pl, *cfg) != IR_OK) return -1;
+  if (build_dncnn_plan(pl, *cfg, ENGINE_TC) != IR_OK) return -1;
   return pl.n_params;
 }
 
 long long ir_dncnn_param_numel(const IrDncnnCfg* cfg, int index) {
   if (!cfg) { set_error("invalid argument: null cfg"); return -1; }
   DncnnPlan pl;
-  if (build_dncnn_plan(pl, *cfg) != IR_OK) return -1;
+  if (build_dncnn_plan(pl, *cfg, ENGINE_TC) != IR_OK) return -1;
   return dncnn_param_numel(pl, index);
 }
 
 size_t ir_dncnn_packed_bytes(const IrDncnnCfg* cfg, int mode) {
   if (!cfg || check_mode(mode) != IR_OK) return 0;
   DncnnPlan pl;
-  if (build_dncnn_plan(pl, *cfg) != IR_OK) return 0;
+  if (build_dncnn_plan(pl, *cfg, engine_of(mode)) != IR_OK) return 0;
   return (size_t)pl.packed_floats * sizeof(float);
 }
 
@@ -148,7 +148,7 @@ int ir_dncnn_pack_weights(const IrDncnnCfg* cfg, const float* const* h_params, i
   IRB_REQUIRE(cfg && h_params && packed, "pack: null argument");
   IRB_TRY(check_mode(mode));
   DncnnPlan pl;
-  IRB_TRY(build_dncnn_plan(pl, *cfg));
+  IRB_TRY(build_dncnn_plan(pl, *cfg, engine_of(mode)));
   IRB_REQUIRE(n_params == pl.n_params, "pack: parameter count does not match the configuration's state_dict");
   if (packed_bytes < (size_t)pl.packed_floats * sizeof(float)) { set_error("packed buffer too small"); return IR_ERR_WORKSPACE; }
   IRB_CUDA(cudaMemsetAsync(packed, 0, (size_t)pl.packed_floats * sizeof(float), (cudaStream_t)stream));
@@ -158,7 +158,7 @@ int ir_dncnn_pack_weights(const IrDncnnCfg* cfg, const float* const* h_params, i
 size_t ir_dncnn_workspace_bytes(const IrDncnnCfg* cfg, int B, int H, int W, int mode) {
   if (!cfg || check_mode(mode) != IR_OK || B <= 0 || H <= 0 || W <= 0) return 0;
   DncnnPlan pl;
-  if (build_dncnn_plan(pl, *cfg) != IR_OK) return 0;
+  if (build_dncnn_plan(pl, *cfg, engine_of(mode)) != IR_OK) return 0;
   return dncnn_workspace_bytes(pl, B, H, W);
 }
 
@@ -167,7 +167,7 @@ int ir_dncnn_forward(const IrDncnnCfg* cfg, const void* packed, const float* x, 
   IRB_REQUIRE(cfg && packed && x && y && workspace, "forward: null argument");
   IRB_TRY(check_mode(mode));
   DncnnPlan pl;
-  IRB_TRY(build_dncnn_plan(pl, *cfg));
+  IRB_TRY(build_dncnn_plan(pl, *cfg, engine_of(mode)));
   return dncnn_forward(pl, (const float*)packed, x, y, B, H, W, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
@@ -257,6 +257,27 @@ int ir_test_conv1x1(int engine, const void* a1v, int lda1, int k1, const void* a
     }
   }
   return launch_gemm_tc(t, s);
+}
+
+int ir_test_conv3x3(int engine, const float* x_nhwc, int ldx, int cin, const float* w_oihw, const float* bias, int cout,
+                    int B, int H, int W, float* y, int ldy, int o_mode, int relu, int op_half, void* scratch,
+                    size_t scratch_bytes, void* stream) {
+  IRB_REQUIRE(x_nhwc && w_oihw && y && scratch && B > 0 && H > 0 && W > 0 && cin > 0 && cout > 0, "test_conv3x3: bad argument");
+  IRB_REQUIRE(o_mode == O_NHWC || o_mode == O_UNSHUFFLE || o_mode == O_SHUFFLE, "test_conv3x3: bad o_mode");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int K = 9 * cin, Kp = (K + 3) / 4 * 4;
+  if (scratch_bytes < (size_t)cout * Kp * sizeof(float)) { set_error("scratch too small"); return IR_ERR_WORKSPACE; }
+  float* wp = (float*)scratch;
+  const bool tc = engine == ENGINE_TC;
+  IRB_REQUIRE(!tc || tc_conv3_supported(cin, cout, op_half != 0), "test_conv3x3: shape not supported by the tcgen05 kernel");
+  PackMat pm{w_oihw, wp, 1, cin, cout, cout, 1, K, Kp, nullptr, !tc ? 0 : op_half ? 2 : 1};
+  IRB_TRY(launch_pack_mat(pm, s));
+  if (tc) return run_conv3_tc(x_nhwc, ldx, cin, wp, bias, cout, cout, B, H, W, y, ldy, o_mode, relu, op_half != 0, s);
+  GemmParams g{};
+  g.a1 = x_nhwc; g.lda1 = ldx; g.k1 = cin; g.a_mode = A_IM2COL_NHWC; g.B = B; g.H = H; g.W = W;
+  g.w = wp; g.N = cout; g.K = K; g.Kp = Kp; g.bias = bias; g.ln_mode = LN_NONE; g.relu = relu; g.acc_sign = 1.f;
+  g.y = y; g.ldy = ldy; g.o_mode = o_mode; g.tag = TAG_CONV3;
+  return launch_gemm_simt(g, s);
 }
 
 int ir_profile_begin(void) {

@@ -2,16 +2,18 @@
 // Restates /root/reference/src/dncnn/models/network_dncnn.py:63-71: nb 3x3 convs (bias) with ReLU between them
 // (eval-mode BatchNorm, basicblock.py:69, folded into the preceding conv at pack time) and `x - model(x)`.
 #include "dncnn.cuh"
+#include "restormer.cuh"
 
 namespace irb {
 
 static inline int round_up4(int v) { return (v + 3) / 4 * 4; }
 
-int build_dncnn_plan(DncnnPlan& pl, const IrDncnnCfg& c) {
+int build_dncnn_plan(DncnnPlan& pl, const IrDncnnCfg& c, int engine) {
   IRB_REQUIRE(c.in_nc > 0 && c.out_nc > 0 && c.nc > 0 && c.nc % 4 == 0, "dncnn: nc must be a positive multiple of 4");
   IRB_REQUIRE(c.nb >= 2, "dncnn: nb must be >= 2");
   IRB_REQUIRE(c.in_nc == c.out_nc, "dncnn: in_nc must equal out_nc (x - model(x), network_dncnn.py:71)");
   pl.cfg = c;
+  pl.half = engine == ENGINE_TC_HALF;
   pl.layers.clear();
   long long off = 0;
   auto alloc = [&](long long n) { const long long o = off; off += (n + 63) / 64 * 64; return o; };
@@ -25,6 +27,9 @@ int build_dncnn_plan(DncnnPlan& pl, const IrDncnnCfg& c) {
     L.b = alloc(L.cout);
     L.p_w = pidx++; L.p_b = pidx++;
     L.p_bn = -1;
+    // the nc -> nc layers run as implicit GEMM on the tcgen05 kernel; head (cin = in_nc) and tail (cout = out_nc)
+    // have 1..3 channels on one side and stay on the CUDA-core kernel
+    L.tc = engine != ENGINE_SIMT && l > 0 && l < c.nb - 1 && tc_conv3_supported(L.cin, L.cout, pl.half);
     if (c.has_bn && l > 0 && l < c.nb - 1) { L.p_bn = pidx; pidx += 5; }  // weight, bias, mean, var, num_batches_tracked
     pl.layers.push_back(L);
   }
@@ -54,7 +59,8 @@ int dncnn_pack(const DncnnPlan& pl, const float* const* params, float* packed, c
                              packed + pl.bn_scale, packed + pl.bn_shift, L.cout, s));
       scale = packed + pl.bn_scale; shift = packed + pl.bn_shift;
     }
-    PackMat pm{params[L.p_w], packed + L.w, 1, L.cin, L.cout, L.cout, 1, L.k, L.kp, scale};
+    PackMat pm{params[L.p_w], packed + L.w, 1, L.cin, L.cout, L.cout, 1, L.k, L.kp, scale,
+               !L.tc ? 0 : pl.half ? 2 : 1};
     IRB_TRY(launch_pack_mat(pm, s));
     IRB_TRY(launch_pack_vec(params[L.p_b], packed + L.b, L.cout, L.cout, 1, scale, shift, s));
   }
@@ -74,6 +80,11 @@ int dncnn_forward(const DncnnPlan& pl, const float* packed, const float* x, floa
   const int nb = (int)pl.layers.size();
   for (int l = 0; l < nb; ++l) {
     const DncnnLayer& L = pl.layers[l];
+    if (L.tc) {
+      IRB_TRY(run_conv3_tc(buf[(l + 1) & 1], pl.cfg.nc, L.cin, packed + L.w, packed + L.b, L.cout, L.cout, B, H, W, buf[l & 1],
+                           pl.cfg.nc, O_NHWC, 1, pl.half, s));
+      continue;
+    }
     GemmParams g{};
     g.B = B; g.H = H; g.W = W;
     g.k1 = L.cin;

@@ -5,16 +5,17 @@
 
 namespace irb {
 
-struct DncnnLayer { int cin, cout, k, kp; long long w, b; int p_w, p_b, p_bn; };
+struct DncnnLayer { int cin, cout, k, kp; long long w, b; int p_w, p_b, p_bn; bool tc; };
 struct DncnnPlan {
   IrDncnnCfg cfg;
+  bool half = false;
   std::vector<DncnnLayer> layers;
   long long bn_scale = 0, bn_shift = 0;   // scratch inside the packed buffer used while folding BatchNorm
   int n_params = 0;
   long long packed_floats = 0;
 };
 
-int build_dncnn_plan(DncnnPlan& pl, const IrDncnnCfg& cfg);
+int build_dncnn_plan(DncnnPlan& pl, const IrDncnnCfg& cfg, int engine);
 long long dncnn_param_numel(const DncnnPlan& pl, int index);
 int dncnn_pack(const DncnnPlan& pl, const float* const* params, float* packed, cudaStream_t s);
 size_t dncnn_workspace_bytes(const DncnnPlan& pl, int B, int H, int W);

@@ -22,6 +22,24 @@ bool tc_gemm_supported(int K, int N, bool half) {
   return tc_gemm_configure(t) != 0;
 }
 
+bool tc_conv3_supported(int cin, int cout, bool half) {
+  TcGemmParams t{};
+  t.K = 9 * cin; t.N = cout; t.k1 = cin; t.k2 = 0; t.ln_mode = LN_NONE; t.a_pad = 1; t.a_mode = 1;
+  t.a_half = 0; t.op_half = half; t.y_half = 0;
+  return tc_gemm_configure(t) != 0;
+}
+
+int run_conv3_tc(const float* in, int ld_in, int cin, const float* w_packed, const float* bias, int cout, int cout_valid,
+                 int B, int H, int W, float* out, int ld_out, int o_mode, int relu, bool half, cudaStream_t s) {
+  TcGemmParams t{};
+  t.a1 = in; t.lda1 = ld_in; t.k1 = cin; t.k2 = 0; t.a_mode = 1; t.H = H; t.W = W;
+  t.B = B; t.HW = H * W;
+  t.w = w_packed; t.N = cout; t.K = 9 * cin; t.bias = bias; t.ln_mode = LN_NONE;
+  t.y = out; t.ldy = ld_out; t.o_mode = o_mode; t.relu = relu; t.acc_sign = 1.f; t.n_valid = cout_valid;
+  t.tag = TAG_CONV3; t.a_pad = 1; t.a_half = 0; t.op_half = half; t.y_half = 0;
+  return launch_gemm_tc(t, s);
+}
+
 int engine_of_mode(int mode) {
   return mode == IR_MODE_FP32_SIMT ? ENGINE_SIMT : mode == IR_MODE_HALF ? ENGINE_TC_HALF : ENGINE_TC;
 }
@@ -100,11 +118,16 @@ int build_block_plan(BlockPlan& bp, std::vector<PackOp>& ops, long long& packed_
   return IR_OK;
 }
 
-static void plan_conv3(Builder& bl, ConvPlan& cp, int cout, int cin, int bias) {
+static void plan_conv3(Builder& bl, ConvPlan& cp, int cout, int cin, int bias, bool scatter = false) {
   cp.cout = cout; cp.cin = cin; cp.k = 9 * cin; cp.kp = round_up(9 * cin, 4);
-  cp.w = bl.alloc((long long)cout * cp.kp);
-  bl.ops.push_back(PackOp{PackOp::MAT3, bl.pidx++, cp.w, cout, cout, 1, 9 * cin, cp.kp, cin, 0});
-  cp.b = -1; cp.tc = false;
+  // the tensor-core kernel wants N % 16 == 0: pad with zero rows (only used with the shuffle-scatter epilogue,
+  // which skips the padding channels), e.g. down1_2: 48 -> 24 channels
+  cp.cout_p = scatter ? round_up(cout, 16) : cout;
+  cp.w = bl.alloc((long long)cp.cout_p * cp.kp);
+  cp.tc = bl.engine != ENGINE_SIMT && bias == 0 && tc_conv3_supported(cin, cp.cout_p, bl.half());
+  if (!cp.tc) cp.cout_p = cout;
+  bl.ops.push_back(PackOp{PackOp::MAT3, bl.pidx++, cp.w, cout, cp.cout_p, 1, 9 * cin, cp.kp, cin, bl.fmt(cp.tc)});
+  cp.b = -1;
   if (bias) {
     cp.b = bl.alloc(cout);
     bl.ops.push_back(PackOp{PackOp::VEC, bl.pidx++, cp.b, cout, cout, 1, 0, 0, 0, 0});
@@ -147,19 +170,19 @@ int build_restormer_plan(RestormerPlan& pl, const IrRestormerCfg& c, int engine)
   };
   plan_conv3(bl, pl.patch_embed, d, c.inp_channels, 0);
   stage(pl.enc[0], d, c.heads[0], c.num_blocks[0]);
-  plan_conv3(bl, pl.down[0], d / 2, d, 0);
+  plan_conv3(bl, pl.down[0], d / 2, d, 0, true);
   stage(pl.enc[1], 2 * d, c.heads[1], c.num_blocks[1]);
-  plan_conv3(bl, pl.down[1], d, 2 * d, 0);
+  plan_conv3(bl, pl.down[1], d, 2 * d, 0, true);
   stage(pl.enc[2], 4 * d, c.heads[2], c.num_blocks[2]);
-  plan_conv3(bl, pl.down[2], 2 * d, 4 * d, 0);
+  plan_conv3(bl, pl.down[2], 2 * d, 4 * d, 0, true);
   stage(pl.enc[3], 8 * d, c.heads[3], c.num_blocks[3]);
-  plan_conv3(bl, pl.up[2], 16 * d, 8 * d, 0);
+  plan_conv3(bl, pl.up[2], 16 * d, 8 * d, 0, true);
   plan_conv1(bl, pl.reduce[2], 4 * d, 8 * d, bias);
   stage(pl.dec[2], 4 * d, c.heads[2], c.num_blocks[2]);
-  plan_conv3(bl, pl.up[1], 8 * d, 4 * d, 0);
+  plan_conv3(bl, pl.up[1], 8 * d, 4 * d, 0, true);
   plan_conv1(bl, pl.reduce[1], 2 * d, 4 * d, bias);
   stage(pl.dec[1], 2 * d, c.heads[1], c.num_blocks[1]);
-  plan_conv3(bl, pl.up[0], 4 * d, 2 * d, 0);
+  plan_conv3(bl, pl.up[0], 4 * d, 2 * d, 0, true);
   stage(pl.dec[0], 2 * d, c.heads[0], c.num_blocks[0]);
   stage(pl.refine, 2 * d, c.heads[0], c.num_refinement_blocks);
   if (c.dual_pixel_task) plan_conv1(bl, pl.skip, 2 * d, d, bias);
@@ -183,7 +206,7 @@ long long pack_op_src_numel(const PackOp& op) {
   switch (op.kind) {
     case PackOp::VEC: return (long long)op.a * op.c;
     case PackOp::MAT1: return (long long)op.a * op.c * op.k_src;
-    case PackOp::MAT3: return (long long)op.a * op.c * op.k_src;
+    case PackOp::MAT3: return (long long)op.a * op.c * op.k_src;   // a = source rows (cout), b = padded rows
     case PackOp::DW: return (long long)op.a * op.c * 9;
     default: return op.a;  // DnCNN-specific kinds carry their numel in a
   }
@@ -204,7 +227,7 @@ int run_pack_ops(const std::vector<PackOp>& ops, const float* const* params, flo
         break;
       }
       case PackOp::MAT3: {
-        PackMat pm{src, dst, 1, op.cin, op.a, op.b, op.c, op.k_src, op.k_dst, nullptr, 0};
+        PackMat pm{src, dst, 1, op.cin, op.a, op.b, op.c, op.k_src, op.k_dst, nullptr, op.fmt};
         IRB_TRY(launch_pack_mat(pm, s));
         break;
       }
@@ -434,7 +457,10 @@ static int run_stage(const std::vector<BlockPlan>& blocks, const float* packed, 
 }
 
 static int conv3(const ConvPlan& cp, const float* packed, const float* in, int ld_in, int a_mode, int B, int H, int W,
-                 float* out, int ld_out, int o_mode, const float* r, cudaStream_t s) {
+                 float* out, int ld_out, int o_mode, const float* r, bool half, cudaStream_t s) {
+  if (cp.tc && a_mode == A_IM2COL_NHWC && o_mode != O_NCHW && r == nullptr)
+    return run_conv3_tc(in, ld_in, cp.cin, packed + cp.w, cp.b >= 0 ? packed + cp.b : nullptr, cp.cout_p, cp.cout, B, H, W,
+                        out, ld_out, o_mode, 0, half, s);
   GemmParams g{};
   g.a1 = in; g.lda1 = ld_in; g.k1 = cp.cin; g.a_mode = a_mode;
   g.B = B; g.H = H; g.W = W;
@@ -473,13 +499,13 @@ int restormer_forward(const RestormerPlan& pl, const float* packed, const float*
 
   // patch_embed (:247): NCHW image -> channels-last [P, dim]
   float* e1_in = dual ? ws.e1_in : ws.e[0];
-  IRB_TRY(conv3(pl.patch_embed, packed, x, 0, A_IM2COL_NCHW, B, H, W, e1_in, d, O_NHWC, nullptr, s));
+  IRB_TRY(conv3(pl.patch_embed, packed, x, 0, A_IM2COL_NCHW, B, H, W, e1_in, d, O_NHWC, nullptr, pl.half, s));
   IRB_TRY(run_stage(pl.enc[0], packed, e1_in, ws.e[0], B, H, W, d, ws.bs, lnb, s));                    // :248
   // encoder levels 2..4 (:250-257): 3x3 conv C->C/2 with PixelUnshuffle folded into the store
   for (int l = 1; l < 4; ++l) {
     const int hi = H >> (l - 1), wi = W >> (l - 1);
     IRB_TRY(conv3(pl.down[l - 1], packed, ws.e[l - 1], d << (l - 1), A_IM2COL_NHWC, B, hi, wi, ws.e[l], d << l,
-                  O_UNSHUFFLE, nullptr, s));
+                  O_UNSHUFFLE, nullptr, pl.half, s));
     IRB_TRY(run_stage(pl.enc[l], packed, ws.e[l], ws.e[l], B, hi / 2, wi / 2, d << l, ws.bs, lnb, s));
   }
   // decoder levels 3, 2 (:259-267): 3x3 conv C->2C with PixelShuffle folded into the store, then the
@@ -488,7 +514,7 @@ int restormer_forward(const RestormerPlan& pl, const float* packed, const float*
   for (int l = 2; l >= 1; --l) {
     const int hi = H >> (l + 1), wi = W >> (l + 1);    // extent of the level below
     const int C = d << l;
-    IRB_TRY(conv3(pl.up[l], packed, below, 2 * C, A_IM2COL_NHWC, B, hi, wi, ws.up_tmp, C, O_SHUFFLE, nullptr, s));
+    IRB_TRY(conv3(pl.up[l], packed, below, 2 * C, A_IM2COL_NHWC, B, hi, wi, ws.up_tmp, C, O_SHUFFLE, nullptr, pl.half, s));
     GemmParams g{};
     g.a1 = ws.up_tmp; g.lda1 = C; g.k1 = C; g.a2 = ws.e[l]; g.lda2 = C; g.k2 = C; g.a_mode = A_PLAIN;
     g.B = B; g.H = hi * 2; g.W = wi * 2;
@@ -500,7 +526,7 @@ int restormer_forward(const RestormerPlan& pl, const float* packed, const float*
     below = ws.d[l];
   }
   // level 1 (:269-273): up2_1 writes channels [0,dim) of the 2*dim-wide stream, the skip fills [dim,2dim)
-  IRB_TRY(conv3(pl.up[0], packed, below, 2 * d, A_IM2COL_NHWC, B, H / 2, W / 2, ws.d[0], 2 * d, O_SHUFFLE, nullptr, s));
+  IRB_TRY(conv3(pl.up[0], packed, below, 2 * d, A_IM2COL_NHWC, B, H / 2, W / 2, ws.d[0], 2 * d, O_SHUFFLE, nullptr, pl.half, s));
   IRB_TRY(launch_copy_channels(ws.e[0], d, ws.d[0] + d, 2 * d, (long long)B * H * W, d, s));
   IRB_TRY(run_stage(pl.dec[0], packed, ws.d[0], ws.d[0], B, H, W, 2 * d, ws.bs, lnb, s));
   IRB_TRY(run_stage(pl.refine, packed, ws.d[0], ws.d[0], B, H, W, 2 * d, ws.bs, lnb, s));
@@ -511,9 +537,9 @@ int restormer_forward(const RestormerPlan& pl, const float* packed, const float*
     g.w = packed + pl.skip.w; g.N = 2 * d; g.K = d; g.Kp = d; g.bias = pl.skip.b >= 0 ? packed + pl.skip.b : nullptr;
     g.ln_mode = LN_NONE; g.acc_sign = 1.f; g.r = ws.d[0]; g.ldr = 2 * d; g.y = ws.d[0]; g.ldy = 2 * d; g.o_mode = O_NHWC; g.tag = TAG_REDUCE;
     IRB_TRY(run_1x1(g, pl.skip.tc, pl.half, false, false, nullptr, s));
-    IRB_TRY(conv3(pl.output, packed, ws.d[0], 2 * d, A_IM2COL_NHWC, B, H, W, y, 0, O_NCHW, nullptr, s));
+    IRB_TRY(conv3(pl.output, packed, ws.d[0], 2 * d, A_IM2COL_NHWC, B, H, W, y, 0, O_NCHW, nullptr, pl.half, s));
   } else {
-    IRB_TRY(conv3(pl.output, packed, ws.d[0], 2 * d, A_IM2COL_NHWC, B, H, W, y, 0, O_NCHW, x, s));   // :281
+    IRB_TRY(conv3(pl.output, packed, ws.d[0], 2 * d, A_IM2COL_NHWC, B, H, W, y, 0, O_NCHW, x, pl.half, s));   // :281
   }
   return IR_OK;
 }

@@ -27,7 +27,7 @@ struct BlockPlan {     // one TransformerBlock (restormer.py:137-150); offsets i
   bool half;                               // ENGINE_TC_HALF: fp16 intermediates (qkv, v, hidden, gated) and fp16 operands
 };
 
-struct ConvPlan { int cout, cin, k, kp; long long w, b; bool tc; };
+struct ConvPlan { int cout, cin, k, kp; long long w, b; bool tc; int cout_p; };   // cout_p: rows in the packed weight (>= cout, zero rows)
 
 struct RestormerPlan {
   IrRestormerCfg cfg;
@@ -52,6 +52,10 @@ int  build_block_plan(BlockPlan& bp, std::vector<PackOp>& ops, long long& packed
                       int bias, int ln_bias, int engine);
 int  build_restormer_plan(RestormerPlan& pl, const IrRestormerCfg& cfg, int engine);
 bool tc_gemm_supported(int K, int N, bool half);
+bool tc_conv3_supported(int cin, int cout, bool half);
+// 3x3 convolution (stride 1, zero pad 1) on the tcgen05 kernel: fp32 channels-last in, fp32 out (o_mode rows / shuffle scatter)
+int  run_conv3_tc(const float* in, int ld_in, int cin, const float* w_packed, const float* bias, int cout, int cout_valid,
+                  int B, int H, int W, float* out, int ld_out, int o_mode, int relu, bool half, cudaStream_t s);
 long long pack_op_src_numel(const PackOp& op);
 int  run_pack_ops(const std::vector<PackOp>& ops, const float* const* params, float* packed, cudaStream_t s);
 

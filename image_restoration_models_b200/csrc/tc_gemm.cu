@@ -207,24 +207,47 @@ __device__ __forceinline__ void produce_stage(const TcGemmParams& p, uint8_t* __
   const int rsub = ptid / lpp;
   const int pp = PROD_THREADS / lpp;                    // pixel rows per pass
   const int units = kc / EPC;                           // units per row in this chunk
+  // implicit-GEMM 3x3: the unit's K range lies inside one filter tap (cin % EPC == 0)
+  int udy[UPL], udx[UPL], uc[UPL];
+  if (p.a_mode == 1) {
+#pragma unroll
+    for (int i = 0; i < UPL; ++i) {
+      const int k = k0 + (q + i * lpp) * EPC;
+      const int tap = k / p.k1;
+      uc[i] = k - tap * p.k1;
+      udy[i] = tap / 3 - 1;
+      udx[i] = tap - (tap / 3) * 3 - 1;
+    }
+  }
   for (int r0 = 0; r0 < TM; r0 += pp * UNR) {
     float v[UNR][UPL][EPC];
 #pragma unroll
     for (int u = 0; u < UNR; ++u) {
       const int r = r0 + u * pp + rsub;
       const bool live = r < valid;                      // valid <= TM
+      int py = 0, px = 0;
+      if (p.a_mode == 1) { py = (p0 + r) / p.W; px = (p0 + r) - py * p.W; }
 #pragma unroll
       for (int i = 0; i < UPL; ++i) {
         const int unit = q + i * lpp;
 #pragma unroll
         for (int e = 0; e < EPC; ++e) v[u][i][e] = 0.f;
         if (live && unit < units) {
+          if (p.a_mode == 1) {
+            const int yy = py + udy[i], xx = px + udx[i];
+            if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W) {
+              const TA* src = a1 + (rowbase + (long long)yy * p.W + xx) * (long long)p.lda1 + uc[i];
 #pragma unroll
-          for (int g = 0; g < VPU; ++g) {
-            const int k = k0 + unit * EPC + g * GVec<TA>::N;
-            const TA* src = (k < p.k1) ? a1 + (rowbase + p0 + r) * (long long)p.lda1 + k
-                                       : a2 + (rowbase + p0 + r) * (long long)p.lda2 + (k - p.k1);
-            load_vec<TA>(src, &v[u][i][g * GVec<TA>::N]);
+              for (int g = 0; g < VPU; ++g) load_vec<TA>(src + g * GVec<TA>::N, &v[u][i][g * GVec<TA>::N]);
+            }
+          } else {
+#pragma unroll
+            for (int g = 0; g < VPU; ++g) {
+              const int k = k0 + unit * EPC + g * GVec<TA>::N;
+              const TA* src = (k < p.k1) ? a1 + (rowbase + p0 + r) * (long long)p.lda1 + k
+                                         : a2 + (rowbase + p0 + r) * (long long)p.lda2 + (k - p.k1);
+              load_vec<TA>(src, &v[u][i][g * GVec<TA>::N]);
+            }
           }
         }
       }
@@ -309,6 +332,9 @@ struct EpiCtx {
   int rows_valid;        // rows of this warp inside the image (may be <= 0)
   int lane;
   float* stg;            // this warp's private staging tile [32][STG_LD]
+  int relu; float sign;  // y = r + sign * act(acc + bias)
+  // PixelUnshuffle / PixelShuffle scatter (o_mode != O_NHWC): image index, extent, pixel index of the warp's first row
+  int o_mode, b, H, W, pix0, n_valid;
 };
 
 // residual of the column group starting at global column n, fetched ahead of use
@@ -344,9 +370,60 @@ __device__ __forceinline__ void epi_group(const EpiCtx<TY>& ec, uint32_t taddr, 
 #pragma unroll
   for (int it = 0; it < CPR; ++it) {
     float4 o = *reinterpret_cast<const float4*>(sbase + it * RPI * STG_LD);
-    if (HAS_R) { o.x += rr[it].x; o.y += rr[it].y; o.z += rr[it].z; o.w += rr[it].w; }
     o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+    if (ec.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+    if (HAS_R) {
+      o.x = fmaf(ec.sign, o.x, rr[it].x); o.y = fmaf(ec.sign, o.y, rr[it].y);
+      o.z = fmaf(ec.sign, o.z, rr[it].z); o.w = fmaf(ec.sign, o.w, rr[it].w);
+    }
     if (it * RPI + rsub < ec.rows_valid) store_out4<TY>(ybase + (long long)it * RPI * ec.ldy, o);
+  }
+  __syncwarp();
+}
+
+// Same drain, but each conv output channel lands at its PixelUnshuffle / PixelShuffle position
+// (restormer.py:176,186).  The scattered 4-byte stores cost little: these convolutions have K = 9*Cin.
+template <typename TY, int NCOLS>
+__device__ __forceinline__ void epi_group_scatter(const EpiCtx<TY>& ec, uint32_t taddr, int n) {
+  constexpr int CPR = NCOLS / 4, RPI = 32 / CPR;
+  float v[32];
+  __syncwarp();
+  if (NCOLS == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
+  tmem_ld_wait();
+#pragma unroll
+  for (int jj = 0; jj < CPR; ++jj)
+    *reinterpret_cast<float4*>(ec.stg + ec.lane * STG_LD + jj * 4) =
+        make_float4(v[4 * jj], v[4 * jj + 1], v[4 * jj + 2], v[4 * jj + 3]);
+  __syncwarp();
+  const int rsub = ec.lane / CPR, c4 = (ec.lane % CPR) * 4;
+  float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (ec.bias) bb = __ldg(reinterpret_cast<const float4*>(ec.bias + n + c4));
+  const float* sbase = ec.stg + rsub * STG_LD + c4;
+#pragma unroll
+  for (int it = 0; it < CPR; ++it) {
+    const int row = it * RPI + rsub;
+    if (row < ec.rows_valid) {
+      const float4 o4 = *reinterpret_cast<const float4*>(sbase + it * RPI * STG_LD);
+      float o[4] = {o4.x + bb.x, o4.y + bb.y, o4.z + bb.z, o4.w + bb.w};
+      const int pix = ec.pix0 + row;
+      const int y = pix / ec.W, x = pix - y * ec.W;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int nn = n + c4 + e;
+        if (nn >= ec.n_valid) continue;
+        float val = ec.relu ? fmaxf(o[e], 0.f) : o[e];
+        long long idx;
+        if (ec.o_mode == O_UNSHUFFLE) {
+          const long long opix = ((long long)ec.b * (ec.H >> 1) + (y >> 1)) * (ec.W >> 1) + (x >> 1);
+          idx = opix * ec.ldy + nn * 4 + (y & 1) * 2 + (x & 1);
+        } else {
+          const int qd = nn & 3;
+          const long long opix = ((long long)ec.b * (2 * ec.H) + 2 * y + (qd >> 1)) * (2 * ec.W) + 2 * x + (qd & 1);
+          idx = opix * ec.ldy + (nn >> 2);
+        }
+        if constexpr (sizeof(TY) == 4) ec.y[idx] = val; else ec.y[idx] = __float2half_rn(val);
+      }
+    }
   }
   __syncwarp();
 }
@@ -359,12 +436,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const TcGemmParams
   float* stg = reinterpret_cast<float*>(smem + HDR_BYTES);
   uint8_t* sW = smem + HDR_BYTES + STG_BYTES;
   const int a_rows_ld = TM + p.a_pad;                       // rows per 16-byte K-chunk slab of A (pad breaks conflicts)
-  const size_t stage_bytes = (size_t)(p.KC / EPC) * a_rows_ld * 16;
+  const size_t a_stage_bytes = (size_t)(p.KC / EPC) * a_rows_ld * 16;
+  // streamed weights: each stage also carries the [KC/EPC][nc][16 B] slice of the weight chunk
+  const size_t stage_bytes = a_stage_bytes + (p.w_stream ? (size_t)(p.KC / EPC) * p.NC * 16 : 0);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n0 = blockIdx.y * p.NC;
   const int nc = min(p.NC, p.N - n0);
-  uint8_t* sA0 = sW + (size_t)p.NC * p.K * sizeof(TOp);
+  uint8_t* sA0 = sW + (p.w_stream ? 0 : (size_t)p.NC * p.K * sizeof(TOp));
 
   if (tid == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -405,7 +484,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const TcGemmParams
   if (warp >= EPI_WARPS && warp < EPI_WARPS + PROD_WARPS) {
     // =============================== producers ===============================
     const int ptid = tid - EPI_THREADS;
-    {
+    const uint4* wg_all = reinterpret_cast<const uint4*>(reinterpret_cast<const TOp*>(p.w) +
+                                                         (long long)blockIdx.z * p.w_bstride);
+    if (!p.w_stream) {
       // stage this CTA's weight chunk once: global [K/EPC][N][16 B] (+ image stride) -> smem [K/EPC][nc][16 B]
       const uint4* wg = reinterpret_cast<const uint4*>(reinterpret_cast<const TOp*>(p.w) +
                                                        (long long)blockIdx.z * p.w_bstride);
@@ -442,6 +523,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const TcGemmParams
           else if (p.unr == 2) produce_stage<TA, TOp, 3, 2>(p, sA, a_rows_ld, rowbase, p0, valid, k0, kc, p.lpp, do_ln);
           else                 produce_stage<TA, TOp, 3, 1>(p, sA, a_rows_ld, rowbase, p0, valid, k0, kc, p.lpp, do_ln);
         }
+        if (p.w_stream) {
+          // weight slice of this K-chunk: global [K/EPC][N][16 B] -> stage [kc/EPC][nc][16 B]; 4 loads in flight
+          uint4* ws = reinterpret_cast<uint4*>(sA + a_stage_bytes);
+          const uint4* wg = wg_all + (size_t)(k0 / EPC) * p.N + n0;
+          const int kqn = kc / EPC;
+          for (int kq = 0; kq < kqn; kq += 4) {
+            uint4 t[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (kq + u < kqn && ptid < nc) t[u] = __ldg(wg + (size_t)(kq + u) * p.N + ptid);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (kq + u < kqn && ptid < nc) ws[(kq + u) * nc + ptid] = t[u];
+          }
+        }
         fence_async_smem();               // generic-proxy smem writes -> visible to the tensor core (async proxy)
         mbar_arrive(smem_u32(&hdr->full[s]));
       }
@@ -461,7 +557,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const TcGemmParams
         if (lane == 0) {
           const int k0 = ch * p.KC, kc = min(p.KC, p.K - k0);
           const uint32_t a_addr = smem_u32(sA0 + (size_t)s * stage_bytes);
-          const uint32_t w_addr = smem_u32(sW) + (uint32_t)(k0 / EPC) * w_lbo;
+          const uint32_t w_addr = p.w_stream ? a_addr + (uint32_t)a_stage_bytes
+                                             : smem_u32(sW) + (uint32_t)(k0 / EPC) * w_lbo;
           const uint32_t d_addr = tmem_base + a * (uint32_t)p.acc_stride;
           for (int ks = 0; ks < kc / (2 * EPC); ++ks) {
             const uint64_t adesc = make_smem_desc(a_addr + (uint32_t)(2 * ks) * a_lbo, a_lbo, 128);
@@ -492,10 +589,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const TcGemmParams
       EpiCtx<TY> ec;
       ec.r = p.r; ec.ldr = p.ldr; ec.y = yout; ec.ldy = p.ldy; ec.bias = p.bias;
       ec.row0 = rowbase + p0 + quarter * 32; ec.rows_valid = valid - quarter * 32; ec.lane = lane; ec.stg = mystg;
+      ec.relu = p.relu; ec.sign = p.acc_sign == 0.f ? 1.f : p.acc_sign;
+      ec.o_mode = p.o_mode; ec.b = b; ec.H = p.H; ec.W = p.W; ec.pix0 = p0 + quarter * 32;
+      ec.n_valid = p.n_valid > 0 ? p.n_valid : p.N;
       const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + a * (uint32_t)p.acc_stride;
       const int n32 = nc >> 5;
       const bool tail16 = (nc & 31) != 0;
       float4 rr[8];
+      if (p.o_mode != O_NHWC) {
+        for (int g = 0; g < n32; ++g) epi_group_scatter<TY, 32>(ec, tbase + (uint32_t)(g * 32), n0 + g * 32);
+        if (tail16) epi_group_scatter<TY, 16>(ec, tbase + (uint32_t)(n32 * 32), n0 + n32 * 32);
+        tc_fence_before();
+        mbar_arrive(smem_u32(&hdr->tmem_empty[a]));
+        continue;
+      }
       if (p.r) { if (n32 > 0) fetch_residual<32>(ec, n0, rr); else fetch_residual<16>(ec, n0, rr); }
       for (int g = 0; g < n32; ++g) {
         const int c0 = g * 32;
@@ -536,8 +643,10 @@ size_t tc_gemm_configure(TcGemmParams& p) {
   if (op_es > a_es) return 0;
   const int epc = 16 / op_es;
   if (p.K <= 0 || p.N <= 0 || p.K % (2 * epc) != 0 || p.N % 16 != 0) return 0;
-  if (p.k1 % (16 / a_es) != 0 || (p.k2 != 0 && p.k2 % (16 / a_es) != 0) || p.k1 + p.k2 != p.K) return 0;
+  if (p.k1 % (16 / a_es) != 0 || (p.k2 != 0 && p.k2 % (16 / a_es) != 0)) return 0;
+  if (p.a_mode == 1 ? p.K != 9 * p.k1 : p.k1 + p.k2 != p.K) return 0;
   if (p.k2 != 0 && p.k1 % epc != 0) return 0;           // a smem chunk must not straddle the two sources
+  if (p.a_mode == 1 && (p.k2 != 0 || p.k1 % epc != 0 || p.ln_mode != LN_NONE)) return 0;   // 3x3: a chunk stays inside one tap
   const int kc_max = 512 / op_es;                       // K elements per stage: 128 (tf32) / 256 (f16) = 64 KB of A
   p.KC = p.K <= kc_max ? p.K : kc_max / 2;
   if (p.ln_mode != LN_NONE && (p.KC != p.K || p.k2 != 0 || p.a_half)) return 0;   // LayerNorm needs the whole fp32 row
@@ -551,24 +660,40 @@ size_t tc_gemm_configure(TcGemmParams& p) {
   p.unr = pp >= TM ? 1 : (TM / pp >= 4 ? 4 : TM / pp);
   if (epc == 8 && p.upl > 2) return 0;
   if (epc == 8 && p.unr > 2) p.unr = 2;                 // register budget: unr * upl * epc floats in flight
-  const size_t stage_bytes = (size_t)units * (TM + p.a_pad) * 16;
+  const size_t a_stage = (size_t)units * (TM + p.a_pad) * 16;
   const size_t fixed = HDR_BYTES + STG_BYTES;
   const size_t budget = 227 * 1024;
-  // fewest N-chunks such that the weights and at least two A stages fit
-  int best = 0;
+  // (1) CTA-resident weights: fewest N-chunks such that the weight chunk and at least two A stages fit
+  int nc_res = 0;
   for (int chunks = 1; chunks <= p.N / 16; ++chunks) {
     int nc = ((p.N + chunks - 1) / chunks + 15) / 16 * 16;
     if (nc > 256) continue;
-    if (fixed + (size_t)nc * p.K * op_es + 2 * stage_bytes <= budget) { best = nc; break; }
+    if (fixed + (size_t)nc * p.K * op_es + 2 * a_stage <= budget) { nc_res = nc; break; }
   }
-  if (!best) return 0;
-  p.NC = best;
-  int stages = (int)((budget - fixed - (size_t)best * p.K * op_es) / stage_bytes);
+  // (2) streamed weights (3x3 convolutions, wide 1x1 at the low-resolution levels): every stage carries its own
+  // K-slice of the weights, so N-chunks can stay 256 wide however long K is
+  int nc_str = 0;
+  if (p.K > p.KC || nc_res == 0) {
+    if (p.K > p.KC) {
+      for (int chunks = 1; chunks <= p.N / 16; ++chunks) {
+        int nc = ((p.N + chunks - 1) / chunks + 15) / 16 * 16;
+        if (nc > 256) continue;
+        if (fixed + 2 * (a_stage + (size_t)units * nc * 16) <= budget) { nc_str = nc; break; }
+      }
+    }
+  }
+  const bool stream = nc_str != 0 && (nc_res == 0 || nc_res < std::min(p.N, 128));
+  if (!stream && !nc_res) return 0;
+  p.w_stream = stream ? 1 : 0;
+  p.NC = stream ? nc_str : nc_res;
+  const size_t stage_bytes = a_stage + (stream ? (size_t)units * p.NC * 16 : 0);
+  const size_t resident = stream ? 0 : (size_t)p.NC * p.K * op_es;
+  int stages = (int)((budget - fixed - resident) / stage_bytes);
   p.stages = std::min(stages, MAX_STAGES);
-  p.acc_stride = (best + 31) / 32 * 32;
+  p.acc_stride = (p.NC + 31) / 32 * 32;
   p.tmem_cols = next_pow2_cols(2 * p.acc_stride);
   if (p.tmem_cols > 512) return 0;
-  return fixed + (size_t)best * p.K * op_es + (size_t)p.stages * stage_bytes;
+  return fixed + resident + (size_t)p.stages * stage_bytes;
 }
 
 template <typename TA, typename TOp, typename TY>
@@ -586,6 +711,9 @@ static int launch_typed(const TcGemmParams& p, dim3 grid, size_t smem, cudaStrea
 int launch_gemm_tc(TcGemmParams p, cudaStream_t s) {
   size_t smem = tc_gemm_configure(p);
   IRB_REQUIRE(smem != 0, "tc_gemm: unsupported shape");
+  IRB_REQUIRE(p.a_mode == 0 || (p.H > 0 && p.W > 0 && p.H * p.W == p.HW), "tc_gemm: 3x3 mode needs H*W == HW");
+  IRB_REQUIRE(p.o_mode == O_NHWC || (p.r == nullptr && p.H * p.W == p.HW), "tc_gemm: scatter epilogue takes no residual");
+  IRB_REQUIRE(p.o_mode != O_UNSHUFFLE || (p.H % 2 == 0 && p.W % 2 == 0), "tc_gemm: unshuffle needs even H, W");
   const int a_vec = p.a_half ? 8 : 4;
   IRB_REQUIRE(p.lda1 % a_vec == 0 && (p.k2 == 0 || p.lda2 % a_vec == 0) && p.ldy % 4 == 0 &&
                   (p.r == nullptr || p.ldr % 4 == 0),
@@ -607,7 +735,8 @@ int launch_gemm_tc(TcGemmParams p, cudaStream_t s) {
   }
   const double rows = (double)p.B * p.HW;
   const double a_es = p.a_half ? 2.0 : 4.0, y_es = p.y_half ? 2.0 : 4.0;
-  ProfScope prof(p.tag, rows * (p.K * a_es + p.N * (y_es + (p.r ? 4.0 : 0.0))), 2.0 * rows * p.N * p.K, s);
+  const double a_elems = p.a_mode == 1 ? p.k1 : p.K;     // 3x3: the nine shifted reads of a pixel hit cache, not HBM
+  ProfScope prof(p.tag, rows * (a_elems * a_es + p.N * (y_es + (p.r ? 4.0 : 0.0))), 2.0 * rows * p.N * p.K, s);
   if (!p.a_half && !p.op_half && !p.y_half) return launch_typed<float, float, float>(p, grid, smem, s);
   if (!p.a_half && p.op_half && p.y_half) return launch_typed<float, __half, __half>(p, grid, smem, s);
   if (!p.a_half && p.op_half && !p.y_half) return launch_typed<float, __half, float>(p, grid, smem, s);

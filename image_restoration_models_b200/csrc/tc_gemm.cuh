@@ -23,6 +23,14 @@ struct TcGemmParams {
   int tag;
   int a_pad;                                             // 0/1: extra row per K-chunk slab of A in smem
   int a_half, op_half, y_half;                           // element types (0 = fp32 / tf32 operand, 1 = fp16)
+  // 3x3 convolution as implicit GEMM: a_mode 1 gathers k = tap*cin + c from the pixel shifted by the tap
+  // (zero padding 1); k1 = cin, K = 9*cin, H x W = spatial extent of one image (HW = H*W)
+  int a_mode, H, W;
+  int o_mode;                                            // OMode: plain rows, or PixelUnshuffle / PixelShuffle scatter
+  int relu;
+  int n_valid;                                           // scatter epilogue: output channels >= n_valid are padding (0 = N)
+  float acc_sign;                                        // y = r + acc_sign * act(acc + bias)   (0 is treated as +1)
+  int w_stream;                                          // filled by configure: weights streamed per K-chunk
   // filled by tc_gemm_configure / launch_gemm_tc
   int NC, KC, lpp, upl, unr, stages, acc_stride, tmem_cols, tiles_per_img, ntiles;
 };

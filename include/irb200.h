@@ -125,6 +125,13 @@ int    ir_test_conv1x1(int engine, const void* a1, int lda1, int k1, const void*
                        int a_half, int op_half, int y_half,   /* element types: a1/a2, tensor-core operands, y */
                        void* scratch, size_t scratch_bytes, void* stream);
 
+/* One 3x3 convolution (stride 1, zero padding 1, PyTorch [cout][cin][3][3] weight) on channels-last fp32 rows.
+ * o_mode: 0 plain rows y[pix*ldy + n]; 1 PixelUnshuffle(2) folded into the store; 2 PixelShuffle(2) folded into the
+ * store (restormer.py:176,186).  engine 0 = tcgen05 implicit GEMM, 1 = CUDA-core fp32.  scratch >= cout*9*cin*4 B. */
+int    ir_test_conv3x3(int engine, const float* x_nhwc, int ldx, int cin, const float* w_oihw, const float* bias,
+                       int cout, int B, int H, int W, float* y, int ldy, int o_mode, int relu, int op_half,
+                       void* scratch, size_t scratch_bytes, void* stream);
+
 /* Layout helpers used at the boundary of unit tests (NCHW fp32 <-> channels-last fp32). */
 int    ir_nchw_to_nhwc(const float* src, float* dst, int B, int C, int H, int W, void* stream);
 int    ir_nhwc_to_nchw(const float* src, float* dst, int B, int C, int H, int W, void* stream);

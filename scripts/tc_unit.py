@@ -14,11 +14,15 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 def child(start):
     import numpy as np
-    from tc_cases import CASES, HALF_CASES, run_case, tolerance
-    CASES = CASES + HALF_CASES
+    from tc_cases import CASES, CONV3_CASES, HALF_CASES, run_case, run_conv3_case, tolerance
+    n1 = len(CASES) + len(HALF_CASES)
+    CASES = CASES + HALF_CASES + CONV3_CASES
     for i in range(start, len(CASES)):
         print(json.dumps({"begin": i}), flush=True)
-        y, y_ref = run_case(CASES[i], 0, seed=i)
+        if i >= n1:
+            y, y_ref = run_conv3_case(CASES[i], 0, seed=i)
+        else:
+            y, y_ref = run_case(CASES[i], 0, seed=i)
         err = float(np.abs(y - y_ref).max()) if np.isfinite(y).all() else float("inf")
         bad = int((~np.isfinite(y)).sum())
         # where is the error? (row / column of the worst element) helps decode layout mistakes
@@ -26,7 +30,7 @@ def child(start):
         r, c = np.unravel_index(int(d.argmax()), d.shape)
         colerr = d.max(axis=0)
         rowerr = d.max(axis=1)
-        tol = tolerance(CASES[i], y_ref)
+        tol = tolerance(CASES[i], y_ref) if i < n1 else 4e-3 * float(np.abs(y_ref).max()) + 1e-5
         print(json.dumps({"case": i, "cfg": CASES[i], "err": err, "tol": tol, "ok": bool(err <= tol), "nonfinite": bad,
                           "worst": [int(r), int(c)], "bad_cols": int((colerr > tol).sum()),
                           "bad_rows": int((rowerr > tol).sum()),
@@ -39,8 +43,8 @@ def main():
     if len(sys.argv) > 2 and sys.argv[1] == "--from":
         child(int(sys.argv[2]))
         return 0
-    from tc_cases import CASES, HALF_CASES
-    CASES = CASES + HALF_CASES
+    from tc_cases import CASES, CONV3_CASES, HALF_CASES
+    CASES = CASES + HALF_CASES + CONV3_CASES
     results, start = [], 0
     while start < len(CASES):
         p = subprocess.Popen([sys.executable, os.path.abspath(__file__), "--from", str(start)], stdout=subprocess.PIPE,

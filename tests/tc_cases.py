@@ -113,3 +113,49 @@ def tolerance(case, y_ref):
     """tf32 / fp16 operands (10-bit mantissa, RN) with fp32 accumulation: relative 2^-11 per operand
     (+ 2^-11 output rounding when y is fp16)."""
     return (5e-3 if len(case) == 11 else 4e-3) * float(np.abs(y_ref).max()) + 1e-5
+
+
+# 3x3 convolution cases: (cin, cout, B, H, W, o_mode, bias, relu, op_half)
+CONV3_CASES = [
+    (64, 64, 1, 24, 40, 0, True, True, 0),       # DnCNN body layer: bias + ReLU, plain rows
+    (64, 64, 2, 19, 31, 0, True, True, 0),       # odd extent, batch 2
+    (48, 32, 1, 16, 24, 1, False, False, 0),     # Downsample level 1 shape family (48 -> 24 is below the N%16 rule; 32 here)
+    (96, 48, 1, 16, 16, 1, False, False, 0),     # down2_3: 96 -> 48 + PixelUnshuffle
+    (192, 96, 2, 8, 8, 1, False, False, 0),      # down3_4
+    (384, 768, 1, 8, 8, 2, False, False, 0),     # up4_3: 384 -> 768 + PixelShuffle, streamed weights, 3 N-chunks
+    (192, 384, 1, 8, 16, 2, False, False, 0),    # up3_2
+    (96, 192, 1, 16, 16, 2, False, False, 0),    # up2_1
+    (96, 192, 1, 16, 16, 2, False, False, 1),    # fp16 operands
+    (64, 64, 1, 32, 32, 0, True, True, 1),
+]
+
+
+def run_conv3_case(case, engine, seed=0):
+    import torch.nn.functional as F
+    cin, cout, B, H, W, o_mode, bias, relu, op_half = case
+    g = torch.Generator().manual_seed(2000 + seed)
+    x = torch.randn(B, cin, H, W, generator=g)
+    w = (torch.rand(cout, cin, 3, 3, generator=g) * 2 - 1) / np.sqrt(9 * cin)
+    bvec = (torch.rand(cout, generator=g) - 0.5) if bias else None
+    ref = F.conv2d(x.double(), w.double(), bvec.double() if bias else None, padding=1)
+    if relu:
+        ref = F.relu(ref)
+    if o_mode == 1:
+        ref = F.pixel_unshuffle(ref, 2)
+    elif o_mode == 2:
+        ref = F.pixel_shuffle(ref, 2)
+    ref = ref.permute(0, 2, 3, 1).contiguous()          # channels-last rows
+    Co = ref.shape[-1]
+    dev = "cuda"
+    lib = _native.lib()
+    xl = x.permute(0, 2, 3, 1).contiguous().to(dev)
+    wd = w.to(dev).contiguous()
+    bd = bvec.to(dev) if bias else None
+    y = torch.full(tuple(ref.shape), float("nan"), device=dev)
+    scratch = torch.empty(cout * 9 * cin * 4 + 1024, dtype=torch.uint8, device=dev)
+    P = lambda t: 0 if t is None else t.data_ptr()
+    st = lib.ir_test_conv3x3(engine, P(xl), cin, cin, P(wd), P(bd), cout, B, H, W, P(y), Co, o_mode, int(relu), op_half,
+                             P(scratch), scratch.numel(), torch.cuda.current_stream().cuda_stream)
+    _native.check(st)
+    torch.cuda.synchronize()
+    return y.cpu().numpy().reshape(-1, Co), ref.numpy().reshape(-1, Co)

@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 
 from conftest import record
-from tc_cases import CASES, HALF_CASES, run_case, tolerance
+from tc_cases import CASES, CONV3_CASES, HALF_CASES, run_case, run_conv3_case, tolerance
 
 pytestmark = pytest.mark.gpu
 
@@ -29,3 +29,17 @@ def test_tc_conv1x1_fp16_operands_match_reference(idx):
     record(f"tc_conv1x1_half_{idx}", cfg=str(case), err_tc=e_tc, tol=tolerance(case, y_ref))
     assert np.isfinite(y_tc).all()
     assert e_tc <= tolerance(case, y_ref), (case, e_tc)
+
+
+@pytest.mark.parametrize("idx", range(len(CONV3_CASES)))
+def test_tc_conv3x3_matches_reference(idx):
+    case = CONV3_CASES[idx]
+    y_tc, y_ref = run_conv3_case(case, 0, seed=idx)
+    y_simt, _ = run_conv3_case(case, 1, seed=idx)
+    e_tc = float(np.abs(y_tc - y_ref).max())
+    e_simt = float(np.abs(y_simt - y_ref).max())
+    tol = 4e-3 * float(np.abs(y_ref).max()) + 1e-5
+    record(f"tc_conv3x3_{idx}", cfg=str(case), err_tc=e_tc, err_simt=e_simt, tol=tol)
+    assert np.isfinite(y_tc).all()
+    assert e_simt <= 2e-5 * max(1.0, float(np.abs(y_ref).max()))
+    assert e_tc <= tol, (case, e_tc)
