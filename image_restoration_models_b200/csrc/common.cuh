@@ -116,6 +116,9 @@ int launch_dwconv_ref(const DwParams& p, cudaStream_t s);   // simt_kernels.cu: 
 int launch_gram(const GramParams& p, cudaStream_t s);         // gram.cu: mma.sync tensor-core kernel
 int launch_gram_ref(const GramParams& p, cudaStream_t s);     // simt_kernels.cu: CUDA-core reference
 int launch_fold(const FoldParams& p, cudaStream_t s);
+// 3x3 conv with 1..4 output channels, channels-last fp32 in, NCHW out: y = r + sign * (conv + bias)
+int launch_conv3x3_small(const float* in, int ld, int cin, const float* w, int kp, const float* bias, int cout, int B,
+                         int H, int W, const float* r, float sign, float* y, cudaStream_t s);
 // standalone channel LayerNorm (levels whose C does not fit the contraction's register-resident prologue)
 int launch_layernorm(const float* x, int ldx, void* y, int ldy, int y_half, long long rows, int C, int ln_mode,
                      const float* w, const float* b, cudaStream_t s);

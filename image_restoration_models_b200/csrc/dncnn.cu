@@ -85,6 +85,12 @@ int dncnn_forward(const DncnnPlan& pl, const float* packed, const float* x, floa
                            pl.cfg.nc, O_NHWC, 1, pl.half, s));
       continue;
     }
+    if (l == nb - 1 && l > 0 && L.cout <= 4 && L.cin % 4 == 0 && pl.cfg.nc == L.cin) {
+      // tail conv: y = x - conv(n)  (network_dncnn.py:70-71)
+      IRB_TRY(launch_conv3x3_small(buf[(l + 1) & 1], pl.cfg.nc, L.cin, packed + L.w, L.kp, packed + L.b, L.cout, B, H, W,
+                                   x, -1.f, y, s));
+      continue;
+    }
     GemmParams g{};
     g.B = B; g.H = H; g.W = W;
     g.k1 = L.cin;

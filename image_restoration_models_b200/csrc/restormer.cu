@@ -461,6 +461,10 @@ static int conv3(const ConvPlan& cp, const float* packed, const float* in, int l
   if (cp.tc && a_mode == A_IM2COL_NHWC && o_mode != O_NCHW && r == nullptr)
     return run_conv3_tc(in, ld_in, cp.cin, packed + cp.w, cp.b >= 0 ? packed + cp.b : nullptr, cp.cout_p, cp.cout, B, H, W,
                         out, ld_out, o_mode, 0, half, s);
+  if (!cp.tc && a_mode == A_IM2COL_NHWC && o_mode == O_NCHW && cp.cout <= 4 && cp.cin % 4 == 0 &&
+      (size_t)cp.cout * 9 * cp.cin * sizeof(float) <= 48 * 1024)
+    return launch_conv3x3_small(in, ld_in, cp.cin, packed + cp.w, cp.kp, cp.b >= 0 ? packed + cp.b : nullptr, cp.cout, B, H,
+                                W, r, 1.f, out, s);
   GemmParams g{};
   g.a1 = in; g.lda1 = ld_in; g.k1 = cp.cin; g.a_mode = a_mode;
   g.B = B; g.H = H; g.W = W;

@@ -10,6 +10,8 @@
 //   PixelUnshuffle / PixelShuffle          restormer/restormer.py:176,186
 #include "common.cuh"
 
+#include <algorithm>
+
 namespace irb {
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -426,6 +428,105 @@ int launch_fold(const FoldParams& p, cudaStream_t s) {
   dim3 grid(p.heads, p.B);
   ProfScope prof(TAG_FOLD, 4.0 * (double)p.B * p.C * p.C, 2.0 * (double)p.B * p.C * p.C * ch, s);
   fold_kernel<<<grid, 256, smem, s>>>(p);
+  IRB_LAUNCH_CHECK();
+  return IR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// 3x3 convolution with 1..4 output channels written as NCHW (+ NCHW residual): the network's `output` conv
+// (restormer.py:243,278-281).  Memory-bound: a warp walks 32 consecutive pixels of one image row; lanes split the
+// input channels (float4 each), a 3x3 register window slides along x (3 new loads per pixel), the per-pixel result
+// is warp-reduced and parked in lane (x mod 32) so the final store / residual load is one coalesced row segment.
+// ---------------------------------------------------------------------------------------------
+template <int COUT>
+__global__ void __launch_bounds__(256) conv3x3_small_kernel(const float* __restrict__ in, int ld, int cin,
+                                                            const float* __restrict__ w, int kp,
+                                                            const float* __restrict__ bias, int B, int H, int W,
+                                                            const float* __restrict__ r, float sign,
+                                                            float* __restrict__ y) {
+  extern __shared__ float wsm[];                  // [COUT][9][cin]
+  for (int i = threadIdx.x; i < COUT * 9 * cin; i += 256) {
+    const int co = i / (9 * cin), k = i - co * 9 * cin;
+    wsm[i] = w[(long long)co * kp + k];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int segs = (W + 31) >> 5;
+  const long long nwarps = (long long)B * H * segs;
+  const int c4n = cin >> 2;
+  for (long long wi = ((long long)blockIdx.x * 256 + threadIdx.x) >> 5; wi < nwarps; wi += ((long long)gridDim.x * 256) >> 5) {
+    const int seg = (int)(wi % segs);
+    const long long by = wi / segs;
+    const int yy = (int)(by % H), b = (int)(by / H);
+    const int x0 = seg * 32;
+    float res[COUT];
+#pragma unroll
+    for (int co = 0; co < COUT; ++co) res[co] = 0.f;
+    for (int cb = 0; cb < c4n; cb += 32) {        // channel blocks of 32 float4 (one per lane)
+      const int c4 = cb + lane;
+      const bool cok = c4 < c4n;
+      float4 win[3][3];                           // [row dy][col: x-1, x, x+1]
+      auto ldv = [&](int ry, int x) -> float4 {
+        const int y2 = yy + ry - 1;
+        if (!cok || y2 < 0 || y2 >= H || x < 0 || x >= W) return make_float4(0.f, 0.f, 0.f, 0.f);
+        return *reinterpret_cast<const float4*>(in + (((long long)b * H + y2) * W + x) * ld + 4 * c4);
+      };
+#pragma unroll
+      for (int ry = 0; ry < 3; ++ry) { win[ry][1] = ldv(ry, x0 - 1); win[ry][2] = ldv(ry, x0); }
+      for (int j = 0; j < 32 && x0 + j < W; ++j) {
+#pragma unroll
+        for (int ry = 0; ry < 3; ++ry) { win[ry][0] = win[ry][1]; win[ry][1] = win[ry][2]; win[ry][2] = ldv(ry, x0 + j + 1); }
+        float acc[COUT];
+#pragma unroll
+        for (int co = 0; co < COUT; ++co) acc[co] = 0.f;
+        if (cok) {
+#pragma unroll
+          for (int ry = 0; ry < 3; ++ry)
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
+              const float4 v = win[ry][dx];
+#pragma unroll
+              for (int co = 0; co < COUT; ++co) {
+                const float4 k = *reinterpret_cast<const float4*>(wsm + (co * 9 + ry * 3 + dx) * cin + 4 * c4);
+                acc[co] = fmaf(v.x, k.x, fmaf(v.y, k.y, fmaf(v.z, k.z, fmaf(v.w, k.w, acc[co]))));
+              }
+            }
+        }
+#pragma unroll
+        for (int co = 0; co < COUT; ++co) {
+          const float t = warp_sum(acc[co]);
+          if (lane == j) res[co] += t;
+        }
+      }
+    }
+    if (x0 + lane < W) {
+#pragma unroll
+      for (int co = 0; co < COUT; ++co) {
+        const long long o = (((long long)b * COUT + co) * H + yy) * W + x0 + lane;
+        float v = res[co] + (bias ? bias[co] : 0.f);
+        v *= sign;
+        if (r) v += r[o];
+        y[o] = v;
+      }
+    }
+  }
+}
+
+int launch_conv3x3_small(const float* in, int ld, int cin, const float* w, int kp, const float* bias, int cout, int B,
+                         int H, int W, const float* r, float sign, float* y, cudaStream_t s) {
+  IRB_REQUIRE(cout >= 1 && cout <= 4 && cin % 4 == 0 && ld % 4 == 0, "conv3x3_small: cout in 1..4, cin % 4 == 0");
+  const size_t smem = (size_t)cout * 9 * cin * sizeof(float);
+  IRB_REQUIRE(smem <= 48 * 1024, "conv3x3_small: weights do not fit shared memory");
+  const long long nwarps = (long long)B * H * ((W + 31) / 32);
+  const int blocks = (int)std::min<long long>(cdivll(nwarps, 8), 148LL * 32);
+  const double pix = (double)B * H * W;
+  ProfScope prof(TAG_CONV3, 4.0 * pix * (cin + cout * (r ? 2.0 : 1.0)), 2.0 * 9.0 * pix * cin * cout, s);
+  switch (cout) {
+    case 1: conv3x3_small_kernel<1><<<blocks, 256, smem, s>>>(in, ld, cin, w, kp, bias, B, H, W, r, sign, y); break;
+    case 2: conv3x3_small_kernel<2><<<blocks, 256, smem, s>>>(in, ld, cin, w, kp, bias, B, H, W, r, sign, y); break;
+    case 3: conv3x3_small_kernel<3><<<blocks, 256, smem, s>>>(in, ld, cin, w, kp, bias, B, H, W, r, sign, y); break;
+    default: conv3x3_small_kernel<4><<<blocks, 256, smem, s>>>(in, ld, cin, w, kp, bias, B, H, W, r, sign, y); break;
+  }
   IRB_LAUNCH_CHECK();
   return IR_OK;
 }

@@ -11,7 +11,8 @@
 // Everything on this path is HBM-bound (K is 48..384, arithmetic intensity 8..40 FLOP/B), so the kernel is a
 // streaming pipeline with a tensor-core stage in the middle.  One persistent CTA per SM, 13 warps, three roles:
 //
-//   producers (8 warps)  coalesced 16-byte global loads of the A rows with several passes in flight, LayerNorm
+//   producers (2 groups of 4 warps, alternating stages, so two stages of loads are always in flight)
+//                        coalesced 16-byte global loads of the A rows with several passes in flight, LayerNorm
 //                        statistics in registers (two-pass, shuffles), rounding to the operand type, stores into
 //                        a ring of smem stages in the UMMA canonical K-major no-swizzle layout
 //                        [K/epc][128 (+1 pad row)][16 bytes]; full[s] mbarrier <- all producer threads
@@ -35,6 +36,8 @@ constexpr int EPI_WARPS = 4;
 constexpr int PROD_WARPS = 8;
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int PROD_THREADS = PROD_WARPS * 32;
+constexpr int PGROUPS = 2;                      // producer groups: alternate stages, so two stages of loads are in flight
+constexpr int PG_THREADS = PROD_THREADS / PGROUPS;
 constexpr int NTHREADS = EPI_THREADS + PROD_THREADS + 32;
 constexpr int MAX_STAGES = 4;
 constexpr int STG_LD = 36;              // floats per staging row (32 + 4 pad -> conflict-free)
@@ -193,23 +196,23 @@ __device__ __forceinline__ void store_chunk<__half>(uint8_t* dst, const float* v
 // LPP consecutive lanes cooperate on one pixel row; each lane owns UPL "units" (one unit = one smem chunk =
 // EPC channels).  UNR row-passes are loaded before any is consumed, to keep enough bytes in flight.
 // ---------------------------------------------------------------------------------------------------
-template <typename TA, typename TOp, int UPL, int UNR>
+// MODE: 0 plain rows (optionally two concatenated sources), 1 LayerNorm prologue, 2 implicit-GEMM 3x3 gather
+template <typename TA, typename TOp, int MODE, int UPL, int UNR>
 __device__ __forceinline__ void produce_stage(const TcGemmParams& p, uint8_t* __restrict__ sA, int a_rows_ld,
                                               long long rowbase, int p0, int valid, int k0, int kc, int lpp,
-                                              bool do_ln) {
+                                              bool do_ln, int ptid) {
   constexpr int EPC = 16 / (int)sizeof(TOp);            // elements per smem chunk
   constexpr int VPU = EPC / GVec<TA>::N;                // global vectors per unit (1 or 2)
   static_assert(VPU >= 1, "operand type must not be wider than the global type");
   const TA* a1 = reinterpret_cast<const TA*>(p.a1);
   const TA* a2 = reinterpret_cast<const TA*>(p.a2);
-  const int ptid = threadIdx.x - EPI_THREADS;
-  const int q = ptid % lpp;
+  const int q = ptid % lpp;                             // ptid: thread index inside the producer group
   const int rsub = ptid / lpp;
-  const int pp = PROD_THREADS / lpp;                    // pixel rows per pass
+  const int pp = PG_THREADS / lpp;                      // pixel rows per pass
   const int units = kc / EPC;                           // units per row in this chunk
   // implicit-GEMM 3x3: the unit's K range lies inside one filter tap (cin % EPC == 0)
   int udy[UPL], udx[UPL], uc[UPL];
-  if (p.a_mode == 1) {
+  if constexpr (MODE == 2) {
 #pragma unroll
     for (int i = 0; i < UPL; ++i) {
       const int k = k0 + (q + i * lpp) * EPC;
@@ -219,6 +222,24 @@ __device__ __forceinline__ void produce_stage(const TcGemmParams& p, uint8_t* __
       udx[i] = tap - (tap / 3) * 3 - 1;
     }
   }
+  // LayerNorm affine parameters of this lane's channels: loaded once per stage, not per row
+  float gw[UPL][EPC], gb[UPL][EPC];
+  if constexpr (MODE == 1) {
+#pragma unroll
+    for (int i = 0; i < UPL; ++i) {
+      const int unit = q + i * lpp;
+#pragma unroll
+      for (int e4 = 0; e4 < EPC; e4 += 4) {
+        float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f), b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (unit < units) {
+          g4 = __ldg(reinterpret_cast<const float4*>(p.ln_w + unit * EPC + e4));
+          if (p.ln_mode == LN_WITHBIAS) b4 = __ldg(reinterpret_cast<const float4*>(p.ln_b + unit * EPC + e4));
+        }
+        gw[i][e4] = g4.x; gw[i][e4 + 1] = g4.y; gw[i][e4 + 2] = g4.z; gw[i][e4 + 3] = g4.w;
+        gb[i][e4] = b4.x; gb[i][e4 + 1] = b4.y; gb[i][e4 + 2] = b4.z; gb[i][e4 + 3] = b4.w;
+      }
+    }
+  }
   for (int r0 = 0; r0 < TM; r0 += pp * UNR) {
     float v[UNR][UPL][EPC];
 #pragma unroll
@@ -226,14 +247,14 @@ __device__ __forceinline__ void produce_stage(const TcGemmParams& p, uint8_t* __
       const int r = r0 + u * pp + rsub;
       const bool live = r < valid;                      // valid <= TM
       int py = 0, px = 0;
-      if (p.a_mode == 1) { py = (p0 + r) / p.W; px = (p0 + r) - py * p.W; }
+      if constexpr (MODE == 2) { py = (p0 + r) / p.W; px = (p0 + r) - py * p.W; }
 #pragma unroll
       for (int i = 0; i < UPL; ++i) {
         const int unit = q + i * lpp;
 #pragma unroll
         for (int e = 0; e < EPC; ++e) v[u][i][e] = 0.f;
         if (live && unit < units) {
-          if (p.a_mode == 1) {
+          if constexpr (MODE == 2) {
             const int yy = py + udy[i], xx = px + udx[i];
             if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W) {
               const TA* src = a1 + (rowbase + (long long)yy * p.W + xx) * (long long)p.lda1 + uc[i];
@@ -255,7 +276,7 @@ __device__ __forceinline__ void produce_stage(const TcGemmParams& p, uint8_t* __
 #pragma unroll
     for (int u = 0; u < UNR; ++u) {
       const int r = r0 + u * pp + rsub;
-      if (do_ln) {
+      if constexpr (MODE == 1) {
         // population variance about the mean, eps inside the sqrt (restormer.py:38,55-56); two-pass in registers
         float s = 0.f;
 #pragma unroll
@@ -281,17 +302,7 @@ __device__ __forceinline__ void produce_stage(const TcGemmParams& p, uint8_t* __
           const int unit = q + i * lpp;
           if (unit < units) {
 #pragma unroll
-            for (int e4 = 0; e4 < EPC; e4 += 4) {
-              const float4 g = __ldg(reinterpret_cast<const float4*>(p.ln_w + unit * EPC + e4));
-              v[u][i][e4 + 0] = (v[u][i][e4 + 0] - sub) * rstd * g.x;
-              v[u][i][e4 + 1] = (v[u][i][e4 + 1] - sub) * rstd * g.y;
-              v[u][i][e4 + 2] = (v[u][i][e4 + 2] - sub) * rstd * g.z;
-              v[u][i][e4 + 3] = (v[u][i][e4 + 3] - sub) * rstd * g.w;
-              if (p.ln_mode == LN_WITHBIAS) {
-                const float4 bb = __ldg(reinterpret_cast<const float4*>(p.ln_b + unit * EPC + e4));
-                v[u][i][e4 + 0] += bb.x; v[u][i][e4 + 1] += bb.y; v[u][i][e4 + 2] += bb.z; v[u][i][e4 + 3] += bb.w;
-              }
-            }
+            for (int e = 0; e < EPC; ++e) v[u][i][e] = fmaf((v[u][i][e] - sub) * rstd, gw[i][e], gb[i][e]);
           }
         }
       }
@@ -428,7 +439,7 @@ __device__ __forceinline__ void epi_group_scatter(const EpiCtx<TY>& ec, uint32_t
   __syncwarp();
 }
 
-template <typename TA, typename TOp, typename TY>
+template <typename TA, typename TOp, typename TY, int MODE>
 __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const TcGemmParams p) {
   constexpr int EPC = 16 / (int)sizeof(TOp);
   extern __shared__ __align__(128) uint8_t smem[];
@@ -447,7 +458,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const TcGemmParams
 
   if (tid == 0) {
     for (int s = 0; s < p.stages; ++s) {
-      mbar_init(smem_u32(&hdr->full[s]), PROD_THREADS);
+      mbar_init(smem_u32(&hdr->full[s]), PG_THREADS);
       mbar_init(smem_u32(&hdr->empty[s]), 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -484,6 +495,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const TcGemmParams
   if (warp >= EPI_WARPS && warp < EPI_WARPS + PROD_WARPS) {
     // =============================== producers ===============================
     const int ptid = tid - EPI_THREADS;
+    const int grp = ptid / PG_THREADS, gtid = ptid - grp * PG_THREADS;
     const uint4* wg_all = reinterpret_cast<const uint4*>(reinterpret_cast<const TOp*>(p.w) +
                                                          (long long)blockIdx.z * p.w_bstride);
     if (!p.w_stream) {
@@ -496,6 +508,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const TcGemmParams
         const int kq = idx / nc, n = idx - kq * nc;
         ws[idx] = __ldg(wg + (size_t)kq * p.N + n0 + n);
       }
+      // the first MMA is released by ONE group's arrivals: order every producer's weight stores before them
+      fence_async_smem();
+      asm volatile("bar.sync 1, %0;" ::"n"(PROD_THREADS) : "memory");
     }
     const bool do_ln = p.ln_mode != LN_NONE;
     uint32_t item = 0;
@@ -505,6 +520,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const TcGemmParams
       const int valid = min(TM, p.HW - p0);
       const long long rowbase = (long long)b * p.HW;
       for (int ch = 0; ch < nchunks; ++ch, ++item) {
+        if ((int)(item % PGROUPS) != grp) continue;       // the other group's stage
         const int s = item % p.stages;
         const uint32_t ph = (item / p.stages) & 1u;
         mbar_wait(smem_u32(&hdr->empty[s]), ph ^ 1u);
@@ -512,30 +528,32 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const TcGemmParams
         const int k0 = ch * p.KC, kc = min(p.KC, p.K - k0);
         if constexpr (EPC == 8) {
           // 8-element chunks: at most 2 units per lane and 2 row passes in flight (register budget)
-          if (p.unr >= 2) produce_stage<TA, TOp, 2, 2>(p, sA, a_rows_ld, rowbase, p0, valid, k0, kc, p.lpp, do_ln);
-          else            produce_stage<TA, TOp, 2, 1>(p, sA, a_rows_ld, rowbase, p0, valid, k0, kc, p.lpp, do_ln);
+          if (p.unr >= 2) produce_stage<TA, TOp, MODE, 2, 2>(p, sA, a_rows_ld, rowbase, p0, valid, k0, kc, p.lpp, do_ln, gtid);
+          else            produce_stage<TA, TOp, MODE, 2, 1>(p, sA, a_rows_ld, rowbase, p0, valid, k0, kc, p.lpp, do_ln, gtid);
         } else if (p.upl <= 2) {
-          if (p.unr >= 4)      produce_stage<TA, TOp, 2, 4>(p, sA, a_rows_ld, rowbase, p0, valid, k0, kc, p.lpp, do_ln);
-          else if (p.unr == 2) produce_stage<TA, TOp, 2, 2>(p, sA, a_rows_ld, rowbase, p0, valid, k0, kc, p.lpp, do_ln);
-          else                 produce_stage<TA, TOp, 2, 1>(p, sA, a_rows_ld, rowbase, p0, valid, k0, kc, p.lpp, do_ln);
+          if (p.unr >= 4)      produce_stage<TA, TOp, MODE, 2, 4>(p, sA, a_rows_ld, rowbase, p0, valid, k0, kc, p.lpp, do_ln, gtid);
+          else if (p.unr == 2) produce_stage<TA, TOp, MODE, 2, 2>(p, sA, a_rows_ld, rowbase, p0, valid, k0, kc, p.lpp, do_ln, gtid);
+          else                 produce_stage<TA, TOp, MODE, 2, 1>(p, sA, a_rows_ld, rowbase, p0, valid, k0, kc, p.lpp, do_ln, gtid);
         } else {
-          if (p.unr >= 4)      produce_stage<TA, TOp, 3, 4>(p, sA, a_rows_ld, rowbase, p0, valid, k0, kc, p.lpp, do_ln);
-          else if (p.unr == 2) produce_stage<TA, TOp, 3, 2>(p, sA, a_rows_ld, rowbase, p0, valid, k0, kc, p.lpp, do_ln);
-          else                 produce_stage<TA, TOp, 3, 1>(p, sA, a_rows_ld, rowbase, p0, valid, k0, kc, p.lpp, do_ln);
+          if (p.unr >= 4)      produce_stage<TA, TOp, MODE, 3, 4>(p, sA, a_rows_ld, rowbase, p0, valid, k0, kc, p.lpp, do_ln, gtid);
+          else if (p.unr == 2) produce_stage<TA, TOp, MODE, 3, 2>(p, sA, a_rows_ld, rowbase, p0, valid, k0, kc, p.lpp, do_ln, gtid);
+          else                 produce_stage<TA, TOp, MODE, 3, 1>(p, sA, a_rows_ld, rowbase, p0, valid, k0, kc, p.lpp, do_ln, gtid);
         }
         if (p.w_stream) {
           // weight slice of this K-chunk: global [K/EPC][N][16 B] -> stage [kc/EPC][nc][16 B]; 4 loads in flight
           uint4* ws = reinterpret_cast<uint4*>(sA + a_stage_bytes);
           const uint4* wg = wg_all + (size_t)(k0 / EPC) * p.N + n0;
           const int kqn = kc / EPC;
-          for (int kq = 0; kq < kqn; kq += 4) {
-            uint4 t[4];
+          for (int n = gtid; n < nc; n += PG_THREADS) {
+            for (int kq = 0; kq < kqn; kq += 4) {
+              uint4 t[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
-              if (kq + u < kqn && ptid < nc) t[u] = __ldg(wg + (size_t)(kq + u) * p.N + ptid);
+              for (int u = 0; u < 4; ++u)
+                if (kq + u < kqn) t[u] = __ldg(wg + (size_t)(kq + u) * p.N + n);
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
-              if (kq + u < kqn && ptid < nc) ws[(kq + u) * nc + ptid] = t[u];
+              for (int u = 0; u < 4; ++u)
+                if (kq + u < kqn) ws[(kq + u) * nc + n] = t[u];
+            }
           }
         }
         fence_async_smem();               // generic-proxy smem writes -> visible to the tensor core (async proxy)
@@ -656,7 +674,7 @@ size_t tc_gemm_configure(TcGemmParams& p) {
   if ((units + lpp - 1) / lpp > 3) return 0;
   p.lpp = lpp;
   p.upl = (units + lpp - 1) / lpp;
-  const int pp = PROD_THREADS / lpp;
+  const int pp = PG_THREADS / lpp;
   p.unr = pp >= TM ? 1 : (TM / pp >= 4 ? 4 : TM / pp);
   if (epc == 8 && p.upl > 2) return 0;
   if (epc == 8 && p.unr > 2) p.unr = 2;                 // register budget: unr * upl * epc floats in flight
@@ -696,16 +714,31 @@ size_t tc_gemm_configure(TcGemmParams& p) {
   return fixed + resident + (size_t)p.stages * stage_bytes;
 }
 
-template <typename TA, typename TOp, typename TY>
-static int launch_typed(const TcGemmParams& p, dim3 grid, size_t smem, cudaStream_t s) {
+template <typename TA, typename TOp, typename TY, int MODE>
+static int launch_one(const TcGemmParams& p, dim3 grid, size_t smem, cudaStream_t s) {
   static bool configured = false;
   if (!configured) {
-    IRB_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<TA, TOp, TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    IRB_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<TA, TOp, TY, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  227 * 1024));
     configured = true;
   }
-  tc_gemm_kernel<TA, TOp, TY><<<grid, NTHREADS, smem, s>>>(p);
+  tc_gemm_kernel<TA, TOp, TY, MODE><<<grid, NTHREADS, smem, s>>>(p);
   IRB_LAUNCH_CHECK();
   return IR_OK;
+}
+
+// producer mode: LayerNorm needs an fp32 source; the 3x3 gather reads / writes the fp32 streams
+template <typename TA, typename TOp, typename TY>
+static int launch_typed(const TcGemmParams& p, dim3 grid, size_t smem, cudaStream_t s) {
+  if (p.a_mode == 1) {
+    if constexpr (sizeof(TA) == 4 && sizeof(TY) == 4) return launch_one<TA, TOp, TY, 2>(p, grid, smem, s);
+    else { set_error("invalid argument: tc_gemm 3x3 mode is fp32 in / fp32 out"); return IR_ERR_INVALID; }
+  }
+  if (p.ln_mode != LN_NONE) {
+    if constexpr (sizeof(TA) == 4) return launch_one<TA, TOp, TY, 1>(p, grid, smem, s);
+    else { set_error("invalid argument: tc_gemm LayerNorm prologue needs an fp32 source"); return IR_ERR_INVALID; }
+  }
+  return launch_one<TA, TOp, TY, 0>(p, grid, smem, s);
 }
 
 int launch_gemm_tc(TcGemmParams p, cudaStream_t s) {

@@ -32,8 +32,13 @@ if [ "$BENCH_RC" = "0" ] && [ "${SKIP_NCU:-0}" = "0" ]; then
       --log-file $OUT/launches_$TAG.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/ncu_list_$TAG.log 2>&1
   echo "ncu list exit $?" | tee -a $OUT/status_$TAG.txt
   echo "== ncu full capture" | tee -a $OUT/status_$TAG.txt
-  timeout 1200 ncu --set full --clock-control none --import-source on -k "regex:${NCU_FULL_REGEX:-gemm_simt}" -s ${NCU_FULL_SKIP:-330} -c 3 \
+  timeout 1200 ncu --set full --clock-control none --import-source on -k "regex:${NCU_FULL_REGEX:-gemm_simt}" -s ${NCU_FULL_SKIP:-330} -c ${NCU_FULL_COUNT:-3} \
       -f -o $OUT/prof_$TAG python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/ncu_full_$TAG.log 2>&1
   echo "ncu full exit $?" | tee -a $OUT/status_$TAG.txt
+  if [ -n "$NCU_FULL_REGEX2" ]; then
+    timeout 1200 ncu --set full --clock-control none --import-source on -k "regex:$NCU_FULL_REGEX2" -s ${NCU_FULL_SKIP2:-0} -c ${NCU_FULL_COUNT2:-2} \
+        -f -o $OUT/prof2_$TAG python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/ncu_full2_$TAG.log 2>&1
+    echo "ncu full2 exit $?" | tee -a $OUT/status_$TAG.txt
+  fi
 fi
 cat $OUT/status_$TAG.txt
