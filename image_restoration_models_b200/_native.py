@@ -72,6 +72,11 @@ SIGNATURES = {
     "ir_test_conv3x3": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                   C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                   C.c_size_t, C.c_void_p]),
+    "ir_tile_gather": (C.c_int, [C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                 C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "ir_tile_blend": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float,
+                                C.c_void_p]),
     "ir_profile_begin": (C.c_int, []),
     "ir_profile_end": (C.c_int, [C.POINTER(IrKernelStat), C.c_int]),
     "ir_profile_tag_name": (C.c_char_p, [C.c_int]),

@@ -3,6 +3,7 @@
 #include "restormer.cuh"
 #include "tc_gemm.cuh"
 
+#include <cstdlib>
 #include <mutex>
 
 namespace irb {
@@ -280,6 +281,19 @@ int ir_test_conv3x3(int engine, const float* x_nhwc, int ldx, int cin, const flo
   return launch_gemm_simt(g, s);
 }
 
+int ir_tile_gather(const void* img, int dtype, float divisor, int H, int W, int C, const int* tile_xy, int T, int th,
+                   int tw, int TH, int TW, float* out, void* stream) {
+  IRB_REQUIRE(img && tile_xy && out && H > 0 && W > 0 && C > 0 && T > 0, "tile_gather: bad argument");
+  return launch_tile_gather(img, dtype, divisor, H, W, C, tile_xy, T, th, tw, TH, TW, out, (cudaStream_t)stream);
+}
+
+int ir_tile_blend(const float* pred, const int* tile_xy, int T, int th, int tw, int TH, int TW, const float* window,
+                  int win_ld, int H, int W, int C, void* out, int dtype, float scale, float lo, float hi, void* stream) {
+  IRB_REQUIRE(pred && tile_xy && window && out && H > 0 && W > 0 && C > 0 && T > 0, "tile_blend: bad argument");
+  return launch_tile_blend(pred, tile_xy, T, th, tw, TH, TW, window, win_ld, H, W, C, out, dtype, scale, lo, hi,
+                           (cudaStream_t)stream);
+}
+
 int ir_profile_begin(void) {
   std::lock_guard<std::mutex> lk(g_prof_mu);
   for (auto& r : g_prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
@@ -294,6 +308,10 @@ int ir_profile_end(IrKernelStat* h_out, int max_rows) {
   IrKernelStat agg[TAG_COUNT];
   for (int t = 0; t < TAG_COUNT; ++t) agg[t] = IrKernelStat{t, 0, 0.0, 0.0, 0.0};
   int status = IR_OK;
+  // IRB_PROFILE_DUMP=<path>: also append one CSV line per launch (sequence, family, ms, algorithmic bytes, flops)
+  const char* dump_path = getenv("IRB_PROFILE_DUMP");
+  FILE* dump = dump_path ? fopen(dump_path, "a") : nullptr;
+  int seq = 0;
   for (auto& r : g_prof) {
     float ms = 0.f;
     cudaError_t e = cudaEventSynchronize(r.e1);
@@ -301,9 +319,12 @@ int ir_profile_end(IrKernelStat* h_out, int max_rows) {
     if (e != cudaSuccess) status = cuda_fail(e, "profile event", __FILE__, __LINE__);
     const int t = (r.tag >= 0 && r.tag < TAG_COUNT) ? r.tag : TAG_OTHER;
     agg[t].launches += 1; agg[t].ms += ms; agg[t].bytes += r.bytes; agg[t].flops += r.flops;
+    if (dump) fprintf(dump, "%d,%s,%.5f,%.0f,%.0f\n", seq, kTagNames[t], ms, r.bytes, r.flops);
+    ++seq;
     cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
   }
   g_prof.clear();
+  if (dump) fclose(dump);
   if (status != IR_OK) return status;
   int n = 0;
   for (int t = 0; t < TAG_COUNT && n < max_rows; ++t)

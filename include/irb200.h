@@ -136,6 +136,16 @@ int    ir_test_conv3x3(int engine, const float* x_nhwc, int ldx, int cin, const 
 int    ir_nchw_to_nhwc(const float* src, float* dst, int B, int C, int H, int W, void* stream);
 int    ir_nhwc_to_nchw(const float* src, float* dst, int B, int C, int H, int W, void* stream);
 
+/* ---- tiled inference harness on the device (replaces the numpy tile loop of run_model_inference,
+ *      src/utils.py:353-454; bit-exact with it given the same tile predictions) ----
+ * dtype: 0 uint8, 1 uint16, 2 float32 (HWC image).  tile_xy: device int32 [T][2] = (h_idx, w_idx) in the reference's
+ * loop order.  Tiles are th x tw pixels, reflect-padded to TH x TW (multiples of 8) for the model.               */
+int    ir_tile_gather(const void* img, int dtype, float divisor /* 255, 65535, max or 1 */, int H, int W, int C,
+                      const int* tile_xy, int T, int th, int tw, int TH, int TW, float* out_nchw_tiles, void* stream);
+int    ir_tile_blend(const float* pred_nchw_tiles, const int* tile_xy, int T, int th, int tw, int TH, int TW,
+                     const float* window /* [.][win_ld] fp32, get_gaussian_weights */, int win_ld, int H, int W, int C,
+                     void* out_img, int dtype, float scale, float lo, float hi, void* stream);
+
 /* ---- per-kernel device timing (bench.py roofline; off by default, adds two events per launch) ----
  * ir_profile_begin() starts recording every launch the calling process issues through this library;
  * ir_profile_end() synchronises the recorded events and returns one aggregate row per kernel family. */

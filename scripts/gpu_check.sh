@@ -18,11 +18,12 @@ timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke_$TAG
 echo "smoke exit $?" | tee -a $OUT/status_$TAG.txt
 tail -5 $OUT/smoke_$TAG.log
 echo "== bench" | tee -a $OUT/status_$TAG.txt
-timeout 900 python bench.py --steps 5 --warmup 3 > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err
+rm -f $OUT/launch_fp32_$TAG.csv $OUT/launch_half_$TAG.csv
+IRB_PROFILE_DUMP=$OUT/launch_fp32_$TAG.csv timeout 900 python bench.py --steps 5 --warmup 3 > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err
 BENCH_RC=$?
 echo "bench exit $BENCH_RC" | tee -a $OUT/status_$TAG.txt
 tail -c 1500 $OUT/bench_$TAG.json; tail -5 $OUT/bench_$TAG.err
-timeout 900 python bench.py --steps 5 --warmup 3 --mode half --no-cpu-baseline > $OUT/bench_half_$TAG.json 2> $OUT/bench_half_$TAG.err
+IRB_PROFILE_DUMP=$OUT/launch_half_$TAG.csv timeout 900 python bench.py --steps 5 --warmup 3 --mode half --no-cpu-baseline > $OUT/bench_half_$TAG.json 2> $OUT/bench_half_$TAG.err
 echo "bench half exit $?" | tee -a $OUT/status_$TAG.txt
 tail -c 1500 $OUT/bench_half_$TAG.json; tail -5 $OUT/bench_half_$TAG.err
 if [ "$BENCH_RC" = "0" ] && [ "${SKIP_NCU:-0}" = "0" ]; then
