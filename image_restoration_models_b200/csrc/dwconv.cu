@@ -15,16 +15,30 @@ namespace irb {
 
 namespace {
 
+// erf-form GELU (F.gelu default, restormer.py:91): 0.5 x (1 + erf(x / sqrt 2)).  The gated kernel is instruction-issue
+// bound, and libdevice erff costs ~40 instructions per element; erf is evaluated with the Abramowitz-Stegun 7.1.26
+// rational form instead (1 MUFU.RCP + 1 MUFU.EX2 + 7 FMA).  Measured in fp32 against the exact function over
+// [-8, 8]: |erf error| <= 6.1e-7, |gelu error| <= 2.6e-7 -- three orders of magnitude inside the 1e-3 parity budget.
 __device__ __forceinline__ float gelu_erf(float x) {
-  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));   // exact erf GELU (F.gelu default)
+  const float ax = fabsf(x) * 0.70710678118654752440f;
+  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+  const float poly = t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 1.061405429f, -1.453152027f), 1.421413741f), -0.284496736f),
+                              0.254829592f);
+  const float y = fmaf(-poly, __expf(-ax * ax), 1.0f);          // erf(|x| / sqrt 2)
+  return 0.5f * x * (1.0f + copysignf(y, x));
 }
 
-template <typename T> __device__ __forceinline__ float4 ld4(const T* p);
-template <> __device__ __forceinline__ float4 ld4<float>(const float* p) {
-  return __ldg(reinterpret_cast<const float4*>(p));
+// Raw 4-channel vectors: loads are issued unconditionally (clamped address) and converted / masked afterwards.
+// A load placed under a condition, or with its conversion inside the condition, gets funnelled through one
+// register set by the compiler and the loads of a row then serialise (measured: 3x slower).
+template <typename T> struct Raw4;
+template <> struct Raw4<float> { using type = float4; };
+template <> struct Raw4<__half> { using type = uint2; };
+template <typename T> __device__ __forceinline__ typename Raw4<T>::type ldraw(const T* p) {
+  return __ldg(reinterpret_cast<const typename Raw4<T>::type*>(p));
 }
-template <> __device__ __forceinline__ float4 ld4<__half>(const __half* p) {
-  const uint2 t = __ldg(reinterpret_cast<const uint2*>(p));
+__device__ __forceinline__ float4 cvt4(const float4& t) { return t; }
+__device__ __forceinline__ float4 cvt4(const uint2& t) {
   const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&t.x));
   const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&t.y));
   return make_float4(a.x, a.y, b.x, b.y);
@@ -91,14 +105,23 @@ __global__ void __launch_bounds__(256, 2) dw_roll_kernel(const DwParams p, const
   for (int yy = y0 - 1; yy <= y1; ++yy) {
     if (yy >= 0 && yy < p.H) {
       float4 v[NS][WT + 2];
+      typename Raw4<TI>::type raw[NS][WT + 2];
       const TI* rowp = in + (img + (long long)yy * p.W) * p.ldi + c;
 #pragma unroll
       for (int s = 0; s < NS; ++s)
 #pragma unroll
         for (int i = 0; i < WT + 2; ++i) {
+          const int x = min(max(x0 - 1 + i, 0), p.W - 1);          // clamped: zero padding applied below
+          raw[s][i] = ldraw<TI>(rowp + (long long)x * p.ldi + s * p.gate_off);
+        }
+#pragma unroll
+      for (int s = 0; s < NS; ++s)
+#pragma unroll
+        for (int i = 0; i < WT + 2; ++i) {
           const int x = x0 - 1 + i;
-          v[s][i] = (x >= 0 && x < p.W) ? ld4<TI>(rowp + (long long)x * p.ldi + s * p.gate_off)
-                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4 t = cvt4(raw[s][i]);
+          const bool in_img = x >= 0 && x < p.W;
+          v[s][i] = make_float4(in_img ? t.x : 0.f, in_img ? t.y : 0.f, in_img ? t.z : 0.f, in_img ? t.w : 0.f);
         }
       // input row yy feeds output rows yy-1 (tap row 2), yy (tap row 1), yy+1 (tap row 0)
 #pragma unroll

@@ -30,12 +30,16 @@ __device__ __forceinline__ void mma_tf32(float* c, const uint32_t* a, const uint
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
-template <typename T> __device__ __forceinline__ float4 ldg4(const T* p);
-template <> __device__ __forceinline__ float4 ldg4<float>(const float* p) {
-  return __ldg(reinterpret_cast<const float4*>(p));
+// raw 4-channel vectors: loaded unconditionally from a clamped row, converted and masked when staged (a load or
+// its conversion under a condition serialises the loads of a chunk, see dwconv.cu)
+template <typename T> struct Raw4;
+template <> struct Raw4<float> { using type = float4; };
+template <> struct Raw4<__half> { using type = uint2; };
+template <typename T> __device__ __forceinline__ typename Raw4<T>::type ldraw(const T* p) {
+  return __ldg(reinterpret_cast<const typename Raw4<T>::type*>(p));
 }
-template <> __device__ __forceinline__ float4 ldg4<__half>(const __half* p) {
-  const uint2 t = __ldg(reinterpret_cast<const uint2*>(p));
+__device__ __forceinline__ float4 cvt4(const float4& t) { return t; }
+__device__ __forceinline__ float4 cvt4(const uint2& t) {
   const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&t.x));
   const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&t.y));
   return make_float4(a.x, a.y, b.x, b.y);
@@ -73,34 +77,35 @@ __global__ void __launch_bounds__(256) gram_mma_kernel(const GramParams p) {
       for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.f;
   float nrm = 0.f;                            // tid < 2*CH: running sum of squares of column tid (q then k)
 
-  float4 stage[LPT];
+  typename Raw4<T>::type stage[LPT];
   auto issue_loads = [&](int ps) {
 #pragma unroll
     for (int l = 0; l < LPT; ++l) {
       const int e = tid + l * 256;
       const int r = e / V, c = e % V;         // pixel in chunk, float4 column (q: [0, CH/4), k: [CH/4, CH/2))
-      stage[l] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (ps + r < pend) {
-        const int off = (c < CH / 4) ? qoff + 4 * c : koff + 4 * (c - CH / 4);
-        stage[l] = ldg4<T>(base + (long long)(ps + r) * p.ld + off);
-      }
+      const int row = min(ps + r, pend - 1);  // clamped; rows past the slice are zeroed when staged
+      const int off = (c < CH / 4) ? qoff + 4 * c : koff + 4 * (c - CH / 4);
+      stage[l] = ldraw<T>(base + (long long)row * p.ld + off);
     }
   };
-  auto store_stage = [&](int buf) {
+  auto store_stage = [&](int buf, int ps) {
     float* dst = sm + (size_t)buf * PT * 2 * LD;
 #pragma unroll
     for (int l = 0; l < LPT; ++l) {
       const int e = tid + l * 256;
       const int r = e / V, c = e % V;
       float* d = dst + (r * 2 + (c < CH / 4 ? 0 : 1)) * LD + 4 * (c < CH / 4 ? c : c - CH / 4);
+      const float4 t = cvt4(stage[l]);
+      const bool live = ps + r < pend;
       // operands are rounded to tf32 once here; the row norms below use the same rounded values
-      d[0] = __uint_as_float(f2tf32(stage[l].x)); d[1] = __uint_as_float(f2tf32(stage[l].y));
-      d[2] = __uint_as_float(f2tf32(stage[l].z)); d[3] = __uint_as_float(f2tf32(stage[l].w));
+      *reinterpret_cast<float4*>(d) =
+          make_float4(live ? __uint_as_float(f2tf32(t.x)) : 0.f, live ? __uint_as_float(f2tf32(t.y)) : 0.f,
+                      live ? __uint_as_float(f2tf32(t.z)) : 0.f, live ? __uint_as_float(f2tf32(t.w)) : 0.f);
     }
   };
 
   int buf = 0;
-  if (pbeg < pend) { issue_loads(pbeg); store_stage(0); }
+  if (pbeg < pend) { issue_loads(pbeg); store_stage(0, pbeg); }
   __syncthreads();
   for (int ps = pbeg; ps < pend; ps += PT) {
     const bool more = ps + PT < pend;
@@ -133,7 +138,7 @@ __global__ void __launch_bounds__(256) gram_mma_kernel(const GramParams p) {
 #pragma unroll 8
       for (int r = 0; r < PT; ++r) { const float v = col[r * 2 * LD]; nrm = fmaf(v, v, nrm); }
     }
-    if (more) store_stage(buf ^ 1);
+    if (more) store_stage(buf ^ 1, ps + PT);
     __syncthreads();
     buf ^= 1;
   }

@@ -160,16 +160,16 @@ template <typename TA> struct GVec;      // one 16-byte global vector
 template <> struct GVec<float> { static constexpr int N = 4; };
 template <> struct GVec<__half> { static constexpr int N = 8; };
 
+// 16 raw bytes -> GVec<TA>::N floats
 template <typename TA>
-__device__ __forceinline__ void load_vec(const TA* src, float* out);
+__device__ __forceinline__ void unpack_vec(const uint4& t, float* out);
 template <>
-__device__ __forceinline__ void load_vec<float>(const float* src, float* out) {
-  const float4 t = __ldg(reinterpret_cast<const float4*>(src));
-  out[0] = t.x; out[1] = t.y; out[2] = t.z; out[3] = t.w;
+__device__ __forceinline__ void unpack_vec<float>(const uint4& t, float* out) {
+  out[0] = __uint_as_float(t.x); out[1] = __uint_as_float(t.y);
+  out[2] = __uint_as_float(t.z); out[3] = __uint_as_float(t.w);
 }
 template <>
-__device__ __forceinline__ void load_vec<__half>(const __half* src, float* out) {
-  const uint4 t = __ldg(reinterpret_cast<const uint4*>(src));
+__device__ __forceinline__ void unpack_vec<__half>(const uint4& t, float* out) {
   const __half2* h = reinterpret_cast<const __half2*>(&t);
 #pragma unroll
   for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(h[i]); out[2 * i] = f.x; out[2 * i + 1] = f.y; }
@@ -241,38 +241,52 @@ __device__ __forceinline__ void produce_stage(const TcGemmParams& p, uint8_t* __
     }
   }
   for (int r0 = 0; r0 < TM; r0 += pp * UNR) {
-    float v[UNR][UPL][EPC];
+    // Loads are UNCONDITIONAL (out-of-range rows / taps / units read a clamped, valid address and are zeroed
+    // afterwards): a load under `if` makes the compiler funnel every load through one register set, which
+    // serialises them (one outstanding load per thread).  Raw 16-byte vectors, converted after all are issued.
+    uint4 raw[UNR][UPL][VPU];
+    bool ok[UNR][UPL];
 #pragma unroll
     for (int u = 0; u < UNR; ++u) {
       const int r = r0 + u * pp + rsub;
       const bool live = r < valid;                      // valid <= TM
+      const int rc = live ? r : 0;                      // clamped row (row 0 of the tile always exists)
       int py = 0, px = 0;
-      if constexpr (MODE == 2) { py = (p0 + r) / p.W; px = (p0 + r) - py * p.W; }
+      if constexpr (MODE == 2) { py = (p0 + rc) / p.W; px = (p0 + rc) - py * p.W; }
 #pragma unroll
       for (int i = 0; i < UPL; ++i) {
         const int unit = q + i * lpp;
-#pragma unroll
-        for (int e = 0; e < EPC; ++e) v[u][i][e] = 0.f;
-        if (live && unit < units) {
-          if constexpr (MODE == 2) {
-            const int yy = py + udy[i], xx = px + udx[i];
-            if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W) {
-              const TA* src = a1 + (rowbase + (long long)yy * p.W + xx) * (long long)p.lda1 + uc[i];
-#pragma unroll
-              for (int g = 0; g < VPU; ++g) load_vec<TA>(src + g * GVec<TA>::N, &v[u][i][g * GVec<TA>::N]);
-            }
-          } else {
-#pragma unroll
-            for (int g = 0; g < VPU; ++g) {
-              const int k = k0 + unit * EPC + g * GVec<TA>::N;
-              const TA* src = (k < p.k1) ? a1 + (rowbase + p0 + r) * (long long)p.lda1 + k
-                                         : a2 + (rowbase + p0 + r) * (long long)p.lda2 + (k - p.k1);
-              load_vec<TA>(src, &v[u][i][g * GVec<TA>::N]);
-            }
-          }
+        const int uu = unit < units ? unit : 0;
+        bool good = live && unit < units;
+        const TA* src;
+        if constexpr (MODE == 2) {
+          const int yy = py + udy[i], xx = px + udx[i];
+          const bool inside = yy >= 0 && yy < p.H && xx >= 0 && xx < p.W;
+          good = good && inside;
+          const int yc = inside ? yy : py, xc = inside ? xx : px;
+          src = a1 + (rowbase + (long long)yc * p.W + xc) * (long long)p.lda1 + (unit < units ? uc[i] : 0);
+        } else {
+          const int k = k0 + uu * EPC;
+          src = (k < p.k1) ? a1 + (rowbase + p0 + rc) * (long long)p.lda1 + k
+                           : a2 + (rowbase + p0 + rc) * (long long)p.lda2 + (k - p.k1);
         }
+        ok[u][i] = good;
+#pragma unroll
+        for (int g = 0; g < VPU; ++g) raw[u][i][g] = __ldg(reinterpret_cast<const uint4*>(src + g * GVec<TA>::N));
       }
     }
+    float v[UNR][UPL][EPC];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u)
+#pragma unroll
+      for (int i = 0; i < UPL; ++i)
+#pragma unroll
+        for (int g = 0; g < VPU; ++g) {
+          float t[GVec<TA>::N];
+          unpack_vec<TA>(raw[u][i][g], t);
+#pragma unroll
+          for (int e = 0; e < GVec<TA>::N; ++e) v[u][i][g * GVec<TA>::N + e] = ok[u][i] ? t[e] : 0.f;
+        }
 #pragma unroll
     for (int u = 0; u < UNR; ++u) {
       const int r = r0 + u * pp + rsub;
@@ -499,14 +513,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const TcGemmParams
     const uint4* wg_all = reinterpret_cast<const uint4*>(reinterpret_cast<const TOp*>(p.w) +
                                                          (long long)blockIdx.z * p.w_bstride);
     if (!p.w_stream) {
-      // stage this CTA's weight chunk once: global [K/EPC][N][16 B] (+ image stride) -> smem [K/EPC][nc][16 B]
-      const uint4* wg = reinterpret_cast<const uint4*>(reinterpret_cast<const TOp*>(p.w) +
-                                                       (long long)blockIdx.z * p.w_bstride);
-      uint4* ws = reinterpret_cast<uint4*>(sW);
-      const int total = (p.K / EPC) * nc;
-      for (int idx = ptid; idx < total; idx += PROD_THREADS) {
-        const int kq = idx / nc, n = idx - kq * nc;
-        ws[idx] = __ldg(wg + (size_t)kq * p.N + n0 + n);
+      // stage this CTA's weight chunk once: global [K/EPC][N][16 B] (+ image stride) -> smem, one block per sub-chunk
+      // sub-chunk i occupies [K/EPC][ns_i][16 B] at 16-byte offset (K/EPC) * i * NS (earlier sub-chunks are full)
+      const int kq_n = p.K / EPC;
+      for (int sub = 0; sub < p.nsub; ++sub) {
+        const int c_lo = sub * p.NS;
+        const int ns = min(p.NS, nc - c_lo);
+        if (ns <= 0) break;
+        uint4* ws = reinterpret_cast<uint4*>(sW) + (size_t)kq_n * c_lo;
+        const int total = kq_n * ns;
+        for (int idx = ptid; idx < total; idx += PROD_THREADS) {
+          const int kq = idx / ns, n = idx - kq * ns;
+          ws[idx] = __ldg(wg_all + (size_t)kq * p.N + n0 + c_lo + n);
+        }
       }
       // the first MMA is released by ONE group's arrivals: order every producer's weight stores before them
       fence_async_smem();
@@ -562,11 +581,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const TcGemmParams
     }
   } else if (warp == EPI_WARPS + PROD_WARPS) {
     // =============================== MMA issuer ===============================
-    const uint32_t idesc = make_idesc<TOp>(nc);
     uint32_t item = 0, j = 0;
     for (long long tile = t_begin; tile < t_end; ++tile, ++j) {
-      const uint32_t a = j & 1u;
-      mbar_wait(smem_u32(&hdr->tmem_empty[a]), ((j >> 1) & 1u) ^ 1u);
+      const uint32_t a = j % (uint32_t)p.nacc;
+      mbar_wait(smem_u32(&hdr->tmem_empty[a]), ((j / (uint32_t)p.nacc) & 1u) ^ 1u);
       tc_fence_after();
       for (int ch = 0; ch < nchunks; ++ch, ++item) {
         const int s = item % p.stages;
@@ -575,13 +593,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const TcGemmParams
         if (lane == 0) {
           const int k0 = ch * p.KC, kc = min(p.KC, p.K - k0);
           const uint32_t a_addr = smem_u32(sA0 + (size_t)s * stage_bytes);
-          const uint32_t w_addr = p.w_stream ? a_addr + (uint32_t)a_stage_bytes
-                                             : smem_u32(sW) + (uint32_t)(k0 / EPC) * w_lbo;
-          const uint32_t d_addr = tmem_base + a * (uint32_t)p.acc_stride;
-          for (int ks = 0; ks < kc / (2 * EPC); ++ks) {
-            const uint64_t adesc = make_smem_desc(a_addr + (uint32_t)(2 * ks) * a_lbo, a_lbo, 128);
-            const uint64_t bdesc = make_smem_desc(w_addr + (uint32_t)(2 * ks) * w_lbo, w_lbo, 128);
-            umma<TOp>(d_addr, adesc, bdesc, idesc, (ch > 0 || ks > 0) ? 1u : 0u);
+          for (int sub = 0; sub < p.nsub; ++sub) {
+            const int c_lo = sub * p.NS;
+            const int ns = min(p.NS, nc - c_lo);
+            if (ns <= 0) break;
+            const uint32_t lbo = (uint32_t)ns * 16u;
+            const uint32_t w_addr = p.w_stream ? a_addr + (uint32_t)a_stage_bytes
+                                               : smem_u32(sW) + (uint32_t)(p.K / EPC) * (uint32_t)c_lo * 16u +
+                                                     (uint32_t)(k0 / EPC) * lbo;
+            const uint32_t d_addr = tmem_base + a * (uint32_t)p.acc_stride + (uint32_t)(sub * p.sub_stride);
+            const uint32_t idesc = make_idesc<TOp>(ns);
+            for (int ks = 0; ks < kc / (2 * EPC); ++ks) {
+              const uint64_t adesc = make_smem_desc(a_addr + (uint32_t)(2 * ks) * a_lbo, a_lbo, 128);
+              const uint64_t bdesc = make_smem_desc(w_addr + (uint32_t)(2 * ks) * lbo, lbo, 128);
+              umma<TOp>(d_addr, adesc, bdesc, idesc, (ch > 0 || ks > 0) ? 1u : 0u);
+            }
           }
           umma_commit(smem_u32(&hdr->empty[s]));
           if (ch == nchunks - 1) umma_commit(smem_u32(&hdr->tmem_full[a]));
@@ -601,8 +627,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const TcGemmParams
       const int p0 = (int)(tile - (long long)b * p.tiles_per_img) * TM;
       const int valid = min(TM, p.HW - p0);
       const long long rowbase = (long long)b * p.HW;
-      const uint32_t a = j & 1u;
-      mbar_wait(smem_u32(&hdr->tmem_full[a]), (j >> 1) & 1u);
+      const uint32_t a = j % (uint32_t)p.nacc;
+      mbar_wait(smem_u32(&hdr->tmem_full[a]), (j / (uint32_t)p.nacc) & 1u);
       tc_fence_after();
       EpiCtx<TY> ec;
       ec.r = p.r; ec.ldr = p.ldr; ec.y = yout; ec.ldy = p.ldy; ec.bias = p.bias;
@@ -610,32 +636,37 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const TcGemmParams
       ec.relu = p.relu; ec.sign = p.acc_sign == 0.f ? 1.f : p.acc_sign;
       ec.o_mode = p.o_mode; ec.b = b; ec.H = p.H; ec.W = p.W; ec.pix0 = p0 + quarter * 32;
       ec.n_valid = p.n_valid > 0 ? p.n_valid : p.N;
-      const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + a * (uint32_t)p.acc_stride;
-      const int n32 = nc >> 5;
-      const bool tail16 = (nc & 31) != 0;
-      float4 rr[8];
-      if (p.o_mode != O_NHWC) {
-        for (int g = 0; g < n32; ++g) epi_group_scatter<TY, 32>(ec, tbase + (uint32_t)(g * 32), n0 + g * 32);
-        if (tail16) epi_group_scatter<TY, 16>(ec, tbase + (uint32_t)(n32 * 32), n0 + n32 * 32);
-        tc_fence_before();
-        mbar_arrive(smem_u32(&hdr->tmem_empty[a]));
-        continue;
-      }
-      if (p.r) { if (n32 > 0) fetch_residual<32>(ec, n0, rr); else fetch_residual<16>(ec, n0, rr); }
-      for (int g = 0; g < n32; ++g) {
-        const int c0 = g * 32;
-        if (p.r) {
-          epi_group<TY, 32, true>(ec, tbase + (uint32_t)c0, n0 + c0, rr);
-          if (g + 1 < n32) fetch_residual<32>(ec, n0 + c0 + 32, rr);
-          else if (tail16) fetch_residual<16>(ec, n0 + c0 + 32, rr);
-        } else {
-          epi_group<TY, 32, false>(ec, tbase + (uint32_t)c0, n0 + c0, rr);
+      for (int sub = 0; sub < p.nsub; ++sub) {
+        const int c_lo = sub * p.NS;
+        const int ns = min(p.NS, nc - c_lo);
+        if (ns <= 0) break;
+        const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + a * (uint32_t)p.acc_stride +
+                               (uint32_t)(sub * p.sub_stride);
+        const int nb = n0 + c_lo;                  // first global column of this sub-chunk
+        const int n32 = ns >> 5;
+        const bool tail16 = (ns & 31) != 0;
+        if (p.o_mode != O_NHWC) {
+          for (int g = 0; g < n32; ++g) epi_group_scatter<TY, 32>(ec, tbase + (uint32_t)(g * 32), nb + g * 32);
+          if (tail16) epi_group_scatter<TY, 16>(ec, tbase + (uint32_t)(n32 * 32), nb + n32 * 32);
+          continue;
         }
-      }
-      if (tail16) {
-        const int c0 = n32 * 32;
-        if (p.r) epi_group<TY, 16, true>(ec, tbase + (uint32_t)c0, n0 + c0, rr);
-        else     epi_group<TY, 16, false>(ec, tbase + (uint32_t)c0, n0 + c0, rr);
+        float4 rr[8];
+        if (p.r) { if (n32 > 0) fetch_residual<32>(ec, nb, rr); else fetch_residual<16>(ec, nb, rr); }
+        for (int g = 0; g < n32; ++g) {
+          const int c0 = g * 32;
+          if (p.r) {
+            epi_group<TY, 32, true>(ec, tbase + (uint32_t)c0, nb + c0, rr);
+            if (g + 1 < n32) fetch_residual<32>(ec, nb + c0 + 32, rr);
+            else if (tail16) fetch_residual<16>(ec, nb + c0 + 32, rr);
+          } else {
+            epi_group<TY, 32, false>(ec, tbase + (uint32_t)c0, nb + c0, rr);
+          }
+        }
+        if (tail16) {
+          const int c0 = n32 * 32;
+          if (p.r) epi_group<TY, 16, true>(ec, tbase + (uint32_t)c0, nb + c0, rr);
+          else     epi_group<TY, 16, false>(ec, tbase + (uint32_t)c0, nb + c0, rr);
+        }
       }
       tc_fence_before();
       mbar_arrive(smem_u32(&hdr->tmem_empty[a]));
@@ -678,38 +709,51 @@ size_t tc_gemm_configure(TcGemmParams& p) {
   p.unr = pp >= TM ? 1 : (TM / pp >= 4 ? 4 : TM / pp);
   if (epc == 8 && p.upl > 2) return 0;
   if (epc == 8 && p.unr > 2) p.unr = 2;                 // register budget: unr * upl * epc floats in flight
-  const size_t a_stage = (size_t)units * (TM + p.a_pad) * 16;
   const size_t fixed = HDR_BYTES + STG_BYTES;
   const size_t budget = 227 * 1024;
-  // (1) CTA-resident weights: fewest N-chunks such that the weight chunk and at least two A stages fit
-  int nc_res = 0;
-  for (int chunks = 1; chunks <= p.N / 16; ++chunks) {
-    int nc = ((p.N + chunks - 1) / chunks + 15) / 16 * 16;
-    if (nc > 256) continue;
-    if (fixed + (size_t)nc * p.K * op_es + 2 * a_stage <= budget) { nc_res = nc; break; }
+  auto round16 = [](int v) { return (v + 15) / 16 * 16; };
+  // (1) CTA-resident weights.  A CTA may own up to 512 output columns as nsub sub-chunks of NS <= 256 (one MMA
+  // each): fewer N-chunks means the A tile is read (and normalised) fewer times.  Fewest chunks wins; the pad row of
+  // the A slabs is dropped when that saves a chunk.
+  int best_chunks = 0, best_pad = p.a_pad, best_ns = 0, best_nsub = 0;
+  for (int chunks = 1; chunks <= p.N / 16 && !best_chunks; ++chunks) {
+    const int nc_cta = round16((p.N + chunks - 1) / chunks);
+    const int nsub = (nc_cta + 255) / 256;
+    const int ns = round16((nc_cta + nsub - 1) / nsub);
+    if (nsub * ((ns + 31) / 32 * 32) > 512) continue;              // TMEM: one accumulator set must fit
+    for (int pad = p.a_pad; pad >= 0 && !best_chunks; --pad) {
+      const size_t a_st = (size_t)units * (TM + pad) * 16;
+      if (fixed + (size_t)ns * nsub * p.K * op_es + 2 * a_st <= budget) {
+        best_chunks = chunks; best_pad = pad; best_ns = ns; best_nsub = nsub;
+      }
+    }
   }
   // (2) streamed weights (3x3 convolutions, wide 1x1 at the low-resolution levels): every stage carries its own
   // K-slice of the weights, so N-chunks can stay 256 wide however long K is
   int nc_str = 0;
-  if (p.K > p.KC || nc_res == 0) {
-    if (p.K > p.KC) {
-      for (int chunks = 1; chunks <= p.N / 16; ++chunks) {
-        int nc = ((p.N + chunks - 1) / chunks + 15) / 16 * 16;
-        if (nc > 256) continue;
-        if (fixed + 2 * (a_stage + (size_t)units * nc * 16) <= budget) { nc_str = nc; break; }
-      }
+  const size_t a_stage_pad = (size_t)units * (TM + p.a_pad) * 16;
+  if (p.K > p.KC) {
+    for (int chunks = 1; chunks <= p.N / 16; ++chunks) {
+      int nc = round16((p.N + chunks - 1) / chunks);
+      if (nc > 256) continue;
+      if (fixed + 2 * (a_stage_pad + (size_t)units * nc * 16) <= budget) { nc_str = nc; break; }
     }
   }
-  const bool stream = nc_str != 0 && (nc_res == 0 || nc_res < std::min(p.N, 128));
-  if (!stream && !nc_res) return 0;
+  const bool stream = nc_str != 0 && (best_chunks == 0 || best_ns * best_nsub < std::min(p.N, 128));
+  if (!stream && !best_chunks) return 0;
   p.w_stream = stream ? 1 : 0;
-  p.NC = stream ? nc_str : nc_res;
+  if (stream) { p.NS = nc_str; p.nsub = 1; }
+  else { p.NS = best_ns; p.nsub = best_nsub; p.a_pad = best_pad; }
+  p.NC = p.NS * p.nsub;
+  const size_t a_stage = (size_t)units * (TM + p.a_pad) * 16;
   const size_t stage_bytes = a_stage + (stream ? (size_t)units * p.NC * 16 : 0);
   const size_t resident = stream ? 0 : (size_t)p.NC * p.K * op_es;
   int stages = (int)((budget - fixed - resident) / stage_bytes);
   p.stages = std::min(stages, MAX_STAGES);
-  p.acc_stride = (p.NC + 31) / 32 * 32;
-  p.tmem_cols = next_pow2_cols(2 * p.acc_stride);
+  p.sub_stride = (p.NS + 31) / 32 * 32;
+  p.acc_stride = p.nsub * p.sub_stride;
+  p.nacc = 2 * p.acc_stride <= 512 ? 2 : 1;
+  p.tmem_cols = next_pow2_cols(p.nacc * p.acc_stride);
   if (p.tmem_cols > 512) return 0;
   return fixed + resident + (size_t)p.stages * stage_bytes;
 }

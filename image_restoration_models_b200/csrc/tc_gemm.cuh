@@ -32,7 +32,8 @@ struct TcGemmParams {
   float acc_sign;                                        // y = r + acc_sign * act(acc + bias)   (0 is treated as +1)
   int w_stream;                                          // filled by configure: weights streamed per K-chunk
   // filled by tc_gemm_configure / launch_gemm_tc
-  int NC, KC, lpp, upl, unr, stages, acc_stride, tmem_cols, tiles_per_img, ntiles;
+  // NC columns per CTA = nsub sub-chunks of NS <= 256 columns (one tcgen05.mma each); nacc accumulator buffers
+  int NC, NS, nsub, sub_stride, nacc, KC, lpp, upl, unr, stages, acc_stride, tmem_cols, tiles_per_img, ntiles;
 };
 
 size_t tc_gemm_configure(TcGemmParams& p);
