@@ -362,16 +362,17 @@ struct EpiCtx {
   int o_mode, b, H, W, pix0, n_valid;
 };
 
-// residual of the column group starting at global column n, fetched ahead of use
+// residual of the column group starting at global column n, fetched ahead of use.  Loads are unconditional (rows past
+// the image are clamped to the warp's last valid row and never stored), so all CPR loads are in flight together.
 template <int NCOLS, typename TY>
 __device__ __forceinline__ void fetch_residual(const EpiCtx<TY>& ec, int n, float4* rr) {
   constexpr int CPR = NCOLS / 4, RPI = 32 / CPR;
   const int rsub = ec.lane / CPR, c4 = (ec.lane % CPR) * 4;     // CPR is a power of two: shifts
+  const int last = ec.rows_valid - 1;                            // >= 0: warps without valid rows skip the epilogue
 #pragma unroll
   for (int it = 0; it < CPR; ++it) {
-    const int row = it * RPI + rsub;
-    rr[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (row < ec.rows_valid) rr[it] = *reinterpret_cast<const float4*>(ec.r + (ec.row0 + row) * ec.ldr + n + c4);
+    const int row = min(it * RPI + rsub, last);
+    rr[it] = *reinterpret_cast<const float4*>(ec.r + (ec.row0 + row) * ec.ldr + n + c4);
   }
 }
 
@@ -388,20 +389,38 @@ __device__ __forceinline__ void epi_group(const EpiCtx<TY>& ec, uint32_t taddr, 
         make_float4(v[4 * jj], v[4 * jj + 1], v[4 * jj + 2], v[4 * jj + 3]);
   __syncwarp();
   const int rsub = ec.lane / CPR, c4 = (ec.lane % CPR) * 4;
-  float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (ec.bias) bb = __ldg(reinterpret_cast<const float4*>(ec.bias + n + c4));
-  TY* ybase = ec.y + (ec.row0 + rsub) * ec.ldy + n + c4;
   const float* sbase = ec.stg + rsub * STG_LD + c4;
+  // straight-line code: all smem reads first (distinct registers), then the arithmetic, then the stores
+  float4 o[CPR];
 #pragma unroll
-  for (int it = 0; it < CPR; ++it) {
-    float4 o = *reinterpret_cast<const float4*>(sbase + it * RPI * STG_LD);
-    o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
-    if (ec.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-    if (HAS_R) {
-      o.x = fmaf(ec.sign, o.x, rr[it].x); o.y = fmaf(ec.sign, o.y, rr[it].y);
-      o.z = fmaf(ec.sign, o.z, rr[it].z); o.w = fmaf(ec.sign, o.w, rr[it].w);
+  for (int it = 0; it < CPR; ++it) o[it] = *reinterpret_cast<const float4*>(sbase + it * RPI * STG_LD);
+  if (ec.bias) {
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(ec.bias + n + c4));
+#pragma unroll
+    for (int it = 0; it < CPR; ++it) { o[it].x += bb.x; o[it].y += bb.y; o[it].z += bb.z; o[it].w += bb.w; }
+  }
+  if (ec.relu) {
+#pragma unroll
+    for (int it = 0; it < CPR; ++it) {
+      o[it].x = fmaxf(o[it].x, 0.f); o[it].y = fmaxf(o[it].y, 0.f); o[it].z = fmaxf(o[it].z, 0.f); o[it].w = fmaxf(o[it].w, 0.f);
     }
-    if (it * RPI + rsub < ec.rows_valid) store_out4<TY>(ybase + (long long)it * RPI * ec.ldy, o);
+  }
+  if (HAS_R) {
+#pragma unroll
+    for (int it = 0; it < CPR; ++it) {
+      o[it].x = fmaf(ec.sign, o[it].x, rr[it].x); o[it].y = fmaf(ec.sign, o[it].y, rr[it].y);
+      o[it].z = fmaf(ec.sign, o[it].z, rr[it].z); o[it].w = fmaf(ec.sign, o[it].w, rr[it].w);
+    }
+  }
+  TY* yrow = ec.y + (ec.row0 + rsub) * ec.ldy + n + c4;
+  const long long step = (long long)RPI * ec.ldy;
+  if (ec.rows_valid >= 32) {              // whole 32-row block inside the image: no per-row predicate
+#pragma unroll
+    for (int it = 0; it < CPR; ++it) store_out4<TY>(yrow + it * step, o[it]);
+  } else {
+#pragma unroll
+    for (int it = 0; it < CPR; ++it)
+      if (it * RPI + rsub < ec.rows_valid) store_out4<TY>(yrow + it * step, o[it]);
   }
   __syncwarp();
 }
@@ -454,7 +473,7 @@ __device__ __forceinline__ void epi_group_scatter(const EpiCtx<TY>& ec, uint32_t
 }
 
 template <typename TA, typename TOp, typename TY, int MODE>
-__global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const TcGemmParams p) {
+__global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const TcGemmParams p) {   // 13 warps are allocated as 16: 128 registers per thread
   constexpr int EPC = 16 / (int)sizeof(TOp);
   extern __shared__ __align__(128) uint8_t smem[];
   Header* hdr = reinterpret_cast<Header*>(smem);
@@ -628,15 +647,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const TcGemmParams
       const int valid = min(TM, p.HW - p0);
       const long long rowbase = (long long)b * p.HW;
       const uint32_t a = j % (uint32_t)p.nacc;
-      mbar_wait(smem_u32(&hdr->tmem_full[a]), (j / (uint32_t)p.nacc) & 1u);
-      tc_fence_after();
       EpiCtx<TY> ec;
       ec.r = p.r; ec.ldr = p.ldr; ec.y = yout; ec.ldy = p.ldy; ec.bias = p.bias;
       ec.row0 = rowbase + p0 + quarter * 32; ec.rows_valid = valid - quarter * 32; ec.lane = lane; ec.stg = mystg;
       ec.relu = p.relu; ec.sign = p.acc_sign == 0.f ? 1.f : p.acc_sign;
       ec.o_mode = p.o_mode; ec.b = b; ec.H = p.H; ec.W = p.W; ec.pix0 = p0 + quarter * 32;
       ec.n_valid = p.n_valid > 0 ? p.n_valid : p.N;
-      for (int sub = 0; sub < p.nsub; ++sub) {
+      // the residual of the tile's first column group does not depend on the MMA: fetch it before waiting
+      float4 rr[8];
+      const int ns0 = min(p.NS, nc);
+      if (p.r && ec.rows_valid > 0 && p.o_mode == O_NHWC) {
+        if (ns0 >= 32) fetch_residual<32>(ec, n0, rr); else fetch_residual<16>(ec, n0, rr);
+      }
+      mbar_wait(smem_u32(&hdr->tmem_full[a]), (j / (uint32_t)p.nacc) & 1u);
+      tc_fence_after();
+      for (int sub = 0; sub < p.nsub && ec.rows_valid > 0; ++sub) {
         const int c_lo = sub * p.NS;
         const int ns = min(p.NS, nc - c_lo);
         if (ns <= 0) break;
@@ -650,8 +675,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const TcGemmParams
           if (tail16) epi_group_scatter<TY, 16>(ec, tbase + (uint32_t)(n32 * 32), nb + n32 * 32);
           continue;
         }
-        float4 rr[8];
-        if (p.r) { if (n32 > 0) fetch_residual<32>(ec, nb, rr); else fetch_residual<16>(ec, nb, rr); }
+        if (p.r && sub > 0) { if (n32 > 0) fetch_residual<32>(ec, nb, rr); else fetch_residual<16>(ec, nb, rr); }
         for (int g = 0; g < n32; ++g) {
           const int c0 = g * 32;
           if (p.r) {

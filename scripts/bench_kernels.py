@@ -54,7 +54,8 @@ def run(name, k1, k2, N, ln, resid, rows, half):
 def main():
     half = "--half" in sys.argv
     rows = 8 * 512 * 512
-    out = [run(*s, rows, half) for s in SHAPES]
+    only = [a.split("=")[1] for a in sys.argv if a.startswith("--only=")]
+    out = [run(*s, rows, half) for s in SHAPES if not only or s[0] in only]
     print(json.dumps({"lib": os.environ.get("IRB200_LIB", "default"), "half": half, "results": out}))
 
 
