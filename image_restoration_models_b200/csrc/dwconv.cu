@@ -21,7 +21,7 @@ namespace {
 // [-8, 8]: |erf error| <= 6.1e-7, |gelu error| <= 2.6e-7 -- three orders of magnitude inside the 1e-3 parity budget.
 __device__ __forceinline__ float gelu_erf(float x) {
   const float ax = fabsf(x) * 0.70710678118654752440f;
-  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));   // MUFU.RCP (the IEEE __frcp_rn is a subroutine call)
   const float poly = t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 1.061405429f, -1.453152027f), 1.421413741f), -0.284496736f),
                               0.254829592f);
   const float y = fmaf(-poly, __expf(-ax * ax), 1.0f);          // erf(|x| / sqrt 2)
@@ -64,7 +64,8 @@ struct DwGeom { int cvb, xb, rows; };   // channel vectors per block, x-tiles pe
 template <typename TI, typename TO, int WT, bool GATE>
 __global__ void __launch_bounds__(256, 2) dw_roll_kernel(const DwParams p, const DwGeom g) {
   constexpr int NS = GATE ? 2 : 1;
-  extern __shared__ float4 wsm[];                      // [NS][9][cvb]
+  constexpr int WS = NS * 9 + 1;                       // float4 per thread slot (odd -> conflict-free LDS.128)
+  extern __shared__ float4 wsm[];                      // [cvb][WS]: a thread's 9 (18) tap vectors are contiguous
   const TI* __restrict__ in = reinterpret_cast<const TI*>(p.in);
   TO* __restrict__ out = reinterpret_cast<TO*>(p.out);
   const int tid = threadIdx.x;
@@ -76,7 +77,7 @@ __global__ void __launch_bounds__(256, 2) dw_roll_kernel(const DwParams p, const
     const int cvl = idx % g.cvb, tap = (idx / g.cvb) % 9, set = idx / (9 * g.cvb);
     float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
     if (cvl < ncv) w = *reinterpret_cast<const float4*>(p.w + tap * p.Cw + set * p.gate_off + (cv0 + cvl) * 4);
-    wsm[idx] = w;
+    wsm[cvl * WS + set * 9 + tap] = w;
   }
   __syncthreads();
 
@@ -87,7 +88,21 @@ __global__ void __launch_bounds__(256, 2) dw_roll_kernel(const DwParams p, const
   const int b = blockIdx.z / nbands, band = blockIdx.z - b * nbands;
   const int y0 = band * g.rows, y1 = min(p.H, y0 + g.rows);
   const int c = (cv0 + cvl) * 4;
-  const long long img = (long long)b * p.H * p.W;
+  const float4* __restrict__ wq = wsm + cvl * WS;
+
+  // everything that does not change from row to row is computed once: clamped column offsets (zero padding is
+  // applied by masking the two edge columns), the row pitch, the output offsets
+  int coff[WT + 2];
+  bool cmask[WT + 2];
+#pragma unroll
+  for (int i = 0; i < WT + 2; ++i) {
+    const int x = x0 - 1 + i;
+    cmask[i] = x >= 0 && x < p.W;
+    coff[i] = min(max(x, 0), p.W - 1) * p.ldi;
+  }
+  const long long in_pitch = (long long)p.W * p.ldi, out_pitch = (long long)p.W * p.ldo;
+  const TI* rowp = in + ((long long)b * p.H + (y0 - 1)) * in_pitch + c;
+  TO* orow = out + ((long long)b * p.H + (y0 - 1)) * out_pitch + (long long)x0 * p.ldo + c;
 
   float4 bias[NS];
 #pragma unroll
@@ -102,26 +117,20 @@ __global__ void __launch_bounds__(256, 2) dw_roll_kernel(const DwParams p, const
 #pragma unroll
       for (int i = 0; i < WT; ++i) acc[s][r][i] = bias[s];
 
-  for (int yy = y0 - 1; yy <= y1; ++yy) {
+  for (int yy = y0 - 1; yy <= y1; ++yy, rowp += in_pitch, orow += out_pitch) {
     if (yy >= 0 && yy < p.H) {
-      float4 v[NS][WT + 2];
       typename Raw4<TI>::type raw[NS][WT + 2];
-      const TI* rowp = in + (img + (long long)yy * p.W) * p.ldi + c;
+#pragma unroll
+      for (int s = 0; s < NS; ++s)
+#pragma unroll
+        for (int i = 0; i < WT + 2; ++i) raw[s][i] = ldraw<TI>(rowp + coff[i] + s * p.gate_off);
+      float4 v[NS][WT + 2];
 #pragma unroll
       for (int s = 0; s < NS; ++s)
 #pragma unroll
         for (int i = 0; i < WT + 2; ++i) {
-          const int x = min(max(x0 - 1 + i, 0), p.W - 1);          // clamped: zero padding applied below
-          raw[s][i] = ldraw<TI>(rowp + (long long)x * p.ldi + s * p.gate_off);
-        }
-#pragma unroll
-      for (int s = 0; s < NS; ++s)
-#pragma unroll
-        for (int i = 0; i < WT + 2; ++i) {
-          const int x = x0 - 1 + i;
           const float4 t = cvt4(raw[s][i]);
-          const bool in_img = x >= 0 && x < p.W;
-          v[s][i] = make_float4(in_img ? t.x : 0.f, in_img ? t.y : 0.f, in_img ? t.z : 0.f, in_img ? t.w : 0.f);
+          v[s][i] = cmask[i] ? t : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       // input row yy feeds output rows yy-1 (tap row 2), yy (tap row 1), yy+1 (tap row 0)
 #pragma unroll
@@ -130,14 +139,13 @@ __global__ void __launch_bounds__(256, 2) dw_roll_kernel(const DwParams p, const
         for (int r = 0; r < 3; ++r)
 #pragma unroll
           for (int dx = 0; dx < 3; ++dx) {
-            const float4 w = wsm[(s * 9 + (2 - r) * 3 + dx) * g.cvb + cvl];
+            const float4 w = wq[s * 9 + (2 - r) * 3 + dx];
 #pragma unroll
             for (int i = 0; i < WT; ++i) fma4(acc[s][r][i], w, v[s][i + dx]);
           }
     }
-    const int yo = yy - 1;
-    if (yo >= y0 && yo < y1) {
-      TO* orow = out + (img + (long long)yo * p.W) * p.ldo + c;
+    if (yy - 1 >= y0) {                     // output row yy-1 (orow points at row yy; the store steps one pitch back)
+      TO* o_ = orow - out_pitch;
 #pragma unroll
       for (int i = 0; i < WT; ++i) {
         if (x0 + i < p.W) {
@@ -147,7 +155,7 @@ __global__ void __launch_bounds__(256, 2) dw_roll_kernel(const DwParams p, const
             o.x = gelu_erf(o.x) * gt.x; o.y = gelu_erf(o.y) * gt.y;
             o.z = gelu_erf(o.z) * gt.z; o.w = gelu_erf(o.w) * gt.w;
           }
-          st4<TO>(orow + (long long)(x0 + i) * p.ldo, o);
+          st4<TO>(o_ + (long long)i * p.ldo, o);
         }
       }
     }
@@ -177,7 +185,7 @@ int launch_typed(const DwParams& p, cudaStream_t s) {
   g.rows = 16;
   const int wt = p.gate ? 2 : 4;
   dim3 grid(cdiv(cv, g.cvb), cdiv(p.W, g.xb * wt), p.B * cdiv(p.H, g.rows));
-  const size_t smem = (size_t)(p.gate ? 2 : 1) * 9 * g.cvb * sizeof(float4);
+  const size_t smem = (size_t)((p.gate ? 2 : 1) * 9 + 1) * g.cvb * sizeof(float4);
   if (p.gate) dw_roll_kernel<TI, TO, 2, true><<<grid, 256, smem, s>>>(p, g);
   else        dw_roll_kernel<TI, TO, 4, false><<<grid, 256, smem, s>>>(p, g);
   IRB_LAUNCH_CHECK();
