@@ -11,6 +11,8 @@
 //   * the 3x3 weights of the block's channel slice live in shared memory.
 #include "common.cuh"
 
+#include <type_traits>
+
 namespace irb {
 
 namespace {
@@ -117,7 +119,11 @@ __global__ void __launch_bounds__(256, 2) dw_roll_kernel(const DwParams p, const
 #pragma unroll
       for (int i = 0; i < WT; ++i) acc[s][r][i] = bias[s];
 
-  for (int yy = y0 - 1; yy <= y1; ++yy, rowp += in_pitch, orow += out_pitch) {
+  // One step consumes input row yy.  The three accumulator rows rotate roles; the rotation is resolved at compile
+  // time (K = step index mod 3: row (K+0)%3 completes output yy-1, (K+1)%3 is output yy, (K+2)%3 is output yy+1),
+  // so no register moves are needed between rows.
+  auto step = [&](auto kc, int yy) {
+    constexpr int K = decltype(kc)::value;
     if (yy >= 0 && yy < p.H) {
       typename Raw4<TI>::type raw[NS][WT + 2];
 #pragma unroll
@@ -141,17 +147,17 @@ __global__ void __launch_bounds__(256, 2) dw_roll_kernel(const DwParams p, const
           for (int dx = 0; dx < 3; ++dx) {
             const float4 w = wq[s * 9 + (2 - r) * 3 + dx];
 #pragma unroll
-            for (int i = 0; i < WT; ++i) fma4(acc[s][r][i], w, v[s][i + dx]);
+            for (int i = 0; i < WT; ++i) fma4(acc[s][(K + r) % 3][i], w, v[s][i + dx]);
           }
     }
-    if (yy - 1 >= y0) {                     // output row yy-1 (orow points at row yy; the store steps one pitch back)
+    if (yy - 1 >= y0) {                     // output row yy-1 is complete (orow points at row yy)
       TO* o_ = orow - out_pitch;
 #pragma unroll
       for (int i = 0; i < WT; ++i) {
         if (x0 + i < p.W) {
-          float4 o = acc[0][0][i];
+          float4 o = acc[0][K % 3][i];
           if (GATE) {
-            const float4 gt = acc[NS - 1][0][i];
+            const float4 gt = acc[NS - 1][K % 3][i];
             o.x = gelu_erf(o.x) * gt.x; o.y = gelu_erf(o.y) * gt.y;
             o.z = gelu_erf(o.z) * gt.z; o.w = gelu_erf(o.w) * gt.w;
           }
@@ -162,11 +168,14 @@ __global__ void __launch_bounds__(256, 2) dw_roll_kernel(const DwParams p, const
 #pragma unroll
     for (int s = 0; s < NS; ++s)
 #pragma unroll
-      for (int i = 0; i < WT; ++i) {
-        acc[s][0][i] = acc[s][1][i];
-        acc[s][1][i] = acc[s][2][i];
-        acc[s][2][i] = bias[s];
-      }
+      for (int i = 0; i < WT; ++i) acc[s][K % 3][i] = bias[s];      // becomes output row yy+2
+    rowp += in_pitch;
+    orow += out_pitch;
+  };
+  for (int yy = y0 - 1; yy <= y1; yy += 3) {
+    step(std::integral_constant<int, 0>{}, yy);
+    if (yy + 1 <= y1) step(std::integral_constant<int, 1>{}, yy + 1);
+    if (yy + 2 <= y1) step(std::integral_constant<int, 2>{}, yy + 2);
   }
 }
 

@@ -366,10 +366,23 @@ __global__ void __launch_bounds__(256) fold_kernel(const FoldParams p) {
   float* nk = nq + ch;           // [ch]
   const int tid = threadIdx.x;
   const long long pb = ((long long)b * p.heads + head) * p.nparts;
-  for (int e = tid; e < ch * ch; e += blockDim.x) {
-    float s = 0.f;
-    for (int part = 0; part < p.nparts; ++part) s += p.s_part[(pb + part) * ch * ch + e];
-    A[e] = s;
+  // deterministic reduction of the pixel-slice partials (fixed order), 16-byte loads, 8 slices in flight per thread
+  for (int e = tid * 4; e < ch * ch; e += blockDim.x * 4) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* src = p.s_part + pb * ch * ch + e;
+    int part = 0;
+    for (; part + 8 <= p.nparts; part += 8) {
+      float4 t[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) t[u] = __ldg(reinterpret_cast<const float4*>(src + (long long)(part + u) * ch * ch));
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { s.x += t[u].x; s.y += t[u].y; s.z += t[u].z; s.w += t[u].w; }
+    }
+    for (; part < p.nparts; ++part) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(src + (long long)part * ch * ch));
+      s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+    }
+    *reinterpret_cast<float4*>(A + e) = s;
   }
   for (int e = tid; e < 2 * ch; e += blockDim.x) {
     float s = 0.f;
@@ -400,8 +413,11 @@ __global__ void __launch_bounds__(256) fold_kernel(const FoldParams p) {
     for (int j = lane; j < ch; j += 32) A[i * ch + j] *= inv;
   }
   __syncthreads();
+  // this CTA's slice of the output rows (grid.z row blocks share the softmax work, split the C x ch products)
   float* we = p.w_eff + (long long)b * p.w_eff_bstride;
-  for (int e = tid; e < p.C * ch; e += blockDim.x) {
+  const int rows_per = (p.C + gridDim.z - 1) / gridDim.z;
+  const int n_lo = blockIdx.z * rows_per, n_hi = min(p.C, n_lo + rows_per);
+  for (int e = n_lo * ch + tid; e < n_hi * ch; e += blockDim.x) {
     const int n = e / ch, j = e - n * ch;
     const float* wrow = p.w_proj + (long long)n * p.C + head * ch;
     float s = 0.f;
@@ -425,7 +441,7 @@ int launch_fold(const FoldParams& p, cudaStream_t s) {
   const size_t smem = (size_t)(ch * ch + 2 * ch) * sizeof(float);
   IRB_REQUIRE(smem <= 48 * 1024 + 0u || ch <= 128, "fold: head dim too large");
   if (smem > 48 * 1024) IRB_CUDA(cudaFuncSetAttribute(fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid(p.heads, p.B);
+  dim3 grid(p.heads, p.B, p.heads * p.B >= 64 ? 1 : 4);
   ProfScope prof(TAG_FOLD, 4.0 * (double)p.B * p.C * p.C, 2.0 * (double)p.B * p.C * p.C * ch, s);
   fold_kernel<<<grid, 256, smem, s>>>(p);
   IRB_LAUNCH_CHECK();

@@ -425,6 +425,52 @@ __device__ __forceinline__ void epi_group(const EpiCtx<TY>& ec, uint32_t taddr, 
   __syncwarp();
 }
 
+// fp16 output, 64 columns at a time: the accumulators are converted to half BEFORE the transpose, so a staged row is
+// 128 bytes and every shared-memory read / global store moves 8 channels (half the instructions of the fp32 path).
+__device__ __forceinline__ void epi_group_h64(const EpiCtx<__half>& ec, uint32_t taddr, int n) {
+  uint4* srow = reinterpret_cast<uint4*>(ec.stg + ec.lane * STG_LD);
+  __syncwarp();
+#pragma unroll
+  for (int hf = 0; hf < 2; ++hf) {            // two 32-column halves, one register set
+    float v[32];
+    tmem_ld32(taddr + hf * 32, v);
+    tmem_ld_wait();
+    if (ec.bias) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] += __ldg(ec.bias + n + hf * 32 + j);
+    }
+    if (ec.relu) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+    }
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      uint4 t;
+      __half2* h = reinterpret_cast<__half2*>(&t);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(v[8 * jj + 2 * e], v[8 * jj + 2 * e + 1]);
+      srow[hf * 4 + jj] = t;
+    }
+  }
+  __syncwarp();
+  const int rsub = ec.lane >> 3, c8 = (ec.lane & 7) * 8;       // 8 chunks of 8 halfs per row, 4 rows per iteration
+  const float* sbase = ec.stg + rsub * STG_LD + (ec.lane & 7) * 4;
+  uint4 o[8];
+#pragma unroll
+  for (int it = 0; it < 8; ++it) o[it] = *reinterpret_cast<const uint4*>(sbase + it * 4 * STG_LD);
+  __half* yrow = ec.y + (ec.row0 + rsub) * ec.ldy + n + c8;
+  const long long step = 4LL * ec.ldy;
+  if (ec.rows_valid >= 32) {
+#pragma unroll
+    for (int it = 0; it < 8; ++it) *reinterpret_cast<uint4*>(yrow + it * step) = o[it];
+  } else {
+#pragma unroll
+    for (int it = 0; it < 8; ++it)
+      if (it * 4 + rsub < ec.rows_valid) *reinterpret_cast<uint4*>(yrow + it * step) = o[it];
+  }
+  __syncwarp();
+}
+
 // Same drain, but each conv output channel lands at its PixelUnshuffle / PixelShuffle position
 // (restormer.py:176,186).  The scattered 4-byte stores cost little: these convolutions have K = 9*Cin.
 template <typename TY, int NCOLS>
@@ -675,8 +721,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const TcGemmParams
           if (tail16) epi_group_scatter<TY, 16>(ec, tbase + (uint32_t)(n32 * 32), nb + n32 * 32);
           continue;
         }
+        int g_first = 0;
+        if constexpr (sizeof(TY) == 2) {
+          if (!p.r && p.ldy % 8 == 0) {         // 64-column fp16 groups; the remainder goes through the generic path
+            const int n64 = ns >> 6;
+            for (int g = 0; g < n64; ++g) epi_group_h64(ec, tbase + (uint32_t)(g * 64), nb + g * 64);
+            g_first = n64 * 2;
+          }
+        }
         if (p.r && sub > 0) { if (n32 > 0) fetch_residual<32>(ec, nb, rr); else fetch_residual<16>(ec, nb, rr); }
-        for (int g = 0; g < n32; ++g) {
+        for (int g = g_first; g < n32; ++g) {
           const int c0 = g * 32;
           if (p.r) {
             epi_group<TY, 32, true>(ec, tbase + (uint32_t)c0, nb + c0, rr);
