@@ -87,8 +87,13 @@ class CudaBackend:
         return out
 
 
+def _run_local(model, input_img, device, patch_size, patch_overlap, pad, tile_batch):
+    """Single-rank restore of one image even when a process group exists (frames partitioned over ranks)."""
+    return run_model_inference(model, input_img, device, patch_size, patch_overlap, pad, tile_batch, solo=True)[0]
+
+
 def run_model_inference(model, input_img: np.ndarray, device, patch_size=None, patch_overlap: int = 32, pad: bool = True,
-                        tile_batch: int = 16, backend=None, group=None):
+                        tile_batch: int = 16, backend=None, group=None, solo: bool = False):
     """Returns (restored image with the input's dtype, inference time in ms), like the reference.
 
     pad=True is the Restormer path (reflect-pad each tile to a multiple of 8, crop the prediction back);
@@ -120,7 +125,7 @@ def run_model_inference(model, input_img: np.ndarray, device, patch_size=None, p
         scale, lo, hi_ = mx, mn, mx
 
     import torch.distributed as dist
-    world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+    world = dist.get_world_size(group) if (not solo and dist.is_available() and dist.is_initialized()) else 1
     rank = dist.get_rank(group) if world > 1 else 0
     lo_t, hi_t = partition(T, world)[rank]
 
