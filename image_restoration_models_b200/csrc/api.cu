@@ -229,11 +229,14 @@ int ir_test_conv1x1(int engine, const void* a1v, int lda1, int k1, const void* a
   cudaStream_t s = (cudaStream_t)stream;
   const int K = k1 + k2;
   const long long rows = (long long)B * HW;
-  const size_t need = ((size_t)N * K + (size_t)rows * K) * sizeof(float);
+  const bool tma = engine == 3;              // the TMA-fed kernel only (error if the shape is not supported)
+  const int Kw = tma ? tma_gemm_kpad(K, op_half != 0) : K;
+  const size_t need = ((size_t)N * Kw + (size_t)rows * K) * sizeof(float);
   if (scratch_bytes < need) { set_error("scratch too small"); return IR_ERR_WORKSPACE; }
   float* wp = (float*)scratch;
-  float* xhat = wp + (size_t)N * K;
-  PackMat pm{w_rowmajor, wp, 0, 0, N, N, 1, K, K, nullptr, engine != ENGINE_TC ? 0 : op_half ? 2 : 1};
+  float* xhat = wp + (size_t)N * Kw;
+  PackMat pm{w_rowmajor, wp, 0, 0, N, N, 1, K, Kw, nullptr,
+             tma ? (op_half ? 4 : 3) : engine != ENGINE_TC ? 0 : op_half ? 2 : 1};
   IRB_TRY(launch_pack_mat(pm, s));
   if (engine == ENGINE_SIMT) {
     IRB_REQUIRE(!a_half && !op_half && !y_half, "test_conv1x1: the CUDA-core engine is fp32 only");
@@ -249,6 +252,11 @@ int ir_test_conv1x1(int engine, const void* a1v, int lda1, int k1, const void* a
   t.w = wp; t.N = N; t.K = K; t.bias = bias; t.ln_mode = ln_mode; t.ln_w = ln_w; t.ln_b = ln_b;
   t.r = r; t.ldr = ldr; t.y = y; t.ldy = ldy; t.a_pad = a_pad;
   t.a_half = a_half; t.op_half = op_half; t.y_half = y_half;
+  if (tma) {
+    const int st = launch_gemm_tma(t, s);
+    if (st == IR_UNSUPPORTED_SHAPE) { set_error("unsupported: shape not handled by the TMA-fed kernel"); return IR_ERR_INVALID; }
+    return st;
+  }
   if (ln_mode != LN_NONE) {
     TcGemmParams probe = t;
     if (tc_gemm_configure(probe) == 0) {

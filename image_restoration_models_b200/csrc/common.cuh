@@ -89,6 +89,8 @@ struct DwParams {
   int gate_off;
   int tag;
   int in_half, out_half;                  // element types of in / out (0 = fp32, 1 = fp16); in/out are then __half*
+  int round_tf32;                         // fp32 output rounded to tf32 (it is read by a tensor-core kernel without a pass
+                                          // through registers, and the hardware would otherwise truncate)
 };
 
 struct GramParams {
@@ -104,7 +106,8 @@ struct FoldParams {
   int B, C, heads, nparts;
   const float* temperature;               // [heads]
   const float* w_proj;                    // [C][C] row-major (project_out)
-  float* w_eff; long long w_eff_bstride;  // [B][C][C] row-major (fmt 0), [B][C/4][C][4] tf32 (fmt 1), [B][C/8][C][8] fp16 (fmt 2);
+  float* w_eff; long long w_eff_bstride;  // [B][C][C] row-major (fmt 0), [B][C/4][C][4] tf32 (fmt 1), [B][C/8][C][8] fp16 (fmt 2),
+                                          // SWIZZLE_128B images (fmt 3 tf32 / 4 fp16, K padded: see PackMat::fmt);
                                           // stride in elements of the output type
   int fmt;
 };
@@ -142,7 +145,8 @@ struct PackMat {
   int k_src, k_dst;                        // logical / padded reduction length (kind 0: zero-pad; kind 1: k_src = 9*cin)
   const float* row_scale;                  // optional per-source-row scale (BatchNorm folding)
   int fmt;                                 // 0: dst[n][k] fp32;  1: dst[k/4][n][k%4] rounded to tf32;  2: dst[k/8][n][k%8] fp16
-                                           // (1, 2: tcgen05 operand layouts)
+                                           // (1, 2: tcgen05 no-swizzle operand layouts); 3 / 4: tf32 / fp16 in the
+                                           // SWIZZLE_128B image of tma_gemm.cu (k_dst a multiple of 32 / 64)
 };
 int launch_pack_mat(const PackMat& p, cudaStream_t s);
 // dst[t][map(c)] = src[c][t]  (depthwise 3x3 [C][1][3][3] -> [9][Cdst])

@@ -30,6 +30,12 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + copysignf(y, x));
 }
 
+__device__ __forceinline__ float rna_tf32(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+
 // Raw 4-channel vectors: loads are issued unconditionally (clamped address) and converted / masked afterwards.
 // A load placed under a condition, or with its conversion inside the condition, gets funnelled through one
 // register set by the compiler and the loads of a row then serialise (measured: 3x slower).
@@ -161,6 +167,7 @@ __global__ void __launch_bounds__(256, 2) dw_roll_kernel(const DwParams p, const
             o.x = gelu_erf(o.x) * gt.x; o.y = gelu_erf(o.y) * gt.y;
             o.z = gelu_erf(o.z) * gt.z; o.w = gelu_erf(o.w) * gt.w;
           }
+          if (std::is_same<TO, float>::value && p.round_tf32) { o.x = rna_tf32(o.x); o.y = rna_tf32(o.y); o.z = rna_tf32(o.z); o.w = rna_tf32(o.w); }
           st4<TO>(o_ + (long long)i * p.ldo, o);
         }
       }

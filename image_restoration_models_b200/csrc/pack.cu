@@ -34,6 +34,14 @@ __global__ void pack_mat_kernel(const PackMat p) {
       p.dst[((long long)(k >> 2) * n_dst + n) * 4 + (k & 3)] = __uint_as_float(u);
     } else if (p.fmt == 2) {
       reinterpret_cast<__half*>(p.dst)[((long long)(k >> 3) * n_dst + n) * 8 + (k & 7)] = __float2half_rn(v);
+    } else if (p.fmt == 3) {          // [k/32][n][128 B], 16-byte chunk c of row n stored at chunk c ^ (n & 7)
+      uint32_t u;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+      const int kb = k >> 5, c = (k & 31) >> 2;
+      p.dst[((long long)kb * n_dst + n) * 32 + ((c ^ (n & 7)) << 2) + (k & 3)] = __uint_as_float(u);
+    } else if (p.fmt == 4) {          // [k/64][n][128 B] fp16, same swizzle
+      const int kb = k >> 6, c = (k & 63) >> 3;
+      reinterpret_cast<__half*>(p.dst)[((long long)kb * n_dst + n) * 64 + ((c ^ (n & 7)) << 3) + (k & 7)] = __float2half_rn(v);
     } else {
       p.dst[idx] = v;
     }

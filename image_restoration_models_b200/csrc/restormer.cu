@@ -52,7 +52,10 @@ struct Builder {
   Builder(std::vector<PackOp>& o, int e) : ops(o), engine(e) {}
   bool half() const { return engine == ENGINE_TC_HALF; }
   bool tc(int K, int N) const { return engine != ENGINE_SIMT && tc_gemm_supported(K, N, half()); }
-  int fmt(bool tc_layer) const { return !tc_layer ? 0 : half() ? 2 : 1; }
+  bool tma(int K, int N, bool ln, bool has_r, bool y_half) const {
+    return engine != ENGINE_SIMT && tma_gemm_shape_supported(K, N, half(), ln, has_r, y_half);
+  }
+  int fmt(bool tc_layer, bool tma_layer = false) const { return !tc_layer ? 0 : tma_layer ? (half() ? 4 : 3) : half() ? 2 : 1; }
   long long alloc(long long n) { const long long o = off; off += (n + 63) / 64 * 64; return o; }
 };
 
@@ -69,9 +72,10 @@ static void plan_block(Builder& bl, BlockPlan& bp, int C, int heads, float ffn, 
     dst = bl.alloc((long long)dst_half * halves);
     bl.ops.push_back(PackOp{PackOp::VEC, bl.pidx++, dst, src_half, dst_half, halves, 0, 0, 0, 0});
   };
-  auto mat = [&](long long& dst, int n_src_half, int n_dst_half, int halves, int k_src, int k_dst, bool tc) {
+  auto mat = [&](long long& dst, int n_src_half, int n_dst_half, int halves, int k_src, int k_dst, bool tc, bool tma = false) {
+    if (tma) k_dst = tma_gemm_kpad(k_dst, bl.half());
     dst = bl.alloc((long long)n_dst_half * halves * k_dst);
-    bl.ops.push_back(PackOp{PackOp::MAT1, bl.pidx++, dst, n_src_half, n_dst_half, halves, k_src, k_dst, 0, bl.fmt(tc)});
+    bl.ops.push_back(PackOp{PackOp::MAT1, bl.pidx++, dst, n_src_half, n_dst_half, halves, k_src, k_dst, 0, bl.fmt(tc, tma)});
   };
   auto dw = [&](long long& dst, int src_half, int dst_half, int halves) {
     dst = bl.alloc(9LL * dst_half * halves);
@@ -84,10 +88,16 @@ static void plan_block(Builder& bl, BlockPlan& bp, int C, int heads, float ffn, 
   bp.tc_attn = bl.tc(C, C);
   bp.tc_pin = bl.tc(C, 2 * bp.hp);
   bp.tc_pout = bl.tc(bp.hp, C);
+  // the TMA-fed kernel takes the layers whose A tile is shared by at most two N-chunks (the high-resolution levels)
+  bp.tma_qkv = bp.tc_qkv && bl.tma(C, 3 * C, true, false, bl.half());
+  bp.tma_attn = bp.tc_attn && bl.tma(C, C, false, true, false);
+  bp.tma_pin = bp.tc_pin && bl.tma(C, 2 * bp.hp, true, false, bl.half());
+  bp.tma_pout = bp.tc_pout && bl.tma(bp.hp, C, false, true, false);
+  bp.kp_attn = bp.tma_attn ? tma_gemm_kpad(C, bl.half()) : C;
   vec(bp.ln1_w, C);
   if (ln_bias) vec(bp.ln1_b, C);
   vec(bp.temp, heads);
-  mat(bp.qkv_w, 3 * C, 3 * C, 1, C, C, bp.tc_qkv);
+  mat(bp.qkv_w, 3 * C, 3 * C, 1, C, C, bp.tc_qkv, bp.tma_qkv);
   if (bias) vec(bp.qkv_b, 3 * C);
   dw(bp.qkvdw_w, 3 * C, 3 * C, 1);
   if (bias) vec(bp.qkvdw_b, 3 * C);
@@ -95,11 +105,11 @@ static void plan_block(Builder& bl, BlockPlan& bp, int C, int heads, float ffn, 
   if (bias) vec(bp.proj_b, C);
   vec(bp.ln2_w, C);
   if (ln_bias) vec(bp.ln2_b, C);
-  mat(bp.pin_w, bp.h, bp.hp, 2, C, C, bp.tc_pin);
+  mat(bp.pin_w, bp.h, bp.hp, 2, C, C, bp.tc_pin, bp.tma_pin);
   if (bias) vec_split(bp.pin_b, bp.h, bp.hp, 2);
   dw(bp.ffdw_w, bp.h, bp.hp, 2);
   if (bias) vec_split(bp.ffdw_b, bp.h, bp.hp, 2);
-  mat(bp.pout_w, C, C, 1, bp.h, bp.hp, bp.tc_pout);
+  mat(bp.pout_w, C, C, 1, bp.h, bp.hp, bp.tc_pout, bp.tma_pout);
   if (bias) vec(bp.pout_b, C);
 }
 
@@ -259,7 +269,7 @@ void block_scratch_need(BlockScratchNeed& n, const BlockPlan& bp, int B, int H, 
   const int parts = gram_parts(B, bp.heads, H * W);
   n.s_part = std::max(n.s_part, (long long)B * bp.heads * parts * ch * ch);
   n.n_part = std::max(n.n_part, (long long)B * bp.heads * parts * 2 * ch);
-  n.w_eff = std::max(n.w_eff, (long long)B * bp.C * bp.C);
+  n.w_eff = std::max(n.w_eff, (long long)B * bp.C * bp.kp_attn);
   if (bp.C > 128) n.xhat = std::max(n.xhat, P * bp.C);
   n.es = bp.half ? 2 : 4;
 }
@@ -328,7 +338,8 @@ size_t restormer_workspace_bytes(const RestormerPlan& pl, int B, int H, int W) {
 // -----------------------------------------------------------------------------------------------
 // Element types in half mode: a_half / y_half say whether the A source / the output are fp16 buffers (the
 // GemmParams pointers are then reinterpreted); weights were packed as fp16 operands at plan time.
-static int run_1x1(const GemmParams& g, bool tc, bool half, bool a_half, bool y_half, void* xhat, cudaStream_t s) {
+static int run_1x1(const GemmParams& g, bool tc, bool half, bool a_half, bool y_half, void* xhat, cudaStream_t s,
+                   bool tma = false) {
   if (!tc) return launch_gemm_simt(g, s);
   TcGemmParams t{};
   t.a1 = g.a1; t.lda1 = g.lda1; t.k1 = g.k1; t.a2 = g.a2; t.lda2 = g.lda2; t.k2 = g.k2;
@@ -337,6 +348,12 @@ static int run_1x1(const GemmParams& g, bool tc, bool half, bool a_half, bool y_
   t.ln_mode = g.ln_mode; t.ln_w = g.ln_w; t.ln_b = g.ln_b;
   t.r = g.r; t.ldr = g.ldr; t.y = g.y; t.ldy = g.ldy; t.tag = g.tag; t.a_pad = 1;
   t.a_half = a_half; t.op_half = half; t.y_half = y_half;
+  if (tma) {
+    // the layer's weights were packed for the TMA-fed kernel at plan time; the plan only selects shapes it supports
+    const int st = launch_gemm_tma(t, s);
+    if (st == IR_UNSUPPORTED_SHAPE) { set_error("internal: layer planned for the TMA kernel is not launchable (alignment)"); return IR_ERR_INVALID; }
+    return st;
+  }
   if (g.ln_mode != LN_NONE) {
     TcGemmParams probe = t;
     if (tc_gemm_configure(probe) == 0) {
@@ -368,7 +385,7 @@ int run_block(const BlockPlan& bp, const float* packed, const float* x_in, float
   g.ln_mode = ln; g.ln_w = P(bp.ln1_w); g.ln_b = P(bp.ln1_b);
   g.relu = 0; g.r = nullptr; g.ldr = 0; g.acc_sign = 1.f;
   g.y = (float*)bs.qkv; g.ldy = 3 * C; g.o_mode = O_NHWC; g.tag = TAG_LN_QKV;
-  IRB_TRY(run_1x1(g, bp.tc_qkv, hf, false, hf, bs.xhat, s));
+  IRB_TRY(run_1x1(g, bp.tc_qkv, hf, false, hf, bs.xhat, s, bp.tma_qkv));
 
   // (2) depthwise 3x3 over the 3C channels (restormer.py:114 qkv_dwconv)
   DwParams dwp{};
@@ -376,6 +393,7 @@ int run_block(const BlockPlan& bp, const float* packed, const float* x_in, float
   dwp.in_half = hf; dwp.out_half = hf;
   dwp.w = P(bp.qkvdw_w); dwp.bias = P(bp.qkvdw_b); dwp.Cw = 3 * C;
   dwp.B = B; dwp.H = H; dwp.W = W; dwp.C = 3 * C; dwp.gate = 0; dwp.gate_off = 0; dwp.tag = TAG_DW_QKV;
+  dwp.round_tf32 = bp.tma_attn && !hf;     // v is read by the tensor core straight from the TMA box
   IRB_TRY(bp.ref_kernels ? launch_dwconv_ref(dwp, s) : launch_dwconv(dwp, s));
 
   // (3) Gram q.k^T and row norms per (image, head) (restormer.py:121-124), split over pixel slices
@@ -389,18 +407,18 @@ int run_block(const BlockPlan& bp, const float* packed, const float* x_in, float
   // (4) normalise, temperature, softmax; fold project_out into a per-image C x C matrix (:124-131)
   FoldParams fp{};
   fp.s_part = bs.s_part; fp.n_part = bs.n_part; fp.B = B; fp.C = C; fp.heads = bp.heads; fp.nparts = gp.nparts;
-  fp.temperature = P(bp.temp); fp.w_proj = P(bp.proj_w); fp.w_eff = (float*)bs.w_eff; fp.w_eff_bstride = (long long)C * C;
-  fp.fmt = !bp.tc_attn ? 0 : hf ? 2 : 1;
+  fp.temperature = P(bp.temp); fp.w_proj = P(bp.proj_w); fp.w_eff = (float*)bs.w_eff; fp.w_eff_bstride = (long long)C * bp.kp_attn;
+  fp.fmt = !bp.tc_attn ? 0 : bp.tma_attn ? (hf ? 4 : 3) : hf ? 2 : 1;
   IRB_TRY(launch_fold(fp, s));
 
   // (5) x_out = x_in + W_eff[b] . v  (+ project_out bias)   (:127-131, :147)
   g = GemmParams{};
   g.a1 = (const float*)((const char*)bs.qkv_dw + (size_t)2 * C * es); g.lda1 = 3 * C; g.k1 = C; g.a_mode = A_PLAIN;
   g.B = B; g.H = H; g.W = W;
-  g.w = (const float*)bs.w_eff; g.w_bstride = (long long)C * C; g.N = C; g.K = C; g.Kp = C; g.bias = P(bp.proj_b);
+  g.w = (const float*)bs.w_eff; g.w_bstride = (long long)C * bp.kp_attn; g.N = C; g.K = C; g.Kp = C; g.bias = P(bp.proj_b);
   g.ln_mode = LN_NONE; g.acc_sign = 1.f;
   g.r = x_in; g.ldr = C; g.y = x_out; g.ldy = C; g.o_mode = O_NHWC; g.tag = TAG_ATTN_OUT;
-  IRB_TRY(run_1x1(g, bp.tc_attn, hf, hf, false, bs.xhat, s));
+  IRB_TRY(run_1x1(g, bp.tc_attn, hf, hf, false, bs.xhat, s, bp.tma_attn));
 
   // (6) norm2 + project_in 1x1 (:148, :89)
   g = GemmParams{};
@@ -409,7 +427,7 @@ int run_block(const BlockPlan& bp, const float* packed, const float* x_in, float
   g.w = P(bp.pin_w); g.N = 2 * hp; g.K = C; g.Kp = C; g.bias = P(bp.pin_b);
   g.ln_mode = ln; g.ln_w = P(bp.ln2_w); g.ln_b = P(bp.ln2_b); g.acc_sign = 1.f;
   g.y = (float*)bs.hidden; g.ldy = 2 * hp; g.o_mode = O_NHWC; g.tag = TAG_LN_PIN;
-  IRB_TRY(run_1x1(g, bp.tc_pin, hf, false, hf, bs.xhat, s));
+  IRB_TRY(run_1x1(g, bp.tc_pin, hf, false, hf, bs.xhat, s, bp.tma_pin));
 
   // (7) depthwise 3x3 + gelu(x1)*x2 (:90-91)
   dwp = DwParams{};
@@ -417,6 +435,7 @@ int run_block(const BlockPlan& bp, const float* packed, const float* x_in, float
   dwp.in_half = hf; dwp.out_half = hf;
   dwp.w = P(bp.ffdw_w); dwp.bias = P(bp.ffdw_b); dwp.Cw = 2 * hp;
   dwp.B = B; dwp.H = H; dwp.W = W; dwp.C = hp; dwp.gate = 1; dwp.gate_off = hp; dwp.tag = TAG_DW_GATE;
+  dwp.round_tf32 = bp.tma_pout && !hf;
   IRB_TRY(bp.ref_kernels ? launch_dwconv_ref(dwp, s) : launch_dwconv(dwp, s));
 
   // (8) x_out += project_out . gated (:92, :148)
@@ -426,7 +445,7 @@ int run_block(const BlockPlan& bp, const float* packed, const float* x_in, float
   g.w = P(bp.pout_w); g.N = C; g.K = hp; g.Kp = hp; g.bias = P(bp.pout_b);
   g.ln_mode = LN_NONE; g.acc_sign = 1.f;
   g.r = x_out; g.ldr = C; g.y = x_out; g.ldy = C; g.o_mode = O_NHWC; g.tag = TAG_FFN_OUT;
-  IRB_TRY(run_1x1(g, bp.tc_pout, hf, hf, false, bs.xhat, s));
+  IRB_TRY(run_1x1(g, bp.tc_pout, hf, hf, false, bs.xhat, s, bp.tma_pout));
   return IR_OK;
 }
 

@@ -23,6 +23,8 @@ struct BlockPlan {     // one TransformerBlock (restormer.py:137-150); offsets i
   long long ln1_w, ln1_b, temp, qkv_w, qkv_b, qkvdw_w, qkvdw_b, proj_w, proj_b;
   long long ln2_w, ln2_b, pin_w, pin_b, ffdw_w, ffdw_b, pout_w, pout_b;
   bool tc_qkv, tc_attn, tc_pin, tc_pout;   // which 1x1 contractions run on the tcgen05 kernel
+  bool tma_qkv, tma_attn, tma_pin, tma_pout;   // ... and of those, which on the TMA-fed kernel (tma_gemm.cu; weights in its layout)
+  int kp_attn;                             // K pitch of the folded attention matrix W_eff (padded for the TMA kernel)
   bool ref_kernels;                        // ENGINE_SIMT: reference CUDA-core kernels everywhere
   bool half;                               // ENGINE_TC_HALF: fp16 intermediates (qkv, v, hidden, gated) and fp16 operands
 };

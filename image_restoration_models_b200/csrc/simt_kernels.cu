@@ -430,6 +430,13 @@ __global__ void __launch_bounds__(256) fold_kernel(const FoldParams p) {
     } else if (p.fmt == 2) {
       __half* wh = reinterpret_cast<__half*>(p.w_eff) + (long long)b * p.w_eff_bstride;
       wh[((long long)(k >> 3) * p.C + n) * 8 + (k & 7)] = __float2half_rn(s);
+    } else if (p.fmt == 3) {
+      uint32_t u;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(s));
+      we[((long long)(k >> 5) * p.C + n) * 32 + ((((k & 31) >> 2) ^ (n & 7)) << 2) + (k & 3)] = __uint_as_float(u);
+    } else if (p.fmt == 4) {
+      __half* wh = reinterpret_cast<__half*>(p.w_eff) + (long long)b * p.w_eff_bstride;
+      wh[((long long)(k >> 6) * p.C + n) * 64 + ((((k & 63) >> 3) ^ (n & 7)) << 3) + (k & 7)] = __float2half_rn(s);
     } else {
       we[(long long)n * p.C + k] = s;
     }

@@ -39,4 +39,12 @@ struct TcGemmParams {
 size_t tc_gemm_configure(TcGemmParams& p);
 int launch_gemm_tc(TcGemmParams p, cudaStream_t s);
 
+// TMA-fed second-generation kernel (tma_gemm.cu).  Weights are packed [K/kc][N][128 B, 16-byte chunks XOR-swizzled by
+// n & 7] (kc = 32 tf32 / 64 fp16 elements; PackMat fmt 3 / 4, K zero-padded to tma_gemm_kpad).  launch_gemm_tma returns
+// IR_UNSUPPORTED_SHAPE when the problem has to go to launch_gemm_tc instead.
+constexpr int IR_UNSUPPORTED_SHAPE = 1000;
+bool tma_gemm_shape_supported(int K, int N, bool op_half, bool ln, bool has_r, bool y_half);
+int tma_gemm_kpad(int K, bool op_half);
+int launch_gemm_tma(const TcGemmParams& t, cudaStream_t s);
+
 }  // namespace irb

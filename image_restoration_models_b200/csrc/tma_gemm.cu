@@ -1,0 +1,669 @@
+// TMA-fed tcgen05 contraction for the 1x1 convolutions of the Restormer block at the high-resolution levels:
+//
+//     y[pixel, n] = (r[pixel, n]) + sum_k A(pixel, k) * W[n, k]        M = 128 pixels per tile, N <= 256 per CTA
+//
+// Same reference scope as tc_gemm.cu (restormer.py:105 qkv + LayerNorm :37-39/:54-57, :127-131 attention output,
+// :82 project_in, :86 project_out, residual adds :147-148).  The first kernel moved every byte through registers
+// (LDG -> LayerNorm -> STS, LDTM -> STS -> LDS -> STG); ncu showed its four epilogue warps stalled on the
+// write-after-read scoreboard of their own STG instructions and the producers idle between load bursts
+// (profiles/r01p_*).  Here every global access is an asynchronous bulk-tensor copy:
+//
+//   A-producer (1 thread)  cp.async.bulk.tensor loads of [128 px][128 B] boxes (SWIZZLE_128B) into a ring, many in flight
+//   transform (4 warps)    LayerNorm prologue only: one thread per pixel row reads its row from the swizzled boxes
+//                          (conflict-free), two-pass statistics, normalises IN PLACE (tf32 operands) or into a
+//                          second fp16 operand ring
+//   MMA (1 thread)         tcgen05.mma kind::tf32 / kind::f16, SWIZZLE_128B K-major descriptors, weights CTA-resident
+//                          (pre-swizzled in HBM, fetched with one bulk copy per K box), double-buffered TMEM accumulator
+//   epilogue (4 warps)     tcgen05.ld -> (+bias, +residual) -> swizzled smem box -> cp.async.bulk.tensor STORE;
+//                          the residual arrives through its own TMA ring (R-producer thread) and is updated in place
+//
+// Out-of-range rows / columns need no code: TMA zero-fills loads and clips stores at the tensor extents
+// ([B][H*W][C] maps, so a tile never straddles two images).
+#include "common.cuh"
+#include "tc_gemm.cuh"
+
+#include <cuda.h>   // CUtensorMap (types only; cuTensorMapEncodeTiled is resolved through the runtime at first use)
+
+namespace irb {
+
+namespace {
+
+constexpr int TM = 128;                  // pixels per tile == UMMA M
+constexpr int BOX = TM * 128;            // bytes of one [128 rows][128 B] box
+constexpr int WBOX = 32 * 128;           // one warp's [32 rows][128 B] slice
+constexpr int EPI_WARPS = 4, XF_WARPS = 4;
+constexpr int WARP_A = 8, WARP_MMA = 9, WARP_R = 10;
+constexpr int NTHREADS = 11 * 32;
+constexpr int MAX_S = 12, MAX_OP = 4, MAX_RB = 8;
+constexpr int HDR = 1024;
+
+struct Bars {
+  unsigned long long a_full[MAX_S], a_empty[MAX_S], a_ready[MAX_S];
+  unsigned long long op_ready[MAX_OP], op_empty[MAX_OP];
+  unsigned long long acc_full[2], acc_empty[2];
+  unsigned long long r_full[MAX_RB], r_empty[MAX_RB];
+  unsigned long long w_full;
+  uint32_t tmem_base;
+};
+static_assert(sizeof(Bars) <= HDR, "barrier block too large");
+
+struct TmaGemmParams {
+  const uint8_t* w; long long w_bstride_bytes;    // swizzled weights [nob][N][128 B]; per-image stride (0 = shared)
+  int B, HW, K, N;
+  int nc;                  // output columns per CTA (grid.y chunks)
+  int nkb, nob;            // raw A boxes / operand boxes per tile
+  int S, SOP, RB;          // ring depths (boxes)
+  int ln_mode; const float* ln_w; const float* ln_b;
+  const float* bias; int has_r;
+  int tiles_per_img, ntiles, per_image;
+  int tmem_cols, acc_stride;
+  uint32_t off_w, off_a, off_op, off_ro, off_ln;  // byte offsets from the 1024-aligned smem base
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+// bounded spin: a protocol error traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t it = 0; !done; ++it) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (it > (1u << 26)) __trap();
+  }
+}
+
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* tm, uint32_t bar, uint32_t dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// UMMA shared-memory descriptor: K-major, SWIZZLE_128B (layout type 2), rows 128 B apart, 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t sw128_desc(uint32_t addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFFu) >> 4);
+  d |= 1ull << 16;                 // leading byte offset (unused with 128B swizzle, canonical value 1)
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= 1ull << 46;                 // descriptor version (sm_100)
+  d |= 2ull << 61;                 // SWIZZLE_128B
+  return d;
+}
+
+template <typename TOp>
+__device__ __forceinline__ uint32_t make_idesc(int n) {
+  const uint32_t fmt = sizeof(TOp) == 4 ? 2u : 0u;      // TF32 = 2, F16 = 0; accumulator F32
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+}
+
+template <typename TOp>
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  if constexpr (sizeof(TOp) == 4) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t* u = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]),
+        "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]),
+        "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]),
+        "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float to_tf32(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, const float4& v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts128u(uint32_t a, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// tile sequence of one CTA (identical in every role)
+struct TileIter {
+  int b, t, step, end, tpi; bool per_image;
+  __device__ TileIter(const TmaGemmParams& p) {
+    per_image = p.per_image != 0; tpi = p.tiles_per_img; step = gridDim.x;
+    if (per_image) { b = blockIdx.z; t = blockIdx.x; end = p.tiles_per_img; }
+    else { t = blockIdx.x; end = p.ntiles; b = 0; }
+  }
+  __device__ bool valid() const { return t < end; }
+  __device__ void next() { t += step; }
+  __device__ int img() const { return per_image ? b : t / tpi; }
+  __device__ int row0() const { return (per_image ? t : t % tpi) * TM; }
+};
+
+// TOp: tensor-core operand type (float = tf32, __half = f16).  LN: LayerNorm prologue over an fp32 source.
+// TY: output element type.  Without LN the A boxes are already operands (fp32 pre-rounded to tf32 by the producing
+// kernel, or fp16).
+template <typename TOp, bool LN, typename TY>
+__global__ void __launch_bounds__(NTHREADS, 1)
+tma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmR,
+                const __grid_constant__ CUtensorMap tmY, const TmaGemmParams p) {
+  constexpr bool OPRING = LN && sizeof(TOp) == 2;          // fp32 raw boxes -> separate fp16 operand boxes
+  constexpr int OPCOLS = 128 / (int)sizeof(TOp);           // K elements per operand box
+  constexpr int GC = 128 / (int)sizeof(TY);                // output columns per store box
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  Bars* bars = reinterpret_cast<Bars*>(smem_raw + (base - smem_u32(smem_raw)));
+  const uint32_t sW = base + p.off_w, sA = base + p.off_a, sOP = base + p.off_op, sRO = base + p.off_ro;
+  float* lnv = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw)) + p.off_ln);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n0 = blockIdx.y * p.nc;
+  const int ncur = min(p.nc, p.N - n0);
+
+  if (tid == 0) {
+    for (int s = 0; s < p.S; ++s) {
+      mbar_init(smem_u32(&bars->a_full[s]), 1);
+      mbar_init(smem_u32(&bars->a_empty[s]), OPRING ? XF_WARPS * 32 : 1);
+      mbar_init(smem_u32(&bars->a_ready[s]), XF_WARPS * 32);
+    }
+    for (int s = 0; s < MAX_OP; ++s) {
+      mbar_init(smem_u32(&bars->op_ready[s]), XF_WARPS * 32);
+      mbar_init(smem_u32(&bars->op_empty[s]), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(smem_u32(&bars->acc_full[a]), 1);
+      mbar_init(smem_u32(&bars->acc_empty[a]), EPI_WARPS * 32);
+    }
+    for (int s = 0; s < MAX_RB; ++s) {
+      mbar_init(smem_u32(&bars->r_full[s]), 1);
+      mbar_init(smem_u32(&bars->r_empty[s]), EPI_WARPS);
+    }
+    mbar_init(smem_u32(&bars->w_full), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)),
+                 "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (LN && warp >= EPI_WARPS && warp < EPI_WARPS + XF_WARPS) {
+    for (int i = tid - EPI_WARPS * 32; i < p.K; i += XF_WARPS * 32) {
+      lnv[i] = p.ln_w[i];
+      lnv[p.K + i] = p.ln_mode == LN_WITHBIAS ? p.ln_b[i] : 0.f;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == WARP_A) {
+    // =============================== A-producer ===============================
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+      TileIter ti(p);
+      if (ti.valid()) {
+        const uint8_t* wsrc = p.w + (long long)(p.per_image ? (int)blockIdx.z : 0) * p.w_bstride_bytes;
+        const uint32_t wb = smem_u32(&bars->w_full);
+        mbar_expect_tx(wb, (uint32_t)(p.nob * ncur * 128));
+        for (int ob = 0; ob < p.nob; ++ob)
+          bulk_load(sW + (uint32_t)(ob * ncur * 128), wsrc + ((size_t)ob * p.N + n0) * 128, (uint32_t)(ncur * 128), wb);
+      }
+      constexpr int RAWCOLS = LN ? 32 : OPCOLS;
+      uint32_t it = 0;
+      for (; ti.valid(); ti.next()) {
+        const int b = ti.img(), row0 = ti.row0();
+        for (int kb = 0; kb < p.nkb; ++kb, ++it) {
+          const uint32_t s = it % (uint32_t)p.S, ph = (it / (uint32_t)p.S) & 1u;
+          mbar_wait(smem_u32(&bars->a_empty[s]), ph ^ 1u);
+          const uint32_t fb = smem_u32(&bars->a_full[s]);
+          mbar_expect_tx(fb, BOX);
+          tma_load_3d(&tmA, fb, sA + s * BOX, kb * RAWCOLS, row0, b);
+        }
+      }
+    }
+  } else if (warp == WARP_R) {
+    // =============================== residual producer ===============================
+    if (lane == 0 && p.has_r) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmR)) : "memory");
+      const int ngroups = (ncur + 31) / 32;
+      uint32_t gc = 0;
+      for (TileIter ti(p); ti.valid(); ti.next()) {
+        const int b = ti.img(), row0 = ti.row0();
+        for (int g = 0; g < ngroups; ++g, ++gc) {
+          const uint32_t s = gc % (uint32_t)p.RB, ph = (gc / (uint32_t)p.RB) & 1u;
+          mbar_wait(smem_u32(&bars->r_empty[s]), ph ^ 1u);
+          const uint32_t fb = smem_u32(&bars->r_full[s]);
+          mbar_expect_tx(fb, BOX);
+          tma_load_3d(&tmR, fb, sRO + s * BOX, n0 + g * 32, row0, b);
+        }
+      }
+    }
+  } else if (warp == WARP_MMA) {
+    // =============================== MMA issuer ===============================
+    TileIter ti(p);
+    if (ti.valid()) {
+      mbar_wait(smem_u32(&bars->w_full), 0);
+      tc_fence_after();
+    }
+    const uint32_t idesc = make_idesc<TOp>(ncur);
+    const uint32_t ring = OPRING ? (uint32_t)p.SOP : (uint32_t)p.S;
+    uint32_t it = 0, j = 0;
+    for (; ti.valid(); ti.next(), ++j) {
+      const uint32_t slot = j & 1u;
+      mbar_wait(smem_u32(&bars->acc_empty[slot]), ((j >> 1) & 1u) ^ 1u);
+      tc_fence_after();
+      for (int ob = 0; ob < p.nob; ++ob, ++it) {
+        const uint32_t s = it % ring, ph = (it / ring) & 1u;
+        const uint32_t rb = OPRING ? smem_u32(&bars->op_ready[s]) : LN ? smem_u32(&bars->a_ready[s]) : smem_u32(&bars->a_full[s]);
+        mbar_wait(rb, ph);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_addr = (OPRING ? sOP : sA) + s * BOX;
+          const uint32_t w_addr = sW + (uint32_t)(ob * ncur * 128);
+          const int kbytes = min(128, (p.K - ob * OPCOLS) * (int)sizeof(TOp));
+          for (int kk = 0; kk < kbytes / 32; ++kk)
+            umma<TOp>(tmem_base + slot * (uint32_t)p.acc_stride, sw128_desc(a_addr + kk * 32), sw128_desc(w_addr + kk * 32),
+                      idesc, (ob > 0 || kk > 0) ? 1u : 0u);
+          umma_commit(OPRING ? smem_u32(&bars->op_empty[s]) : smem_u32(&bars->a_empty[s]));
+          if (ob == p.nob - 1) umma_commit(smem_u32(&bars->acc_full[slot]));
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp >= EPI_WARPS) {
+    // =============================== LayerNorm transform ===============================
+    if constexpr (LN) {
+      const int r = tid - EPI_WARPS * 32;                    // pixel row of the tile owned by this thread
+      const uint32_t rsw = (uint32_t)(r & 7);
+      const float inv_k = 1.0f / (float)p.K;
+      const bool withbias = p.ln_mode == LN_WITHBIAS;
+      uint32_t it = 0, ot = 0;
+      for (TileIter ti(p); ti.valid(); ti.next()) {
+        for (int kb = 0; kb < p.nkb; ++kb) {
+          const uint32_t s = (it + kb) % (uint32_t)p.S, ph = ((it + kb) / (uint32_t)p.S) & 1u;
+          mbar_wait(smem_u32(&bars->a_full[s]), ph);
+        }
+        // population variance about the mean, eps inside the sqrt (restormer.py:38,55-56), two passes over smem
+        float sum = 0.f;
+        for (int kb = 0; kb < p.nkb; ++kb) {
+          const uint32_t row = sA + ((it + kb) % (uint32_t)p.S) * BOX + (uint32_t)r * 128u;
+          const int nch = min(8, (p.K - kb * 32) >> 2);
+          for (int c = 0; c < nch; ++c) {
+            const float4 v = lds128(row + (((uint32_t)c ^ rsw) << 4));
+            sum += (v.x + v.y) + (v.z + v.w);
+          }
+        }
+        const float mu = sum * inv_k;
+        float ss = 0.f;
+        for (int kb = 0; kb < p.nkb; ++kb) {
+          const uint32_t row = sA + ((it + kb) % (uint32_t)p.S) * BOX + (uint32_t)r * 128u;
+          const int nch = min(8, (p.K - kb * 32) >> 2);
+          for (int c = 0; c < nch; ++c) {
+            const float4 v = lds128(row + (((uint32_t)c ^ rsw) << 4));
+            const float d0 = v.x - mu, d1 = v.y - mu, d2 = v.z - mu, d3 = v.w - mu;
+            ss = fmaf(d0, d0, ss); ss = fmaf(d1, d1, ss); ss = fmaf(d2, d2, ss); ss = fmaf(d3, d3, ss);
+          }
+        }
+        const float rstd = rsqrtf(ss * inv_k + 1e-5f);
+        const float sub = withbias ? mu : 0.f;
+        if constexpr (!OPRING) {
+          for (int kb = 0; kb < p.nkb; ++kb) {
+            const uint32_t row = sA + ((it + kb) % (uint32_t)p.S) * BOX + (uint32_t)r * 128u;
+            const int nch = min(8, (p.K - kb * 32) >> 2);
+            for (int c = 0; c < nch; ++c) {
+              const uint32_t a = row + (((uint32_t)c ^ rsw) << 4);
+              float4 v = lds128(a);
+              const float4 g = *reinterpret_cast<const float4*>(lnv + kb * 32 + c * 4);
+              const float4 bb = *reinterpret_cast<const float4*>(lnv + p.K + kb * 32 + c * 4);
+              v.x = to_tf32(fmaf((v.x - sub) * rstd, g.x, bb.x)); v.y = to_tf32(fmaf((v.y - sub) * rstd, g.y, bb.y));
+              v.z = to_tf32(fmaf((v.z - sub) * rstd, g.z, bb.z)); v.w = to_tf32(fmaf((v.w - sub) * rstd, g.w, bb.w));
+              sts128(a, v);
+            }
+          }
+          fence_async_smem();
+          for (int kb = 0; kb < p.nkb; ++kb) mbar_arrive(smem_u32(&bars->a_ready[(it + kb) % (uint32_t)p.S]));
+        } else {
+          for (int ob = 0; ob < p.nob; ++ob, ++ot) {
+            const uint32_t o = ot % (uint32_t)p.SOP, ph = (ot / (uint32_t)p.SOP) & 1u;
+            mbar_wait(smem_u32(&bars->op_empty[o]), ph ^ 1u);
+            const uint32_t orow = sOP + o * BOX + (uint32_t)r * 128u;
+#pragma unroll
+            for (int c8 = 0; c8 < 8; ++c8) {
+              const int k = ob * 64 + c8 * 8;
+              uint4 t = make_uint4(0u, 0u, 0u, 0u);
+              if (k < p.K) {
+                const uint32_t row = sA + ((it + (k >> 5)) % (uint32_t)p.S) * BOX + (uint32_t)r * 128u;
+                const uint32_t c = (uint32_t)(k & 31) >> 2;
+                const float4 v0 = lds128(row + ((c ^ rsw) << 4));
+                const float4 v1 = lds128(row + (((c + 1) ^ rsw) << 4));
+                const float4 g0 = *reinterpret_cast<const float4*>(lnv + k), g1 = *reinterpret_cast<const float4*>(lnv + k + 4);
+                const float4 b0 = *reinterpret_cast<const float4*>(lnv + p.K + k), b1 = *reinterpret_cast<const float4*>(lnv + p.K + k + 4);
+                __half2* h = reinterpret_cast<__half2*>(&t);
+                h[0] = __floats2half2_rn(fmaf((v0.x - sub) * rstd, g0.x, b0.x), fmaf((v0.y - sub) * rstd, g0.y, b0.y));
+                h[1] = __floats2half2_rn(fmaf((v0.z - sub) * rstd, g0.z, b0.z), fmaf((v0.w - sub) * rstd, g0.w, b0.w));
+                h[2] = __floats2half2_rn(fmaf((v1.x - sub) * rstd, g1.x, b1.x), fmaf((v1.y - sub) * rstd, g1.y, b1.y));
+                h[3] = __floats2half2_rn(fmaf((v1.z - sub) * rstd, g1.z, b1.z), fmaf((v1.w - sub) * rstd, g1.w, b1.w));
+              }
+              sts128u(orow + (((uint32_t)c8 ^ rsw) << 4), t);
+            }
+            fence_async_smem();
+            mbar_arrive(smem_u32(&bars->op_ready[o]));
+          }
+          for (int kb = 0; kb < p.nkb; ++kb) mbar_arrive(smem_u32(&bars->a_empty[(it + kb) % (uint32_t)p.S]));
+        }
+        it += (uint32_t)p.nkb;
+      }
+    }
+  } else {
+    // =============================== epilogue ===============================
+    const int q = warp;                                       // TMEM lane quarter == tile rows [32q, 32q+32)
+    const uint32_t lsw = (uint32_t)(lane & 7);
+    const int ngroups = (ncur + GC - 1) / GC;
+    if (lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmY)) : "memory");
+    uint32_t j = 0, gc = 0;
+    for (TileIter ti(p); ti.valid(); ti.next(), ++j) {
+      const int b = ti.img(), row0 = ti.row0();
+      const uint32_t slot = j & 1u;
+      mbar_wait(smem_u32(&bars->acc_full[slot]), (j >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + slot * (uint32_t)p.acc_stride;
+      for (int g = 0; g < ngroups; ++g, ++gc) {
+        const int col = n0 + g * GC;
+        uint32_t box;
+        if (p.has_r) {
+          const uint32_t s = gc % (uint32_t)p.RB, ph = (gc / (uint32_t)p.RB) & 1u;
+          mbar_wait(smem_u32(&bars->r_full[s]), ph);
+          box = sRO + s * BOX + (uint32_t)q * WBOX;
+        } else {
+          box = sRO + (uint32_t)(q * 2 + (int)(gc & 1u)) * WBOX;
+          if (lane == 0) bulk_wait_read<1>();                 // the store that last read this buffer has drained it
+          __syncwarp();
+        }
+        const uint32_t myrow = box + (uint32_t)lane * 128u;
+        if constexpr (sizeof(TY) == 4) {
+          float v[32];
+          tmem_ld32(tacc + (uint32_t)(g * 32), v);
+          tmem_ld_wait();
+          if (g == ngroups - 1) { tc_fence_before(); mbar_arrive(smem_u32(&bars->acc_empty[slot])); }
+          if (p.bias) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) v[e] += (col + e < p.N) ? __ldg(p.bias + col + e) : 0.f;
+          }
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const uint32_t a = myrow + (((uint32_t)c ^ lsw) << 4);
+            float4 o = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+            if (p.has_r) {
+              const float4 rr = lds128(a);
+              o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+            }
+            sts128(a, o);
+          }
+        } else {
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            float v[32];
+            tmem_ld32(tacc + (uint32_t)(g * 64 + hf * 32), v);
+            tmem_ld_wait();
+            if (g == ngroups - 1 && hf == 1) { tc_fence_before(); mbar_arrive(smem_u32(&bars->acc_empty[slot])); }
+            if (p.bias) {
+#pragma unroll
+              for (int e = 0; e < 32; ++e) v[e] += (col + hf * 32 + e < p.N) ? __ldg(p.bias + col + hf * 32 + e) : 0.f;
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              uint4 t;
+              __half2* h = reinterpret_cast<__half2*>(&t);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(v[8 * c + 2 * e], v[8 * c + 2 * e + 1]);
+              sts128u(myrow + (((uint32_t)(hf * 4 + c) ^ lsw) << 4), t);
+            }
+          }
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_3d(&tmY, box, col, row0 + q * 32, b);
+          bulk_commit();
+          if (p.has_r && gc > 0) {                           // the previous group's store has finished reading its box
+            bulk_wait_read<1>();
+            mbar_arrive(smem_u32(&bars->r_empty[(gc - 1) % (uint32_t)p.RB]));
+          }
+        }
+      }
+    }
+    if (lane == 0) bulk_wait_read<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+  }
+}
+
+// ---- host side -------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      f = nullptr;
+    return (EncodeTiledFn)f;
+  }();
+  return fn;
+}
+
+// [B][rows][inner] view with a 128-byte-wide, SWIZZLE_128B box of box_rows rows
+int make_map(CUtensorMap* tm, const void* ptr, bool half, int inner, long long row_stride_elems, int rows, int B,
+             int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return IR_ERR_CUDA; }
+  const int es = half ? 2 : 4;
+  cuuint64_t gdim[3] = {(cuuint64_t)inner, (cuuint64_t)rows, (cuuint64_t)B};
+  cuuint64_t gstr[2] = {(cuuint64_t)row_stride_elems * es, (cuuint64_t)row_stride_elems * es * (cuuint64_t)rows};
+  cuuint32_t box[3] = {(cuuint32_t)(128 / es), (cuuint32_t)box_rows, 1u};
+  cuuint32_t estr[3] = {1u, 1u, 1u};
+  const CUresult r = fn(tm, half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                        const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (code " + std::to_string((int)r) + ")");
+    return IR_ERR_CUDA;
+  }
+  return IR_OK;
+}
+
+struct TmaCfg { int nc, nchunks, nkb, nob, S, SOP, RB; uint32_t off_w, off_a, off_op, off_ro, off_ln; size_t smem; };
+
+// Shape-only feasibility + shared-memory carve-up.  ln: fused LayerNorm prologue.
+bool configure(int K, int N, bool op_half, bool ln, bool has_r, bool y_half, TmaCfg& c) {
+  const int op_es = op_half ? 2 : 4;
+  if (K <= 0 || N <= 0 || N % 16 != 0 || (K * op_es) % 32 != 0) return false;
+  if (ln && K % 4 != 0) return false;
+  if (has_r && y_half) return false;
+  const int opcols = 128 / op_es, rawcols = ln ? 32 : opcols;
+  c.nkb = (K + rawcols - 1) / rawcols;
+  c.nob = (K + opcols - 1) / opcols;
+  const bool opring = ln && op_half;
+  const int gcs = y_half ? 64 : 32;
+  const size_t budget = 227 * 1024 - 1024 /*alignment slack*/;
+  for (int chunks = 1; chunks <= N / 16; ++chunks) {
+    int nc = (N + chunks - 1) / chunks;
+    nc = chunks == 1 ? N : (nc + gcs - 1) / gcs * gcs;
+    if (nc > 256) continue;
+    size_t off = HDR;
+    c.off_w = (uint32_t)off; off += (size_t)c.nob * nc * 128; off = (off + 1023) / 1024 * 1024;
+    const size_t w_end = off;
+    const size_t ro = has_r ? 0 : (size_t)EPI_WARPS * 2 * WBOX;
+    const size_t lnb = ln ? (size_t)2 * K * 4 + 16 : 0;
+    if (w_end + ro + lnb > budget) continue;
+    size_t rest = budget - w_end - ro - lnb;
+    int S, SOP = 0, RB = 0;
+    if (opring) {
+      // raw fp32 ring (two tiles deep if it fits) + fp16 operand ring
+      SOP = std::min(MAX_OP, 2 * c.nob);
+      if (rest < (size_t)(c.nkb + c.nob) * BOX) continue;
+      S = (int)std::min<size_t>(MAX_S, (rest - (size_t)SOP * BOX) / BOX);
+      if (S < 2 * c.nkb) { SOP = c.nob; S = (int)std::min<size_t>(MAX_S, (rest - (size_t)SOP * BOX) / BOX); }
+      if (S < c.nkb) continue;
+    } else if (has_r) {
+      const int boxes = (int)(rest / BOX);
+      if (boxes < 4) continue;
+      RB = std::min(MAX_RB, std::max(2, boxes / 3));
+      S = std::min(MAX_S, boxes - RB);
+      if (S < 2) continue;
+    } else {
+      S = (int)std::min<size_t>(MAX_S, rest / BOX);
+      if (S < (ln ? c.nkb : 2)) continue;
+      if (ln && S < 2 * c.nkb && chunks < N / 64) continue;      // prefer two tiles in flight: split N further
+    }
+    c.nc = nc; c.nchunks = (N + nc - 1) / nc; c.S = S; c.SOP = SOP; c.RB = RB;
+    c.off_a = (uint32_t)off; off += (size_t)S * BOX;
+    c.off_op = (uint32_t)off; off += (size_t)SOP * BOX;
+    c.off_ro = (uint32_t)off; off += has_r ? (size_t)RB * BOX : ro;
+    c.off_ln = (uint32_t)off; off += lnb;
+    c.smem = off + 1024;
+    return true;
+  }
+  return false;
+}
+
+template <typename TOp, bool LN, typename TY>
+int launch_inst(const CUtensorMap& tA, const CUtensorMap& tR, const CUtensorMap& tY, const TmaGemmParams& p, dim3 grid,
+                size_t smem, cudaStream_t s) {
+  static bool configured = false;
+  if (!configured) {
+    IRB_CUDA(cudaFuncSetAttribute(tma_gemm_kernel<TOp, LN, TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
+  }
+  tma_gemm_kernel<TOp, LN, TY><<<grid, NTHREADS, smem, s>>>(tA, tR, tY, p);
+  IRB_LAUNCH_CHECK();
+  return IR_OK;
+}
+
+}  // namespace
+
+// The plan uses this kernel when the A tile is re-read by at most two N-chunks (wider layers re-read A from L2 too
+// often; they stay on the first-generation kernel, which streams the weights instead).
+bool tma_gemm_shape_supported(int K, int N, bool op_half, bool ln, bool has_r, bool y_half) {
+  TmaCfg c;
+  return configure(K, N, op_half, ln, has_r, y_half, c) && c.nchunks <= 2;
+}
+
+int tma_gemm_kpad(int K, bool op_half) { const int oc = op_half ? 64 : 32; return (K + oc - 1) / oc * oc; }
+
+// Returns IR_OK, an error, or IR_UNSUPPORTED_SHAPE (> 0) when the caller should use the first-generation kernel.
+int launch_gemm_tma(const TcGemmParams& t, cudaStream_t s) {
+  const bool ln = t.ln_mode != LN_NONE;
+  const bool op_half = t.op_half != 0, a_half = t.a_half != 0, y_half = t.y_half != 0, has_r = t.r != nullptr;
+  if (t.k2 != 0 || t.a_mode != 0 || t.o_mode != O_NHWC || t.relu || (t.acc_sign != 0.f && t.acc_sign != 1.f))
+    return IR_UNSUPPORTED_SHAPE;
+  if (ln ? a_half : (a_half != op_half)) return IR_UNSUPPORTED_SHAPE;
+  TmaCfg c;
+  if (!configure(t.K, t.N, op_half, ln, has_r, y_half, c)) return IR_UNSUPPORTED_SHAPE;
+  const int a_es = a_half ? 2 : 4, y_es = y_half ? 2 : 4;
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+  if (!al16(t.a1) || !al16(t.y) || !al16(t.w) || (has_r && !al16(t.r)) || (t.lda1 * a_es) % 16 != 0 ||
+      (t.ldy * y_es) % 16 != 0 || (has_r && (t.ldr * 4) % 16 != 0) || (t.w_bstride * (op_half ? 2 : 4)) % 16 != 0)
+    return IR_UNSUPPORTED_SHAPE;
+
+  CUtensorMap tA, tR, tY;
+  IRB_TRY(make_map(&tA, t.a1, a_half, t.K, t.lda1, t.HW, t.B, TM));
+  IRB_TRY(make_map(&tY, t.y, y_half, t.N, t.ldy, t.HW, t.B, 32));
+  if (has_r) IRB_TRY(make_map(&tR, t.r, false, t.N, t.ldr, t.HW, t.B, TM));
+  else tR = tY;
+
+  TmaGemmParams p{};
+  p.w = reinterpret_cast<const uint8_t*>(t.w);
+  p.w_bstride_bytes = t.w_bstride * (op_half ? 2 : 4);
+  p.B = t.B; p.HW = t.HW; p.K = t.K; p.N = t.N;
+  p.nc = c.nc; p.nkb = c.nkb; p.nob = c.nob; p.S = c.S; p.SOP = c.SOP; p.RB = c.RB;
+  p.ln_mode = t.ln_mode; p.ln_w = t.ln_w; p.ln_b = t.ln_b; p.bias = t.bias; p.has_r = has_r ? 1 : 0;
+  p.tiles_per_img = cdiv(t.HW, TM); p.ntiles = p.tiles_per_img * t.B; p.per_image = t.w_bstride != 0 ? 1 : 0;
+  p.acc_stride = y_half ? (c.nc + 63) / 64 * 64 : (c.nc + 31) / 32 * 32;   // whole store groups: the tail group reads (and TMA clips) past nc
+  int cols = 32; while (cols < 2 * p.acc_stride) cols <<= 1;
+  p.tmem_cols = cols;
+  p.off_w = c.off_w; p.off_a = c.off_a; p.off_op = c.off_op; p.off_ro = c.off_ro; p.off_ln = c.off_ln;
+
+  dim3 grid;
+  if (p.per_image) grid = dim3(std::max(1, std::min(p.tiles_per_img, 148 / (c.nchunks * t.B))), c.nchunks, t.B);
+  else grid = dim3(std::max(1, std::min(p.ntiles, 148 / c.nchunks)), c.nchunks, 1);
+  // one CTA per SM: the kernel owns up to 512 TMEM columns
+  const size_t smem = std::max<size_t>(c.smem, 120 * 1024);
+
+  const double rows = (double)t.B * t.HW;
+  ProfScope prof(t.tag, rows * ((double)t.K * a_es + (double)t.N * (y_es + (has_r ? 4.0 : 0.0))), 2.0 * rows * t.N * t.K, s);
+  if (!op_half && !ln && !y_half) return launch_inst<float, false, float>(tA, tR, tY, p, grid, smem, s);
+  if (!op_half && ln && !y_half) return launch_inst<float, true, float>(tA, tR, tY, p, grid, smem, s);
+  if (op_half && ln && y_half) return launch_inst<__half, true, __half>(tA, tR, tY, p, grid, smem, s);
+  if (op_half && ln && !y_half) return launch_inst<__half, true, float>(tA, tR, tY, p, grid, smem, s);
+  if (op_half && !ln && !y_half) return launch_inst<__half, false, float>(tA, tR, tY, p, grid, smem, s);
+  if (op_half && !ln && y_half) return launch_inst<__half, false, __half>(tA, tR, tY, p, grid, smem, s);
+  return IR_UNSUPPORTED_SHAPE;
+}
+
+}  // namespace irb

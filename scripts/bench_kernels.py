@@ -33,7 +33,7 @@ def run(name, k1, k2, N, ln, resid, rows, half):
     w = torch.randn(N, K, device=dev) / K ** 0.5
     lw = torch.ones(k1, device=dev)
     y = torch.zeros(rows, N, device=dev, dtype=torch.float16 if y_half else torch.float32)
-    scratch = torch.empty((N * K + rows * K) * 4 + 1024, dtype=torch.uint8, device=dev)
+    scratch = torch.empty((N * (K + 64) + rows * K) * 4 + 1024, dtype=torch.uint8, device=dev)
     st = torch.cuda.current_stream().cuda_stream
     def call():
         _native.check(lib.ir_test_conv1x1(0, a1.data_ptr(), k1, k1, 0, 0, 0, w.data_ptr(), 0, ln, lw.data_ptr(), lw.data_ptr(),
@@ -61,7 +61,7 @@ def main():
 
 
 
-def run_block(Cc, heads, B, H, W, mode):
+def run_block(Cc, heads, B, H, W, mode, ncu=False):
     """All eight kernels of one TransformerBlock at full resolution, per-family times from the profiler."""
     import numpy as np
     lib = _native.lib()
@@ -84,6 +84,12 @@ def run_block(Cc, heads, B, H, W, mode):
     for _ in range(2):
         call()
     torch.cuda.synchronize()
+    if ncu:
+        torch.cuda.profiler.start()
+        call()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return {}
     with _native.kernel_profile() as prof:
         for _ in range(3):
             call()
@@ -91,6 +97,19 @@ def run_block(Cc, heads, B, H, W, mode):
     return {r["name"]: {"ms": round(r["ms"] / r["launches"], 4),
                         "GBps": round(r["bytes"] / r["launches"] / 1e9 / (r["ms"] / r["launches"] / 1e3), 0)} for r in prof.rows}
 
+
+if "--ncu" in sys.argv:
+    # one profiled forward of one block per (mode, C): run under `ncu --profile-from-start off`
+    Bn = 2
+    modes = [int(m) for m in os.environ.get("NCU_MODES", "0,1").split(",")]
+    cs = [int(c) for c in os.environ.get("NCU_CS", "48,96,192").split(",")]
+    for mode in modes:
+        for Cc, heads in ((48, 1), (96, 1), (192, 4)):
+            if Cc not in cs:
+                continue
+            lib = _native.lib()
+            run_block(Cc, heads, Bn, 512 if Cc < 192 else 256, 512 if Cc < 192 else 256, mode, ncu=True)
+    sys.exit(0)
 
 if "--blocks" in sys.argv:
     for mode, nm in ((0, "fp32"), (1, "half")):

@@ -12,17 +12,26 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
+TMA = "--tma" in sys.argv      # bring-up of the TMA-fed kernel (engine 3) on TMA_CASES
+
+
+def all_cases():
+    from tc_cases import CASES, CONV3_CASES, HALF_CASES, TMA_CASES
+    if TMA:
+        return list(TMA_CASES), len(TMA_CASES)
+    return CASES + HALF_CASES + CONV3_CASES, len(CASES) + len(HALF_CASES)
+
+
 def child(start):
     import numpy as np
-    from tc_cases import CASES, CONV3_CASES, HALF_CASES, run_case, run_conv3_case, tolerance
-    n1 = len(CASES) + len(HALF_CASES)
-    CASES = CASES + HALF_CASES + CONV3_CASES
+    from tc_cases import run_case, run_conv3_case, tolerance
+    CASES, n1 = all_cases()
     for i in range(start, len(CASES)):
         print(json.dumps({"begin": i}), flush=True)
         if i >= n1:
             y, y_ref = run_conv3_case(CASES[i], 0, seed=i)
         else:
-            y, y_ref = run_case(CASES[i], 0, seed=i)
+            y, y_ref = run_case(CASES[i], 3 if TMA else 0, seed=i)
         err = float(np.abs(y - y_ref).max()) if np.isfinite(y).all() else float("inf")
         bad = int((~np.isfinite(y)).sum())
         # where is the error? (row / column of the worst element) helps decode layout mistakes
@@ -40,14 +49,14 @@ def child(start):
 
 
 def main():
-    if len(sys.argv) > 2 and sys.argv[1] == "--from":
-        child(int(sys.argv[2]))
+    if "--from" in sys.argv:
+        child(int(sys.argv[sys.argv.index("--from") + 1]))
         return 0
-    from tc_cases import CASES, CONV3_CASES, HALF_CASES
-    CASES = CASES + HALF_CASES + CONV3_CASES
+    CASES, _ = all_cases()
     results, start = [], 0
     while start < len(CASES):
-        p = subprocess.Popen([sys.executable, os.path.abspath(__file__), "--from", str(start)], stdout=subprocess.PIPE,
+        p = subprocess.Popen([sys.executable, os.path.abspath(__file__), "--from", str(start)] + (["--tma"] if TMA else []),
+                             stdout=subprocess.PIPE,
                              stderr=subprocess.PIPE, text=True)
         try:
             out, err = p.communicate(timeout=600)
@@ -73,7 +82,7 @@ def main():
         else:
             start = len(CASES)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    json.dump(results, open(os.path.join(ROOT, "gpurun_out", "tc_unit.json"), "w"), indent=1)
+    json.dump(results, open(os.path.join(ROOT, "gpurun_out", "tma_unit.json" if TMA else "tc_unit.json"), "w"), indent=1)
     n_ok = sum(1 for r in results if r.get("ok"))
     print(f"tc_unit: {n_ok}/{len(CASES)} ok")
     for r in results:

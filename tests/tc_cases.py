@@ -49,6 +49,33 @@ HALF_CASES = [
 ]
 
 
+# cases for the TMA-fed kernel (engine 3): same tuple layouts as CASES / HALF_CASES; leading dimensions keep rows
+# 16-byte aligned for fp16 outputs as well (a TMA requirement, always true inside the network)
+TMA_CASES = [
+    (48, 0, 144, 1, 256, 1, False, False, 1),              # K1 enc1: LN(BiasFree) in place, tail group of 16 columns
+    (48, 0, 144, 2, 200, 2, True, False, 1),               # WithBias LN + conv bias, ragged tiles, batch 2
+    (48, 0, 256, 1, 384, 1, False, False, 1),              # K5 enc1
+    (128, 0, 48, 1, 300, 0, False, True, 1),               # K6 enc1: residual ring, in place
+    (48, 0, 48, 3, 130, 0, False, True, 1),                # K4 enc1
+    (96, 0, 288, 1, 512, 1, False, False, 1),              # K1 level 2: two N-chunks (160 + 128)
+    (96, 0, 512, 2, 256, 2, False, False, 1),              # K5 level 2: two N-chunks of 256
+    (256, 0, 96, 1, 256, 0, True, True, 1),                # K6 level 2: 8 K boxes, bias + residual
+    (96, 0, 96, 1, 128, 0, False, True, 1),                # K4 level 2
+    (192, 0, 192, 2, 200, 0, False, True, 1),              # K4 level 3
+    (88, 0, 32, 1, 77, 0, False, False, 1),                # K not a multiple of the box width
+    (96, 0, 288, 4, 4096, 1, False, False, 1),             # many tiles per CTA: ring wrap-around, both accumulators
+    (256, 0, 96, 3, 5000, 0, False, True, 1),              # residual ring wrap-around
+    (48, 0, 144, 1, 256, 1, False, False, 1, 0, 1),        # fp16: LN -> fp16 operand ring -> fp16 out
+    (96, 0, 288, 2, 200, 2, True, False, 1, 0, 1),
+    (96, 0, 512, 1, 300, 1, False, False, 1, 0, 1),
+    (48, 0, 48, 2, 130, 0, False, True, 1, 1, 0),          # fp16 v -> fp32 residual stream
+    (128, 0, 48, 1, 256, 0, False, True, 1, 1, 0),
+    (256, 0, 96, 1, 384, 0, True, True, 1, 1, 0),
+    (512, 0, 192, 1, 200, 0, False, True, 1, 1, 0),        # K6 level 3 in fp16: two N-chunks
+    (96, 0, 512, 3, 4096, 1, False, False, 1, 0, 1),       # many tiles, fp16
+]
+
+
 def run_case(case, engine, seed=0):
     """Returns (y, y_ref64) as numpy arrays; y from the C-ABI test entry on the given engine (0 tc, 1 simt)."""
     a_half = y_half = op_half = 0
@@ -60,7 +87,7 @@ def run_case(case, engine, seed=0):
     g = torch.Generator().manual_seed(1000 + seed)
     K = k1 + k2
     rows = B * HW
-    lda1, lda2, ldy = k1 + 8, (k2 + 4 if k2 else 0), N + 12      # non-trivial leading dimensions
+    lda1, lda2, ldy = k1 + 8, (k2 + 4 if k2 else 0), N + (16 if engine == 3 else 12)   # non-trivial leading dimensions
     a1 = torch.randn(rows, lda1, generator=g) * 1.5 + 0.3
     a2 = torch.randn(rows, lda2, generator=g) if k2 else None
     if a_half:      # the source tensor itself is fp16: the reference sees the same rounded values
@@ -98,7 +125,7 @@ def run_case(case, engine, seed=0):
     y = d(r) if resid else torch.full((rows, ldy), float("nan"), device=dev)
     if y_half:
         y = y.half()
-    scratch = torch.empty((N * K + rows * K) * 4 + 1024, dtype=torch.uint8, device=dev)
+    scratch = torch.empty((N * (K + 64) + rows * K) * 4 + 1024, dtype=torch.uint8, device=dev)
     P = lambda t: 0 if t is None else t.data_ptr()
     stream = torch.cuda.current_stream().cuda_stream
     st = lib.ir_test_conv1x1(engine, P(a1d), lda1, k1, P(a2d), lda2, k2, P(wd), P(bd), ln_mode, P(lwd), P(lbd),

@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 
 from conftest import record
-from tc_cases import CASES, CONV3_CASES, HALF_CASES, run_case, run_conv3_case, tolerance
+from tc_cases import CASES, CONV3_CASES, HALF_CASES, TMA_CASES, run_case, run_conv3_case, tolerance
 
 pytestmark = pytest.mark.gpu
 
@@ -27,6 +27,17 @@ def test_tc_conv1x1_fp16_operands_match_reference(idx):
     y_tc, y_ref = run_case(case, 0, seed=100 + idx)
     e_tc = float(np.abs(y_tc - y_ref).max())
     record(f"tc_conv1x1_half_{idx}", cfg=str(case), err_tc=e_tc, tol=tolerance(case, y_ref))
+    assert np.isfinite(y_tc).all()
+    assert e_tc <= tolerance(case, y_ref), (case, e_tc)
+
+
+@pytest.mark.parametrize("idx", range(len(TMA_CASES)))
+def test_tma_conv1x1_matches_reference(idx):
+    """The TMA-fed kernel (tma_gemm.cu) on its own: engine 3 fails loudly if the shape is not supported."""
+    case = TMA_CASES[idx]
+    y_tc, y_ref = run_case(case, 3, seed=200 + idx)
+    e_tc = float(np.abs(y_tc - y_ref).max())
+    record(f"tma_conv1x1_{idx}", cfg=str(case), err_tc=e_tc, tol=tolerance(case, y_ref))
     assert np.isfinite(y_tc).all()
     assert e_tc <= tolerance(case, y_ref), (case, e_tc)
 
