@@ -56,6 +56,8 @@ struct TmaGemmParams {
   int ln_mode; const float* ln_w; const float* ln_b;
   const float* bias; int has_r;
   int tiles_per_img, ntiles, per_image;
+  int split;               // > 0: 1-D grid, CTAs [0, split) own N-chunk 0 and the rest chunk 1 (uneven chunks get
+                           // CTA counts in proportion to their bytes); 0: blockIdx.y is the chunk
   int tmem_cols, acc_stride;
   uint32_t off_w, off_a, off_op, off_ro, off_ln;  // byte offsets from the 1024-aligned smem base
 };
@@ -187,12 +189,102 @@ struct TileIter {
     per_image = p.per_image != 0; tpi = p.tiles_per_img; step = gridDim.x;
     if (per_image) { b = blockIdx.z; t = blockIdx.x; end = p.tiles_per_img; }
     else { t = blockIdx.x; end = p.ntiles; b = 0; }
+    if (p.split > 0) {
+      const bool second = (int)blockIdx.x >= p.split;
+      t = second ? blockIdx.x - p.split : blockIdx.x;
+      step = second ? gridDim.x - p.split : p.split;
+    }
   }
   __device__ bool valid() const { return t < end; }
   __device__ void next() { t += step; }
   __device__ int img() const { return per_image ? b : t / tpi; }
   __device__ int row0() const { return (per_image ? t : t % tpi) * TM; }
 };
+
+// LayerNorm prologue (restormer.py:37-39 BiasFree, :54-57 WithBias): thread r owns pixel row r of the tile.  The row
+// (NKB boxes of 32 fp32 channels, K <= 32*NKB) is read once into registers -- all loads of a box are independent and
+// conflict-free under the 128-byte swizzle -- the population variance is taken about the mean (two passes over the
+// registers), and the normalised row goes back IN PLACE rounded to tf32, or into the fp16 operand ring.
+template <typename TOp, int NKB>
+__device__ __forceinline__ void ln_transform(const TmaGemmParams& p, Bars* bars, uint32_t sA, uint32_t sOP,
+                                             const float* lnv, int r) {
+  constexpr bool OPRING = sizeof(TOp) == 2;
+  const uint32_t rsw = (uint32_t)(r & 7);
+  const float inv_k = 1.0f / (float)p.K;
+  const bool withbias = p.ln_mode == LN_WITHBIAS;
+  const uint32_t S = (uint32_t)p.S, SOP = (uint32_t)p.SOP;
+  uint32_t it = 0, ot = 0;
+  for (TileIter ti(p); ti.valid(); ti.next()) {
+    float4 x[NKB * 8];
+    uint32_t rowa[NKB];
+#pragma unroll
+    for (int kb = 0; kb < NKB; ++kb) {
+      const uint32_t s = (it + kb) % S, ph = ((it + kb) / S) & 1u;
+      mbar_wait(smem_u32(&bars->a_full[s]), ph);
+      rowa[kb] = sA + s * BOX + (uint32_t)r * 128u;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) x[kb * 8 + c] = lds128(rowa[kb] + (((uint32_t)c ^ rsw) << 4));   // columns >= K are zero (TMA fill)
+    }
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NKB * 8; ++i) { s0 += x[i].x; s1 += x[i].y; s2 += x[i].z; s3 += x[i].w; }
+    const float mu = ((s0 + s1) + (s2 + s3)) * inv_k;
+    s0 = s1 = s2 = s3 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NKB * 8; ++i) {
+      if (i * 4 < p.K) {
+        const float d0 = x[i].x - mu, d1 = x[i].y - mu, d2 = x[i].z - mu, d3 = x[i].w - mu;
+        s0 = fmaf(d0, d0, s0); s1 = fmaf(d1, d1, s1); s2 = fmaf(d2, d2, s2); s3 = fmaf(d3, d3, s3);
+      }
+    }
+    const float rstd = rsqrtf(((s0 + s1) + (s2 + s3)) * inv_k + 1e-5f);
+    const float sub = withbias ? mu : 0.f;
+#pragma unroll
+    for (int i = 0; i < NKB * 8; ++i) {
+      if (i * 4 < p.K) {
+        const float4 g = *reinterpret_cast<const float4*>(lnv + i * 4);
+        const float4 bb = *reinterpret_cast<const float4*>(lnv + p.K + i * 4);
+        x[i].x = fmaf((x[i].x - sub) * rstd, g.x, bb.x); x[i].y = fmaf((x[i].y - sub) * rstd, g.y, bb.y);
+        x[i].z = fmaf((x[i].z - sub) * rstd, g.z, bb.z); x[i].w = fmaf((x[i].w - sub) * rstd, g.w, bb.w);
+      }
+    }
+    if constexpr (!OPRING) {
+#pragma unroll
+      for (int i = 0; i < NKB * 8; ++i) {
+        if (i * 4 < p.K)
+          sts128(rowa[i >> 3] + (((uint32_t)(i & 7) ^ rsw) << 4),
+                 make_float4(to_tf32(x[i].x), to_tf32(x[i].y), to_tf32(x[i].z), to_tf32(x[i].w)));
+      }
+      fence_async_smem();
+#pragma unroll
+      for (int kb = 0; kb < NKB; ++kb) mbar_arrive(smem_u32(&bars->a_ready[(it + kb) % S]));
+    } else {
+      // the raw boxes are free as soon as the row sits in registers
+#pragma unroll
+      for (int kb = 0; kb < NKB; ++kb) mbar_arrive(smem_u32(&bars->a_empty[(it + kb) % S]));
+#pragma unroll
+      for (int ob = 0; ob < (NKB + 1) / 2; ++ob, ++ot) {
+        const uint32_t o = ot % SOP, ph = (ot / SOP) & 1u;
+        mbar_wait(smem_u32(&bars->op_empty[o]), ph ^ 1u);
+        const uint32_t orow = sOP + o * BOX + (uint32_t)r * 128u;
+#pragma unroll
+        for (int c8 = 0; c8 < 8; ++c8) {
+          const int i = ob * 16 + c8 * 2;                    // float4 index of the first of the two source chunks
+          uint4 t = make_uint4(0u, 0u, 0u, 0u);
+          if (i + 1 < NKB * 8 && i * 4 < p.K) {
+            __half2* h = reinterpret_cast<__half2*>(&t);
+            h[0] = __floats2half2_rn(x[i].x, x[i].y); h[1] = __floats2half2_rn(x[i].z, x[i].w);
+            h[2] = __floats2half2_rn(x[i + 1].x, x[i + 1].y); h[3] = __floats2half2_rn(x[i + 1].z, x[i + 1].w);
+          }
+          sts128u(orow + (((uint32_t)c8 ^ rsw) << 4), t);
+        }
+        fence_async_smem();
+        mbar_arrive(smem_u32(&bars->op_ready[o]));
+      }
+    }
+    it += NKB;
+  }
+}
 
 // TOp: tensor-core operand type (float = tf32, __half = f16).  LN: LayerNorm prologue over an fp32 source.
 // TY: output element type.  Without LN the A boxes are already operands (fp32 pre-rounded to tf32 by the producing
@@ -211,7 +303,7 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   float* lnv = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw)) + p.off_ln);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int n0 = blockIdx.y * p.nc;
+  const int n0 = (p.split > 0 ? ((int)blockIdx.x >= p.split ? 1 : 0) : (int)blockIdx.y) * p.nc;
   const int ncur = min(p.nc, p.N - n0);
 
   if (tid == 0) {
@@ -330,85 +422,11 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   } else if (warp >= EPI_WARPS) {
     // =============================== LayerNorm transform ===============================
     if constexpr (LN) {
-      const int r = tid - EPI_WARPS * 32;                    // pixel row of the tile owned by this thread
-      const uint32_t rsw = (uint32_t)(r & 7);
-      const float inv_k = 1.0f / (float)p.K;
-      const bool withbias = p.ln_mode == LN_WITHBIAS;
-      uint32_t it = 0, ot = 0;
-      for (TileIter ti(p); ti.valid(); ti.next()) {
-        for (int kb = 0; kb < p.nkb; ++kb) {
-          const uint32_t s = (it + kb) % (uint32_t)p.S, ph = ((it + kb) / (uint32_t)p.S) & 1u;
-          mbar_wait(smem_u32(&bars->a_full[s]), ph);
-        }
-        // population variance about the mean, eps inside the sqrt (restormer.py:38,55-56), two passes over smem
-        float sum = 0.f;
-        for (int kb = 0; kb < p.nkb; ++kb) {
-          const uint32_t row = sA + ((it + kb) % (uint32_t)p.S) * BOX + (uint32_t)r * 128u;
-          const int nch = min(8, (p.K - kb * 32) >> 2);
-          for (int c = 0; c < nch; ++c) {
-            const float4 v = lds128(row + (((uint32_t)c ^ rsw) << 4));
-            sum += (v.x + v.y) + (v.z + v.w);
-          }
-        }
-        const float mu = sum * inv_k;
-        float ss = 0.f;
-        for (int kb = 0; kb < p.nkb; ++kb) {
-          const uint32_t row = sA + ((it + kb) % (uint32_t)p.S) * BOX + (uint32_t)r * 128u;
-          const int nch = min(8, (p.K - kb * 32) >> 2);
-          for (int c = 0; c < nch; ++c) {
-            const float4 v = lds128(row + (((uint32_t)c ^ rsw) << 4));
-            const float d0 = v.x - mu, d1 = v.y - mu, d2 = v.z - mu, d3 = v.w - mu;
-            ss = fmaf(d0, d0, ss); ss = fmaf(d1, d1, ss); ss = fmaf(d2, d2, ss); ss = fmaf(d3, d3, ss);
-          }
-        }
-        const float rstd = rsqrtf(ss * inv_k + 1e-5f);
-        const float sub = withbias ? mu : 0.f;
-        if constexpr (!OPRING) {
-          for (int kb = 0; kb < p.nkb; ++kb) {
-            const uint32_t row = sA + ((it + kb) % (uint32_t)p.S) * BOX + (uint32_t)r * 128u;
-            const int nch = min(8, (p.K - kb * 32) >> 2);
-            for (int c = 0; c < nch; ++c) {
-              const uint32_t a = row + (((uint32_t)c ^ rsw) << 4);
-              float4 v = lds128(a);
-              const float4 g = *reinterpret_cast<const float4*>(lnv + kb * 32 + c * 4);
-              const float4 bb = *reinterpret_cast<const float4*>(lnv + p.K + kb * 32 + c * 4);
-              v.x = to_tf32(fmaf((v.x - sub) * rstd, g.x, bb.x)); v.y = to_tf32(fmaf((v.y - sub) * rstd, g.y, bb.y));
-              v.z = to_tf32(fmaf((v.z - sub) * rstd, g.z, bb.z)); v.w = to_tf32(fmaf((v.w - sub) * rstd, g.w, bb.w));
-              sts128(a, v);
-            }
-          }
-          fence_async_smem();
-          for (int kb = 0; kb < p.nkb; ++kb) mbar_arrive(smem_u32(&bars->a_ready[(it + kb) % (uint32_t)p.S]));
-        } else {
-          for (int ob = 0; ob < p.nob; ++ob, ++ot) {
-            const uint32_t o = ot % (uint32_t)p.SOP, ph = (ot / (uint32_t)p.SOP) & 1u;
-            mbar_wait(smem_u32(&bars->op_empty[o]), ph ^ 1u);
-            const uint32_t orow = sOP + o * BOX + (uint32_t)r * 128u;
-#pragma unroll
-            for (int c8 = 0; c8 < 8; ++c8) {
-              const int k = ob * 64 + c8 * 8;
-              uint4 t = make_uint4(0u, 0u, 0u, 0u);
-              if (k < p.K) {
-                const uint32_t row = sA + ((it + (k >> 5)) % (uint32_t)p.S) * BOX + (uint32_t)r * 128u;
-                const uint32_t c = (uint32_t)(k & 31) >> 2;
-                const float4 v0 = lds128(row + ((c ^ rsw) << 4));
-                const float4 v1 = lds128(row + (((c + 1) ^ rsw) << 4));
-                const float4 g0 = *reinterpret_cast<const float4*>(lnv + k), g1 = *reinterpret_cast<const float4*>(lnv + k + 4);
-                const float4 b0 = *reinterpret_cast<const float4*>(lnv + p.K + k), b1 = *reinterpret_cast<const float4*>(lnv + p.K + k + 4);
-                __half2* h = reinterpret_cast<__half2*>(&t);
-                h[0] = __floats2half2_rn(fmaf((v0.x - sub) * rstd, g0.x, b0.x), fmaf((v0.y - sub) * rstd, g0.y, b0.y));
-                h[1] = __floats2half2_rn(fmaf((v0.z - sub) * rstd, g0.z, b0.z), fmaf((v0.w - sub) * rstd, g0.w, b0.w));
-                h[2] = __floats2half2_rn(fmaf((v1.x - sub) * rstd, g1.x, b1.x), fmaf((v1.y - sub) * rstd, g1.y, b1.y));
-                h[3] = __floats2half2_rn(fmaf((v1.z - sub) * rstd, g1.z, b1.z), fmaf((v1.w - sub) * rstd, g1.w, b1.w));
-              }
-              sts128u(orow + (((uint32_t)c8 ^ rsw) << 4), t);
-            }
-            fence_async_smem();
-            mbar_arrive(smem_u32(&bars->op_ready[o]));
-          }
-          for (int kb = 0; kb < p.nkb; ++kb) mbar_arrive(smem_u32(&bars->a_empty[(it + kb) % (uint32_t)p.S]));
-        }
-        it += (uint32_t)p.nkb;
+      switch (p.nkb) {
+        case 1: ln_transform<TOp, 1>(p, bars, sA, sOP, lnv, tid - EPI_WARPS * 32); break;
+        case 2: ln_transform<TOp, 2>(p, bars, sA, sOP, lnv, tid - EPI_WARPS * 32); break;
+        case 3: ln_transform<TOp, 3>(p, bars, sA, sOP, lnv, tid - EPI_WARPS * 32); break;
+        default: ln_transform<TOp, 4>(p, bars, sA, sOP, lnv, tid - EPI_WARPS * 32); break;
       }
     }
   } else {
@@ -543,7 +561,7 @@ struct TmaCfg { int nc, nchunks, nkb, nob, S, SOP, RB; uint32_t off_w, off_a, of
 bool configure(int K, int N, bool op_half, bool ln, bool has_r, bool y_half, TmaCfg& c) {
   const int op_es = op_half ? 2 : 4;
   if (K <= 0 || N <= 0 || N % 16 != 0 || (K * op_es) % 32 != 0) return false;
-  if (ln && K % 4 != 0) return false;
+  if (ln && (K % 4 != 0 || K > 128)) return false;          // the transform keeps a row of <= 4 boxes in registers
   if (has_r && y_half) return false;
   const int opcols = 128 / op_es, rawcols = ln ? 32 : opcols;
   c.nkb = (K + rawcols - 1) / rawcols;
@@ -652,6 +670,13 @@ int launch_gemm_tma(const TcGemmParams& t, cudaStream_t s) {
   dim3 grid;
   if (p.per_image) grid = dim3(std::max(1, std::min(p.tiles_per_img, 148 / (c.nchunks * t.B))), c.nchunks, t.B);
   else grid = dim3(std::max(1, std::min(p.ntiles, 148 / c.nchunks)), c.nchunks, 1);
+  if (!p.per_image && c.nchunks == 2 && p.ntiles >= 148) {
+    // two uneven chunks (e.g. 288 = 160 + 128 columns): split the 148 CTAs in proportion to the bytes each chunk moves
+    const double per_col = y_half ? 2.0 : 4.0 + (has_r ? 4.0 : 0.0);
+    const double c0 = (double)t.K * a_es + c.nc * per_col, c1 = (double)t.K * a_es + (t.N - c.nc) * per_col;
+    p.split = std::min(147, std::max(1, (int)(148.0 * c0 / (c0 + c1) + 0.5)));
+    grid = dim3(148, 1, 1);
+  }
   // one CTA per SM: the kernel owns up to 512 TMEM columns
   const size_t smem = std::max<size_t>(c.smem, 120 * 1024);
 
