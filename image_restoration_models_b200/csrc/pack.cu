@@ -1,6 +1,7 @@
 // One-time weight packing: PyTorch-layout fp32 parameters -> the layouts the kernels read.
 // (state_dict contract: SURVEY.md Appendix A; BatchNorm eval folding: basicblock.py:69.)
 #include "common.cuh"
+#include "ffn_tail.cuh"
 
 namespace irb {
 
@@ -70,6 +71,21 @@ __global__ void pack_dw_kernel(const float* __restrict__ src, float* __restrict_
 int launch_pack_dw(const float* src, float* dst, int c_src_half, int c_dst_half, int n_halves, cudaStream_t s) {
   const int total = 9 * c_dst_half * n_halves;
   pack_dw_kernel<<<cdiv(total, 256), 256, 0, s>>>(src, dst, c_src_half, c_dst_half, n_halves);
+  IRB_LAUNCH_CHECK();
+  return IR_OK;
+}
+
+__global__ void pack_dw_chunked_kernel(const float* __restrict__ src, float* __restrict__ dst, int h, int hp, int kc) {
+  const int total = 2 * 9 * hp;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int c = idx % kc, tap = (idx / kc) % 9, half = (idx / (9 * kc)) % 2, chunk = idx / (18 * kc);
+    const int ch = chunk * kc + c;
+    dst[idx] = ch < h ? src[(half * h + ch) * 9 + tap] : 0.f;
+  }
+}
+
+int launch_pack_dw_chunked(const float* src, float* dst, int h, int hp, int kc, cudaStream_t s) {
+  pack_dw_chunked_kernel<<<cdiv(18 * hp, 256), 256, 0, s>>>(src, dst, h, hp, kc);
   IRB_LAUNCH_CHECK();
   return IR_OK;
 }

@@ -5,6 +5,7 @@
 // into the first (patch_embed) and last (output) 3x3 convs.
 #include "restormer.cuh"
 #include "tc_gemm.cuh"
+#include "ffn_tail.cuh"
 
 #include <algorithm>
 
@@ -94,6 +95,8 @@ static void plan_block(Builder& bl, BlockPlan& bp, int C, int heads, float ffn, 
   bp.tma_pin = bp.tc_pin && bl.tma(C, 2 * bp.hp, true, false, bl.half());
   bp.tma_pout = bp.tc_pout && bl.tma(bp.hp, C, false, true, false);
   bp.kp_attn = bp.tma_attn ? tma_gemm_kpad(C, bl.half()) : C;
+  // GDFN tail in one kernel (no biases: every shipped configuration has bias=False)
+  bp.fuse_tail = bl.engine != ENGINE_SIMT && !bias && ffn_tail_supported(C, bp.hp, bl.half());
   vec(bp.ln1_w, C);
   if (ln_bias) vec(bp.ln1_b, C);
   vec(bp.temp, heads);
@@ -107,9 +110,14 @@ static void plan_block(Builder& bl, BlockPlan& bp, int C, int heads, float ffn, 
   if (ln_bias) vec(bp.ln2_b, C);
   mat(bp.pin_w, bp.h, bp.hp, 2, C, C, bp.tc_pin, bp.tma_pin);
   if (bias) vec_split(bp.pin_b, bp.h, bp.hp, 2);
-  dw(bp.ffdw_w, bp.h, bp.hp, 2);
+  if (bp.fuse_tail) {
+    bp.ffdw_w = bl.alloc(18LL * bp.hp);
+    bl.ops.push_back(PackOp{PackOp::DWC, bl.pidx++, bp.ffdw_w, bp.h, bp.hp, 2, 0, ffn_tail_kc(bl.half()), 0, 0});
+  } else {
+    dw(bp.ffdw_w, bp.h, bp.hp, 2);
+  }
   if (bias) vec_split(bp.ffdw_b, bp.h, bp.hp, 2);
-  mat(bp.pout_w, C, C, 1, bp.h, bp.hp, bp.tc_pout, bp.tma_pout);
+  mat(bp.pout_w, C, C, 1, bp.h, bp.hp, bp.tc_pout || bp.fuse_tail, bp.tma_pout || bp.fuse_tail);
   if (bias) vec(bp.pout_b, C);
 }
 
@@ -218,6 +226,7 @@ long long pack_op_src_numel(const PackOp& op) {
     case PackOp::MAT1: return (long long)op.a * op.c * op.k_src;
     case PackOp::MAT3: return (long long)op.a * op.c * op.k_src;   // a = source rows (cout), b = padded rows
     case PackOp::DW: return (long long)op.a * op.c * 9;
+    case PackOp::DWC: return (long long)op.a * op.c * 9;
     default: return op.a;  // DnCNN-specific kinds carry their numel in a
   }
 }
@@ -243,6 +252,9 @@ int run_pack_ops(const std::vector<PackOp>& ops, const float* const* params, flo
       }
       case PackOp::DW:
         IRB_TRY(launch_pack_dw(src, dst, op.a, op.b, op.c, s));
+        break;
+      case PackOp::DWC:
+        IRB_TRY(launch_pack_dw_chunked(src, dst, op.a, op.b, op.k_dst, s));
         break;
       default:
         IRB_REQUIRE(false, "pack: unknown op");
@@ -429,6 +441,13 @@ int run_block(const BlockPlan& bp, const float* packed, const float* x_in, float
   g.y = (float*)bs.hidden; g.ldy = 2 * hp; g.o_mode = O_NHWC; g.tag = TAG_LN_PIN;
   IRB_TRY(run_1x1(g, bp.tc_pin, hf, false, hf, bs.xhat, s, bp.tma_pin));
 
+  if (bp.fuse_tail) {
+    // (7+8) depthwise 3x3 + gelu(x1)*x2 + project_out + residual (:90-92, :148) in one kernel
+    FfnTailArgs fa{};
+    fa.hidden = bs.hidden; fa.half = hf; fa.x = x_out; fa.w_out = P(bp.pout_w); fa.dw_chunked = P(bp.ffdw_w);
+    fa.bias = nullptr; fa.B = B; fa.H = H; fa.W = W; fa.C = C; fa.hp = hp;
+    return launch_ffn_tail(fa, s);
+  }
   // (7) depthwise 3x3 + gelu(x1)*x2 (:90-91)
   dwp = DwParams{};
   dwp.in = (const float*)bs.hidden; dwp.ldi = 2 * hp; dwp.out = (float*)bs.gated; dwp.ldo = hp;
@@ -497,7 +516,7 @@ int restormer_launch_count(const RestormerPlan& pl) {
   int n = 0;
   auto blocks = [&](const std::vector<BlockPlan>& v) {
     for (const auto& bp : v) {
-      n += 8;
+      n += bp.fuse_tail ? 7 : 8;
       if (bp.C > 128) n += (bp.tc_qkv ? 1 : 0) + (bp.tc_pin ? 1 : 0);   // standalone LayerNorm on the wide levels
     }
   };

@@ -8,7 +8,7 @@ namespace irb {
 
 // One weight-packing step: parameter `param` (state_dict order) -> packed[dst ...].
 struct PackOp {
-  enum Kind { VEC = 0, MAT1 = 1, MAT3 = 2, DW = 3 };
+  enum Kind { VEC = 0, MAT1 = 1, MAT3 = 2, DW = 3, DWC = 4 };   // DWC: depthwise taps chunked for ffn_tail.cu (k_dst = chunk width)
   int kind;
   int param;
   long long dst;       // float offset into the packed buffer
@@ -24,6 +24,7 @@ struct BlockPlan {     // one TransformerBlock (restormer.py:137-150); offsets i
   long long ln2_w, ln2_b, pin_w, pin_b, ffdw_w, ffdw_b, pout_w, pout_b;
   bool tc_qkv, tc_attn, tc_pin, tc_pout;   // which 1x1 contractions run on the tcgen05 kernel
   bool tma_qkv, tma_attn, tma_pin, tma_pout;   // ... and of those, which on the TMA-fed kernel (tma_gemm.cu; weights in its layout)
+  bool fuse_tail;                          // dwconv + gate + project_out + residual in one kernel (ffn_tail.cu)
   int kp_attn;                             // K pitch of the folded attention matrix W_eff (padded for the TMA kernel)
   bool ref_kernels;                        // ENGINE_SIMT: reference CUDA-core kernels everywhere
   bool half;                               // ENGINE_TC_HALF: fp16 intermediates (qkv, v, hidden, gated) and fp16 operands
