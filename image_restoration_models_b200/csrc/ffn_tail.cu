@@ -10,7 +10,7 @@
 //   H-producer (1 thread)  per hidden-channel chunk (32 fp32 / 64 fp16 channels = 128 B per pixel): two 4-D bulk-tensor
 //                          loads of the (8+2) x (16+2) halo patch (x1 and x2 halves; TMA zero-fills the image border,
 //                          which IS the conv's zero padding), plus the chunk's project_out rows and 3x3 taps
-//   dw warps (8)           thread = 4 channels x a 2 x BW pixel block: 3x3 taps from the smem halo patch, exact-erf
+//   dw warps (8)           thread = 2 channels x a 2x4 / 4x4 pixel block: 3x3 taps from the smem halo patch, exact-erf
 //                          GELU gate, result stored as the chunk's [128 px][128 B] SWIZZLE_128B operand box
 //   MMA (1 thread)         tcgen05.mma (tf32 / f16) of the operand box with the chunk's W_out rows, accumulating over
 //                          the hp/32 (hp/64) chunks in TMEM (double buffered across tiles)
@@ -33,9 +33,7 @@ constexpr int HPIX = (TH + 2) * (TW + 2);      // 180 halo pixels
 constexpr int HBOX = HPIX * 128;               // bytes of one halo box (one half of one chunk)
 constexpr int OPBOX = TM * 128;                // operand / residual box
 constexpr int WBOX = 32 * 128;
-constexpr int EPI_WARPS = 4, DW_WARPS = 8;
-constexpr int WARP_H = 12, WARP_MMA = 13, WARP_R = 14;
-constexpr int NTHREADS = 15 * 32;
+constexpr int EPI_WARPS = 4;
 constexpr int NST = 2, NOP = 2, MAX_RB = 4;
 constexpr int HDR = 1024;
 
@@ -58,33 +56,65 @@ struct FfnTailParams {
   int round_out;
 };
 
-// exact-erf GELU (F.gelu default, restormer.py:91) through the Abramowitz-Stegun 7.1.26 rational form
-// (|gelu error| <= 2.6e-7 in fp32; see dwconv.cu)
-__device__ __forceinline__ float gelu_erf(float x) {
-  const float ax = fabsf(x) * 0.70710678118654752440f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
-  const float poly = t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 1.061405429f, -1.453152027f), 1.421413741f), -0.284496736f),
-                              0.254829592f);
-  const float y = fmaf(-poly, __expf(-ax * ax), 1.0f);
-  return 0.5f * x * (1.0f + copysignf(y, x));
+// ---- packed fp32 pairs (sm_100 FFMA2 / FMUL2): a dw thread owns two adjacent channels, so every multiply-add of the
+// depthwise taps and of the GELU polynomial is one instruction for both channels.  The kernel is bound by FP32
+// instruction issue, not by bytes: this halves the issue slots of its inner loops.
+typedef unsigned long long f2_t;
+__device__ __forceinline__ f2_t pack2(float lo, float hi) { f2_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpack2(f2_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f2_t fma2(f2_t a, f2_t b, f2_t c) { f2_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f2_t mul2(f2_t a, f2_t b) { f2_t d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float ex2_approx(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
+// gelu(x) * gate for a channel pair.  Exact-erf GELU (F.gelu default, restormer.py:91) through the Abramowitz-Stegun
+// 7.1.26 rational form, erf(u) = 1 - (a1 t + .. + a5 t^5) exp(-u^2), t = 1/(1 + p u), u = |x|/sqrt2 (|gelu error| <=
+// 3e-7 in fp32, see dwconv.cu).  z = u * sqrt(log2 e), so that exp(-u^2) = 2^(-z^2) is a bare MUFU.EX2.
+__device__ __forceinline__ f2_t gelu_gate2(f2_t x, f2_t gate) {
+  const f2_t C1 = pack2(0.84932180028801904272f, 0.84932180028801904272f);       // sqrt(log2 e) / sqrt 2
+  const float PZ = 0.27273629f;                                                    // 0.3275911 / sqrt(log2 e)
+  const f2_t A5 = pack2(-1.061405429f, -1.061405429f), A4 = pack2(1.453152027f, 1.453152027f),
+             A3 = pack2(-1.421413741f, -1.421413741f), A2 = pack2(0.284496736f, 0.284496736f),
+             A1 = pack2(-0.254829592f, -0.254829592f), ONE = pack2(1.0f, 1.0f), HALF = pack2(0.5f, 0.5f);
+  const f2_t z = mul2(x, C1);
+  float zx, zy, xx, xy;
+  unpack2(z, zx, zy);
+  unpack2(x, xx, xy);
+  const f2_t t = pack2(rcp_approx(fmaf(PZ, fabsf(zx), 1.0f)), rcp_approx(fmaf(PZ, fabsf(zy), 1.0f)));
+  const f2_t sq = mul2(z, z);
+  float sx, sy;
+  unpack2(sq, sx, sy);
+  const f2_t e = pack2(ex2_approx(-sx), ex2_approx(-sy));
+  f2_t poly = fma2(t, A5, A4);
+  poly = fma2(t, poly, A3);
+  poly = fma2(t, poly, A2);
+  poly = fma2(t, poly, A1);
+  poly = mul2(poly, t);                                  // -(a1 t + ... + a5 t^5)
+  const f2_t y = fma2(poly, e, ONE);                     // erf(|x| / sqrt 2)
+  float yx, yy;
+  unpack2(y, yx, yy);
+  const f2_t ys = pack2(copysignf(yx, xx), copysignf(yy, xy));
+  const f2_t hx = mul2(x, HALF);
+  return mul2(fma2(hx, ys, hx), gate);                   // 0.5 x (1 + erf(x / sqrt 2)) * gate
 }
 
-__device__ __forceinline__ void fma4(float4& acc, const float4& w, const float4& x) {
-  acc.x = fmaf(w.x, x.x, acc.x); acc.y = fmaf(w.y, x.y, acc.y);
-  acc.z = fmaf(w.z, x.z, acc.z); acc.w = fmaf(w.w, x.w, acc.w);
-}
-
+// A dw thread owns 2 channels x a BH x BW pixel block of the patch: every staged value is read (BH+2)(BW+2)/(BH BW)
+// times and the taps once per block.  CP channel pairs per chunk x (8/BH)(16/BW) blocks = 256 dw threads.
 template <typename TH_> struct Geo;
-template <> struct Geo<float>  { static constexpr int CQ = 8,  BW = 2, KC = 32, EB = 16; };   // EB: bytes of 4 channels
-template <> struct Geo<__half> { static constexpr int CQ = 16, BW = 4, KC = 64, EB = 8; };
+template <> struct Geo<float>  { static constexpr int CP = 16, KC = 32, EB = 8, BH = 2, BW = 4, DW_WARPS = 8; };   // EB: bytes of 2 channels
+template <> struct Geo<__half> { static constexpr int CP = 32, KC = 64, EB = 4, BH = 4, BW = 4, DW_WARPS = 8; };
 
-template <typename T> __device__ __forceinline__ float4 ld4(uint32_t a);
-template <> __device__ __forceinline__ float4 ld4<float>(uint32_t a) { return lds128(a); }
-template <> __device__ __forceinline__ float4 ld4<__half>(uint32_t a) {
-  const uint2 t = lds64u(a);
-  const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&t.x));
-  const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&t.y));
-  return make_float4(lo.x, lo.y, hi.x, hi.y);
+template <typename T> __device__ __forceinline__ f2_t ld2(uint32_t a);
+template <> __device__ __forceinline__ f2_t ld2<float>(uint32_t a) {
+  f2_t v;
+  asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(a));
+  return v;
+}
+template <> __device__ __forceinline__ f2_t ld2<__half>(uint32_t a) {
+  uint32_t t;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(t) : "r"(a));
+  const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&t));
+  return pack2(f.x, f.y);
 }
 
 struct TileIter {
@@ -99,11 +129,12 @@ struct TileIter {
 
 // TH_: element type of the hidden tensor == tensor-core operand type (float -> tf32, __half -> f16)
 template <typename TH_>
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __launch_bounds__((EPI_WARPS + Geo<TH_>::DW_WARPS + 3) * 32, 1)
 ffn_tail_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmR,
                 const __grid_constant__ CUtensorMap tmY, const FfnTailParams p) {
   using G = Geo<TH_>;
-  constexpr int KC = G::KC, CQ = G::CQ, BW = G::BW;
+  constexpr int KC = G::KC, CP = G::CP, DW_WARPS = G::DW_WARPS;
+  constexpr int WARP_H = EPI_WARPS + DW_WARPS, WARP_MMA = WARP_H + 1, WARP_R = WARP_H + 2;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   Bars* bars = reinterpret_cast<Bars*>(smem_raw + (base - smem_u32(smem_raw)));
@@ -210,42 +241,42 @@ ffn_tail_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__
     }
   } else if (warp >= EPI_WARPS) {
     // =============================== depthwise 3x3 + gate -> operand box ===============================
+    constexpr int BH = G::BH, BW = G::BW;
     const int ctid = tid - EPI_WARPS * 32;
-    const int cq = ctid % CQ, pg = ctid / CQ;
-    const int by = pg / (TW / BW), bx = pg % (TW / BW);
-    // halo-patch byte offset of this thread's window origin, and operand-box rows of its 2 x BW outputs
-    const uint32_t win0 = (uint32_t)((2 * by) * (TW + 2) + BW * bx) * 128u + (uint32_t)cq * G::EB;
+    const int cp = ctid % CP, blk = ctid / CP;
+    const int by = blk / (TW / BW), bx = blk % (TW / BW);
+    const uint32_t win0 = (uint32_t)((BH * by) * (TW + 2) + BW * bx) * 128u + (uint32_t)cp * G::EB;
     uint32_t it = 0;
     for (TileIter ti(p); ti.valid(); ti.next()) {
       for (int ch = 0; ch < p.nchunk; ++ch, ++it) {
         const uint32_t s = it % NST, o = it % NOP;
         mbar_wait(smem_u32(&bars->h_full[s]), (it / NST) & 1u);
         const uint32_t st = sST + s * p.stage_bytes;
-        const uint32_t dws = st + 2 * HBOX + wbytes + (uint32_t)cq * 16u;
-        float4 acc[2][2][BW];
+        const uint32_t dws = st + 2 * HBOX + wbytes + (uint32_t)cp * 8u;
+        f2_t acc[2][BH][BW];
 #pragma unroll
         for (int set = 0; set < 2; ++set) {
-          float4 w[9];
+          f2_t w[9];
 #pragma unroll
-          for (int t = 0; t < 9; ++t) w[t] = lds128(dws + (uint32_t)((set * 9 + t) * KC) * 4u);
-#pragma unroll
-          for (int oy = 0; oy < 2; ++oy)
-#pragma unroll
-            for (int ox = 0; ox < BW; ++ox) acc[set][oy][ox] = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int t = 0; t < 9; ++t) w[t] = ld2<float>(dws + (uint32_t)((set * 9 + t) * KC) * 4u);
           const uint32_t src = st + set * HBOX + win0;
 #pragma unroll
-          for (int iy = 0; iy < 4; ++iy) {
-            float4 v[BW + 2];
+          for (int iy = 0; iy < BH + 2; ++iy) {
+            f2_t v[BW + 2];
 #pragma unroll
-            for (int ix = 0; ix < BW + 2; ++ix) v[ix] = ld4<TH_>(src + (uint32_t)(iy * (TW + 2) + ix) * 128u);
+            for (int ix = 0; ix < BW + 2; ++ix) v[ix] = ld2<TH_>(src + (uint32_t)(iy * (TW + 2) + ix) * 128u);
 #pragma unroll
-            for (int oy = 0; oy < 2; ++oy) {
+            for (int oy = 0; oy < BH; ++oy) {
               const int ky = iy - oy;
               if (ky < 0 || ky > 2) continue;
 #pragma unroll
-              for (int ox = 0; ox < BW; ++ox)
-#pragma unroll
-                for (int kx = 0; kx < 3; ++kx) fma4(acc[set][oy][ox], w[ky * 3 + kx], v[ox + kx]);
+              for (int ox = 0; ox < BW; ++ox) {
+                // the first tap that reaches an output (ky = 0, kx = 0) initialises it: no zero-fill pass
+                if (ky == 0) acc[set][oy][ox] = mul2(w[0], v[ox]);
+                else acc[set][oy][ox] = fma2(w[ky * 3], v[ox], acc[set][oy][ox]);
+                acc[set][oy][ox] = fma2(w[ky * 3 + 1], v[ox + 1], acc[set][oy][ox]);
+                acc[set][oy][ox] = fma2(w[ky * 3 + 2], v[ox + 2], acc[set][oy][ox]);
+              }
             }
           }
         }
@@ -255,20 +286,20 @@ ffn_tail_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__
         mbar_wait(smem_u32(&bars->op_empty[o]), ((it / NOP) & 1u) ^ 1u);
         const uint32_t ob = sOP + o * OPBOX;
 #pragma unroll
-        for (int oy = 0; oy < 2; ++oy)
+        for (int oy = 0; oy < BH; ++oy)
 #pragma unroll
           for (int ox = 0; ox < BW; ++ox) {
-            const float4 a = acc[0][oy][ox], g = acc[1][oy][ox];
-            float4 r4 = make_float4(gelu_erf(a.x) * g.x, gelu_erf(a.y) * g.y, gelu_erf(a.z) * g.z, gelu_erf(a.w) * g.w);
-            const uint32_t row = (uint32_t)((2 * by + oy) * TW + BW * bx + ox);
+            float gx, gy;
+            unpack2(gelu_gate2(acc[0][oy][ox], acc[1][oy][ox]), gx, gy);
+            const uint32_t row = (uint32_t)((BH * by + oy) * TW + BW * bx + ox);
             if constexpr (std::is_same<TH_, float>::value) {
-              r4 = make_float4(to_tf32(r4.x), to_tf32(r4.y), to_tf32(r4.z), to_tf32(r4.w));
-              sts128(ob + row * 128u + ((((uint32_t)cq) ^ (row & 7u)) << 4), r4);
+              // 2 tf32 values = 8 bytes: 16-byte chunk cp/2 of the row, swizzled by the row
+              uint2 t = make_uint2(__float_as_uint(to_tf32(gx)), __float_as_uint(to_tf32(gy)));
+              sts64u(ob + row * 128u + ((((uint32_t)cp >> 1) ^ (row & 7u)) << 4) + ((uint32_t)cp & 1u) * 8u, t);
             } else {
-              uint2 t;
-              *reinterpret_cast<__half2*>(&t.x) = __floats2half2_rn(r4.x, r4.y);
-              *reinterpret_cast<__half2*>(&t.y) = __floats2half2_rn(r4.z, r4.w);
-              sts64u(ob + row * 128u + ((((uint32_t)cq >> 1) ^ (row & 7u)) << 4) + ((uint32_t)cq & 1u) * 8u, t);
+              const __half2 h = __floats2half2_rn(gx, gy);
+              const uint32_t a = ob + row * 128u + ((((uint32_t)cp >> 2) ^ (row & 7u)) << 4) + ((uint32_t)cp & 3u) * 4u;
+              asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(*reinterpret_cast<const uint32_t*>(&h)) : "memory");
             }
           }
         fence_async_smem();
@@ -340,7 +371,7 @@ int launch_inst(const CUtensorMap& tH, const CUtensorMap& tR, const CUtensorMap&
     IRB_CUDA(cudaFuncSetAttribute(ffn_tail_kernel<TH_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
-  ffn_tail_kernel<TH_><<<grid, NTHREADS, smem, s>>>(tH, tR, tY, p);
+  ffn_tail_kernel<TH_><<<grid, (EPI_WARPS + Geo<TH_>::DW_WARPS + 3) * 32, smem, s>>>(tH, tR, tY, p);
   IRB_LAUNCH_CHECK();
   return IR_OK;
 }

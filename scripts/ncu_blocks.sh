@@ -4,7 +4,7 @@
 TAG=${1:-blk}
 OUT=gpurun_out
 mkdir -p $OUT
-timeout 800 ncu --set full --clock-control none --profile-from-start off -f -o /tmp/prof_$TAG \
+timeout 800 ncu --set full --clock-control none --profile-from-start off ${NCU_K:+-k regex:$NCU_K} -f -o /tmp/prof_$TAG \
     python scripts/bench_kernels.py --ncu > $OUT/ncu_$TAG.log 2>&1
 echo "ncu exit $?"
 ncu -i /tmp/prof_$TAG.ncu-rep --page raw --csv > $OUT/ncu_raw_$TAG.csv 2>/dev/null
