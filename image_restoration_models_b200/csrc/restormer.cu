@@ -90,9 +90,11 @@ static void plan_block(Builder& bl, BlockPlan& bp, int C, int heads, float ffn, 
   bp.tc_pin = bl.tc(C, 2 * bp.hp);
   bp.tc_pout = bl.tc(bp.hp, C);
   // the TMA-fed kernel takes the layers whose A tile is shared by at most two N-chunks (the high-resolution levels)
-  bp.tma_qkv = bp.tc_qkv && bl.tma(C, 3 * C, true, false, bl.half());
+  // (LayerNorm is fused into the contraction up to C = 128; wider levels normalise into a scratch tensor first)
+  const bool ln_fused = C <= 128;
+  bp.tma_qkv = bp.tc_qkv && bl.tma(C, 3 * C, ln_fused, false, bl.half());
   bp.tma_attn = bp.tc_attn && bl.tma(C, C, false, true, false);
-  bp.tma_pin = bp.tc_pin && bl.tma(C, 2 * bp.hp, true, false, bl.half());
+  bp.tma_pin = bp.tc_pin && bl.tma(C, 2 * bp.hp, ln_fused, false, bl.half());
   bp.tma_pout = bp.tc_pout && bl.tma(bp.hp, C, false, true, false);
   bp.kp_attn = bp.tma_attn ? tma_gemm_kpad(C, bl.half()) : C;
   // GDFN tail in one kernel (no biases: every shipped configuration has bias=False)
@@ -362,6 +364,11 @@ static int run_1x1(const GemmParams& g, bool tc, bool half, bool a_half, bool y_
   t.a_half = a_half; t.op_half = half; t.y_half = y_half;
   if (tma) {
     // the layer's weights were packed for the TMA-fed kernel at plan time; the plan only selects shapes it supports
+    if (g.ln_mode != LN_NONE && g.K > 128) {
+      IRB_TRY(launch_layernorm(g.a1, g.lda1, xhat, g.K, half ? 1 : 0, (long long)g.B * g.H * g.W, g.K, g.ln_mode,
+                               g.ln_w, g.ln_b, s));
+      t.a1 = xhat; t.lda1 = g.K; t.ln_mode = LN_NONE; t.a_half = half;
+    }
     const int st = launch_gemm_tma(t, s);
     if (st == IR_UNSUPPORTED_SHAPE) { set_error("internal: layer planned for the TMA kernel is not launchable (alignment)"); return IR_ERR_INVALID; }
     return st;
@@ -517,7 +524,16 @@ int restormer_launch_count(const RestormerPlan& pl) {
   auto blocks = [&](const std::vector<BlockPlan>& v) {
     for (const auto& bp : v) {
       n += bp.fuse_tail ? 7 : 8;
-      if (bp.C > 128) n += (bp.tc_qkv ? 1 : 0) + (bp.tc_pin ? 1 : 0);   // standalone LayerNorm on the wide levels
+      // standalone LayerNorm where the contraction cannot take it as a prologue (the wide levels)
+      auto ln_standalone = [&](bool tc, bool tma, int N) {
+        if (!tc) return false;
+        if (tma) return bp.C > 128;
+        TcGemmParams t{};
+        t.K = bp.C; t.N = N; t.k1 = bp.C; t.k2 = 0; t.ln_mode = LN_BIASFREE; t.a_pad = 1;
+        t.a_half = 0; t.op_half = bp.half; t.y_half = bp.half;
+        return tc_gemm_configure(t) == 0;
+      };
+      n += (ln_standalone(bp.tc_qkv, bp.tma_qkv, 3 * bp.C) ? 1 : 0) + (ln_standalone(bp.tc_pin, bp.tma_pin, 2 * bp.hp) ? 1 : 0);
     }
   };
   for (int l = 0; l < 4; ++l) blocks(pl.enc[l]);

@@ -25,6 +25,8 @@
 #include "sm100.cuh"
 #include "tmap.cuh"
 
+#include <cstdlib>
+
 namespace irb {
 
 namespace {
@@ -482,11 +484,15 @@ int launch_inst(const CUtensorMap& tA, const CUtensorMap& tR, const CUtensorMap&
 
 }  // namespace
 
-// The plan uses this kernel when the A tile is re-read by at most two N-chunks (wider layers re-read A from L2 too
-// often; they stay on the first-generation kernel, which streams the weights instead).
+// The plan uses this kernel when the A tile is re-read by few N-chunks: at most two at the high-resolution levels
+// (K <= 128), more at the low-resolution levels, whose whole A tensor (1/16 or 1/64 of the pixels) stays in the 126 MB L2.
 bool tma_gemm_shape_supported(int K, int N, bool op_half, bool ln, bool has_r, bool y_half) {
   TmaCfg c;
-  return configure(K, N, op_half, ln, has_r, y_half, c) && c.nchunks <= 2;
+  if (!configure(K, N, op_half, ln, has_r, y_half, c)) return false;
+  const int lim = K <= 128 ? 2 : has_r ? 6 : 24;
+  const char* e = getenv("IRB_TMA_CHUNK_LIMIT");      // bring-up knob: 0 keeps the low-resolution levels on the first kernel
+  if (e && K > 128) return c.nchunks <= atoi(e);
+  return c.nchunks <= lim;
 }
 
 int tma_gemm_kpad(int K, bool op_half) { const int oc = op_half ? 64 : 32; return (K + oc - 1) / oc * oc; }
