@@ -17,7 +17,8 @@ struct FfnTailArgs {
 bool ffn_tail_supported(int C, int hp, bool half);
 int  ffn_tail_kc(bool half);
 int  launch_ffn_tail(const FfnTailArgs& a, cudaStream_t s);
-// dst[((chunk*2 + half)*9 + tap)*kc + c] = src[(half*h + chunk*kc + c)*9 + tap]   (zero for padded channels >= h)
-int  launch_pack_dw_chunked(const float* src, float* dst, int h, int hp, int kc, cudaStream_t s);
+// dst[((chunk*nsets + set)*9 + tap)*kc + c] = src[(set*h + chunk*kc + c)*9 + tap]   (zero for padded channels >= h;
+// hp = h padded to a multiple of kc; nsets = 2 for the GDFN halves, 1 for the qkv depthwise conv)
+int  launch_pack_dw_chunked(const float* src, float* dst, int h, int hp, int kc, int nsets, cudaStream_t s);
 
 }  // namespace irb

@@ -75,17 +75,18 @@ int launch_pack_dw(const float* src, float* dst, int c_src_half, int c_dst_half,
   return IR_OK;
 }
 
-__global__ void pack_dw_chunked_kernel(const float* __restrict__ src, float* __restrict__ dst, int h, int hp, int kc) {
-  const int total = 2 * 9 * hp;
+__global__ void pack_dw_chunked_kernel(const float* __restrict__ src, float* __restrict__ dst, int h, int hp, int kc,
+                                       int nsets) {
+  const int total = nsets * 9 * hp;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-    const int c = idx % kc, tap = (idx / kc) % 9, half = (idx / (9 * kc)) % 2, chunk = idx / (18 * kc);
+    const int c = idx % kc, tap = (idx / kc) % 9, half = (idx / (9 * kc)) % nsets, chunk = idx / (nsets * 9 * kc);
     const int ch = chunk * kc + c;
     dst[idx] = ch < h ? src[(half * h + ch) * 9 + tap] : 0.f;
   }
 }
 
-int launch_pack_dw_chunked(const float* src, float* dst, int h, int hp, int kc, cudaStream_t s) {
-  pack_dw_chunked_kernel<<<cdiv(18 * hp, 256), 256, 0, s>>>(src, dst, h, hp, kc);
+int launch_pack_dw_chunked(const float* src, float* dst, int h, int hp, int kc, int nsets, cudaStream_t s) {
+  pack_dw_chunked_kernel<<<cdiv(nsets * 9 * hp, 256), 256, 0, s>>>(src, dst, h, hp, kc, nsets);
   IRB_LAUNCH_CHECK();
   return IR_OK;
 }

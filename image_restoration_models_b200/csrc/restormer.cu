@@ -6,6 +6,7 @@
 #include "restormer.cuh"
 #include "tc_gemm.cuh"
 #include "ffn_tail.cuh"
+#include "attn_front.cuh"
 
 #include <algorithm>
 
@@ -97,14 +98,21 @@ static void plan_block(Builder& bl, BlockPlan& bp, int C, int heads, float ffn, 
   bp.tma_pin = bp.tc_pin && bl.tma(C, 2 * bp.hp, ln_fused, false, bl.half());
   bp.tma_pout = bp.tc_pout && bl.tma(bp.hp, C, false, true, false);
   bp.kp_attn = bp.tma_attn ? tma_gemm_kpad(C, bl.half()) : C;
-  // GDFN tail in one kernel (no biases: every shipped configuration has bias=False)
+  // MDTA front / GDFN tail in one kernel each (no biases: every shipped configuration has bias=False)
+  bp.fuse_front = bl.engine != ENGINE_SIMT && !bias && bp.tc_attn && attn_front_supported(C, heads, bl.half());
   bp.fuse_tail = bl.engine != ENGINE_SIMT && !bias && ffn_tail_supported(C, bp.hp, bl.half());
   vec(bp.ln1_w, C);
   if (ln_bias) vec(bp.ln1_b, C);
   vec(bp.temp, heads);
   mat(bp.qkv_w, 3 * C, 3 * C, 1, C, C, bp.tc_qkv, bp.tma_qkv);
   if (bias) vec(bp.qkv_b, 3 * C);
-  dw(bp.qkvdw_w, 3 * C, 3 * C, 1);
+  if (bp.fuse_front) {
+    const int cpad = round_up(3 * C, 32);
+    bp.qkvdw_w = bl.alloc(9LL * cpad);
+    bl.ops.push_back(PackOp{PackOp::DWC, bl.pidx++, bp.qkvdw_w, 3 * C, cpad, 1, 0, 32, 0, 0});
+  } else {
+    dw(bp.qkvdw_w, 3 * C, 3 * C, 1);
+  }
   if (bias) vec(bp.qkvdw_b, 3 * C);
   mat(bp.proj_w, C, C, 1, C, C, false);   // consumed by the softmax/fold kernel, never a GEMM operand
   if (bias) vec(bp.proj_b, C);
@@ -256,7 +264,7 @@ int run_pack_ops(const std::vector<PackOp>& ops, const float* const* params, flo
         IRB_TRY(launch_pack_dw(src, dst, op.a, op.b, op.c, s));
         break;
       case PackOp::DWC:
-        IRB_TRY(launch_pack_dw_chunked(src, dst, op.a, op.b, op.k_dst, s));
+        IRB_TRY(launch_pack_dw_chunked(src, dst, op.a, op.b, op.k_dst, op.c, s));
         break;
       default:
         IRB_REQUIRE(false, "pack: unknown op");
@@ -280,7 +288,7 @@ void block_scratch_need(BlockScratchNeed& n, const BlockPlan& bp, int B, int H, 
   n.qkv = std::max(n.qkv, P * 3 * bp.C);
   n.hidden = std::max(n.hidden, P * 2 * bp.hp);
   n.gated = std::max(n.gated, P * bp.hp);
-  const int parts = gram_parts(B, bp.heads, H * W);
+  const int parts = bp.fuse_front ? attn_front_parts(B, H, W) : gram_parts(B, bp.heads, H * W);
   n.s_part = std::max(n.s_part, (long long)B * bp.heads * parts * ch * ch);
   n.n_part = std::max(n.n_part, (long long)B * bp.heads * parts * 2 * ch);
   n.w_eff = std::max(n.w_eff, (long long)B * bp.C * bp.kp_attn);
@@ -406,8 +414,21 @@ int run_block(const BlockPlan& bp, const float* packed, const float* x_in, float
   g.y = (float*)bs.qkv; g.ldy = 3 * C; g.o_mode = O_NHWC; g.tag = TAG_LN_QKV;
   IRB_TRY(run_1x1(g, bp.tc_qkv, hf, false, hf, bs.xhat, s, bp.tma_qkv));
 
-  // (2) depthwise 3x3 over the 3C channels (restormer.py:114 qkv_dwconv)
   DwParams dwp{};
+  GramParams gp{};
+  const void* v_ptr = (const char*)bs.qkv_dw + (size_t)2 * C * es;
+  int v_ld = 3 * C;
+  if (bp.fuse_front) {
+    // (2+3) depthwise 3x3 + q.k^T Gram partials + squared norms; only v is written (:114-115, :121-124)
+    AttnFrontArgs fa{};
+    fa.qkv = bs.qkv; fa.half = hf; fa.v = bs.qkv_dw; fa.dw_chunked = P(bp.qkvdw_w);
+    fa.s_part = bs.s_part; fa.n_part = bs.n_part; fa.parts = attn_front_parts(B, H, W);
+    fa.B = B; fa.H = H; fa.W = W; fa.C = C; fa.heads = bp.heads;
+    IRB_TRY(launch_attn_front(fa, s));
+    gp.nparts = fa.parts;
+    v_ptr = bs.qkv_dw; v_ld = C;
+  } else {
+  // (2) depthwise 3x3 over the 3C channels (restormer.py:114 qkv_dwconv)
   dwp.in = (const float*)bs.qkv; dwp.ldi = 3 * C; dwp.out = (float*)bs.qkv_dw; dwp.ldo = 3 * C;
   dwp.in_half = hf; dwp.out_half = hf;
   dwp.w = P(bp.qkvdw_w); dwp.bias = P(bp.qkvdw_b); dwp.Cw = 3 * C;
@@ -416,12 +437,12 @@ int run_block(const BlockPlan& bp, const float* packed, const float* x_in, float
   IRB_TRY(bp.ref_kernels ? launch_dwconv_ref(dwp, s) : launch_dwconv(dwp, s));
 
   // (3) Gram q.k^T and row norms per (image, head) (restormer.py:121-124), split over pixel slices
-  GramParams gp{};
   gp.qkv = (const float*)bs.qkv_dw; gp.ld = 3 * C; gp.B = B; gp.HW = H * W; gp.C = C; gp.heads = bp.heads;
   gp.in_half = hf;
   gp.nparts = gram_parts(B, bp.heads, H * W);
   gp.s_part = bs.s_part; gp.n_part = bs.n_part;
   IRB_TRY(bp.ref_kernels ? launch_gram_ref(gp, s) : launch_gram(gp, s));
+  }
 
   // (4) normalise, temperature, softmax; fold project_out into a per-image C x C matrix (:124-131)
   FoldParams fp{};
@@ -432,7 +453,7 @@ int run_block(const BlockPlan& bp, const float* packed, const float* x_in, float
 
   // (5) x_out = x_in + W_eff[b] . v  (+ project_out bias)   (:127-131, :147)
   g = GemmParams{};
-  g.a1 = (const float*)((const char*)bs.qkv_dw + (size_t)2 * C * es); g.lda1 = 3 * C; g.k1 = C; g.a_mode = A_PLAIN;
+  g.a1 = (const float*)v_ptr; g.lda1 = v_ld; g.k1 = C; g.a_mode = A_PLAIN;
   g.B = B; g.H = H; g.W = W;
   g.w = (const float*)bs.w_eff; g.w_bstride = (long long)C * bp.kp_attn; g.N = C; g.K = C; g.Kp = C; g.bias = P(bp.proj_b);
   g.ln_mode = LN_NONE; g.acc_sign = 1.f;
@@ -523,7 +544,7 @@ int restormer_launch_count(const RestormerPlan& pl) {
   int n = 0;
   auto blocks = [&](const std::vector<BlockPlan>& v) {
     for (const auto& bp : v) {
-      n += bp.fuse_tail ? 7 : 8;
+      n += 8 - (bp.fuse_tail ? 1 : 0) - (bp.fuse_front ? 1 : 0);
       // standalone LayerNorm where the contraction cannot take it as a prologue (the wide levels)
       auto ln_standalone = [&](bool tc, bool tma, int N) {
         if (!tc) return false;

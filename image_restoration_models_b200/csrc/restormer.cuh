@@ -24,6 +24,7 @@ struct BlockPlan {     // one TransformerBlock (restormer.py:137-150); offsets i
   long long ln2_w, ln2_b, pin_w, pin_b, ffdw_w, ffdw_b, pout_w, pout_b;
   bool tc_qkv, tc_attn, tc_pin, tc_pout;   // which 1x1 contractions run on the tcgen05 kernel
   bool tma_qkv, tma_attn, tma_pin, tma_pout;   // ... and of those, which on the TMA-fed kernel (tma_gemm.cu; weights in its layout)
+  bool fuse_front;                         // qkv dwconv + Gram + norms + v store in one kernel (attn_front.cu)
   bool fuse_tail;                          // dwconv + gate + project_out + residual in one kernel (ffn_tail.cu)
   int kp_attn;                             // K pitch of the folded attention matrix W_eff (padded for the TMA kernel)
   bool ref_kernels;                        // ENGINE_SIMT: reference CUDA-core kernels everywhere
