@@ -159,17 +159,17 @@ attn_front_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
     // =============================== patch / tap producer ===============================
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmH)) : "memory");
-      uint32_t it = 0;
+      uint32_t s = 0, ph = 0;                              // stage ring position and its phase bit
       for (TileIter ti(p); ti.valid(); ti.next()) {
         const int y0 = ti.y0(), x0 = ti.x0();
-        for (int ch = 0; ch < nchunk; ++ch, ++it) {
-          const uint32_t s = it % (uint32_t)p.nst, ph = (it / (uint32_t)p.nst) & 1u;
+        for (int ch = 0; ch < nchunk; ++ch) {
           mbar_wait(smem_u32(&bars->h_empty[s]), ph ^ 1u);
           const uint32_t fb = smem_u32(&bars->h_full[s]);
           const uint32_t st = sST + s * p.stage_bytes;
           mbar_expect_tx(fb, (uint32_t)(HPIX * PXB + TAPB));
           tma_load_4d(&tmH, fb, st, ch * KC, x0 - 1, y0 - 1, b);
           bulk_load(st + HPIX * PXB, reinterpret_cast<const uint8_t*>(p.dw) + (size_t)ch * TAPB, TAPB, fb);
+          if (++s == (uint32_t)p.nst) { s = 0; ph ^= 1u; }
         }
       }
     }
@@ -203,9 +203,12 @@ attn_front_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
     f2_t nrm[NQK];
 #pragma unroll
     for (int i = 0; i < NQK; ++i) nrm[i] = pack2(0.f, 0.f);
-    uint32_t it = 0, j = 0, vc = 0;
+    uint32_t s = 0, ph = 0, j = 0, vc = 0;
+    const int dwi = warp - EPI_WARPS;                       // this warp's pixels: rows 2(dwi/2)..+1, columns 8(dwi%2)..+7
+    const uint32_t vwarp = sV + (uint32_t)dwi * (2u * 16u * PXB);
     for (TileIter ti(p); ti.valid(); ti.next(), ++j) {
       const int y0 = ti.y0(), x0 = ti.x0();
+      const bool partial = (y0 + TH > p.H) || (x0 + TW > p.W);
       // Output pixels past the right / bottom image edge still see taps from inside the image; they must not reach
       // the Gram or the norms (the v store is clipped by TMA).
       bool okp[BH][BW];
@@ -216,14 +219,14 @@ attn_front_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
       // the MMA of the previous tile has read the X tile (it ran while this CTA produced that tile's v chunks)
       mbar_wait(smem_u32(&bars->x_empty), (j & 1u) ^ 1u);
 #pragma unroll
-      for (int ch = 0; ch < NQK; ++ch, ++it) {
-        const uint32_t s = it % (uint32_t)p.nst;
-        mbar_wait(smem_u32(&bars->h_full[s]), (it / (uint32_t)p.nst) & 1u);
+      for (int ch = 0; ch < NQK; ++ch) {
+        mbar_wait(smem_u32(&bars->h_full[s]), ph);
         const uint32_t st = sST + s * p.stage_bytes;
         f2_t acc[BH][BW];
         dw_chunk<TH_>(st + win0, st + HPIX * PXB + (uint32_t)cp * 8u, acc);
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&bars->h_empty[s]));
+        if (++s == (uint32_t)p.nst) { s = 0; ph ^= 1u; }
         // transposed store: rows = channels ch*32 + 2cp (+1), columns = the block's pixels (4 consecutive per row)
         const uint32_t r0 = (uint32_t)(ch * KC + 2 * cp);
 #pragma unroll
@@ -231,10 +234,12 @@ attn_front_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
           float a0, a1, b0, b1, c0, c1, d0, d1;
           unpack2(acc[oy][0], a0, a1); unpack2(acc[oy][1], b0, b1);
           unpack2(acc[oy][2], c0, c1); unpack2(acc[oy][3], d0, d1);
-          if (!okp[oy][0]) { a0 = 0.f; a1 = 0.f; }
-          if (!okp[oy][1]) { b0 = 0.f; b1 = 0.f; }
-          if (!okp[oy][2]) { c0 = 0.f; c1 = 0.f; }
-          if (!okp[oy][3]) { d0 = 0.f; d1 = 0.f; }
+          if (partial) {
+            if (!okp[oy][0]) { a0 = 0.f; a1 = 0.f; }
+            if (!okp[oy][1]) { b0 = 0.f; b1 = 0.f; }
+            if (!okp[oy][2]) { c0 = 0.f; c1 = 0.f; }
+            if (!okp[oy][3]) { d0 = 0.f; d1 = 0.f; }
+          }
           if constexpr (F32) {
             a0 = to_tf32(a0); b0 = to_tf32(b0); c0 = to_tf32(c0); d0 = to_tf32(d0);
             a1 = to_tf32(a1); b1 = to_tf32(b1); c1 = to_tf32(c1); d1 = to_tf32(d1);
@@ -269,45 +274,45 @@ attn_front_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
       fence_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&bars->x_ready));
-      // ---- v chunks: [pixel][channel] staging box -> TMA store ----
-      for (int ch = 0; ch < p.nv; ++ch, ++it, ++vc) {
-        const uint32_t s = it % (uint32_t)p.nst;
-        mbar_wait(smem_u32(&bars->h_full[s]), (it / (uint32_t)p.nst) & 1u);
+      // ---- v chunks: each warp stages its own 2 x 8 pixel region ([pixel][channel]) and stores it with its own
+      //      bulk-tensor copy: no block-wide barrier on the path ----
+      for (int ch = 0; ch < p.nv; ++ch, ++vc) {
+        mbar_wait(smem_u32(&bars->h_full[s]), ph);
         const uint32_t st = sST + s * p.stage_bytes;
         f2_t acc[BH][BW];
         dw_chunk<TH_>(st + win0, st + HPIX * PXB + (uint32_t)cp * 8u, acc);
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&bars->h_empty[s]));
-        const uint32_t vb = sV + (vc & 1u) * VBOX;
-        // the store that last read this staging box (two v chunks ago) has drained it
-        if (ctid == 0) bulk_wait_read<1>();
-        asm volatile("bar.sync 1, %0;" ::"n"(DW_WARPS * 32) : "memory");
+        if (++s == (uint32_t)p.nst) { s = 0; ph ^= 1u; }
+        const uint32_t vb = vwarp + (vc & 1u) * (16u * PXB);
+        if (lane == 0) bulk_wait_read<1>();                  // the store that last read this buffer has drained it
+        __syncwarp();
 #pragma unroll
         for (int oy = 0; oy < BH; ++oy)
 #pragma unroll
           for (int ox = 0; ox < BW; ++ox) {
             float gx, gy;
             unpack2(acc[oy][ox], gx, gy);
-            const uint32_t row = (uint32_t)((BH * by + oy) * TW + BW * bx + ox);
+            const uint32_t lp = (uint32_t)(oy * 8 + (lane >> 4) * 4 + ox);     // pixel inside the warp's 2 x 8 region
             if constexpr (F32) {
               // rounded to tf32: the attention-output contraction feeds v to the tensor core straight from its TMA box
               uint2 t = make_uint2(__float_as_uint(to_tf32(gx)), __float_as_uint(to_tf32(gy)));
-              sts64u(vb + row * 128u + ((((uint32_t)cp >> 1) ^ (row & 7u)) << 4) + ((uint32_t)cp & 1u) * 8u, t);
+              sts64u(vb + lp * 128u + ((((uint32_t)cp >> 1) ^ (lp & 7u)) << 4) + ((uint32_t)cp & 1u) * 8u, t);
             } else {
               const __half2 h = __floats2half2_rn(gx, gy);
-              asm volatile("st.shared.b32 [%0], %1;" ::"r"(vb + row * 64u + (uint32_t)cp * 4u),
+              asm volatile("st.shared.b32 [%0], %1;" ::"r"(vb + lp * 64u + (uint32_t)cp * 4u),
                            "r"(*reinterpret_cast<const uint32_t*>(&h)) : "memory");
             }
           }
         fence_async_smem();
-        asm volatile("bar.sync 1, %0;" ::"n"(DW_WARPS * 32) : "memory");
-        if (ctid == 0) {
-          tma_store_4d(&tmV, vb, ch * KC, x0, y0, b);
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_4d(&tmV, vb, ch * KC, x0 + 8 * (dwi & 1), y0 + 2 * (dwi >> 1), b);
           bulk_commit();
         }
       }
     }
-    if (ctid == 0) bulk_wait_read<0>();
+    if (lane == 0) bulk_wait_read<0>();
     // ---- norm partials: reduce the 16 pixel blocks of every channel in a fixed order ----
 #pragma unroll
     for (int ch = 0; ch < NQK; ++ch) {
@@ -426,7 +431,7 @@ int launch_attn_front(const AttnFrontArgs& a, cudaStream_t s) {
   {
     cuuint64_t d[4] = {(cuuint64_t)a.C, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.B};
     cuuint64_t st[3] = {(cuuint64_t)a.C * es, (cuuint64_t)a.C * es * a.W, (cuuint64_t)a.C * es * a.W * a.H};
-    cuuint32_t box[4] = {KC, TW, TH, 1};
+    cuuint32_t box[4] = {KC, 8, 2, 1};                 // one dw warp's region
     IRB_TRY(make_tmap(&tV, a.v, a.half != 0, 4, d, st, box, !a.half));   // fp32 staging rows are 128 B (swizzled), fp16 64 B
   }
   FrontParams p{};
