@@ -241,9 +241,15 @@ def main():
     e2e_value = world * pix_per_step / 1e6 / (e2e_ms / 1e3)
 
     # ---- per-kernel breakdown (separate pass: two events per launch) ------------------------------
+    # (IRB_NCU_RANGE=1: this one forward is the cudaProfiler range that scripts/ncu_traffic.sh captures)
+    ncu_range = os.environ.get("IRB_NCU_RANGE") == "1"
+    if ncu_range:
+        torch.cuda.profiler.start()
     with _native.kernel_profile() as prof:
         model(x_dev)
         torch.cuda.synchronize()
+    if ncu_range:
+        torch.cuda.profiler.stop()
     rows = sorted(prof.rows, key=lambda r: -r["ms"])
     hbm_peak, tc_peak, peak_kind = load_peaks()
     kernels = []
@@ -256,8 +262,20 @@ def main():
     top = rows[0]
     top_ms_per_launch = top["ms"] / top["launches"]
     achieved = top["bytes"] / top["launches"] / 1e9 / (top_ms_per_launch / 1e3)
+    # DRAM bytes per launch of that family from the committed ncu pass of this same command (scripts/ncu_traffic.sh)
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", f"traffic_{args.mode}.json")
+    if os.path.exists(tpath):
+        try:
+            fam = json.load(open(tpath))["families"].get(top["name"])
+            if fam and fam["launches"] == top["launches"]:
+                traffic = fam["dram_bytes_per_launch"]
+                traffic_src = f"profiles/traffic_{args.mode}.json (ncu dram__bytes_read.sum + dram__bytes_write.sum)"
+        except Exception:
+            pass
     roofline = {"kernel": top["name"], "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)",
+                "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_src,
+                "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)",
                 "avg_launch_ms": top_ms_per_launch, "share_of_step": top["ms"] / sum(r["ms"] for r in rows),
                 "algorithmic_bytes_per_launch": top["bytes"] / top["launches"]}
     step_bytes = sum(r["bytes"] for r in rows)

@@ -275,9 +275,18 @@ int ir_test_conv3x3(int engine, const float* x_nhwc, int ldx, int cin, const flo
   IRB_REQUIRE(x_nhwc && w_oihw && y && scratch && B > 0 && H > 0 && W > 0 && cin > 0 && cout > 0, "test_conv3x3: bad argument");
   IRB_REQUIRE(o_mode == O_NHWC || o_mode == O_UNSHUFFLE || o_mode == O_SHUFFLE, "test_conv3x3: bad o_mode");
   cudaStream_t s = (cudaStream_t)stream;
-  const int K = 9 * cin, Kp = (K + 3) / 4 * 4;
+  const int K = 9 * cin;
+  const bool tma = engine == 3;                  // the TMA-fed implicit GEMM only (shuffle-scatter epilogues)
+  const int Kp = tma ? 9 * tma_conv3_kpt(cin, op_half != 0) : (K + 3) / 4 * 4;
   if (scratch_bytes < (size_t)cout * Kp * sizeof(float)) { set_error("scratch too small"); return IR_ERR_WORKSPACE; }
   float* wp = (float*)scratch;
+  if (tma) {
+    IRB_REQUIRE(tma_conv3_supported(cin, cout, op_half != 0) && o_mode != O_NHWC && !bias && !relu,
+                "test_conv3x3: shape / epilogue not handled by the TMA-fed kernel");
+    PackMat pm{w_oihw, wp, 2, cin, cout, cout, 1, K, Kp, nullptr, op_half ? 4 : 3};
+    IRB_TRY(launch_pack_mat(pm, s));
+    return launch_conv3_tma(x_nhwc, ldx, cin, wp, cout, cout, B, H, W, y, ldy, o_mode, op_half != 0, s);
+  }
   const bool tc = engine == ENGINE_TC;
   IRB_REQUIRE(!tc || tc_conv3_supported(cin, cout, op_half != 0), "test_conv3x3: shape not supported by the tcgen05 kernel");
   PackMat pm{w_oihw, wp, 1, cin, cout, cout, 1, K, Kp, nullptr, !tc ? 0 : op_half ? 2 : 1};

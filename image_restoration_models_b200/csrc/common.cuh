@@ -139,7 +139,8 @@ int launch_tile_blend(const float* pred, const int* tile_xy, int T, int th, int 
 // weight packing (pack.cu)
 struct PackMat {
   const float* src; float* dst;
-  int kind;            // 0: src[n][k] (1x1 / linear), 1: src[n][cin][3][3] -> k = tap*cin + c
+  int kind;            // 0: src[n][k] (1x1 / linear), 1: src[n][cin][3][3] -> k = tap*cin + c,
+                       // 2: src[n][cin][3][3] -> k = tap*(k_dst/9) + c (taps padded to whole operand boxes)
   int cin;             // kind 1 only
   int n_src_half, n_dst_half, n_halves;   // row split-pad mapping (GDFN hidden padding)
   int k_src, k_dst;                        // logical / padded reduction length (kind 0: zero-pad; kind 1: k_src = 9*cin)

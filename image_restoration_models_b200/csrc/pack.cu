@@ -20,9 +20,13 @@ __global__ void pack_mat_kernel(const PackMat p) {
     const int n = (int)(idx / p.k_dst), k = (int)(idx - (long long)n * p.k_dst);
     const int ns = map_src(n, p.n_src_half, p.n_dst_half);
     float v = 0.f;
-    if (ns >= 0 && k < p.k_src) {
+    if (ns >= 0 && (k < p.k_src || p.kind == 2)) {
       if (p.kind == 0) {
         v = p.src[(long long)ns * p.k_src + k];
+      } else if (p.kind == 2) {
+        // 3x3 weights for tma_conv3.cu: k = tap * kpt + c, every tap padded to kpt = k_dst / 9 channels
+        const int kpt = p.k_dst / 9, tap = k / kpt, c = k - tap * kpt;
+        v = c < p.cin ? p.src[((long long)ns * p.cin + c) * 9 + tap] : 0.f;
       } else {
         const int tap = k / p.cin, c = k - tap * p.cin;
         v = p.src[((long long)ns * p.cin + c) * 9 + tap];

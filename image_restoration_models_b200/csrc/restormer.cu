@@ -151,10 +151,13 @@ static void plan_conv3(Builder& bl, ConvPlan& cp, int cout, int cin, int bias, b
   // the tensor-core kernel wants N % 16 == 0: pad with zero rows (only used with the shuffle-scatter epilogue,
   // which skips the padding channels), e.g. down1_2: 48 -> 24 channels
   cp.cout_p = scatter ? round_up(cout, 16) : cout;
-  cp.w = bl.alloc((long long)cp.cout_p * cp.kp);
   cp.tc = bl.engine != ENGINE_SIMT && bias == 0 && tc_conv3_supported(cin, cp.cout_p, bl.half());
+  // the shuffle-scatter convolutions run on the TMA-fed implicit GEMM (taps padded to whole operand boxes)
+  cp.tma = cp.tc && scatter && tma_conv3_supported(cin, cp.cout_p, bl.half());
+  if (cp.tma) cp.kp = 9 * tma_conv3_kpt(cin, bl.half());
   if (!cp.tc) cp.cout_p = cout;
-  bl.ops.push_back(PackOp{PackOp::MAT3, bl.pidx++, cp.w, cout, cp.cout_p, 1, 9 * cin, cp.kp, cin, bl.fmt(cp.tc)});
+  cp.w = bl.alloc((long long)cp.cout_p * cp.kp);
+  bl.ops.push_back(PackOp{PackOp::MAT3, bl.pidx++, cp.w, cout, cp.cout_p, 1, 9 * cin, cp.kp, cin, bl.fmt(cp.tc, cp.tma)});
   cp.b = -1;
   if (bias) {
     cp.b = bl.alloc(cout);
@@ -256,7 +259,7 @@ int run_pack_ops(const std::vector<PackOp>& ops, const float* const* params, flo
         break;
       }
       case PackOp::MAT3: {
-        PackMat pm{src, dst, 1, op.cin, op.a, op.b, op.c, op.k_src, op.k_dst, nullptr, op.fmt};
+        PackMat pm{src, dst, op.fmt >= 3 ? 2 : 1, op.cin, op.a, op.b, op.c, op.k_src, op.k_dst, nullptr, op.fmt};
         IRB_TRY(launch_pack_mat(pm, s));
         break;
       }
@@ -524,6 +527,8 @@ static int run_stage(const std::vector<BlockPlan>& blocks, const float* packed, 
 
 static int conv3(const ConvPlan& cp, const float* packed, const float* in, int ld_in, int a_mode, int B, int H, int W,
                  float* out, int ld_out, int o_mode, const float* r, bool half, cudaStream_t s) {
+  if (cp.tma && a_mode == A_IM2COL_NHWC && (o_mode == O_UNSHUFFLE || o_mode == O_SHUFFLE) && r == nullptr)
+    return launch_conv3_tma(in, ld_in, cp.cin, packed + cp.w, cp.cout_p, cp.cout, B, H, W, out, ld_out, o_mode, half, s);
   if (cp.tc && a_mode == A_IM2COL_NHWC && o_mode != O_NCHW && r == nullptr)
     return run_conv3_tc(in, ld_in, cp.cin, packed + cp.w, cp.b >= 0 ? packed + cp.b : nullptr, cp.cout_p, cp.cout, B, H, W,
                         out, ld_out, o_mode, 0, half, s);

@@ -31,7 +31,7 @@ struct BlockPlan {     // one TransformerBlock (restormer.py:137-150); offsets i
   bool half;                               // ENGINE_TC_HALF: fp16 intermediates (qkv, v, hidden, gated) and fp16 operands
 };
 
-struct ConvPlan { int cout, cin, k, kp; long long w, b; bool tc; int cout_p; };   // cout_p: rows in the packed weight (>= cout, zero rows)
+struct ConvPlan { int cout, cin, k, kp; long long w, b; bool tc; int cout_p; bool tma = false; };   // cout_p: rows in the packed weight (>= cout, zero rows)
 
 struct RestormerPlan {
   IrRestormerCfg cfg;

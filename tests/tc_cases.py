@@ -157,6 +157,21 @@ CONV3_CASES = [
 ]
 
 
+# shuffle-scatter cases for the TMA-fed implicit GEMM (engine 3): (cin, cout, B, H, W, o_mode, bias, relu, op_half)
+TMA_CONV3_CASES = [
+    (48, 32, 1, 16, 24, 1, False, False, 0),     # down1_2 family: 1.5 boxes per tap, ragged patch grid
+    (96, 48, 1, 16, 16, 1, False, False, 0),     # down2_3
+    (192, 96, 2, 8, 8, 1, False, False, 0),      # down3_4, batch 2, one patch per image
+    (384, 768, 1, 8, 8, 2, False, False, 0),     # up4_3: three N-chunks of 256
+    (192, 384, 1, 8, 16, 2, False, False, 0),    # up3_2: two N-chunks
+    (96, 192, 1, 16, 16, 2, False, False, 0),    # up2_1
+    (96, 192, 2, 40, 72, 2, False, False, 0),    # several patches per CTA, partial patches on both edges
+    (48, 32, 1, 64, 96, 1, False, False, 1),     # fp16 operands
+    (96, 192, 1, 24, 40, 2, False, False, 1),
+    (384, 768, 1, 8, 8, 2, False, False, 1),
+]
+
+
 def run_conv3_case(case, engine, seed=0):
     import torch.nn.functional as F
     cin, cout, B, H, W, o_mode, bias, relu, op_half = case
@@ -179,7 +194,7 @@ def run_conv3_case(case, engine, seed=0):
     wd = w.to(dev).contiguous()
     bd = bvec.to(dev) if bias else None
     y = torch.full(tuple(ref.shape), float("nan"), device=dev)
-    scratch = torch.empty(cout * 9 * cin * 4 + 1024, dtype=torch.uint8, device=dev)
+    scratch = torch.empty(cout * 9 * (cin + 64) * 4 + 1024, dtype=torch.uint8, device=dev)
     P = lambda t: 0 if t is None else t.data_ptr()
     st = lib.ir_test_conv3x3(engine, P(xl), cin, cin, P(wd), P(bd), cout, B, H, W, P(y), Co, o_mode, int(relu), op_half,
                              P(scratch), scratch.numel(), torch.cuda.current_stream().cuda_stream)

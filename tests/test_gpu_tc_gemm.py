@@ -3,7 +3,8 @@ import numpy as np
 import pytest
 
 from conftest import record
-from tc_cases import CASES, CONV3_CASES, HALF_CASES, TMA_CASES, run_case, run_conv3_case, tolerance
+from tc_cases import (CASES, CONV3_CASES, HALF_CASES, TMA_CASES, TMA_CONV3_CASES, run_case, run_conv3_case,
+                      tolerance)
 
 pytestmark = pytest.mark.gpu
 
@@ -53,4 +54,16 @@ def test_tc_conv3x3_matches_reference(idx):
     record(f"tc_conv3x3_{idx}", cfg=str(case), err_tc=e_tc, err_simt=e_simt, tol=tol)
     assert np.isfinite(y_tc).all()
     assert e_simt <= 2e-5 * max(1.0, float(np.abs(y_ref).max()))
+    assert e_tc <= tol, (case, e_tc)
+
+
+@pytest.mark.parametrize("idx", range(len(TMA_CONV3_CASES)))
+def test_tma_conv3x3_matches_reference(idx):
+    """The TMA-fed implicit-GEMM 3x3 convolution (tma_conv3.cu) with the PixelUnshuffle / PixelShuffle scatter."""
+    case = TMA_CONV3_CASES[idx]
+    y_tc, y_ref = run_conv3_case(case, 3, seed=300 + idx)
+    e_tc = float(np.abs(y_tc - y_ref).max())
+    tol = 4e-3 * float(np.abs(y_ref).max()) + 1e-5
+    record(f"tma_conv3x3_{idx}", cfg=str(case), err_tc=e_tc, tol=tol)
+    assert np.isfinite(y_tc).all()
     assert e_tc <= tol, (case, e_tc)
