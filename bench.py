@@ -155,6 +155,14 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE JSON line: anything a library prints there (e.g. the NCCL version banner) goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
 
     config = {"workload": "Restormer gray Gaussian denoise (1->1 ch, dim=48, blocks [4,6,6,8]), batch 8 of synthetic "
                           "512x512 per GPU (BASELINE config 2)",
@@ -171,7 +179,7 @@ def main():
                 "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": mpix, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
                 "e2e": {"value": mpix, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     import torch
@@ -320,7 +328,7 @@ def main():
             "step_algorithmic_GB": step_bytes / 1e9, "step_TFLOP": step_flops / 1e12,
             "step_hbm_frac": step_bytes / 1e9 / (ms_step / 1e3) / hbm_peak,
             "kernels": kernels}
-    print(json.dumps(line))
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
     return 0
