@@ -106,9 +106,8 @@ def run_model_inference(model, input_img: np.ndarray, device, patch_size=None, p
         raise ValueError(f"unsupported image dtype {input_img.dtype}")
     be = backend or CudaBackend(device)
     h, w = input_img.shape[:2]
-    Cc = min(3, input_img.shape[2])
-    if input_img.shape[2] != Cc:
-        raise ValueError("images with more than 3 channels: pass the channels the model consumes")
+    Cin = input_img.shape[2]                  # every input channel goes to the model (dual-pixel: 6, src/utils.py:405)
+    Cc = min(3, Cin)                          # channels of the output image / weight map (src/utils.py:394-395)
     h_idx, w_idx, ps = tile_grid(h, w, patch_size, patch_overlap)
     th, tw = min(ps, h), min(ps, w)
     TH, TW = (padded_extent(th), padded_extent(tw)) if pad else (th, tw)
@@ -137,8 +136,11 @@ def run_model_inference(model, input_img: np.ndarray, device, patch_size=None, p
         preds = []
         for s in range(0, hi_t - lo_t, max(1, tile_batch)):
             e = min(hi_t - lo_t, s + max(1, tile_batch))
-            tiles = be.gather(img_dev, code, divisor, h, w, Cc, mine[s:e].contiguous(), e - s, th, tw, TH, TW)
-            preds.append(model(tiles))
+            tiles = be.gather(img_dev, code, divisor, h, w, Cin, mine[s:e].contiguous(), e - s, th, tw, TH, TW)
+            pred = model(tiles)
+            if pred.shape[1] != Cc:
+                raise ValueError(f"model returned {pred.shape[1]} channels for an output image of {Cc}")
+            preds.append(pred)
         local = torch.cat(preds, 0) if preds else torch.empty((0, Cc, TH, TW), dtype=torch.float32,
                                                               device=img_dev.device)
         if world > 1:

@@ -138,3 +138,28 @@ def test_tiled_restormer_matches_oracle_harness():
     out, _ = tiling.run_model_inference(m.cuda(), img, "cuda", 64, 16, pad=True, tile_batch=8)
     diff = np.abs(out.astype(np.int32) - ref.astype(np.int32))
     assert diff.max() <= 1 and (diff > 0).mean() < 0.02
+
+
+class DualStandIn(torch.nn.Module):
+    """6 -> 3 channel stand-in for the dual-pixel model (left / right views in, one image out)."""
+
+    def forward(self, x):
+        return 0.5 * (x[:, :3] + x[:, 3:]) * 0.9 + 0.03
+
+
+def test_dual_pixel_six_channel_input_three_channel_output_host_logic():
+    """BASELINE config 5 shape family: the harness feeds all 6 channels to the model and blends min(3, C) = 3 output
+    channels (src/utils.py:394-395,405); uint16 in, uint16 out."""
+    img = make_image("uint16", 45, 64, 6, 77)
+    ref = tiling_ref.run_model_inference(DualStandIn().eval(), img, 40, 12, True)
+    out, _ = tiling.run_model_inference(DualStandIn().eval(), img, "cpu", 40, 12, pad=True, tile_batch=2,
+                                        backend=NumpyBackend())
+    assert out.shape == (45, 64, 3) and out.dtype == np.uint16 and np.array_equal(out, ref)
+
+
+@pytest.mark.gpu
+def test_dual_pixel_six_channel_input_cuda_kernels_bit_exact():
+    img = make_image("uint16", 45, 64, 6, 77)
+    ref = tiling_ref.run_model_inference(DualStandIn().eval(), img, 40, 12, True)
+    out, _ = tiling.run_model_inference(DualStandIn().eval().cuda(), img, "cuda", 40, 12, pad=True, tile_batch=4)
+    assert out.shape == (45, 64, 3) and np.array_equal(out, ref)
