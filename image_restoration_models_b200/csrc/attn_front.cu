@@ -394,11 +394,8 @@ bool configure(int C, int heads, bool half, FrontCfg& c) {
 
 template <typename TH_, int NQK>
 int launch_inst(const CUtensorMap& tH, const CUtensorMap& tV, const FrontParams& p, dim3 grid, size_t smem, cudaStream_t s) {
-  static bool configured = false;
-  if (!configured) {
-    IRB_CUDA(cudaFuncSetAttribute(attn_front_kernel<TH_, NQK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = true;
-  }
+  static SmemOptIn optin;
+  IRB_TRY(opt_in_smem(attn_front_kernel<TH_, NQK>, optin));
   attn_front_kernel<TH_, NQK><<<grid, NTHREADS, smem, s>>>(tH, tV, p);
   IRB_LAUNCH_CHECK();
   return IR_OK;

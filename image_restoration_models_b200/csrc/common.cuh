@@ -34,6 +34,19 @@ int  cuda_fail(cudaError_t e, const char* what, const char* file, int line);
   do { int _s = (expr); if (_s != IR_OK) return _s; } while (0)
 
 __host__ __device__ static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// Opt a kernel into `bytes` of dynamic shared memory once per DEVICE (the attribute is per device, and one process may
+// drive several); `done` is the caller's per-kernel table.
+struct SmemOptIn { bool done[64] = {}; };
+template <typename K>
+static inline int opt_in_smem(K kernel, SmemOptIn& st, int bytes = 227 * 1024) {
+  int dev = 0;
+  IRB_CUDA(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && st.done[dev]) return IR_OK;
+  IRB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  if (dev >= 0 && dev < 64) st.done[dev] = true;
+  return IR_OK;
+}
 static inline long long cdivll(long long a, long long b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 

@@ -366,11 +366,8 @@ ffn_tail_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__
 template <typename TH_>
 int launch_inst(const CUtensorMap& tH, const CUtensorMap& tR, const CUtensorMap& tY, const FfnTailParams& p, int grid,
                 size_t smem, cudaStream_t s) {
-  static bool configured = false;
-  if (!configured) {
-    IRB_CUDA(cudaFuncSetAttribute(ffn_tail_kernel<TH_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = true;
-  }
+  static SmemOptIn optin;
+  IRB_TRY(opt_in_smem(ffn_tail_kernel<TH_>, optin));
   ffn_tail_kernel<TH_><<<grid, (EPI_WARPS + Geo<TH_>::DW_WARPS + 3) * 32, smem, s>>>(tH, tR, tY, p);
   IRB_LAUNCH_CHECK();
   return IR_OK;

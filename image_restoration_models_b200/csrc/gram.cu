@@ -172,11 +172,8 @@ template <typename T, int CH, int QS>
 int launch_mma(const GramParams& p, cudaStream_t s) {
   constexpr int LD = CH + 4;
   const size_t smem = std::max((size_t)2 * PT * 2 * LD * sizeof(float), (size_t)CH * CH * sizeof(float));
-  static bool configured = false;
-  if (!configured && smem > 48 * 1024) {
-    IRB_CUDA(cudaFuncSetAttribute(gram_mma_kernel<T, CH, QS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
+  static SmemOptIn optin;
+  if (smem > 48 * 1024) IRB_TRY(opt_in_smem(gram_mma_kernel<T, CH, QS>, optin, (int)smem));
   dim3 grid(p.nparts, p.heads, p.B);
   gram_mma_kernel<T, CH, QS><<<grid, 256, smem, s>>>(p);
   IRB_LAUNCH_CHECK();

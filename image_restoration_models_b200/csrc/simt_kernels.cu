@@ -448,7 +448,10 @@ int launch_fold(const FoldParams& p, cudaStream_t s) {
   const size_t smem = (size_t)(ch * ch + 2 * ch) * sizeof(float);
   IRB_REQUIRE(smem <= 48 * 1024 + 0u || ch <= 128, "fold: head dim too large");
   if (smem > 48 * 1024) IRB_CUDA(cudaFuncSetAttribute(fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid(p.heads, p.B, p.heads * p.B >= 64 ? 1 : 4);
+  // the C x ch products are split over grid.z row blocks so that about two waves of CTAs share them (every block
+  // repeats the cheap partial reduction and softmax of its head)
+  const int zb = std::max(1, std::min(8, cdiv(2 * 148, p.heads * p.B)));
+  dim3 grid(p.heads, p.B, zb);
   ProfScope prof(TAG_FOLD, 4.0 * (double)p.B * p.C * p.C, 2.0 * (double)p.B * p.C * p.C * ch, s);
   fold_kernel<<<grid, 256, smem, s>>>(p);
   IRB_LAUNCH_CHECK();

@@ -838,12 +838,8 @@ size_t tc_gemm_configure(TcGemmParams& p) {
 
 template <typename TA, typename TOp, typename TY, int MODE>
 static int launch_one(const TcGemmParams& p, dim3 grid, size_t smem, cudaStream_t s) {
-  static bool configured = false;
-  if (!configured) {
-    IRB_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<TA, TOp, TY, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  227 * 1024));
-    configured = true;
-  }
+  static SmemOptIn optin;
+  IRB_TRY(opt_in_smem(tc_gemm_kernel<TA, TOp, TY, MODE>, optin));
   tc_gemm_kernel<TA, TOp, TY, MODE><<<grid, NTHREADS, smem, s>>>(p);
   IRB_LAUNCH_CHECK();
   return IR_OK;

@@ -301,11 +301,8 @@ bool configure(int cin, int n, bool half, Conv3Cfg& c) {
 
 template <typename TOp>
 int launch_inst(const CUtensorMap& tA, const Conv3Params& p, dim3 grid, size_t smem, cudaStream_t s) {
-  static bool configured = false;
-  if (!configured) {
-    IRB_CUDA(cudaFuncSetAttribute(tma_conv3_kernel<TOp>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = true;
-  }
+  static SmemOptIn optin;
+  IRB_TRY(opt_in_smem(tma_conv3_kernel<TOp>, optin));
   tma_conv3_kernel<TOp><<<grid, NTHREADS, smem, s>>>(tA, p);
   IRB_LAUNCH_CHECK();
   return IR_OK;

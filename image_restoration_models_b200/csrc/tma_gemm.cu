@@ -472,11 +472,8 @@ bool configure(int K, int N, bool op_half, bool ln, bool has_r, bool y_half, Tma
 template <typename TOp, bool LN, typename TY>
 int launch_inst(const CUtensorMap& tA, const CUtensorMap& tR, const CUtensorMap& tY, const TmaGemmParams& p, dim3 grid,
                 size_t smem, cudaStream_t s) {
-  static bool configured = false;
-  if (!configured) {
-    IRB_CUDA(cudaFuncSetAttribute(tma_gemm_kernel<TOp, LN, TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = true;
-  }
+  static SmemOptIn optin;
+  IRB_TRY(opt_in_smem(tma_gemm_kernel<TOp, LN, TY>, optin));
   tma_gemm_kernel<TOp, LN, TY><<<grid, NTHREADS, smem, s>>>(tA, tR, tY, p);
   IRB_LAUNCH_CHECK();
   return IR_OK;
