@@ -281,11 +281,11 @@ int ir_test_conv3x3(int engine, const float* x_nhwc, int ldx, int cin, const flo
   if (scratch_bytes < (size_t)cout * Kp * sizeof(float)) { set_error("scratch too small"); return IR_ERR_WORKSPACE; }
   float* wp = (float*)scratch;
   if (tma) {
-    IRB_REQUIRE(tma_conv3_supported(cin, cout, op_half != 0) && o_mode != O_NHWC && !bias && !relu,
+    IRB_REQUIRE(tma_conv3_supported(cin, cout, op_half != 0) && (o_mode == O_NHWC || (!bias && !relu)),
                 "test_conv3x3: shape / epilogue not handled by the TMA-fed kernel");
     PackMat pm{w_oihw, wp, 2, cin, cout, cout, 1, K, Kp, nullptr, op_half ? 4 : 3};
     IRB_TRY(launch_pack_mat(pm, s));
-    return launch_conv3_tma(x_nhwc, ldx, cin, wp, cout, cout, B, H, W, y, ldy, o_mode, op_half != 0, s);
+    return launch_conv3_tma(x_nhwc, ldx, cin, wp, bias, relu, cout, cout, B, H, W, y, ldy, o_mode, op_half != 0, s);
   }
   const bool tc = engine == ENGINE_TC;
   IRB_REQUIRE(!tc || tc_conv3_supported(cin, cout, op_half != 0), "test_conv3x3: shape not supported by the tcgen05 kernel");

@@ -3,6 +3,7 @@
 // (eval-mode BatchNorm, basicblock.py:69, folded into the preceding conv at pack time) and `x - model(x)`.
 #include "dncnn.cuh"
 #include "restormer.cuh"
+#include "tc_gemm.cuh"
 
 namespace irb {
 
@@ -23,13 +24,16 @@ int build_dncnn_plan(DncnnPlan& pl, const IrDncnnCfg& c, int engine) {
     L.cin = l == 0 ? c.in_nc : c.nc;
     L.cout = l == c.nb - 1 ? c.out_nc : c.nc;
     L.k = 9 * L.cin; L.kp = round_up4(L.k);
+    // the nc -> nc layers run on the TMA-fed implicit GEMM when their shape allows (taps padded to whole operand boxes)
+    L.tma = engine != ENGINE_SIMT && l > 0 && l < c.nb - 1 && L.cout % 16 == 0 && tma_conv3_supported(L.cin, L.cout, pl.half);
+    if (L.tma) L.kp = 9 * tma_conv3_kpt(L.cin, pl.half);
     L.w = alloc((long long)L.cout * L.kp);
     L.b = alloc(L.cout);
     L.p_w = pidx++; L.p_b = pidx++;
     L.p_bn = -1;
     // the nc -> nc layers run as implicit GEMM on the tcgen05 kernel; head (cin = in_nc) and tail (cout = out_nc)
     // have 1..3 channels on one side and stay on the CUDA-core kernel
-    L.tc = engine != ENGINE_SIMT && l > 0 && l < c.nb - 1 && tc_conv3_supported(L.cin, L.cout, pl.half);
+    L.tc = L.tma || (engine != ENGINE_SIMT && l > 0 && l < c.nb - 1 && tc_conv3_supported(L.cin, L.cout, pl.half));
     if (c.has_bn && l > 0 && l < c.nb - 1) { L.p_bn = pidx; pidx += 5; }  // weight, bias, mean, var, num_batches_tracked
     pl.layers.push_back(L);
   }
@@ -59,8 +63,8 @@ int dncnn_pack(const DncnnPlan& pl, const float* const* params, float* packed, c
                              packed + pl.bn_scale, packed + pl.bn_shift, L.cout, s));
       scale = packed + pl.bn_scale; shift = packed + pl.bn_shift;
     }
-    PackMat pm{params[L.p_w], packed + L.w, 1, L.cin, L.cout, L.cout, 1, L.k, L.kp, scale,
-               !L.tc ? 0 : pl.half ? 2 : 1};
+    PackMat pm{params[L.p_w], packed + L.w, L.tma ? 2 : 1, L.cin, L.cout, L.cout, 1, L.k, L.kp, scale,
+               !L.tc ? 0 : L.tma ? (pl.half ? 4 : 3) : pl.half ? 2 : 1};
     IRB_TRY(launch_pack_mat(pm, s));
     IRB_TRY(launch_pack_vec(params[L.p_b], packed + L.b, L.cout, L.cout, 1, scale, shift, s));
   }
@@ -80,6 +84,11 @@ int dncnn_forward(const DncnnPlan& pl, const float* packed, const float* x, floa
   const int nb = (int)pl.layers.size();
   for (int l = 0; l < nb; ++l) {
     const DncnnLayer& L = pl.layers[l];
+    if (L.tma) {
+      IRB_TRY(launch_conv3_tma(buf[(l + 1) & 1], pl.cfg.nc, L.cin, packed + L.w, packed + L.b, 1, L.cout, L.cout, B, H, W,
+                               buf[l & 1], pl.cfg.nc, O_NHWC, pl.half, s));
+      continue;
+    }
     if (L.tc) {
       IRB_TRY(run_conv3_tc(buf[(l + 1) & 1], pl.cfg.nc, L.cin, packed + L.w, packed + L.b, L.cout, L.cout, B, H, W, buf[l & 1],
                            pl.cfg.nc, O_NHWC, 1, pl.half, s));

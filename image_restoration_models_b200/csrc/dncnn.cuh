@@ -5,7 +5,7 @@
 
 namespace irb {
 
-struct DncnnLayer { int cin, cout, k, kp; long long w, b; int p_w, p_b, p_bn; bool tc; };
+struct DncnnLayer { int cin, cout, k, kp; long long w, b; int p_w, p_b, p_bn; bool tc; bool tma; };   // tma: tma_conv3.cu (weights in its layout)
 struct DncnnPlan {
   IrDncnnCfg cfg;
   bool half = false;

@@ -47,11 +47,11 @@ bool tma_gemm_shape_supported(int K, int N, bool op_half, bool ln, bool has_r, b
 int tma_gemm_kpad(int K, bool op_half);
 int launch_gemm_tma(const TcGemmParams& t, cudaStream_t s);
 
-// TMA-fed 3x3 implicit GEMM with the PixelUnshuffle / PixelShuffle scatter (tma_conv3.cu): fp32 channels-last in and
-// out; weights packed with PackMat kind 2, fmt 3 / 4, K pitch 9 * tma_conv3_kpt.
+// TMA-fed 3x3 implicit GEMM (tma_conv3.cu): PixelUnshuffle / PixelShuffle scatter, or plain rows with bias + ReLU
+// (DnCNN body); fp32 channels-last in and out; weights packed with PackMat kind 2, fmt 3 / 4, K pitch 9 * tma_conv3_kpt.
 bool tma_conv3_supported(int cin, int cout_p, bool half);
 int  tma_conv3_kpt(int cin, bool half);
-int  launch_conv3_tma(const float* in, int ld_in, int cin, const void* w_packed, int cout_p, int cout_valid, int B, int H,
-                      int W, float* out, int ld_out, int o_mode, bool half, cudaStream_t s);
+int  launch_conv3_tma(const float* in, int ld_in, int cin, const void* w_packed, const float* bias, int relu, int cout_p,
+                      int cout_valid, int B, int H, int W, float* out, int ld_out, int o_mode, bool half, cudaStream_t s);
 
 }  // namespace irb

@@ -42,6 +42,7 @@ struct Bars {
 struct Conv3Params {
   const uint8_t* w;        // [9 * nob_t boxes][N][128 B] swizzled operand image (PackMat kind 2, fmt 3 / 4)
   float* y; int ldy;
+  const float* bias; int relu;          // plain-row epilogue only (DnCNN body: conv + bias [+ folded BN] + ReLU)
   int B, H, W, Cin, N, n_valid, o_mode;
   int nc;                  // output columns per CTA
   int nkb_t, nob_t;        // raw (32 fp32 channel) boxes / operand boxes per tap
@@ -245,7 +246,27 @@ tma_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const Conv3Params p) {
         if (g == ngroups - 1) { tc_fence_before(); mbar_arrive(smem_u32(&bars->acc_empty[slot])); }
         if (!live) continue;
         const int c0 = n0 + g * 32;
-        if (p.o_mode == O_UNSHUFFLE) {
+        if (p.o_mode == O_NHWC) {
+          // plain rows: this thread's pixel, 32 consecutive channels (one full 128-byte line)
+          if (p.bias) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) v[e] += (c0 + e < p.n_valid) ? __ldg(p.bias + c0 + e) : 0.f;
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) v[e] = fmaxf(v[e], 0.f);
+          }
+          float* dst = p.y + (((long long)b * p.H + y) * p.W + x) * p.ldy + c0;
+          if (c0 + 32 <= p.n_valid) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              *reinterpret_cast<float4*>(dst + 4 * e) = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              if (c0 + e < p.n_valid) dst[e] = v[e];
+          }
+        } else if (p.o_mode == O_UNSHUFFLE) {
           // out[c*4 + 2*(y&1) + (x&1), y/2, x/2] = conv[c, y, x]   (restormer.py:176)
           float* dst = p.y + (((long long)b * (p.H >> 1) + (y >> 1)) * (p.W >> 1) + (x >> 1)) * p.ldy + (y & 1) * 2 + (x & 1);
 #pragma unroll
@@ -318,11 +339,12 @@ bool tma_conv3_supported(int cin, int cout_p, bool half) {
 // K pitch of the packed weights: per tap, the channels padded to whole operand boxes
 int tma_conv3_kpt(int cin, bool half) { const int oc = half ? 64 : 32; return (cin + oc - 1) / oc * oc; }
 
-int launch_conv3_tma(const float* in, int ld_in, int cin, const void* w_packed, int cout_p, int cout_valid, int B, int H,
-                     int W, float* out, int ld_out, int o_mode, bool half, cudaStream_t s) {
+int launch_conv3_tma(const float* in, int ld_in, int cin, const void* w_packed, const float* bias, int relu, int cout_p,
+                     int cout_valid, int B, int H, int W, float* out, int ld_out, int o_mode, bool half, cudaStream_t s) {
   Conv3Cfg c;
   IRB_REQUIRE(configure(cin, cout_p, half, c), "conv3_tma: unsupported shape");
-  IRB_REQUIRE(o_mode == O_UNSHUFFLE || o_mode == O_SHUFFLE, "conv3_tma: the epilogue is the shuffle scatter");
+  IRB_REQUIRE(o_mode == O_UNSHUFFLE || o_mode == O_SHUFFLE || o_mode == O_NHWC, "conv3_tma: plain rows or the shuffle scatter");
+  IRB_REQUIRE(o_mode == O_NHWC || (bias == nullptr && !relu), "conv3_tma: bias / ReLU belong to the plain-row epilogue");
   IRB_REQUIRE(o_mode != O_UNSHUFFLE || (H % 2 == 0 && W % 2 == 0), "conv3_tma: unshuffle needs even H, W");
   IRB_REQUIRE(ld_in % 4 == 0 && (reinterpret_cast<uintptr_t>(in) & 15u) == 0 && ld_out % 4 == 0 &&
                   (reinterpret_cast<uintptr_t>(out) & 15u) == 0 && (reinterpret_cast<uintptr_t>(w_packed) & 15u) == 0,
@@ -335,7 +357,7 @@ int launch_conv3_tma(const float* in, int ld_in, int cin, const void* w_packed, 
     IRB_TRY(make_tmap(&tA, in, false, 4, d, st, box, true));
   }
   Conv3Params p{};
-  p.w = reinterpret_cast<const uint8_t*>(w_packed); p.y = out; p.ldy = ld_out;
+  p.w = reinterpret_cast<const uint8_t*>(w_packed); p.y = out; p.ldy = ld_out; p.bias = bias; p.relu = relu;
   p.B = B; p.H = H; p.W = W; p.Cin = cin; p.N = cout_p; p.n_valid = cout_valid; p.o_mode = o_mode;
   p.nc = c.nc; p.nkb_t = (cin + 31) / 32; p.nob_t = (cin + 63) / 64;
   p.S = c.S; p.SOP = c.SOP; p.NW = c.NW;

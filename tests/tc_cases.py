@@ -169,6 +169,9 @@ TMA_CONV3_CASES = [
     (48, 32, 1, 64, 96, 1, False, False, 1),     # fp16 operands
     (96, 192, 1, 24, 40, 2, False, False, 1),
     (384, 768, 1, 8, 8, 2, False, False, 1),
+    (64, 64, 2, 19, 31, 0, True, True, 0),       # DnCNN body layer on the TMA kernel: plain rows, bias + ReLU, odd extent
+    (64, 64, 1, 32, 32, 0, True, True, 1),
+    (64, 48, 1, 16, 24, 0, True, False, 0),      # 1.5 output groups, no activation
 ]
 
 
