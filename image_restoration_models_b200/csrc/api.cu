@@ -8,6 +8,8 @@
 
 namespace irb {
 
+int probe_shifted_descriptor(const float* a, const float* w, float* d, int shift, int base_off, cudaStream_t s);
+
 static thread_local std::string g_err;
 
 void set_error(const std::string& msg) { g_err = msg; }
@@ -276,7 +278,7 @@ int ir_test_conv3x3(int engine, const float* x_nhwc, int ldx, int cin, const flo
   IRB_REQUIRE(o_mode == O_NHWC || o_mode == O_UNSHUFFLE || o_mode == O_SHUFFLE, "test_conv3x3: bad o_mode");
   cudaStream_t s = (cudaStream_t)stream;
   const int K = 9 * cin;
-  const bool tma = engine == 3;                  // the TMA-fed implicit GEMM only (shuffle-scatter epilogues)
+  const bool tma = engine == 3 || engine == 4;   // 3: the TMA-fed patch kernel only; 4: the row-strip kernel only
   const int Kp = tma ? 9 * tma_conv3_kpt(cin, op_half != 0) : (K + 3) / 4 * 4;
   if (scratch_bytes < (size_t)cout * Kp * sizeof(float)) { set_error("scratch too small"); return IR_ERR_WORKSPACE; }
   float* wp = (float*)scratch;
@@ -285,6 +287,10 @@ int ir_test_conv3x3(int engine, const float* x_nhwc, int ldx, int cin, const flo
                 "test_conv3x3: shape / epilogue not handled by the TMA-fed kernel");
     PackMat pm{w_oihw, wp, 2, cin, cout, cout, 1, K, Kp, nullptr, op_half ? 4 : 3};
     IRB_TRY(launch_pack_mat(pm, s));
+    if (engine == 4) {
+      IRB_REQUIRE(conv3_row_supported(cin, cout, op_half != 0) && o_mode != O_SHUFFLE, "test_conv3x3: not a row-strip shape");
+      return launch_conv3_row(x_nhwc, ldx, cin, wp, bias, relu, cout, cout, B, H, W, y, ldy, o_mode, op_half != 0, s);
+    }
     return launch_conv3_tma(x_nhwc, ldx, cin, wp, bias, relu, cout, cout, B, H, W, y, ldy, o_mode, op_half != 0, s);
   }
   const bool tc = engine == ENGINE_TC;
@@ -297,6 +303,11 @@ int ir_test_conv3x3(int engine, const float* x_nhwc, int ldx, int cin, const flo
   g.w = wp; g.N = cout; g.K = K; g.Kp = Kp; g.bias = bias; g.ln_mode = LN_NONE; g.relu = relu; g.acc_sign = 1.f;
   g.y = y; g.ldy = ldy; g.o_mode = o_mode; g.tag = TAG_CONV3;
   return launch_gemm_simt(g, s);
+}
+
+int ir_probe_shifted_descriptor(const float* a, const float* w, float* d, int shift, int base_off, void* stream) {
+  IRB_REQUIRE(a && w && d && shift >= 0 && shift <= 32, "probe: bad argument");
+  return probe_shifted_descriptor(a, w, d, shift, base_off, (cudaStream_t)stream);
 }
 
 int ir_tile_gather(const void* img, int dtype, float divisor, int H, int W, int C, const int* tile_xy, int T, int th,

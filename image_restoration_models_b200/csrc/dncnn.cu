@@ -84,6 +84,11 @@ int dncnn_forward(const DncnnPlan& pl, const float* packed, const float* x, floa
   const int nb = (int)pl.layers.size();
   for (int l = 0; l < nb; ++l) {
     const DncnnLayer& L = pl.layers[l];
+    if (L.tma && W >= 96 && conv3_row_supported(L.cin, L.cout, pl.half)) {
+      IRB_TRY(launch_conv3_row(buf[(l + 1) & 1], pl.cfg.nc, L.cin, packed + L.w, packed + L.b, 1, L.cout, L.cout, B, H, W,
+                               buf[l & 1], pl.cfg.nc, O_NHWC, pl.half, s));
+      continue;
+    }
     if (L.tma) {
       IRB_TRY(launch_conv3_tma(buf[(l + 1) & 1], pl.cfg.nc, L.cin, packed + L.w, packed + L.b, 1, L.cout, L.cout, B, H, W,
                                buf[l & 1], pl.cfg.nc, O_NHWC, pl.half, s));

@@ -527,6 +527,10 @@ static int run_stage(const std::vector<BlockPlan>& blocks, const float* packed, 
 
 static int conv3(const ConvPlan& cp, const float* packed, const float* in, int ld_in, int a_mode, int B, int H, int W,
                  float* out, int ld_out, int o_mode, const float* r, bool half, cudaStream_t s) {
+  // wide rows of a narrow input (down1_2): every row crosses L2 once instead of nine times
+  if (cp.tma && a_mode == A_IM2COL_NHWC && o_mode == O_UNSHUFFLE && r == nullptr && W >= 96 &&
+      conv3_row_supported(cp.cin, cp.cout_p, half))
+    return launch_conv3_row(in, ld_in, cp.cin, packed + cp.w, nullptr, 0, cp.cout_p, cp.cout, B, H, W, out, ld_out, o_mode, half, s);
   if (cp.tma && a_mode == A_IM2COL_NHWC && (o_mode == O_UNSHUFFLE || o_mode == O_SHUFFLE) && r == nullptr)
     return launch_conv3_tma(in, ld_in, cp.cin, packed + cp.w, nullptr, 0, cp.cout_p, cp.cout, B, H, W, out, ld_out, o_mode, half, s);
   if (cp.tc && a_mode == A_IM2COL_NHWC && o_mode != O_NCHW && r == nullptr)

@@ -54,4 +54,10 @@ int  tma_conv3_kpt(int cin, bool half);
 int  launch_conv3_tma(const float* in, int ld_in, int cin, const void* w_packed, const float* bias, int relu, int cout_p,
                       int cout_valid, int B, int H, int W, float* out, int ld_out, int o_mode, bool half, cudaStream_t s);
 
+// Row-strip variant for Cin <= 64 (tma_conv3_row.cu): every image row is loaded once and the nine taps are row-shifted
+// descriptors into the strips.  Same weight layout as launch_conv3_tma; plain rows (bias + ReLU) or PixelUnshuffle.
+bool conv3_row_supported(int cin, int cout_p, bool half);
+int  launch_conv3_row(const float* in, int ld_in, int cin, const void* w_packed, const float* bias, int relu, int cout_p,
+                      int cout_valid, int B, int H, int W, float* out, int ld_out, int o_mode, bool half, cudaStream_t s);
+
 }  // namespace irb

@@ -132,6 +132,11 @@ int    ir_test_conv3x3(int engine, const float* x_nhwc, int ldx, int cin, const 
                        int cout, int B, int H, int W, float* y, int ldy, int o_mode, int relu, int op_half,
                        void* scratch, size_t scratch_bytes, void* stream);
 
+/* Hardware probe (bring-up): D[128][32] = A[shift : shift+128][32] . W[32][32]^T with the A operand descriptor's start
+ * address shifted by `shift` rows inside one TMA-written SWIZZLE_128B box and `base_off` in its base-offset field. */
+int    ir_probe_shifted_descriptor(const float* a /* [160][32] */, const float* w /* [32][32] */, float* d /* [128][32] */,
+                                   int shift, int base_off, void* stream);
+
 /* Layout helpers used at the boundary of unit tests (NCHW fp32 <-> channels-last fp32). */
 int    ir_nchw_to_nhwc(const float* src, float* dst, int B, int C, int H, int W, void* stream);
 int    ir_nhwc_to_nchw(const float* src, float* dst, int B, int C, int H, int W, void* stream);

@@ -175,6 +175,18 @@ TMA_CONV3_CASES = [
 ]
 
 
+# row-strip kernel (engine 4): Cin <= 64, plain rows or PixelUnshuffle
+ROW_CONV3_CASES = [
+    (64, 64, 1, 24, 200, 0, True, True, 0),      # DnCNN body: two strips, the second ragged; one row segment
+    (64, 64, 2, 40, 130, 0, True, True, 0),      # batch 2, strip of 2 pixels
+    (48, 32, 1, 32, 256, 1, False, False, 0),    # down1_2 family: 1.5 boxes per row, PixelUnshuffle
+    (64, 48, 1, 9, 96, 0, True, False, 0),       # odd height, 1.5 output groups
+    (64, 64, 1, 300, 128, 0, True, True, 0),     # many row segments, ring wrap-around
+    (64, 64, 1, 33, 160, 0, True, True, 1),      # fp16 operand rows
+    (48, 32, 1, 16, 128, 1, False, False, 1),
+]
+
+
 def run_conv3_case(case, engine, seed=0):
     import torch.nn.functional as F
     cin, cout, B, H, W, o_mode, bias, relu, op_half = case

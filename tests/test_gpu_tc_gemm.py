@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 
 from conftest import record
-from tc_cases import (CASES, CONV3_CASES, HALF_CASES, TMA_CASES, TMA_CONV3_CASES, run_case, run_conv3_case,
+from tc_cases import (CASES, CONV3_CASES, HALF_CASES, ROW_CONV3_CASES, TMA_CASES, TMA_CONV3_CASES, run_case, run_conv3_case,
                       tolerance)
 
 pytestmark = pytest.mark.gpu
@@ -67,3 +67,32 @@ def test_tma_conv3x3_matches_reference(idx):
     record(f"tma_conv3x3_{idx}", cfg=str(case), err_tc=e_tc, tol=tol)
     assert np.isfinite(y_tc).all()
     assert e_tc <= tol, (case, e_tc)
+
+
+@pytest.mark.parametrize("idx", range(len(ROW_CONV3_CASES)))
+def test_row_strip_conv3x3_matches_reference(idx):
+    """The row-strip 3x3 convolution (tma_conv3_row.cu): nine row-shifted descriptors into strips loaded once."""
+    case = ROW_CONV3_CASES[idx]
+    y_tc, y_ref = run_conv3_case(case, 4, seed=400 + idx)
+    e_tc = float(np.abs(y_tc - y_ref).max())
+    tol = 4e-3 * float(np.abs(y_ref).max()) + 1e-5
+    record(f"row_conv3x3_{idx}", cfg=str(case), err_tc=e_tc, tol=tol)
+    assert np.isfinite(y_tc).all()
+    assert e_tc <= tol, (case, e_tc)
+
+
+def test_shifted_descriptor_probe():
+    """tcgen05 applies the 128-byte swizzle to absolute shared-memory address bits: an operand descriptor shifted by whole
+    rows inside a TMA-written box reads the rows TMA wrote with base-offset 0 (the fact tma_conv3_row.cu is built on)."""
+    import torch
+    from image_restoration_models_b200 import _native
+    lib = _native.lib()
+    g = torch.Generator().manual_seed(0)
+    a = torch.randint(-8, 9, (160, 32), generator=g).float().cuda()
+    w = torch.randint(-4, 5, (32, 32), generator=g).float().cuda()
+    for shift in (0, 1, 2, 7, 9, 17):
+        d = torch.full((128, 32), float("nan"), device="cuda")
+        _native.check(lib.ir_probe_shifted_descriptor(a.data_ptr(), w.data_ptr(), d.data_ptr(), shift, 0,
+                                                      torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        assert torch.equal(d, a[shift:shift + 128] @ w.t()), shift
