@@ -103,6 +103,30 @@ __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t b
         : "memory");
   }
 }
+// Warp-uniform variants: the WHOLE (converged) warp executes them and one elected lane issues.  Under a divergent
+// `if (lane == 0)` the compiler wraps every tcgen05 instruction in an elect / branch loop over the active lanes (4 extra
+// issue slots per MMA); with elect.sync as the guard it emits the bare instruction.
+template <typename TOp>
+__device__ __forceinline__ void umma_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  if constexpr (sizeof(TOp) == 4) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\telect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\telect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }

@@ -65,7 +65,7 @@ __device__ __forceinline__ Item item_of(const RowParams& p, int it) {
   return r;
 }
 
-// The MMA issue loop, run by ONE thread.  ncu showed this thread -- not the tensor core, the loads or the epilogue --
+// The MMA issue loop, run by the whole (converged) MMA warp with one elected lane issuing.  ncu showed this thread -- not the tensor core, the loads or the epilogue --
 // pacing the kernel: 72 small MMAs (N = 64, K = 8) per tile, each costing ~10 issue slots of descriptor arithmetic and
 // lane election at ~9 cycles apiece.  Everything that can be a compile-time constant is one: boxes per row (NOB), K steps
 // of the last box (NKL), resident weights (RES), the nine taps; descriptors are a constant plus (address >> 4).
@@ -113,18 +113,18 @@ __device__ __forceinline__ void mma_loop(const RowParams& p, Bars* bars, uint32_
           }
 #pragma unroll
           for (int kk = 0; kk < (ob == NOB - 1 ? NKL : 4); ++kk)
-            umma<TOp>(dacc, ad + (uint64_t)(2 * kk), wd + (uint64_t)(2 * kk), idesc, (tap | ob | kk) != 0 ? 1u : 0u);
+            umma_elect<TOp>(dacc, ad + (uint64_t)(2 * kk), wd + (uint64_t)(2 * kk), idesc, (tap | ob | kk) != 0 ? 1u : 0u);
           if (!RES) {
-            umma_commit(smem_u32(&bars->w_empty[sw]));
+            umma_commit_elect(smem_u32(&bars->w_empty[sw]));
             if (++sw == (uint32_t)p.NW) { sw = 0; pw ^= 1u; }
           }
         }
       }
-      umma_commit(smem_u32(&bars->acc_full[slot]));
-      umma_commit(smem_u32(&rel[s0]));                      // row i is not needed any more
+      umma_commit_elect(smem_u32(&bars->acc_full[slot]));
+      umma_commit_elect(smem_u32(&rel[s0]));                      // row i is not needed any more
       if (i == n - 1) {                                     // the item's last two rows as well
-        umma_commit(smem_u32(&rel[s1]));
-        umma_commit(smem_u32(&rel[s2]));
+        umma_commit_elect(smem_u32(&rel[s1]));
+        umma_commit_elect(smem_u32(&rel[s2]));
       }
       s0 = s1; p0 = p1; s1 = s2; p1 = p2;
       if (++s2 == R) { s2 = 0; p2 ^= 1u; }
@@ -217,7 +217,7 @@ conv3_row_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp == WARP_MMA) {
     // =============================== MMA issuer ===============================
-    if (lane == 0) {
+    {
       const int nk_last = ((p.Cin - (p.nob - 1) * (OPRING ? 64 : 32)) * (int)sizeof(TOp) + 31) / 32;
       const int key = (p.nob - 1) * 8 + (nk_last - 1) * 2 + (p.w_resident ? 1 : 0);
       switch (key) {
