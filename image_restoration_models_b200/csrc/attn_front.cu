@@ -180,20 +180,20 @@ attn_front_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
     for (TileIter ti(p); ti.valid(); ti.next(), ++j) {
       mbar_wait(smem_u32(&bars->x_ready), j & 1u);
       tc_fence_after();
-      if (lane == 0) {
+      {
 #pragma unroll
         for (int a = 0; a < NB; ++a)
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
             const uint32_t qa = sX + (uint32_t)a * xbox + kk * 32;              // q rows start at row 0
             const uint32_t ka = qa + (uint32_t)p.C * 128u;                      // k rows start at row C
-            umma<TH_>(tmem_base, sw128_desc(qa), sw128_desc(ka), idesc, (j > 0 || a > 0 || kk > 0) ? 1u : 0u);
+            umma_elect<TH_>(tmem_base, sw128_desc(qa), sw128_desc(ka), idesc, (j > 0 || a > 0 || kk > 0) ? 1u : 0u);
           }
-        umma_commit(smem_u32(&bars->x_empty));
+        umma_commit_elect(smem_u32(&bars->x_empty));
       }
       __syncwarp();
     }
-    if (lane == 0) umma_commit(smem_u32(&bars->acc_done));
+    umma_commit_elect(smem_u32(&bars->acc_done));
   } else if (warp >= EPI_WARPS) {
     // =============================== depthwise 3x3 -> X tile (q, k) / v staging ===============================
     const int ctid = tid - EPI_WARPS * 32;

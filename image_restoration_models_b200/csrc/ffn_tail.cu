@@ -225,16 +225,16 @@ ffn_tail_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__
         mbar_wait(smem_u32(&bars->h_full[s]), (it / NST) & 1u);          // the chunk's W_out rows (already there)
         mbar_wait(smem_u32(&bars->op_ready[o]), (it / NOP) & 1u);
         tc_fence_after();
-        if (lane == 0) {
+        {
           const uint32_t a_addr = sOP + o * OPBOX;
           const uint32_t w_addr = sST + s * p.stage_bytes + 2 * HBOX;
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
-            umma<TH_>(tmem_base + slot * (uint32_t)p.acc_stride, sw128_desc(a_addr + kk * 32), sw128_desc(w_addr + kk * 32),
-                      idesc, (ch > 0 || kk > 0) ? 1u : 0u);
-          umma_commit(smem_u32(&bars->op_empty[o]));
-          umma_commit(smem_u32(&bars->h_empty[s]));
-          if (ch == p.nchunk - 1) umma_commit(smem_u32(&bars->acc_full[slot]));
+            umma_elect<TH_>(tmem_base + slot * (uint32_t)p.acc_stride, sw128_desc(a_addr + kk * 32),
+                            sw128_desc(w_addr + kk * 32), idesc, (ch > 0 || kk > 0) ? 1u : 0u);
+          umma_commit_elect(smem_u32(&bars->op_empty[o]));
+          umma_commit_elect(smem_u32(&bars->h_empty[s]));
+          if (ch == p.nchunk - 1) umma_commit_elect(smem_u32(&bars->acc_full[slot]));
         }
         __syncwarp();
       }

@@ -139,34 +139,46 @@ tma_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const Conv3Params p) {
     }
   } else if (warp == WARP_MMA) {
     // =============================== MMA issuer ===============================
+    // the whole converged warp runs the loop and one elected lane issues; ring positions advance by compare-and-wrap
+    // and descriptors are a constant plus (address >> 4): this warp's instruction stream, not the tensor core, paces a
+    // convolution made of many small MMAs (ncu, see tma_conv3_row.cu)
     const uint32_t idesc = make_idesc<TOp>(ncur);
+    const uint64_t dhi = sw128_desc(0);
+    const int nbox_t = OPRING ? p.nob_t : p.nkb_t;                       // operand boxes per tap
+    constexpr int OC = OPRING ? 64 : 32;
+    const int nk_last = ((p.Cin - (nbox_t - 1) * OC) * (int)sizeof(TOp) + 31) / 32;
+    const uint32_t ring = (uint32_t)(OPRING ? p.SOP : p.S);
+    const uint32_t abase = OPRING ? sOP : sA;
+    unsigned long long* a_rel = OPRING ? bars->op_empty : bars->a_empty;
+    unsigned long long* a_rdy = OPRING ? bars->op_ready : bars->a_ready;
     uint32_t so = 0, po = 0, sw = 0, pw = 0, j = 0;
     for (TileIter ti(p); ti.valid(); ti.next(), ++j) {
       const uint32_t slot = p.nacc == 2 ? (j & 1u) : 0u;
       const uint32_t use = p.nacc == 2 ? (j >> 1) : j;
       mbar_wait(smem_u32(&bars->acc_empty[slot]), (use & 1u) ^ 1u);
       tc_fence_after();
-      for (int i = 0; i < nop; ++i) {
-        const int ob = OPRING ? i % p.nob_t : i % p.nkb_t;                 // box index inside the tap
-        const int cvalid = min(OPRING ? 64 : 32, p.Cin - ob * (OPRING ? 64 : 32));
-        const int nk = (cvalid * (int)sizeof(TOp) + 31) / 32;              // 32-byte K steps that hold real channels
-        mbar_wait(OPRING ? smem_u32(&bars->op_ready[so]) : smem_u32(&bars->a_ready[so]), po);
-        mbar_wait(smem_u32(&bars->w_full[sw]), pw);
-        tc_fence_after();
-        if (lane == 0) {
-          const uint32_t a_addr = (OPRING ? sOP : sA) + so * BOX;
-          const uint32_t w_addr = sW + sw * p.wstage;
-          for (int kk = 0; kk < nk; ++kk)
-            umma<TOp>(tmem_base + slot * (uint32_t)p.acc_stride, sw128_desc(a_addr + kk * 32), sw128_desc(w_addr + kk * 32),
-                      idesc, (i > 0 || kk > 0) ? 1u : 0u);
-          umma_commit(OPRING ? smem_u32(&bars->op_empty[so]) : smem_u32(&bars->a_empty[so]));
-          umma_commit(smem_u32(&bars->w_empty[sw]));
-          if (i == nop - 1) umma_commit(smem_u32(&bars->acc_full[slot]));
+      const uint32_t dacc = tmem_base + slot * (uint32_t)p.acc_stride;
+      uint32_t acc = 0u;
+      for (int tap = 0; tap < 9; ++tap) {
+        for (int ob = 0; ob < nbox_t; ++ob) {
+          const int nk = ob == nbox_t - 1 ? nk_last : 4;
+          mbar_wait(smem_u32(&a_rdy[so]), po);
+          mbar_wait(smem_u32(&bars->w_full[sw]), pw);
+          tc_fence_after();
+          const uint64_t ad = dhi | (uint64_t)((abase + so * BOX) >> 4);
+          const uint64_t wd = dhi | (uint64_t)((sW + sw * p.wstage) >> 4);
+          for (int kk = 0; kk < nk; ++kk) {
+            umma_elect<TOp>(dacc, ad + (uint64_t)(2 * kk), wd + (uint64_t)(2 * kk), idesc, acc);
+            acc = 1u;
+          }
+          umma_commit_elect(smem_u32(&a_rel[so]));
+          umma_commit_elect(smem_u32(&bars->w_empty[sw]));
+          if (++so == ring) { so = 0; po ^= 1u; }
+          if (++sw == (uint32_t)p.NW) { sw = 0; pw ^= 1u; }
         }
-        __syncwarp();
-        if (++so == (uint32_t)(OPRING ? p.SOP : p.S)) { so = 0; po ^= 1u; }
-        if (++sw == (uint32_t)p.NW) { sw = 0; pw ^= 1u; }
       }
+      umma_commit_elect(smem_u32(&bars->acc_full[slot]));
+      __syncwarp();
     }
   } else if (warp >= EPI_WARPS) {
     // =============================== operand rounding ===============================

@@ -291,15 +291,16 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const uint32_t rb = OPRING ? smem_u32(&bars->op_ready[s]) : LN ? smem_u32(&bars->a_ready[s]) : smem_u32(&bars->a_full[s]);
         mbar_wait(rb, ph);
         tc_fence_after();
-        if (lane == 0) {
+        {
+          // the whole converged warp runs this; one elected lane issues (no per-instruction election loop)
           const uint32_t a_addr = (OPRING ? sOP : sA) + s * BOX;
           const uint32_t w_addr = sW + (uint32_t)(ob * ncur * 128);
           const int kbytes = min(128, (p.K - ob * OPCOLS) * (int)sizeof(TOp));
           for (int kk = 0; kk < kbytes / 32; ++kk)
-            umma<TOp>(tmem_base + slot * (uint32_t)p.acc_stride, sw128_desc(a_addr + kk * 32), sw128_desc(w_addr + kk * 32),
-                      idesc, (ob > 0 || kk > 0) ? 1u : 0u);
-          umma_commit(OPRING ? smem_u32(&bars->op_empty[s]) : smem_u32(&bars->a_empty[s]));
-          if (ob == p.nob - 1) umma_commit(smem_u32(&bars->acc_full[slot]));
+            umma_elect<TOp>(tmem_base + slot * (uint32_t)p.acc_stride, sw128_desc(a_addr + kk * 32),
+                            sw128_desc(w_addr + kk * 32), idesc, (ob > 0 || kk > 0) ? 1u : 0u);
+          umma_commit_elect(OPRING ? smem_u32(&bars->op_empty[s]) : smem_u32(&bars->a_empty[s]));
+          if (ob == p.nob - 1) umma_commit_elect(smem_u32(&bars->acc_full[slot]));
         }
         __syncwarp();
       }
