@@ -1,0 +1,52 @@
+// Packed-pair fp32 arithmetic and the exact-erf GELU gate shared by the GDFN kernels (ffn_tail.cu, ffn_fused.cu).
+#pragma once
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+namespace irb {
+namespace gdfn {
+
+// ---- packed fp32 pairs (sm_100 FFMA2 / FMUL2): a dw thread owns two adjacent channels, so every multiply-add of the
+// depthwise taps and of the GELU polynomial is one instruction for both channels.  The kernel is bound by FP32
+// instruction issue, not by bytes: this halves the issue slots of its inner loops.
+typedef unsigned long long f2_t;
+__device__ __forceinline__ f2_t pack2(float lo, float hi) { f2_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpack2(f2_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f2_t fma2(f2_t a, f2_t b, f2_t c) { f2_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f2_t mul2(f2_t a, f2_t b) { f2_t d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float ex2_approx(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
+// gelu(x) * gate for a channel pair.  Exact-erf GELU (F.gelu default, restormer.py:91) through the Abramowitz-Stegun
+// 7.1.26 rational form, erf(u) = 1 - (a1 t + .. + a5 t^5) exp(-u^2), t = 1/(1 + p u), u = |x|/sqrt2 (|gelu error| <=
+// 3e-7 in fp32, see dwconv.cu).  z = u * sqrt(log2 e), so that exp(-u^2) = 2^(-z^2) is a bare MUFU.EX2.
+__device__ __forceinline__ f2_t gelu_gate2(f2_t x, f2_t gate) {
+  const f2_t C1 = pack2(0.84932180028801904272f, 0.84932180028801904272f);       // sqrt(log2 e) / sqrt 2
+  const float PZ = 0.27273629f;                                                    // 0.3275911 / sqrt(log2 e)
+  const f2_t A5 = pack2(-1.061405429f, -1.061405429f), A4 = pack2(1.453152027f, 1.453152027f),
+             A3 = pack2(-1.421413741f, -1.421413741f), A2 = pack2(0.284496736f, 0.284496736f),
+             A1 = pack2(-0.254829592f, -0.254829592f), ONE = pack2(1.0f, 1.0f), HALF = pack2(0.5f, 0.5f);
+  const f2_t z = mul2(x, C1);
+  float zx, zy, xx, xy;
+  unpack2(z, zx, zy);
+  unpack2(x, xx, xy);
+  const f2_t t = pack2(rcp_approx(fmaf(PZ, fabsf(zx), 1.0f)), rcp_approx(fmaf(PZ, fabsf(zy), 1.0f)));
+  const f2_t sq = mul2(z, z);
+  float sx, sy;
+  unpack2(sq, sx, sy);
+  const f2_t e = pack2(ex2_approx(-sx), ex2_approx(-sy));
+  f2_t poly = fma2(t, A5, A4);
+  poly = fma2(t, poly, A3);
+  poly = fma2(t, poly, A2);
+  poly = fma2(t, poly, A1);
+  poly = mul2(poly, t);                                  // -(a1 t + ... + a5 t^5)
+  const f2_t y = fma2(poly, e, ONE);                     // erf(|x| / sqrt 2)
+  float yx, yy;
+  unpack2(y, yx, yy);
+  const f2_t ys = pack2(copysignf(yx, xx), copysignf(yy, xy));
+  const f2_t hx = mul2(x, HALF);
+  return mul2(fma2(hx, ys, hx), gate);                   // 0.5 x (1 + erf(x / sqrt 2)) * gate
+}
+
+}  // namespace gdfn
+}  // namespace irb

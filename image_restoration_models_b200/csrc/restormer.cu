@@ -7,8 +7,10 @@
 #include "tc_gemm.cuh"
 #include "ffn_tail.cuh"
 #include "attn_front.cuh"
+#include "ffn_fused.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace irb {
 
@@ -74,10 +76,13 @@ static void plan_block(Builder& bl, BlockPlan& bp, int C, int heads, float ffn, 
     dst = bl.alloc((long long)dst_half * halves);
     bl.ops.push_back(PackOp{PackOp::VEC, bl.pidx++, dst, src_half, dst_half, halves, 0, 0, 0, 0});
   };
-  auto mat = [&](long long& dst, int n_src_half, int n_dst_half, int halves, int k_src, int k_dst, bool tc, bool tma = false) {
-    if (tma) k_dst = tma_gemm_kpad(k_dst, bl.half());
+  // f16_image: the fp16 SWIZZLE_128B operand image (fmt 4) whatever the mode (the fused GDFN kernel's operands)
+  auto mat = [&](long long& dst, int n_src_half, int n_dst_half, int halves, int k_src, int k_dst, bool tc, bool tma = false,
+                 bool f16_image = false) {
+    if (tma || f16_image) k_dst = tma_gemm_kpad(k_dst, bl.half() || f16_image);
     dst = bl.alloc((long long)n_dst_half * halves * k_dst);
-    bl.ops.push_back(PackOp{PackOp::MAT1, bl.pidx++, dst, n_src_half, n_dst_half, halves, k_src, k_dst, 0, bl.fmt(tc, tma)});
+    bl.ops.push_back(PackOp{PackOp::MAT1, bl.pidx++, dst, n_src_half, n_dst_half, halves, k_src, k_dst, 0,
+                            f16_image ? 4 : bl.fmt(tc, tma)});
   };
   auto dw = [&](long long& dst, int src_half, int dst_half, int halves) {
     dst = bl.alloc(9LL * dst_half * halves);
@@ -101,6 +106,12 @@ static void plan_block(Builder& bl, BlockPlan& bp, int C, int heads, float ffn, 
   // MDTA front / GDFN tail in one kernel each (no biases: every shipped configuration has bias=False)
   bp.fuse_front = bl.engine != ENGINE_SIMT && !bias && bp.tc_attn && attn_front_supported(C, heads, bl.half());
   bp.fuse_tail = bl.engine != ENGINE_SIMT && !bias && ffn_tail_supported(C, bp.hp, bl.half());
+  // the whole GDFN in one kernel (ffn_fused.cu).  Its operands are fp16 images in BOTH tensor-core modes: the hidden
+  // tensor lives only in shared memory, where fp32 storage does not fit; fp16 carries the same 10-bit mantissa as the
+  // tf32 operands it replaces, and accumulation stays fp32.
+  static const bool no_fused = getenv("IRB_NO_FFN_FUSED") != nullptr;      // A/B switch for benchmarks
+  bp.fuse_ffn = !no_fused && bl.engine != ENGINE_SIMT && !bias && ffn_fused_supported(C, bp.hp);
+  if (bp.fuse_ffn) bp.fuse_tail = false;
   vec(bp.ln1_w, C);
   if (ln_bias) vec(bp.ln1_b, C);
   vec(bp.temp, heads);
@@ -118,16 +129,16 @@ static void plan_block(Builder& bl, BlockPlan& bp, int C, int heads, float ffn, 
   if (bias) vec(bp.proj_b, C);
   vec(bp.ln2_w, C);
   if (ln_bias) vec(bp.ln2_b, C);
-  mat(bp.pin_w, bp.h, bp.hp, 2, C, C, bp.tc_pin, bp.tma_pin);
+  mat(bp.pin_w, bp.h, bp.hp, 2, C, C, bp.tc_pin, bp.tma_pin, bp.fuse_ffn);
   if (bias) vec_split(bp.pin_b, bp.h, bp.hp, 2);
-  if (bp.fuse_tail) {
+  if (bp.fuse_tail || bp.fuse_ffn) {
     bp.ffdw_w = bl.alloc(18LL * bp.hp);
-    bl.ops.push_back(PackOp{PackOp::DWC, bl.pidx++, bp.ffdw_w, bp.h, bp.hp, 2, 0, ffn_tail_kc(bl.half()), 0, 0});
+    bl.ops.push_back(PackOp{PackOp::DWC, bl.pidx++, bp.ffdw_w, bp.h, bp.hp, 2, 0, bp.fuse_ffn ? 64 : ffn_tail_kc(bl.half()), 0, 0});
   } else {
     dw(bp.ffdw_w, bp.h, bp.hp, 2);
   }
   if (bias) vec_split(bp.ffdw_b, bp.h, bp.hp, 2);
-  mat(bp.pout_w, C, C, 1, bp.h, bp.hp, bp.tc_pout || bp.fuse_tail, bp.tma_pout || bp.fuse_tail);
+  mat(bp.pout_w, C, C, 1, bp.h, bp.hp, bp.tc_pout || bp.fuse_tail, bp.tma_pout || bp.fuse_tail, bp.fuse_ffn);
   if (bias) vec(bp.pout_b, C);
 }
 
@@ -289,13 +300,13 @@ void block_scratch_need(BlockScratchNeed& n, const BlockPlan& bp, int B, int H, 
   const long long P = (long long)B * H * W;
   const int ch = bp.C / bp.heads;
   n.qkv = std::max(n.qkv, P * 3 * bp.C);
-  n.hidden = std::max(n.hidden, P * 2 * bp.hp);
-  n.gated = std::max(n.gated, P * bp.hp);
+  if (!bp.fuse_ffn) n.hidden = std::max(n.hidden, P * 2 * bp.hp);            // fused GDFN: the hidden tensor stays on chip
+  if (!bp.fuse_ffn && !bp.fuse_tail) n.gated = std::max(n.gated, P * bp.hp);
   const int parts = bp.fuse_front ? attn_front_parts(B, H, W) : gram_parts(B, bp.heads, H * W);
   n.s_part = std::max(n.s_part, (long long)B * bp.heads * parts * ch * ch);
   n.n_part = std::max(n.n_part, (long long)B * bp.heads * parts * 2 * ch);
   n.w_eff = std::max(n.w_eff, (long long)B * bp.C * bp.kp_attn);
-  if (bp.C > 128) n.xhat = std::max(n.xhat, P * bp.C);
+  if (bp.C > 128 || bp.fuse_ffn) n.xhat = std::max(n.xhat, P * bp.C);
   n.es = bp.half ? 2 : 4;
 }
 
@@ -463,6 +474,16 @@ int run_block(const BlockPlan& bp, const float* packed, const float* x_in, float
   g.r = x_in; g.ldr = C; g.y = x_out; g.ldy = C; g.o_mode = O_NHWC; g.tag = TAG_ATTN_OUT;
   IRB_TRY(run_1x1(g, bp.tc_attn, hf, hf, false, bs.xhat, s, bp.tma_attn));
 
+  if (bp.fuse_ffn) {
+    // (6-8) norm2 into an fp16 operand tensor, then project_in + depthwise 3x3 + gate + project_out + residual
+    // (:148, :89-92) in one kernel: the hidden tensor never exists in HBM
+    IRB_TRY(launch_layernorm(x_out, C, bs.xhat, C, 1, (long long)B * H * W, C, ln, P(bp.ln2_w), P(bp.ln2_b), s));
+    FfnFusedArgs fa{};
+    fa.xn = bs.xhat; fa.x = x_out; fa.w_in = P(bp.pin_w); fa.w_out = P(bp.pout_w); fa.dw_chunked = P(bp.ffdw_w);
+    fa.B = B; fa.H = H; fa.W = W; fa.C = C; fa.hp = hp;
+    return launch_ffn_fused(fa, s);
+  }
+
   // (6) norm2 + project_in 1x1 (:148, :89)
   g = GemmParams{};
   g.a1 = x_out; g.lda1 = C; g.k1 = C; g.a_mode = A_PLAIN;
@@ -553,7 +574,7 @@ int restormer_launch_count(const RestormerPlan& pl) {
   int n = 0;
   auto blocks = [&](const std::vector<BlockPlan>& v) {
     for (const auto& bp : v) {
-      n += 8 - (bp.fuse_tail ? 1 : 0) - (bp.fuse_front ? 1 : 0);
+      n += 8 - (bp.fuse_tail || bp.fuse_ffn ? 1 : 0) - (bp.fuse_front ? 1 : 0);
       // standalone LayerNorm where the contraction cannot take it as a prologue (the wide levels)
       auto ln_standalone = [&](bool tc, bool tma, int N) {
         if (!tc) return false;

@@ -616,6 +616,76 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   }
 }
 
+// Narrow rows (C = 4 * LPR * V, e.g. 48 / 96 / 192 / 384 with V = 3): LPR lanes share a pixel, a warp normalises
+// 32 / LPR pixels per pass with every load a full 16-byte lane access and 64-128 contiguous bytes per pixel segment.
+// Same two-pass statistics as above.
+template <typename TY, int LPR, int V>
+__global__ void __launch_bounds__(256) layernorm_rows_kernel(const float* __restrict__ x, TY* __restrict__ y, long long rows,
+                                                             int ln_mode, const float* __restrict__ w,
+                                                             const float* __restrict__ b) {
+  constexpr int C = 4 * LPR * V, RPW = 32 / LPR;
+  const int lane = threadIdx.x & 31, l = lane % LPR, r = lane / LPR;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  float4 g[V], bb[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    g[i] = __ldg(reinterpret_cast<const float4*>(w) + i * LPR + l);
+    bb[i] = ln_mode == LN_WITHBIAS ? __ldg(reinterpret_cast<const float4*>(b) + i * LPR + l) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (long long row0 = warp0 * RPW; row0 < rows; row0 += nwarps * RPW) {
+    const long long row = row0 + r;
+    const bool ok = row < rows;
+    float4 v[V];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      v[i] = ok ? __ldcs(reinterpret_cast<const float4*>(x + row * C) + i * LPR + l) : make_float4(0.f, 0.f, 0.f, 0.f);
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mu = s / (float)C;
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const float dx = v[i].x - mu, dy = v[i].y - mu, dz = v[i].z - mu, dw = v[i].w - mu;
+      ss += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float rstd = 1.0f / sqrtf(ss / (float)C + 1e-5f);
+    const float sub = ln_mode == LN_WITHBIAS ? mu : 0.f;
+    if (!ok) continue;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      float4 o;
+      o.x = (v[i].x - sub) * rstd * g[i].x + bb[i].x; o.y = (v[i].y - sub) * rstd * g[i].y + bb[i].y;
+      o.z = (v[i].z - sub) * rstd * g[i].z + bb[i].z; o.w = (v[i].w - sub) * rstd * g[i].w + bb[i].w;
+      if constexpr (sizeof(TY) == 4) {
+        reinterpret_cast<float4*>(y + row * C)[i * LPR + l] = o;
+      } else {
+        uint2 t;
+        *reinterpret_cast<__half2*>(&t.x) = __floats2half2_rn(o.x, o.y);
+        *reinterpret_cast<__half2*>(&t.y) = __floats2half2_rn(o.z, o.w);
+        reinterpret_cast<uint2*>(y + row * C)[i * LPR + l] = t;
+      }
+    }
+  }
+}
+
+template <int LPR>
+static int launch_layernorm_rows(const float* x, void* y, int y_half, long long rows, int ln_mode, const float* w,
+                                 const float* b, cudaStream_t s) {
+  constexpr int RPB = 8 * (32 / LPR);      // pixels per block pass
+  const long long need = cdivll(rows, RPB);
+  const int blocks = (int)(need < 148LL * 8 ? (need > 0 ? need : 1) : 148LL * 8);
+  if (y_half) layernorm_rows_kernel<__half, LPR, 3><<<blocks, 256, 0, s>>>(x, (__half*)y, rows, ln_mode, w, b);
+  else        layernorm_rows_kernel<float, LPR, 3><<<blocks, 256, 0, s>>>(x, (float*)y, rows, ln_mode, w, b);
+  IRB_LAUNCH_CHECK();
+  return IR_OK;
+}
+
 int launch_layernorm(const float* x, int ldx, void* y, int ldy, int y_half, long long rows, int C, int ln_mode,
                      const float* w, const float* b, cudaStream_t s) {
   IRB_REQUIRE(C % 4 == 0 && C <= 1024 && ldx % 4 == 0 && ldy % 4 == 0, "layernorm: C must be a multiple of 4, <= 1024");
@@ -623,6 +693,15 @@ int launch_layernorm(const float* x, int ldx, void* y, int ldy, int y_half, long
   const long long blocks_needed = cdivll(rows, 8);
   const int blocks = (int)(blocks_needed < 148LL * 8 ? blocks_needed : 148LL * 8);
   ProfScope prof(TAG_LAYERNORM, (y_half ? 6.0 : 8.0) * (double)rows * C, 0.0, s);
+  if (ldx == C && ldy == C && (reinterpret_cast<uintptr_t>(x) & 15u) == 0 && (reinterpret_cast<uintptr_t>(y) & 15u) == 0) {
+    switch (C) {
+      case 48:  return launch_layernorm_rows<4>(x, y, y_half, rows, ln_mode, w, b, s);
+      case 96:  return launch_layernorm_rows<8>(x, y, y_half, rows, ln_mode, w, b, s);
+      case 192: return launch_layernorm_rows<16>(x, y, y_half, rows, ln_mode, w, b, s);
+      case 384: return launch_layernorm_rows<32>(x, y, y_half, rows, ln_mode, w, b, s);
+      default: break;
+    }
+  }
   if (y_half) layernorm_kernel<__half><<<blocks > 0 ? blocks : 1, 256, 0, s>>>(x, ldx, (__half*)y, ldy, rows, C, ln_mode, w, b);
   else        layernorm_kernel<float><<<blocks > 0 ? blocks : 1, 256, 0, s>>>(x, ldx, (float*)y, ldy, rows, C, ln_mode, w, b);
   IRB_LAUNCH_CHECK();
