@@ -50,7 +50,9 @@ constexpr int UC = 64;                         // hidden channels per unit
 constexpr int WINBOX = UC * 128;               // one 64-channel K box of a unit's project_in rows
 constexpr int OPBOX = TM * 128;                // MMA2 operand box, and one 32-channel staging group of the epilogue
 constexpr int EPI_WARPS = 4, CVB_WARPS = 2;
-// warp roles; BH = rows of a depthwise thread's pixel block: 4 -> 8 dw warps (4x4 blocks), 2 -> 16 dw warps (2x4 blocks)
+// warp roles; BH = rows of a depthwise thread's pixel block: 4 -> 8 dw warps (4x4 blocks), 2 -> 16 dw warps (2x4 blocks).
+// Measured: 16 warps of 2x4 blocks are 9 % SLOWER (more halo loads and conversions per output; the kernel is bound by
+// the FP32 pipe, not by latency), so only BH = 4 is instantiated.
 template <int BH> struct Roles {
   static constexpr int DW_WARPS = 32 / BH;
   static constexpr int WARP_DW = EPI_WARPS, WARP_MMA = WARP_DW + DW_WARPS, WARP_PROD = WARP_MMA + 1, WARP_CVB = WARP_PROD + 1;
@@ -103,6 +105,9 @@ __device__ __forceinline__ f2_t ld_h2(uint32_t a) {
   return pack2(f.x, f.y);
 }
 
+// Measured alternatives for the tap arithmetic, all slower than packed FFMA2 on converted operands: mixed-precision
+// FHFMA (fma.rn.f32.f16, no conversions, two scalar instructions per channel pair): +18 %; FFMA2 alternated with
+// scalar FFMA pairs: +6 %; 16 dw warps of 2x4 blocks: +9 %.
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   const __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<const uint32_t*>(&h);
@@ -144,7 +149,9 @@ __device__ __forceinline__ void convert_unit(Bars* bars, uint32_t g, uint32_t tm
   if (lane == 0) mbar_arrive(smem_u32(&bars->h_full[s]));
 }
 
-template <int BH>
+// DBG != 0: timing experiments only (results are garbage): 1 no W_in reloads, 2 no xn patch reloads, 4 no depthwise taps,
+// 8 no W_out reloads
+template <int BH, int DBG>
 __global__ void __launch_bounds__(Roles<BH>::NWARPS * 32, 1)
 ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmY, const FusedParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -199,9 +206,13 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t ja = 0;
       auto load_a = [&]() {
         const uint32_t buf = ja & 1u, fb = smem_u32(&bars->a_full[buf]);
-        mbar_expect_tx(fb, patch_bytes);
-        for (int kb = 0; kb < p.nkb; ++kb)
-          tma_load_4d(&tmA, fb, sA + buf * p.a_bytes + (uint32_t)kb * ABOX, kb * 64, ta.x0() - 1, ta.y0() - 1, ta.img());
+        if ((DBG & 2) && ja >= 2) {
+          mbar_arrive(fb);
+        } else {
+          mbar_expect_tx(fb, patch_bytes);
+          for (int kb = 0; kb < p.nkb; ++kb)
+            tma_load_4d(&tmA, fb, sA + buf * p.a_bytes + (uint32_t)kb * ABOX, kb * 64, ta.x0() - 1, ta.y0() - 1, ta.img());
+        }
         ta.next();
         ++ja;
       };
@@ -210,8 +221,12 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       auto load_wout = [&]() {
         const uint32_t s = cc & 1u, fb = smem_u32(&bars->w2_full[s]), ch = cc % (uint32_t)p.nchunk;
         mbar_wait(smem_u32(&bars->w2_empty[s]), ((cc >> 1) & 1u) ^ 1u);
-        mbar_expect_tx(fb, (uint32_t)p.C * 128u);
-        bulk_load(sWout + s * p.wout_bytes, p.w_out + (size_t)ch * p.C * 128, (uint32_t)p.C * 128u, fb);
+        if ((DBG & 8) && cc >= 2) {
+          mbar_arrive(fb);
+        } else {
+          mbar_expect_tx(fb, (uint32_t)p.C * 128u);
+          bulk_load(sWout + s * p.wout_bytes, p.w_out + (size_t)ch * p.C * 128, (uint32_t)p.C * 128u, fb);
+        }
         ++cc;
       };
       for (TileIter ti(p); ti.valid(); ti.next(), ++j) {
@@ -220,10 +235,14 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           {
             const uint32_t s = g & 1u, fb = smem_u32(&bars->w1_full[s]);
             mbar_wait(smem_u32(&bars->w1_empty[s]), ((g >> 1) & 1u) ^ 1u);
-            mbar_expect_tx(fb, (uint32_t)p.nkb * WINBOX);
-            const size_t n0 = (size_t)set * p.hp + (size_t)ch * UC;
-            for (int kb = 0; kb < p.nkb; ++kb)
-              bulk_load(sWin + s * p.win_bytes + (uint32_t)kb * WINBOX, p.w_in + ((size_t)kb * 2 * p.hp + n0) * 128, WINBOX, fb);
+            if ((DBG & 1) && g >= 2) {
+              mbar_arrive(fb);
+            } else {
+              mbar_expect_tx(fb, (uint32_t)p.nkb * WINBOX);
+              const size_t n0 = (size_t)set * p.hp + (size_t)ch * UC;
+              for (int kb = 0; kb < p.nkb; ++kb)
+                bulk_load(sWin + s * p.win_bytes + (uint32_t)kb * WINBOX, p.w_in + ((size_t)kb * 2 * p.hp + n0) * 128, WINBOX, fb);
+            }
           }
           // project_out rows of the PREVIOUS chunk: its slot was released by the MMA2 three chunks back, so this wait
           // never holds up the project_in loads behind it (the chunk's own MMA2 is still several units away)
@@ -317,6 +336,12 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint32_t s = g & 1u;
           mbar_wait(smem_u32(&bars->h_full[s]), (g >> 1) & 1u);
           const uint32_t src = sH + s * HSTAGE + win0;
+          if (DBG & 4) {
+#pragma unroll
+            for (int oy = 0; oy < BH; ++oy)
+#pragma unroll
+              for (int ox = 0; ox < BW; ++ox) acc[set][oy][ox] = w[oy];
+          } else
 #pragma unroll
           for (int iy = 0; iy < BH + 2; ++iy) {
             f2_t v[BW + 2];
@@ -487,16 +512,25 @@ int launch_ffn_fused(const FfnFusedArgs& a, cudaStream_t s) {
   const double pix = (double)a.B * a.H * a.W;
   // algorithmic bytes: xn read (fp16) + x read-modify-write (fp32); flops: project_in + depthwise + project_out
   ProfScope prof(TAG_FFN_FUSED, pix * (2.0 * a.C + 8.0 * a.C), pix * (4.0 * a.hp * a.C + 36.0 * a.hp + 2.0 * a.hp * a.C), s);
-  static const bool dw16 = getenv("IRB_FUSED_DW16") != nullptr;     // A/B switch: 16 dw warps of 2x4 blocks
-  if (dw16) {
-    static SmemOptIn optin;
-    IRB_TRY(opt_in_smem(ffn_fused_kernel<2>, optin));
-    ffn_fused_kernel<2><<<grid, Roles<2>::NWARPS * 32, smem, s>>>(tA, tY, p);
-  } else {
-    static SmemOptIn optin;
-    IRB_TRY(opt_in_smem(ffn_fused_kernel<4>, optin));
-    ffn_fused_kernel<4><<<grid, Roles<4>::NWARPS * 32, smem, s>>>(tA, tY, p);
+  auto go = [&](auto kernel) -> int {
+    static SmemOptIn optin;      // one per instantiation of this lambda's template, i.e. per kernel
+    IRB_TRY(opt_in_smem(kernel, optin));
+    kernel<<<grid, Roles<4>::NWARPS * 32, smem, s>>>(tA, tY, p);
+    return IR_OK;
+  };
+#ifdef IRB_FUSED_EXPERIMENTS
+  static const int dbg = getenv("IRB_FUSED_DBG") ? atoi(getenv("IRB_FUSED_DBG")) : 0;
+  switch (dbg) {
+    case 0: IRB_TRY(go(ffn_fused_kernel<4, 0>)); break;
+    case 1: IRB_TRY(go(ffn_fused_kernel<4, 1>)); break;
+    case 3: IRB_TRY(go(ffn_fused_kernel<4, 3>)); break;
+    case 4: IRB_TRY(go(ffn_fused_kernel<4, 4>)); break;
+    case 11: IRB_TRY(go(ffn_fused_kernel<4, 11>)); break;
+    default: IRB_TRY(go(ffn_fused_kernel<4, 15>)); break;
   }
+#else
+  IRB_TRY(go(ffn_fused_kernel<4, 0>));
+#endif
   IRB_LAUNCH_CHECK();
   return IR_OK;
 }

@@ -3,7 +3,7 @@
 TAG=${1:-ab}
 OUT=gpurun_out
 mkdir -p $OUT
-for V in "" "IRB_FUSED_DW16=1"; do
+for V in "" "IRB_FUSED_FHFMA=1"; do
   N=${V:-default}
   env $V timeout 300 python -m pytest tests/test_gpu_parity.py -k "block or gray_64 or motion" -x -q --timeout 200 > $OUT/pytest_${TAG}_$N.log 2>&1
   echo "[$N] parity exit $?"; tail -3 $OUT/pytest_${TAG}_$N.log
