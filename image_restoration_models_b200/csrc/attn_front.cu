@@ -48,7 +48,8 @@ struct FrontParams {
   const float* dw;         // taps per chunk [nchunk][9][32]
   float* s_part;           // [B][heads][parts][ch][ch]
   float* n_part;           // [B][heads][parts][2][ch]
-  int B, H, W, C, heads, parts;
+  int B, H, W, C, heads, parts;   // C, heads: of ONE channel group (blockIdx.z); a group is a whole number of heads
+  int Ct, heads_total, ngroups;   // the tensor's channel count / heads; groups = Ct / C (1 for C = 48 / 96, C = 96 above that)
   int nqk, nv;             // chunks of q|k (2C/32) and of v (ceil(C/32))
   int tiles_x, tiles_y, tiles_per_img;
   int xrows;               // rows allocated per X box (>= 128)
@@ -130,7 +131,7 @@ attn_front_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
   const uint32_t xbox = (uint32_t)p.xrows * 128u;      // bytes of one X box
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int b = blockIdx.y, part = blockIdx.x;
+  const int b = blockIdx.y, part = blockIdx.x, grp = blockIdx.z;
   const int nchunk = p.nqk + p.nv;
 
   if (tid == 0) {
@@ -167,8 +168,17 @@ attn_front_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
           const uint32_t fb = smem_u32(&bars->h_full[s]);
           const uint32_t st = sST + s * p.stage_bytes;
           mbar_expect_tx(fb, (uint32_t)(HPIX * PXB + TAPB));
-          tma_load_4d(&tmH, fb, st, ch * KC, x0 - 1, y0 - 1, b);
-          bulk_load(st + HPIX * PXB, reinterpret_cast<const uint8_t*>(p.dw) + (size_t)ch * TAPB, TAPB, fb);
+          // channel of the chunk in the 3*Ct-wide qkv tensor: one group -> q | k | v are consecutive chunks; several
+          // groups -> this group's C channels of q, of k, of v (C % 32 == 0 there)
+          int chan = ch * KC;
+          if (p.ngroups > 1) {
+            const int hq = p.nqk / 2;
+            chan = ch < hq ? grp * p.C + ch * KC
+                 : ch < p.nqk ? p.Ct + grp * p.C + (ch - hq) * KC
+                              : 2 * p.Ct + grp * p.C + (ch - p.nqk) * KC;
+          }
+          tma_load_4d(&tmH, fb, st, chan, x0 - 1, y0 - 1, b);
+          bulk_load(st + HPIX * PXB, reinterpret_cast<const uint8_t*>(p.dw) + (size_t)(chan / KC) * TAPB, TAPB, fb);
           if (++s == (uint32_t)p.nst) { s = 0; ph ^= 1u; }
         }
       }
@@ -307,7 +317,7 @@ attn_front_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
         fence_async_smem();
         __syncwarp();
         if (lane == 0) {
-          tma_store_4d(&tmV, vb, ch * KC, x0 + 8 * (dwi & 1), y0 + 2 * (dwi >> 1), b);
+          tma_store_4d(&tmV, vb, grp * p.C + ch * KC, x0 + 8 * (dwi & 1), y0 + 2 * (dwi >> 1), b);
           bulk_commit();
         }
       }
@@ -329,7 +339,7 @@ attn_front_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
       // channel ctid of q|k -> n_part[b][head][part][which][c]
       const int which = ctid >= p.C ? 1 : 0, c = ctid - which * p.C;
       const int chd = p.C / p.heads, head = c / chd, cc = c - head * chd;
-      p.n_part[((((long long)b * p.heads + head) * p.parts + part) * 2 + which) * chd + cc] = sum;
+      p.n_part[((((long long)b * p.heads_total + grp * p.heads + head) * p.parts + part) * 2 + which) * chd + cc] = sum;
     }
   } else {
     // =============================== epilogue: the CTA's partial Gram ===============================
@@ -352,7 +362,7 @@ attn_front_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
         for (int e = 0; e < 32; ++e) v[e] = 0.f;
       }
       if (i < p.C) {
-        float* dst = p.s_part + ((((long long)b * p.heads + head) * p.parts + part) * chd + ii) * chd;
+        float* dst = p.s_part + ((((long long)b * p.heads_total + grp * p.heads + head) * p.parts + part) * chd + ii) * chd;
 #pragma unroll
         for (int e = 0; e < 32; ++e) {
           const int jn = c0 + e - head * chd;                // column inside this head's diagonal block
@@ -372,9 +382,17 @@ attn_front_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
 
 struct FrontCfg { int xrows, nst; uint32_t stage_bytes, off_stage, off_x, off_v, off_red; size_t smem; };
 
-bool configure(int C, int heads, bool half, FrontCfg& c) {
-  if (C != 48 && C != 96) return false;                 // NQK instantiations (2C/32 = 3, 6); M = 128 >= C
-  if (heads <= 0 || C % heads != 0) return false;
+// channels one CTA takes: the whole tensor at C = 48 / 96, groups of 96 channels (whole heads) above that
+int group_channels(int C, int heads) {
+  if (heads <= 0 || C % heads != 0) return 0;
+  if (C == 48 || C == 96) return C;
+  const int chd = C / heads;
+  return (C % 96 == 0 && 96 % chd == 0) ? 96 : 0;
+}
+
+bool configure(int Ct, int heads_total, bool half, FrontCfg& c) {
+  const int C = group_channels(Ct, heads_total);        // NQK instantiations (2C/32 = 3, 6); M = 128 >= C
+  if (C == 0) return false;
   const int es = half ? 2 : 4;
   const int nb = TM * es / 128;
   c.xrows = std::max(2 * C, 128);                       // A reads 128 rows from row 0 (M = 128), B reads C rows from row C
@@ -408,9 +426,11 @@ bool attn_front_supported(int C, int heads, bool half) {
   return configure(C, heads, half, c);
 }
 
-int attn_front_parts(int B, int H, int W) {
+int attn_front_parts(int B, int H, int W, int C, int heads) {
   const int tiles = cdiv(W, TW) * cdiv(H, TH);
-  return std::max(1, std::min(tiles, 148 / std::max(1, B)));
+  const int cg = group_channels(C, heads);
+  const int groups = cg > 0 ? C / cg : 1;
+  return std::max(1, std::min(tiles, 148 / std::max(1, B * groups)));
 }
 
 int launch_attn_front(const AttnFrontArgs& a, cudaStream_t s) {
@@ -433,20 +453,22 @@ int launch_attn_front(const AttnFrontArgs& a, cudaStream_t s) {
   }
   FrontParams p{};
   p.dw = a.dw_chunked; p.s_part = a.s_part; p.n_part = a.n_part;
-  p.B = a.B; p.H = a.H; p.W = a.W; p.C = a.C; p.heads = a.heads;
-  p.parts = attn_front_parts(a.B, a.H, a.W);
+  const int cg = group_channels(a.C, a.heads);
+  p.B = a.B; p.H = a.H; p.W = a.W; p.C = cg; p.heads = cg / (a.C / a.heads);
+  p.Ct = a.C; p.heads_total = a.heads; p.ngroups = a.C / cg;
+  p.parts = attn_front_parts(a.B, a.H, a.W, a.C, a.heads);
   IRB_REQUIRE(p.parts == a.parts, "attn_front: partial count mismatch");
-  p.nqk = 2 * a.C / KC; p.nv = cdiv(a.C, KC);
+  p.nqk = 2 * cg / KC; p.nv = cdiv(cg, KC);
   p.tiles_x = cdiv(a.W, TW); p.tiles_y = cdiv(a.H, TH); p.tiles_per_img = p.tiles_x * p.tiles_y;
   p.xrows = c.xrows; p.nst = c.nst;
-  int cols = 32; while (cols < a.C) cols <<= 1;
+  int cols = 32; while (cols < cg) cols <<= 1;
   p.tmem_cols = cols;
   p.stage_bytes = c.stage_bytes; p.off_stage = c.off_stage; p.off_x = c.off_x; p.off_v = c.off_v; p.off_red = c.off_red;
-  dim3 grid(p.parts, a.B, 1);
+  dim3 grid(p.parts, a.B, p.ngroups);
   const size_t smem = std::max<size_t>(c.smem, 120 * 1024);
   const double pix = (double)a.B * a.H * a.W;
   ProfScope prof(TAG_ATTN_FRONT, pix * 4.0 * a.C * es, pix * (2.0 * 9 * 3 * a.C + 2.0 * a.C * (a.C / a.heads)), s);
-  if (a.C == 48) return a.half ? launch_inst<__half, 3>(tH, tV, p, grid, smem, s) : launch_inst<float, 3>(tH, tV, p, grid, smem, s);
+  if (cg == 48) return a.half ? launch_inst<__half, 3>(tH, tV, p, grid, smem, s) : launch_inst<float, 3>(tH, tV, p, grid, smem, s);
   return a.half ? launch_inst<__half, 6>(tH, tV, p, grid, smem, s) : launch_inst<float, 6>(tH, tV, p, grid, smem, s);
 }
 

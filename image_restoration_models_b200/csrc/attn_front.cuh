@@ -11,12 +11,12 @@ struct AttnFrontArgs {
   const float* dw_chunked; // taps [ceil(3C/32)][9][32] (launch_pack_dw_chunked with one set)
   float* s_part;           // [B][heads][parts][ch][ch]
   float* n_part;           // [B][heads][parts][2][ch]
-  int parts;               // must equal attn_front_parts(B, H, W)
+  int parts;               // must equal attn_front_parts(B, H, W, C, heads)
   int B, H, W, C, heads;
 };
 
 bool attn_front_supported(int C, int heads, bool half);
-int  attn_front_parts(int B, int H, int W);
+int  attn_front_parts(int B, int H, int W, int C, int heads);
 int  launch_attn_front(const AttnFrontArgs& a, cudaStream_t s);
 
 }  // namespace irb

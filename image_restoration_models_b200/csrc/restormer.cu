@@ -302,7 +302,7 @@ void block_scratch_need(BlockScratchNeed& n, const BlockPlan& bp, int B, int H, 
   n.qkv = std::max(n.qkv, P * 3 * bp.C);
   if (!bp.fuse_ffn) n.hidden = std::max(n.hidden, P * 2 * bp.hp);            // fused GDFN: the hidden tensor stays on chip
   if (!bp.fuse_ffn && !bp.fuse_tail) n.gated = std::max(n.gated, P * bp.hp);
-  const int parts = bp.fuse_front ? attn_front_parts(B, H, W) : gram_parts(B, bp.heads, H * W);
+  const int parts = bp.fuse_front ? attn_front_parts(B, H, W, bp.C, bp.heads) : gram_parts(B, bp.heads, H * W);
   n.s_part = std::max(n.s_part, (long long)B * bp.heads * parts * ch * ch);
   n.n_part = std::max(n.n_part, (long long)B * bp.heads * parts * 2 * ch);
   n.w_eff = std::max(n.w_eff, (long long)B * bp.C * bp.kp_attn);
@@ -436,7 +436,7 @@ int run_block(const BlockPlan& bp, const float* packed, const float* x_in, float
     // (2+3) depthwise 3x3 + q.k^T Gram partials + squared norms; only v is written (:114-115, :121-124)
     AttnFrontArgs fa{};
     fa.qkv = bs.qkv; fa.half = hf; fa.v = bs.qkv_dw; fa.dw_chunked = P(bp.qkvdw_w);
-    fa.s_part = bs.s_part; fa.n_part = bs.n_part; fa.parts = attn_front_parts(B, H, W);
+    fa.s_part = bs.s_part; fa.n_part = bs.n_part; fa.parts = attn_front_parts(B, H, W, C, bp.heads);
     fa.B = B; fa.H = H; fa.W = W; fa.C = C; fa.heads = bp.heads;
     IRB_TRY(launch_attn_front(fa, s));
     gp.nparts = fa.parts;
