@@ -62,6 +62,9 @@ struct TmaGemmParams {
   int split;               // > 0: 1-D grid, CTAs [0, split) own N-chunk 0 and the rest chunk 1 (uneven chunks get
                            // CTA counts in proportion to their bytes); 0: blockIdx.y is the chunk
   int tmem_cols, acc_stride;
+  int wstream;             // 1: the weight chunk does not fit next to the rings (K * nc too large): every stage carries
+                           // the [nc][128 B] weight box of its K box next to the A box (no LayerNorm prologue in this mode)
+  uint32_t a_stride;       // bytes from one A stage to the next (BOX, or BOX + the weight box when streaming)
   uint32_t off_w, off_a, off_op, off_ro, off_ln;  // byte offsets from the 1024-aligned smem base
 };
 
@@ -106,7 +109,7 @@ __device__ __forceinline__ void ln_transform(const TmaGemmParams& p, Bars* bars,
     for (int kb = 0; kb < NKB; ++kb) {
       const uint32_t s = (it + kb) % S, ph = ((it + kb) / S) & 1u;
       mbar_wait(smem_u32(&bars->a_full[s]), ph);
-      rowa[kb] = sA + s * BOX + (uint32_t)r * 128u;
+      rowa[kb] = sA + s * p.a_stride + (uint32_t)r * 128u;
 #pragma unroll
       for (int c = 0; c < 8; ++c) x[kb * 8 + c] = lds128(rowa[kb] + (((uint32_t)c ^ rsw) << 4));   // columns >= K are zero (TMA fill)
     }
@@ -235,8 +238,8 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
       TileIter ti(p);
-      if (ti.valid()) {
-        const uint8_t* wsrc = p.w + (long long)(p.per_image ? (int)blockIdx.z : 0) * p.w_bstride_bytes;
+      const uint8_t* wsrc = p.w + (long long)(p.per_image ? (int)blockIdx.z : 0) * p.w_bstride_bytes;
+      if (ti.valid() && !p.wstream) {
         const uint32_t wb = smem_u32(&bars->w_full);
         mbar_expect_tx(wb, (uint32_t)(p.nob * ncur * 128));
         for (int ob = 0; ob < p.nob; ++ob)
@@ -250,8 +253,13 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           const uint32_t s = it % (uint32_t)p.S, ph = (it / (uint32_t)p.S) & 1u;
           mbar_wait(smem_u32(&bars->a_empty[s]), ph ^ 1u);
           const uint32_t fb = smem_u32(&bars->a_full[s]);
-          mbar_expect_tx(fb, BOX);
-          tma_load_3d(&tmA, fb, sA + s * BOX, kb * RAWCOLS, row0, b);
+          if (p.wstream) {
+            mbar_expect_tx(fb, BOX + (uint32_t)(ncur * 128));
+            bulk_load(sA + s * p.a_stride + BOX, wsrc + ((size_t)kb * p.N + n0) * 128, (uint32_t)(ncur * 128), fb);
+          } else {
+            mbar_expect_tx(fb, BOX);
+          }
+          tma_load_3d(&tmA, fb, sA + s * p.a_stride, kb * RAWCOLS, row0, b);
         }
       }
     }
@@ -275,7 +283,7 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   } else if (warp == WARP_MMA) {
     // =============================== MMA issuer ===============================
     TileIter ti(p);
-    if (ti.valid()) {
+    if (ti.valid() && !p.wstream) {
       mbar_wait(smem_u32(&bars->w_full), 0);
       tc_fence_after();
     }
@@ -293,8 +301,8 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         tc_fence_after();
         {
           // the whole converged warp runs this; one elected lane issues (no per-instruction election loop)
-          const uint32_t a_addr = (OPRING ? sOP : sA) + s * BOX;
-          const uint32_t w_addr = sW + (uint32_t)(ob * ncur * 128);
+          const uint32_t a_addr = OPRING ? sOP + s * BOX : sA + s * p.a_stride;
+          const uint32_t w_addr = p.wstream ? a_addr + BOX : sW + (uint32_t)(ob * ncur * 128);
           const int kbytes = min(128, (p.K - ob * OPCOLS) * (int)sizeof(TOp));
           for (int kk = 0; kk < kbytes / 32; ++kk)
             umma_elect<TOp>(tmem_base + slot * (uint32_t)p.acc_stride, sw128_desc(a_addr + kk * 32),
@@ -415,7 +423,7 @@ int make_map(CUtensorMap* tm, const void* ptr, bool half, int inner, long long r
   return make_tmap(tm, ptr, half, 3, gdim, gstr, box, true);
 }
 
-struct TmaCfg { int nc, nchunks, nkb, nob, S, SOP, RB; uint32_t off_w, off_a, off_op, off_ro, off_ln; size_t smem; };
+struct TmaCfg { int nc, nchunks, nkb, nob, S, SOP, RB, wstream; uint32_t a_stride, off_w, off_a, off_op, off_ro, off_ln; size_t smem; };
 
 // Shape-only feasibility + shared-memory carve-up.  ln: fused LayerNorm prologue.
 bool configure(int K, int N, bool op_half, bool ln, bool has_r, bool y_half, TmaCfg& c) {
@@ -459,7 +467,7 @@ bool configure(int K, int N, bool op_half, bool ln, bool has_r, bool y_half, Tma
       if (S < (ln ? c.nkb : 2)) continue;
       if (ln && S < 2 * c.nkb && chunks < N / 64) continue;      // prefer two tiles in flight: split N further
     }
-    c.nc = nc; c.nchunks = (N + nc - 1) / nc; c.S = S; c.SOP = SOP; c.RB = RB;
+    c.nc = nc; c.nchunks = (N + nc - 1) / nc; c.S = S; c.SOP = SOP; c.RB = RB; c.wstream = 0; c.a_stride = BOX;
     c.off_a = (uint32_t)off; off += (size_t)S * BOX;
     c.off_op = (uint32_t)off; off += (size_t)SOP * BOX;
     c.off_ro = (uint32_t)off; off += has_r ? (size_t)RB * BOX : ro;
@@ -468,6 +476,52 @@ bool configure(int K, int N, bool op_half, bool ln, bool has_r, bool y_half, Tma
     return true;
   }
   return false;
+}
+
+// Streamed-weights carve-up for the wide low-resolution layers (K * N too large for a CTA-resident weight chunk):
+// stages of [A box | weight box of <= 128 columns], at least four deep; the A tensor is re-read once per N-chunk (from L2
+// at these levels).
+bool configure_stream(int K, int N, bool op_half, bool has_r, bool y_half, TmaCfg& c) {
+  const int op_es = op_half ? 2 : 4;
+  if (K <= 0 || N <= 0 || N % 16 != 0 || (K * op_es) % 32 != 0 || (has_r && y_half)) return false;
+  const int opcols = 128 / op_es, gcs = y_half ? 64 : 32;
+  c.nkb = c.nob = (K + opcols - 1) / opcols;
+  const size_t budget = 227 * 1024 - 1024;
+  for (int nc = 256; nc >= 64; nc -= gcs) {
+    if (nc < N && N % nc != 0) continue;                        // equal chunks only
+    const int ncc = std::min(nc, N);
+    const size_t wbox = ((size_t)ncc * 128 + 1023) / 1024 * 1024;
+    const size_t stage = BOX + wbox;
+    const size_t ro = has_r ? (size_t)3 * BOX : (size_t)EPI_WARPS * 2 * WBOX;
+    if (HDR + 4 * stage + ro > budget) continue;
+    const int S = (int)std::min<size_t>(MAX_S, (budget - HDR - ro) / stage);
+    size_t off = HDR;
+    c.off_w = (uint32_t)off;
+    c.nc = ncc; c.nchunks = (N + ncc - 1) / ncc; c.S = S; c.SOP = 0; c.RB = has_r ? 3 : 0; c.wstream = 1;
+    c.a_stride = (uint32_t)stage;
+    c.off_a = (uint32_t)off; off += (size_t)S * stage;
+    c.off_op = (uint32_t)off;
+    c.off_ro = (uint32_t)off; off += ro;
+    c.off_ln = (uint32_t)off;
+    c.smem = off + 1024;
+    return true;
+  }
+  return false;
+}
+
+// resident weights where the chunk count stays small, streamed weights otherwise
+bool configure_any(int K, int N, bool op_half, bool ln, bool has_r, bool y_half, TmaCfg& c) {
+  const int lim = K <= 128 ? 2 : has_r ? 6 : 24;
+  if (configure(K, N, op_half, ln, has_r, y_half, c)) {
+    if (c.nchunks <= lim) {
+      if (ln || K <= 128 || c.nchunks <= 2) return true;
+      TmaCfg st;                                                 // many small chunks: prefer wide streamed chunks
+      if (c.nchunks > 8 && configure_stream(K, N, op_half, has_r, y_half, st) && st.nchunks * 2 <= c.nchunks) { c = st; return true; }
+      return true;
+    }
+  }
+  if (ln || K <= 128) return false;
+  return configure_stream(K, N, op_half, has_r, y_half, c);
 }
 
 template <typename TOp, bool LN, typename TY>
@@ -486,11 +540,9 @@ int launch_inst(const CUtensorMap& tA, const CUtensorMap& tR, const CUtensorMap&
 // (K <= 128), more at the low-resolution levels, whose whole A tensor (1/16 or 1/64 of the pixels) stays in the 126 MB L2.
 bool tma_gemm_shape_supported(int K, int N, bool op_half, bool ln, bool has_r, bool y_half) {
   TmaCfg c;
-  if (!configure(K, N, op_half, ln, has_r, y_half, c)) return false;
-  const int lim = K <= 128 ? 2 : has_r ? 6 : 24;
   const char* e = getenv("IRB_TMA_CHUNK_LIMIT");      // bring-up knob: 0 keeps the low-resolution levels on the first kernel
-  if (e && K > 128) return c.nchunks <= atoi(e);
-  return c.nchunks <= lim;
+  if (e && K > 128) return configure(K, N, op_half, ln, has_r, y_half, c) && c.nchunks <= atoi(e);
+  return configure_any(K, N, op_half, ln, has_r, y_half, c);
 }
 
 int tma_gemm_kpad(int K, bool op_half) { const int oc = op_half ? 64 : 32; return (K + oc - 1) / oc * oc; }
@@ -503,7 +555,7 @@ int launch_gemm_tma(const TcGemmParams& t, cudaStream_t s) {
     return IR_UNSUPPORTED_SHAPE;
   if (ln ? a_half : (a_half != op_half)) return IR_UNSUPPORTED_SHAPE;
   TmaCfg c;
-  if (!configure(t.K, t.N, op_half, ln, has_r, y_half, c)) return IR_UNSUPPORTED_SHAPE;
+  if (!configure_any(t.K, t.N, op_half, ln, has_r, y_half, c)) return IR_UNSUPPORTED_SHAPE;
   const int a_es = a_half ? 2 : 4, y_es = y_half ? 2 : 4;
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
   if (!al16(t.a1) || !al16(t.y) || !al16(t.w) || (has_r && !al16(t.r)) || (t.lda1 * a_es) % 16 != 0 ||
@@ -527,6 +579,7 @@ int launch_gemm_tma(const TcGemmParams& t, cudaStream_t s) {
   int cols = 32; while (cols < 2 * p.acc_stride) cols <<= 1;
   p.tmem_cols = cols;
   p.off_w = c.off_w; p.off_a = c.off_a; p.off_op = c.off_op; p.off_ro = c.off_ro; p.off_ln = c.off_ln;
+  p.wstream = c.wstream; p.a_stride = c.a_stride;
 
   dim3 grid;
   if (p.per_image) grid = dim3(std::max(1, std::min(p.tiles_per_img, 148 / (c.nchunks * t.B))), c.nchunks, t.B);
