@@ -112,6 +112,8 @@ static void plan_block(Builder& bl, BlockPlan& bp, int C, int heads, float ffn, 
   static const bool no_fused = getenv("IRB_NO_FFN_FUSED") != nullptr;      // A/B switch for benchmarks
   bp.fuse_ffn = !no_fused && bl.engine != ENGINE_SIMT && !bias && ffn_fused_supported(C, bp.hp);
   if (bp.fuse_ffn) bp.fuse_tail = false;
+  static const bool no_k4xn = getenv("IRB_NO_K4_XN") != nullptr;           // A/B switch for benchmarks
+  bp.k4_xn = !no_k4xn && bp.fuse_ffn && bp.tma_attn && !bias && tma_gemm_xn_supported(C, bl.half());
   vec(bp.ln1_w, C);
   if (ln_bias) vec(bp.ln1_b, C);
   vec(bp.temp, heads);
@@ -374,8 +376,10 @@ size_t restormer_workspace_bytes(const RestormerPlan& pl, int B, int H, int W) {
 // -----------------------------------------------------------------------------------------------
 // Element types in half mode: a_half / y_half say whether the A source / the output are fp16 buffers (the
 // GemmParams pointers are then reinterpreted); weights were packed as fp16 operands at plan time.
+struct XnOut { void* xn = nullptr; int ld = 0; int ln_mode = 0; const float* w = nullptr; const float* b = nullptr; };
+
 static int run_1x1(const GemmParams& g, bool tc, bool half, bool a_half, bool y_half, void* xhat, cudaStream_t s,
-                   bool tma = false) {
+                   bool tma = false, const XnOut* xo = nullptr) {
   if (!tc) return launch_gemm_simt(g, s);
   TcGemmParams t{};
   t.a1 = g.a1; t.lda1 = g.lda1; t.k1 = g.k1; t.a2 = g.a2; t.lda2 = g.lda2; t.k2 = g.k2;
@@ -391,6 +395,7 @@ static int run_1x1(const GemmParams& g, bool tc, bool half, bool a_half, bool y_
                                g.ln_w, g.ln_b, s));
       t.a1 = xhat; t.lda1 = g.K; t.ln_mode = LN_NONE; t.a_half = half;
     }
+    if (xo && xo->xn) { t.xn = xo->xn; t.ldxn = xo->ld; t.xn_ln_mode = xo->ln_mode; t.xn_w = xo->w; t.xn_b = xo->b; }
     const int st = launch_gemm_tma(t, s);
     if (st == IR_UNSUPPORTED_SHAPE) { set_error("internal: layer planned for the TMA kernel is not launchable (alignment)"); return IR_ERR_INVALID; }
     return st;
@@ -472,12 +477,15 @@ int run_block(const BlockPlan& bp, const float* packed, const float* x_in, float
   g.w = (const float*)bs.w_eff; g.w_bstride = (long long)C * bp.kp_attn; g.N = C; g.K = C; g.Kp = C; g.bias = P(bp.proj_b);
   g.ln_mode = LN_NONE; g.acc_sign = 1.f;
   g.r = x_in; g.ldr = C; g.y = x_out; g.ldy = C; g.o_mode = O_NHWC; g.tag = TAG_ATTN_OUT;
-  IRB_TRY(run_1x1(g, bp.tc_attn, hf, hf, false, bs.xhat, s, bp.tma_attn));
+  XnOut xo;
+  if (bp.k4_xn) { xo.xn = bs.xhat; xo.ld = C; xo.ln_mode = ln; xo.w = P(bp.ln2_w); xo.b = P(bp.ln2_b); }
+  IRB_TRY(run_1x1(g, bp.tc_attn, hf, hf, false, bs.xhat, s, bp.tma_attn, &xo));
 
   if (bp.fuse_ffn) {
     // (6-8) norm2 into an fp16 operand tensor, then project_in + depthwise 3x3 + gate + project_out + residual
     // (:148, :89-92) in one kernel: the hidden tensor never exists in HBM
-    IRB_TRY(launch_layernorm(x_out, C, bs.xhat, C, 1, (long long)B * H * W, C, ln, P(bp.ln2_w), P(bp.ln2_b), s));
+    if (!bp.k4_xn)
+      IRB_TRY(launch_layernorm(x_out, C, bs.xhat, C, 1, (long long)B * H * W, C, ln, P(bp.ln2_w), P(bp.ln2_b), s));
     FfnFusedArgs fa{};
     fa.xn = bs.xhat; fa.x = x_out; fa.w_in = P(bp.pin_w); fa.w_out = P(bp.pout_w); fa.dw_chunked = P(bp.ffdw_w);
     fa.B = B; fa.H = H; fa.W = W; fa.C = C; fa.hp = hp;
@@ -574,7 +582,7 @@ int restormer_launch_count(const RestormerPlan& pl) {
   int n = 0;
   auto blocks = [&](const std::vector<BlockPlan>& v) {
     for (const auto& bp : v) {
-      n += 8 - (bp.fuse_tail || bp.fuse_ffn ? 1 : 0) - (bp.fuse_front ? 1 : 0);
+      n += 8 - (bp.fuse_tail || bp.fuse_ffn ? 1 : 0) - (bp.fuse_front ? 1 : 0) - (bp.k4_xn ? 1 : 0);
       // standalone LayerNorm where the contraction cannot take it as a prologue (the wide levels)
       auto ln_standalone = [&](bool tc, bool tma, int N) {
         if (!tc) return false;

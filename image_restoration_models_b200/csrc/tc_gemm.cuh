@@ -30,6 +30,9 @@ struct TcGemmParams {
   int relu;
   int n_valid;                                           // scatter epilogue: output channels >= n_valid are padding (0 = N)
   float acc_sign;                                        // y = r + acc_sign * act(acc + bias)   (0 is treated as +1)
+  // optional second output of the TMA-fed kernel: xn = LayerNorm(y) as fp16 [rows][N] (the next kernel's tensor-core
+  // operand), computed in the epilogue while the row is in registers (N <= 96, one N-chunk, fp32 y)
+  void* xn; int ldxn; int xn_ln_mode; const float* xn_w; const float* xn_b;
   int w_stream;                                          // filled by configure: weights streamed per K-chunk
   // filled by tc_gemm_configure / launch_gemm_tc
   // NC columns per CTA = nsub sub-chunks of NS <= 256 columns (one tcgen05.mma each); nacc accumulator buffers
@@ -46,6 +49,8 @@ constexpr int IR_UNSUPPORTED_SHAPE = 1000;
 bool tma_gemm_shape_supported(int K, int N, bool op_half, bool ln, bool has_r, bool y_half);
 int tma_gemm_kpad(int K, bool op_half);
 int launch_gemm_tma(const TcGemmParams& t, cudaStream_t s);
+// can launch_gemm_tma also emit xn = LayerNorm(y) for this residual contraction (K = N = C)?
+bool tma_gemm_xn_supported(int C, bool op_half);
 
 // TMA-fed 3x3 implicit GEMM (tma_conv3.cu): PixelUnshuffle / PixelShuffle scatter, or plain rows with bias + ReLU
 // (DnCNN body); fp32 channels-last in and out; weights packed with PackMat kind 2, fmt 3 / 4, K pitch 9 * tma_conv3_kpt.

@@ -25,6 +25,8 @@
 #include "sm100.cuh"
 #include "tmap.cuh"
 
+#include <type_traits>
+
 #include <cstdlib>
 
 namespace irb {
@@ -62,6 +64,10 @@ struct TmaGemmParams {
   int split;               // > 0: 1-D grid, CTAs [0, split) own N-chunk 0 and the rest chunk 1 (uneven chunks get
                            // CTA counts in proportion to their bytes); 0: blockIdx.y is the chunk
   int tmem_cols, acc_stride;
+  int xn_mode;             // LnMode of the second output xn = LayerNorm(y) (fp16), 0 = none
+  const float* xn_w; const float* xn_b;
+  int xn_boxes;            // 64-channel boxes of an xn row (1 or 2)
+  uint32_t off_xn;         // per-warp xn staging boxes
   int wstream;             // 1: the weight chunk does not fit next to the rings (K * nc too large): every stage carries
                            // the [nc][128 B] weight box of its K box next to the A box (no LayerNorm prologue in this mode)
   uint32_t a_stride;       // bytes from one A stage to the next (BOX, or BOX + the weight box when streaming)
@@ -180,7 +186,7 @@ __device__ __forceinline__ void ln_transform(const TmaGemmParams& p, Bars* bars,
 template <typename TOp, bool LN, typename TY>
 __global__ void __launch_bounds__(NTHREADS, 1)
 tma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmR,
-                const __grid_constant__ CUtensorMap tmY, const TmaGemmParams p) {
+                const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmXn, const TmaGemmParams p) {
   constexpr bool OPRING = LN && sizeof(TOp) == 2;          // fp32 raw boxes -> separate fp16 operand boxes
   constexpr int OPCOLS = 128 / (int)sizeof(TOp);           // K elements per operand box
   constexpr int GC = 128 / (int)sizeof(TY);                // output columns per store box
@@ -221,6 +227,12 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                  "r"((uint32_t)p.tmem_cols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (!LN && p.xn_mode && warp < EPI_WARPS) {
+    for (int i = tid; i < p.N; i += EPI_WARPS * 32) {
+      lnv[i] = p.xn_w[i];
+      lnv[p.N + i] = p.xn_mode == LN_WITHBIAS ? p.xn_b[i] : 0.f;
+    }
   }
   if (LN && warp >= EPI_WARPS && warp < EPI_WARPS + XF_WARPS) {
     for (int i = tid - EPI_WARPS * 32; i < p.K; i += XF_WARPS * 32) {
@@ -330,6 +342,114 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int ngroups = (ncur + GC - 1) / GC;
     if (lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmY)) : "memory");
     uint32_t j = 0, gc = 0;
+    bool xn_done = false;
+    if constexpr (!LN && sizeof(TY) == 4) {
+      if (p.xn_mode) {
+        // ---- residual epilogue that also emits xn = LayerNorm(y) (norm2, restormer.py:148) as the fp16 operand of the
+        //      fused GDFN: the thread owns a whole pixel row (<= 3 groups of 32 columns), so the row stays in registers,
+        //      the statistics are two passes over them, and the LayerNorm pass over HBM disappears ----
+        xn_done = true;
+        const uint32_t sXN = base + p.off_xn + (uint32_t)q * (uint32_t)p.xn_boxes * WBOX + (uint32_t)lane * 128u;
+        if (lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmXn)) : "memory");
+        // NC = N as a compile-time constant (48 or 96): no predicates in the statistics, four independent sums
+        auto xn_path = [&](auto nc_tag) {
+          constexpr int NC = decltype(nc_tag)::value, NG = (NC + 31) / 32, NV = NC / 4;
+          const float inv_n = 1.0f / (float)NC;
+          for (TileIter ti(p); ti.valid(); ti.next(), ++j) {
+            const int b = ti.img(), row0 = ti.row0();
+            const uint32_t slot = j & 1u;
+            mbar_wait(smem_u32(&bars->acc_full[slot]), (j >> 1) & 1u);
+            tc_fence_after();
+            const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + slot * (uint32_t)p.acc_stride;
+            float4 xr[NG * 8];
+#pragma unroll
+            for (int g = 0; g < NG; ++g, ++gc) {
+              const int col = n0 + g * GC;
+              uint32_t box;
+              if (p.has_r) {
+                const uint32_t s = gc % (uint32_t)p.RB, ph = (gc / (uint32_t)p.RB) & 1u;
+                mbar_wait(smem_u32(&bars->r_full[s]), ph);
+                box = sRO + s * BOX + (uint32_t)q * WBOX;
+              } else {
+                box = sRO + (uint32_t)(q * 2 + (int)(gc & 1u)) * WBOX;
+                if (lane == 0) bulk_wait_read<1>();
+                __syncwarp();
+              }
+              const uint32_t myrow = box + (uint32_t)lane * 128u;
+              float v[32];
+              tmem_ld32(tacc + (uint32_t)(g * 32), v);
+              tmem_ld_wait();
+              if (g == NG - 1) { tc_fence_before(); mbar_arrive(smem_u32(&bars->acc_empty[slot])); }
+              if (p.bias) {
+#pragma unroll
+                for (int e = 0; e < 32; ++e) v[e] += (col + e < p.N) ? __ldg(p.bias + col + e) : 0.f;
+              }
+#pragma unroll
+              for (int c = 0; c < 8; ++c) {
+                const uint32_t a = myrow + (((uint32_t)c ^ lsw) << 4);
+                float4 o = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+                if (p.has_r) {
+                  const float4 rr = lds128(a);
+                  o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+                }
+                sts128(a, o);
+                xr[g * 8 + c] = o;
+              }
+              fence_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_3d(&tmY, box, col, row0 + q * 32, b);
+                bulk_commit();
+                if (p.has_r && gc > 0) {
+                  bulk_wait_read<1>();
+                  mbar_arrive(smem_u32(&bars->r_empty[(gc - 1) % (uint32_t)p.RB]));
+                }
+              }
+            }
+            // statistics over the NC valid columns (TMEM columns past N were never written: not read here)
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+            for (int i = 0; i < NV; ++i) { s0 += xr[i].x; s1 += xr[i].y; s2 += xr[i].z; s3 += xr[i].w; }
+            const float mu = ((s0 + s1) + (s2 + s3)) * inv_n;
+            s0 = s1 = s2 = s3 = 0.f;
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+              const float d0 = xr[i].x - mu, d1 = xr[i].y - mu, d2 = xr[i].z - mu, d3 = xr[i].w - mu;
+              s0 = fmaf(d0, d0, s0); s1 = fmaf(d1, d1, s1); s2 = fmaf(d2, d2, s2); s3 = fmaf(d3, d3, s3);
+            }
+            const float rstd = 1.0f / sqrtf(((s0 + s1) + (s2 + s3)) * inv_n + 1e-5f);
+            const float sub = p.xn_mode == LN_WITHBIAS ? mu : 0.f;
+            // the previous tile's xn store has read the staging boxes (it is older than this tile's y stores)
+            if (lane == 0) bulk_wait_read<NG>();
+            __syncwarp();
+#pragma unroll
+            for (int c8 = 0; c8 < NC / 8; ++c8) {                   // 16-byte chunks of 8 fp16 channels
+              uint4 t;
+              __half2* h = reinterpret_cast<__half2*>(&t);
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const float4 x = xr[c8 * 2 + e];
+                const float4 gw = *reinterpret_cast<const float4*>(lnv + c8 * 8 + e * 4);
+                const float4 gb = *reinterpret_cast<const float4*>(lnv + NC + c8 * 8 + e * 4);
+                h[2 * e] = __floats2half2_rn(fmaf((x.x - sub) * rstd, gw.x, gb.x), fmaf((x.y - sub) * rstd, gw.y, gb.y));
+                h[2 * e + 1] = __floats2half2_rn(fmaf((x.z - sub) * rstd, gw.z, gb.z), fmaf((x.w - sub) * rstd, gw.w, gb.w));
+              }
+              sts128u(sXN + (uint32_t)(c8 >> 3) * WBOX + ((((uint32_t)c8 & 7u) ^ lsw) << 4), t);
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              for (int xb = 0; xb < p.xn_boxes; ++xb)
+                tma_store_3d(&tmXn, sXN - (uint32_t)lane * 128u + (uint32_t)xb * WBOX, xb * 64, row0 + q * 32, b);
+              bulk_commit();
+            }
+          }
+        };
+        if (p.N == 96) xn_path(std::integral_constant<int, 96>{});
+        else xn_path(std::integral_constant<int, 48>{});
+      }
+    }
+    if (!xn_done)
     for (TileIter ti(p); ti.valid(); ti.next(), ++j) {
       const int b = ti.img(), row0 = ti.row0();
       const uint32_t slot = j & 1u;
@@ -423,10 +543,10 @@ int make_map(CUtensorMap* tm, const void* ptr, bool half, int inner, long long r
   return make_tmap(tm, ptr, half, 3, gdim, gstr, box, true);
 }
 
-struct TmaCfg { int nc, nchunks, nkb, nob, S, SOP, RB, wstream; uint32_t a_stride, off_w, off_a, off_op, off_ro, off_ln; size_t smem; };
+struct TmaCfg { int nc, nchunks, nkb, nob, S, SOP, RB, wstream; uint32_t a_stride, off_w, off_a, off_op, off_ro, off_ln, off_xn; size_t smem; };
 
 // Shape-only feasibility + shared-memory carve-up.  ln: fused LayerNorm prologue.
-bool configure(int K, int N, bool op_half, bool ln, bool has_r, bool y_half, TmaCfg& c) {
+bool configure(int K, int N, bool op_half, bool ln, bool has_r, bool y_half, TmaCfg& c, bool xn = false) {
   const int op_es = op_half ? 2 : 4;
   if (K <= 0 || N <= 0 || N % 16 != 0 || (K * op_es) % 32 != 0) return false;
   if (ln && (K % 4 != 0 || K > 128)) return false;          // the transform keeps a row of <= 4 boxes in registers
@@ -436,7 +556,10 @@ bool configure(int K, int N, bool op_half, bool ln, bool has_r, bool y_half, Tma
   c.nob = (K + opcols - 1) / opcols;
   const bool opring = ln && op_half;
   const int gcs = y_half ? 64 : 32;
-  const size_t budget = 227 * 1024 - 1024 /*alignment slack*/;
+  // xn second output: per-warp staging boxes + the LayerNorm parameters; the row must be whole (one N-chunk, <= 3 groups)
+  if (xn && (ln || y_half || (N != 48 && N != 96))) return false;
+  const size_t xn_bytes = xn ? (size_t)EPI_WARPS * ((N + 63) / 64) * WBOX + (size_t)2 * N * 4 + 16 : 0;
+  const size_t budget = 227 * 1024 - 1024 /*alignment slack*/ - xn_bytes;
   for (int chunks = 1; chunks <= N / 16; ++chunks) {
     int nc = (N + chunks - 1) / chunks;
     nc = chunks == 1 ? N : (nc + gcs - 1) / gcs * gcs;
@@ -472,6 +595,11 @@ bool configure(int K, int N, bool op_half, bool ln, bool has_r, bool y_half, Tma
     c.off_op = (uint32_t)off; off += (size_t)SOP * BOX;
     c.off_ro = (uint32_t)off; off += has_r ? (size_t)RB * BOX : ro;
     c.off_ln = (uint32_t)off; off += lnb;
+    if (xn) {
+      if (chunks != 1) return false;
+      c.off_xn = (uint32_t)off; off += (size_t)EPI_WARPS * ((N + 63) / 64) * WBOX;
+      c.off_ln = (uint32_t)off; off += (size_t)2 * N * 4 + 16;
+    }
     c.smem = off + 1024;
     return true;
   }
@@ -525,11 +653,11 @@ bool configure_any(int K, int N, bool op_half, bool ln, bool has_r, bool y_half,
 }
 
 template <typename TOp, bool LN, typename TY>
-int launch_inst(const CUtensorMap& tA, const CUtensorMap& tR, const CUtensorMap& tY, const TmaGemmParams& p, dim3 grid,
-                size_t smem, cudaStream_t s) {
+int launch_inst(const CUtensorMap& tA, const CUtensorMap& tR, const CUtensorMap& tY, const CUtensorMap& tXn,
+                const TmaGemmParams& p, dim3 grid, size_t smem, cudaStream_t s) {
   static SmemOptIn optin;
   IRB_TRY(opt_in_smem(tma_gemm_kernel<TOp, LN, TY>, optin));
-  tma_gemm_kernel<TOp, LN, TY><<<grid, NTHREADS, smem, s>>>(tA, tR, tY, p);
+  tma_gemm_kernel<TOp, LN, TY><<<grid, NTHREADS, smem, s>>>(tA, tR, tY, tXn, p);
   IRB_LAUNCH_CHECK();
   return IR_OK;
 }
@@ -545,6 +673,11 @@ bool tma_gemm_shape_supported(int K, int N, bool op_half, bool ln, bool has_r, b
   return configure_any(K, N, op_half, ln, has_r, y_half, c);
 }
 
+bool tma_gemm_xn_supported(int C, bool op_half) {
+  TmaCfg c;
+  return configure(C, C, op_half, false, true, false, c, true);
+}
+
 int tma_gemm_kpad(int K, bool op_half) { const int oc = op_half ? 64 : 32; return (K + oc - 1) / oc * oc; }
 
 // Returns IR_OK, an error, or IR_UNSUPPORTED_SHAPE (> 0) when the caller should use the first-generation kernel.
@@ -555,7 +688,11 @@ int launch_gemm_tma(const TcGemmParams& t, cudaStream_t s) {
     return IR_UNSUPPORTED_SHAPE;
   if (ln ? a_half : (a_half != op_half)) return IR_UNSUPPORTED_SHAPE;
   TmaCfg c;
-  if (!configure_any(t.K, t.N, op_half, ln, has_r, y_half, c)) return IR_UNSUPPORTED_SHAPE;
+  const bool xn = t.xn != nullptr;
+  if (xn) {
+    if (!configure(t.K, t.N, op_half, ln, has_r, y_half, c, true)) return IR_UNSUPPORTED_SHAPE;
+    c.wstream = 0; c.a_stride = BOX;
+  } else if (!configure_any(t.K, t.N, op_half, ln, has_r, y_half, c)) return IR_UNSUPPORTED_SHAPE;
   const int a_es = a_half ? 2 : 4, y_es = y_half ? 2 : 4;
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
   if (!al16(t.a1) || !al16(t.y) || !al16(t.w) || (has_r && !al16(t.r)) || (t.lda1 * a_es) % 16 != 0 ||
@@ -567,6 +704,11 @@ int launch_gemm_tma(const TcGemmParams& t, cudaStream_t s) {
   IRB_TRY(make_map(&tY, t.y, y_half, t.N, t.ldy, t.HW, t.B, 32));
   if (has_r) IRB_TRY(make_map(&tR, t.r, false, t.N, t.ldr, t.HW, t.B, TM));
   else tR = tY;
+  CUtensorMap tXn = tY;
+  if (xn) {
+    if (!al16(t.xn) || (t.ldxn * 2) % 16 != 0) return IR_UNSUPPORTED_SHAPE;
+    IRB_TRY(make_map(&tXn, t.xn, true, t.N, t.ldxn, t.HW, t.B, 32));
+  }
 
   TmaGemmParams p{};
   p.w = reinterpret_cast<const uint8_t*>(t.w);
@@ -580,6 +722,7 @@ int launch_gemm_tma(const TcGemmParams& t, cudaStream_t s) {
   p.tmem_cols = cols;
   p.off_w = c.off_w; p.off_a = c.off_a; p.off_op = c.off_op; p.off_ro = c.off_ro; p.off_ln = c.off_ln;
   p.wstream = c.wstream; p.a_stride = c.a_stride;
+  p.xn_mode = xn ? t.xn_ln_mode : 0; p.xn_w = t.xn_w; p.xn_b = t.xn_b; p.xn_boxes = (t.N + 63) / 64; p.off_xn = c.off_xn;
 
   dim3 grid;
   if (p.per_image) grid = dim3(std::max(1, std::min(p.tiles_per_img, 148 / (c.nchunks * t.B))), c.nchunks, t.B);
@@ -595,13 +738,13 @@ int launch_gemm_tma(const TcGemmParams& t, cudaStream_t s) {
   const size_t smem = std::max<size_t>(c.smem, 120 * 1024);
 
   const double rows = (double)t.B * t.HW;
-  ProfScope prof(t.tag, rows * ((double)t.K * a_es + (double)t.N * (y_es + (has_r ? 4.0 : 0.0))), 2.0 * rows * t.N * t.K, s);
-  if (!op_half && !ln && !y_half) return launch_inst<float, false, float>(tA, tR, tY, p, grid, smem, s);
-  if (!op_half && ln && !y_half) return launch_inst<float, true, float>(tA, tR, tY, p, grid, smem, s);
-  if (op_half && ln && y_half) return launch_inst<__half, true, __half>(tA, tR, tY, p, grid, smem, s);
-  if (op_half && ln && !y_half) return launch_inst<__half, true, float>(tA, tR, tY, p, grid, smem, s);
-  if (op_half && !ln && !y_half) return launch_inst<__half, false, float>(tA, tR, tY, p, grid, smem, s);
-  if (op_half && !ln && y_half) return launch_inst<__half, false, __half>(tA, tR, tY, p, grid, smem, s);
+  ProfScope prof(t.tag, rows * ((double)t.K * a_es + (double)t.N * (y_es + (has_r ? 4.0 : 0.0) + (xn ? 2.0 : 0.0))), 2.0 * rows * t.N * t.K, s);
+  if (!op_half && !ln && !y_half) return launch_inst<float, false, float>(tA, tR, tY, tXn, p, grid, smem, s);
+  if (!op_half && ln && !y_half) return launch_inst<float, true, float>(tA, tR, tY, tXn, p, grid, smem, s);
+  if (op_half && ln && y_half) return launch_inst<__half, true, __half>(tA, tR, tY, tXn, p, grid, smem, s);
+  if (op_half && ln && !y_half) return launch_inst<__half, true, float>(tA, tR, tY, tXn, p, grid, smem, s);
+  if (op_half && !ln && !y_half) return launch_inst<__half, false, float>(tA, tR, tY, tXn, p, grid, smem, s);
+  if (op_half && !ln && y_half) return launch_inst<__half, false, __half>(tA, tR, tY, tXn, p, grid, smem, s);
   return IR_UNSUPPORTED_SHAPE;
 }
 
