@@ -113,8 +113,10 @@ __device__ __forceinline__ void dw_chunk(uint32_t patch, uint32_t taps, f2_t (&a
   }
 }
 
-// TH_: element type of qkv / v == tensor-core operand type.  NQK: q|k chunks per tile (2C/32: 3 for C = 48, 6 for C = 96)
-template <typename TH_, int NQK>
+// TH_: element type of qkv == the Gram's operand type.  NQK: q|k chunks per tile (2C/32: 3 for C = 48, 6 for C = 96).
+// VH: v is stored as fp16 (always with fp16 qkv; with fp32 qkv when the attention-output contraction takes fp16 operands:
+// the tensor core would round v to a 10-bit mantissa anyway, and the fp16 tensor is half the bytes)
+template <typename TH_, int NQK, bool VH>
 __global__ void __launch_bounds__(NTHREADS, 1)
 attn_front_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmV, const FrontParams p) {
   constexpr bool F32 = std::is_same<TH_, float>::value;
@@ -304,7 +306,7 @@ attn_front_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
             float gx, gy;
             unpack2(acc[oy][ox], gx, gy);
             const uint32_t lp = (uint32_t)(oy * 8 + (lane >> 4) * 4 + ox);     // pixel inside the warp's 2 x 8 region
-            if constexpr (F32) {
+            if constexpr (F32 && !VH) {
               // rounded to tf32: the attention-output contraction feeds v to the tensor core straight from its TMA box
               uint2 t = make_uint2(__float_as_uint(to_tf32(gx)), __float_as_uint(to_tf32(gy)));
               sts64u(vb + lp * 128u + ((((uint32_t)cp >> 1) ^ (lp & 7u)) << 4) + ((uint32_t)cp & 1u) * 8u, t);
@@ -410,11 +412,11 @@ bool configure(int Ct, int heads_total, bool half, FrontCfg& c) {
   return false;
 }
 
-template <typename TH_, int NQK>
+template <typename TH_, int NQK, bool VH>
 int launch_inst(const CUtensorMap& tH, const CUtensorMap& tV, const FrontParams& p, dim3 grid, size_t smem, cudaStream_t s) {
   static SmemOptIn optin;
-  IRB_TRY(opt_in_smem(attn_front_kernel<TH_, NQK>, optin));
-  attn_front_kernel<TH_, NQK><<<grid, NTHREADS, smem, s>>>(tH, tV, p);
+  IRB_TRY(opt_in_smem(attn_front_kernel<TH_, NQK, VH>, optin));
+  attn_front_kernel<TH_, NQK, VH><<<grid, NTHREADS, smem, s>>>(tH, tV, p);
   IRB_LAUNCH_CHECK();
   return IR_OK;
 }
@@ -446,10 +448,12 @@ int launch_attn_front(const AttnFrontArgs& a, cudaStream_t s) {
     IRB_TRY(make_tmap(&tH, a.qkv, a.half != 0, 4, d, st, box, false));
   }
   {
+    const bool vh = a.half || a.v_half;
+    const int ves = vh ? 2 : 4;
     cuuint64_t d[4] = {(cuuint64_t)a.C, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.B};
-    cuuint64_t st[3] = {(cuuint64_t)a.C * es, (cuuint64_t)a.C * es * a.W, (cuuint64_t)a.C * es * a.W * a.H};
+    cuuint64_t st[3] = {(cuuint64_t)a.C * ves, (cuuint64_t)a.C * ves * a.W, (cuuint64_t)a.C * ves * a.W * a.H};
     cuuint32_t box[4] = {KC, 8, 2, 1};                 // one dw warp's region
-    IRB_TRY(make_tmap(&tV, a.v, a.half != 0, 4, d, st, box, !a.half));   // fp32 staging rows are 128 B (swizzled), fp16 64 B
+    IRB_TRY(make_tmap(&tV, a.v, vh, 4, d, st, box, !vh));   // fp32 staging rows are 128 B (swizzled), fp16 64 B
   }
   FrontParams p{};
   p.dw = a.dw_chunked; p.s_part = a.s_part; p.n_part = a.n_part;
@@ -467,9 +471,13 @@ int launch_attn_front(const AttnFrontArgs& a, cudaStream_t s) {
   dim3 grid(p.parts, a.B, p.ngroups);
   const size_t smem = std::max<size_t>(c.smem, 120 * 1024);
   const double pix = (double)a.B * a.H * a.W;
-  ProfScope prof(TAG_ATTN_FRONT, pix * 4.0 * a.C * es, pix * (2.0 * 9 * 3 * a.C + 2.0 * a.C * (a.C / a.heads)), s);
-  if (cg == 48) return a.half ? launch_inst<__half, 3>(tH, tV, p, grid, smem, s) : launch_inst<float, 3>(tH, tV, p, grid, smem, s);
-  return a.half ? launch_inst<__half, 6>(tH, tV, p, grid, smem, s) : launch_inst<float, 6>(tH, tV, p, grid, smem, s);
+  ProfScope prof(TAG_ATTN_FRONT, pix * a.C * (3.0 * es + (a.half || a.v_half ? 2.0 : 4.0)),
+                 pix * (2.0 * 9 * 3 * a.C + 2.0 * a.C * (a.C / a.heads)), s);
+  if (cg == 48)
+    return a.half ? launch_inst<__half, 3, true>(tH, tV, p, grid, smem, s)
+         : a.v_half ? launch_inst<float, 3, true>(tH, tV, p, grid, smem, s) : launch_inst<float, 3, false>(tH, tV, p, grid, smem, s);
+  return a.half ? launch_inst<__half, 6, true>(tH, tV, p, grid, smem, s)
+       : a.v_half ? launch_inst<float, 6, true>(tH, tV, p, grid, smem, s) : launch_inst<float, 6, false>(tH, tV, p, grid, smem, s);
 }
 
 }  // namespace irb

@@ -7,7 +7,8 @@ namespace irb {
 struct AttnFrontArgs {
   const void* qkv;         // [B*H*W][3C] qkv 1x1 output (fp32, or fp16 when half)
   int half;
-  void* v;                 // [B*H*W][C] depthwise-convolved v (same element type; fp32 rounded to tf32)
+  int v_half;              // fp32 qkv, but v stored as fp16 (the attention-output contraction then runs on fp16 operands)
+  void* v;                 // [B*H*W][C] depthwise-convolved v (fp16 when half || v_half, else fp32 rounded to tf32)
   const float* dw_chunked; // taps [ceil(3C/32)][9][32] (launch_pack_dw_chunked with one set)
   float* s_part;           // [B][heads][parts][ch][ch]
   float* n_part;           // [B][heads][parts][2][ch]

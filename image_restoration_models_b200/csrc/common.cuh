@@ -135,6 +135,10 @@ int launch_fold(const FoldParams& p, cudaStream_t s);
 // 3x3 conv with 1..4 output channels, channels-last fp32 in, NCHW out: y = r + sign * (conv + bias)
 int launch_conv3x3_small(const float* in, int ld, int cin, const float* w, int kp, const float* bias, int cout, int B,
                          int H, int W, const float* r, float sign, float* y, cudaStream_t s);
+// first 3x3 conv of a network: NCHW image with 1 / 3 / 6 channels -> channels-last rows (+ bias, ReLU); w row-major [cout][kp], k = tap*cin + c
+bool conv3x3_first_supported(int cin, int cout);
+int launch_conv3x3_first(const float* x_nchw, int cin, const float* w, int kp, const float* bias, int relu, int cout, int B,
+                         int H, int W, float* y, int ldy, cudaStream_t s);
 // standalone channel LayerNorm (levels whose C does not fit the contraction's register-resident prologue)
 int launch_layernorm(const float* x, int ldx, void* y, int ldy, int y_half, long long rows, int C, int ln_mode,
                      const float* w, const float* b, cudaStream_t s);

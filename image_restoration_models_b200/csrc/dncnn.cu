@@ -105,6 +105,11 @@ int dncnn_forward(const DncnnPlan& pl, const float* packed, const float* x, floa
                                    x, -1.f, y, s));
       continue;
     }
+    if (l == 0 && l < nb - 1 && conv3x3_first_supported(L.cin, L.cout)) {
+      // head conv + bias + ReLU straight from the NCHW image (network_dncnn.py:63)
+      IRB_TRY(launch_conv3x3_first(x, L.cin, packed + L.w, L.kp, packed + L.b, 1, L.cout, B, H, W, buf[l & 1], pl.cfg.nc, s));
+      continue;
+    }
     GemmParams g{};
     g.B = B; g.H = H; g.W = W;
     g.k1 = L.cin;

@@ -102,9 +102,14 @@ static void plan_block(Builder& bl, BlockPlan& bp, int C, int heads, float ffn, 
   bp.tma_attn = bp.tc_attn && bl.tma(C, C, false, true, false);
   bp.tma_pin = bp.tc_pin && bl.tma(C, 2 * bp.hp, ln_fused, false, bl.half());
   bp.tma_pout = bp.tc_pout && bl.tma(bp.hp, C, false, true, false);
-  bp.kp_attn = bp.tma_attn ? tma_gemm_kpad(C, bl.half()) : C;
   // MDTA front / GDFN tail in one kernel each (no biases: every shipped configuration has bias=False)
   bp.fuse_front = bl.engine != ENGINE_SIMT && !bias && bp.tc_attn && attn_front_supported(C, heads, bl.half());
+  // fp32 mode: v is only ever a tensor-core operand (rounded to a 10-bit mantissa either way), so the fused front stores it
+  // as fp16 and the attention-output contraction takes fp16 operands (v and the per-image folded matrix)
+  static const bool no_vhalf = getenv("IRB_NO_V_HALF") != nullptr;         // A/B switch for benchmarks
+  bp.v_half = !no_vhalf && bl.engine == ENGINE_TC && bp.fuse_front && tma_gemm_shape_supported(C, C, true, false, true, false);
+  if (bp.v_half) bp.tma_attn = true;
+  bp.kp_attn = bp.tma_attn ? tma_gemm_kpad(C, bl.half() || bp.v_half) : C;
   bp.fuse_tail = bl.engine != ENGINE_SIMT && !bias && ffn_tail_supported(C, bp.hp, bl.half());
   // the whole GDFN in one kernel (ffn_fused.cu).  Its operands are fp16 images in BOTH tensor-core modes: the hidden
   // tensor lives only in shared memory, where fp32 storage does not fit; fp16 carries the same 10-bit mantissa as the
@@ -113,7 +118,7 @@ static void plan_block(Builder& bl, BlockPlan& bp, int C, int heads, float ffn, 
   bp.fuse_ffn = !no_fused && bl.engine != ENGINE_SIMT && !bias && ffn_fused_supported(C, bp.hp);
   if (bp.fuse_ffn) bp.fuse_tail = false;
   static const bool no_k4xn = getenv("IRB_NO_K4_XN") != nullptr;           // A/B switch for benchmarks
-  bp.k4_xn = !no_k4xn && bp.fuse_ffn && bp.tma_attn && !bias && tma_gemm_xn_supported(C, bl.half());
+  bp.k4_xn = !no_k4xn && bp.fuse_ffn && bp.tma_attn && !bias && tma_gemm_xn_supported(C, bl.half() || bp.v_half);
   vec(bp.ln1_w, C);
   if (ln_bias) vec(bp.ln1_b, C);
   vec(bp.temp, heads);
@@ -440,7 +445,7 @@ int run_block(const BlockPlan& bp, const float* packed, const float* x_in, float
   if (bp.fuse_front) {
     // (2+3) depthwise 3x3 + q.k^T Gram partials + squared norms; only v is written (:114-115, :121-124)
     AttnFrontArgs fa{};
-    fa.qkv = bs.qkv; fa.half = hf; fa.v = bs.qkv_dw; fa.dw_chunked = P(bp.qkvdw_w);
+    fa.qkv = bs.qkv; fa.half = hf; fa.v_half = bp.v_half; fa.v = bs.qkv_dw; fa.dw_chunked = P(bp.qkvdw_w);
     fa.s_part = bs.s_part; fa.n_part = bs.n_part; fa.parts = attn_front_parts(B, H, W, C, bp.heads);
     fa.B = B; fa.H = H; fa.W = W; fa.C = C; fa.heads = bp.heads;
     IRB_TRY(launch_attn_front(fa, s));
@@ -467,7 +472,8 @@ int run_block(const BlockPlan& bp, const float* packed, const float* x_in, float
   FoldParams fp{};
   fp.s_part = bs.s_part; fp.n_part = bs.n_part; fp.B = B; fp.C = C; fp.heads = bp.heads; fp.nparts = gp.nparts;
   fp.temperature = P(bp.temp); fp.w_proj = P(bp.proj_w); fp.w_eff = (float*)bs.w_eff; fp.w_eff_bstride = (long long)C * bp.kp_attn;
-  fp.fmt = !bp.tc_attn ? 0 : bp.tma_attn ? (hf ? 4 : 3) : hf ? 2 : 1;
+  const bool ah = hf || bp.v_half;          // operand type of the attention-output contraction
+  fp.fmt = !bp.tc_attn ? 0 : bp.tma_attn ? (ah ? 4 : 3) : hf ? 2 : 1;
   IRB_TRY(launch_fold(fp, s));
 
   // (5) x_out = x_in + W_eff[b] . v  (+ project_out bias)   (:127-131, :147)
@@ -479,7 +485,7 @@ int run_block(const BlockPlan& bp, const float* packed, const float* x_in, float
   g.r = x_in; g.ldr = C; g.y = x_out; g.ldy = C; g.o_mode = O_NHWC; g.tag = TAG_ATTN_OUT;
   XnOut xo;
   if (bp.k4_xn) { xo.xn = bs.xhat; xo.ld = C; xo.ln_mode = ln; xo.w = P(bp.ln2_w); xo.b = P(bp.ln2_b); }
-  IRB_TRY(run_1x1(g, bp.tc_attn, hf, hf, false, bs.xhat, s, bp.tma_attn, &xo));
+  IRB_TRY(run_1x1(g, bp.tc_attn, ah, ah, false, bs.xhat, s, bp.tma_attn, &xo));
 
   if (bp.fuse_ffn) {
     // (6-8) norm2 into an fp16 operand tensor, then project_in + depthwise 3x3 + gate + project_out + residual
@@ -565,6 +571,9 @@ static int conv3(const ConvPlan& cp, const float* packed, const float* in, int l
   if (cp.tc && a_mode == A_IM2COL_NHWC && o_mode != O_NCHW && r == nullptr)
     return run_conv3_tc(in, ld_in, cp.cin, packed + cp.w, cp.b >= 0 ? packed + cp.b : nullptr, cp.cout_p, cp.cout, B, H, W,
                         out, ld_out, o_mode, 0, half, s);
+  if (!cp.tc && a_mode == A_IM2COL_NCHW && o_mode == O_NHWC && r == nullptr && conv3x3_first_supported(cp.cin, cp.cout))
+    return launch_conv3x3_first(in, cp.cin, packed + cp.w, cp.kp, cp.b >= 0 ? packed + cp.b : nullptr, 0, cp.cout, B, H, W, out,
+                                ld_out, s);
   if (!cp.tc && a_mode == A_IM2COL_NHWC && o_mode == O_NCHW && cp.cout <= 4 && cp.cin % 4 == 0 &&
       (size_t)cp.cout * 9 * cp.cin * sizeof(float) <= 48 * 1024)
     return launch_conv3x3_small(in, ld_in, cp.cin, packed + cp.w, cp.kp, cp.b >= 0 ? packed + cp.b : nullptr, cp.cout, B, H,

@@ -27,6 +27,7 @@ struct BlockPlan {     // one TransformerBlock (restormer.py:137-150); offsets i
   bool fuse_front;                         // qkv dwconv + Gram + norms + v store in one kernel (attn_front.cu)
   bool fuse_tail;                          // dwconv + gate + project_out + residual in one kernel (ffn_tail.cu)
   bool fuse_ffn;                           // the whole GDFN in one kernel behind a standalone LayerNorm (ffn_fused.cu)
+  bool v_half;                             // fp32 mode: v and the folded attention matrix are fp16 operands (same mantissa as tf32)
   bool k4_xn;                              // the attention-output contraction also emits norm2(x) as the fused GDFN's fp16 operand
   int kp_attn;                             // K pitch of the folded attention matrix W_eff (padded for the TMA kernel)
   bool ref_kernels;                        // ENGINE_SIMT: reference CUDA-core kernels everywhere

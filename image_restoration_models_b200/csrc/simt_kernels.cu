@@ -558,6 +558,68 @@ int launch_conv3x3_small(const float* in, int ld, int cin, const float* w, int k
 }
 
 // ---------------------------------------------------------------------------------------------
+// First 3x3 convolution of a network (patch_embed restormer.py:160-165, DnCNN head network_dncnn.py:63): an NCHW image
+// with 1-8 channels -> channels-last [pixel][cout] (+ bias, ReLU).  Pure store bandwidth (48-64 floats out per 1-6 in):
+// cout/4 consecutive threads own one pixel and write one float4 each, so a warp's store is one contiguous segment;
+// the 9*cin inputs of a pixel are broadcast loads shared by its threads and by the neighbouring pixels through L1.
+// ---------------------------------------------------------------------------------------------
+template <int CIN>
+__global__ void __launch_bounds__(256) conv3x3_first_kernel(const float* __restrict__ x, const float* __restrict__ w, int kp,
+                                                            const float* __restrict__ bias, int relu, int cout, int B, int H,
+                                                            int W, float* __restrict__ y, int ldy) {
+  extern __shared__ float wsm[];                  // [9*CIN][cout] (transposed: a thread's 4 outputs are one float4)
+  for (int i = threadIdx.x; i < cout * 9 * CIN; i += 256) {
+    const int co = i / (9 * CIN), k = i - co * 9 * CIN;      // k = tap * CIN + c (PackMat kind 1 order)
+    wsm[k * cout + co] = w[(long long)co * kp + k];
+  }
+  __syncthreads();
+  const int q4 = cout >> 2;
+  const long long total = (long long)B * H * W * q4;
+  for (long long idx = (long long)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (long long)gridDim.x * 256) {
+    const long long pix = idx / q4;
+    const int q = (int)(idx - pix * q4);
+    const int xx = (int)(pix % W);
+    const long long t = pix / W;
+    const int yy = (int)(t % H), b = (int)(t / H);
+    float4 acc = bias ? *reinterpret_cast<const float4*>(bias + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int y2 = yy + tap / 3 - 1, x2 = xx + tap % 3 - 1;
+      if (y2 < 0 || y2 >= H || x2 < 0 || x2 >= W) continue;
+#pragma unroll
+      for (int c = 0; c < CIN; ++c) {
+        const float v = __ldg(x + (((long long)b * CIN + c) * H + y2) * W + x2);
+        const float4 ww = *reinterpret_cast<const float4*>(wsm + (tap * CIN + c) * cout + 4 * q);
+        acc.x = fmaf(v, ww.x, acc.x); acc.y = fmaf(v, ww.y, acc.y); acc.z = fmaf(v, ww.z, acc.z); acc.w = fmaf(v, ww.w, acc.w);
+      }
+    }
+    if (relu) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
+    *reinterpret_cast<float4*>(y + pix * ldy + 4 * q) = acc;
+  }
+}
+
+bool conv3x3_first_supported(int cin, int cout) {
+  return (cin == 1 || cin == 3 || cin == 6) && cout % 4 == 0 && (size_t)cout * 9 * cin * sizeof(float) <= 48 * 1024;
+}
+
+int launch_conv3x3_first(const float* x_nchw, int cin, const float* w, int kp, const float* bias, int relu, int cout, int B,
+                         int H, int W, float* y, int ldy, cudaStream_t s) {
+  IRB_REQUIRE(conv3x3_first_supported(cin, cout) && ldy % 4 == 0, "conv3x3_first: unsupported shape");
+  const long long total = (long long)B * H * W * (cout / 4);
+  const int blocks = (int)std::min<long long>(cdivll(total, 256), 148LL * 32);
+  const size_t smem = (size_t)cout * 9 * cin * sizeof(float);
+  const double pix = (double)B * H * W;
+  ProfScope prof(TAG_CONV3, 4.0 * pix * (cin + cout), 2.0 * 9.0 * pix * cin * cout, s);
+  switch (cin) {
+    case 1: conv3x3_first_kernel<1><<<blocks, 256, smem, s>>>(x_nchw, w, kp, bias, relu, cout, B, H, W, y, ldy); break;
+    case 3: conv3x3_first_kernel<3><<<blocks, 256, smem, s>>>(x_nchw, w, kp, bias, relu, cout, B, H, W, y, ldy); break;
+    default: conv3x3_first_kernel<6><<<blocks, 256, smem, s>>>(x_nchw, w, kp, bias, relu, cout, B, H, W, y, ldy); break;
+  }
+  IRB_LAUNCH_CHECK();
+  return IR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // standalone channel LayerNorm, one warp per pixel (C <= 1024), two-pass statistics in registers
 // ---------------------------------------------------------------------------------------------
 template <typename TY>
