@@ -573,14 +573,15 @@ __global__ void __launch_bounds__(256) conv3x3_first_kernel(const float* __restr
     wsm[k * cout + co] = w[(long long)co * kp + k];
   }
   __syncthreads();
+  // grid.y walks the B*H image rows, grid.x the W * cout/4 (pixel, quad) pairs of a row: 32-bit index arithmetic only
+  // (64-bit divisions per thread cost more than the convolution)
   const int q4 = cout >> 2;
-  const long long total = (long long)B * H * W * q4;
-  for (long long idx = (long long)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (long long)gridDim.x * 256) {
-    const long long pix = idx / q4;
-    const int q = (int)(idx - pix * q4);
-    const int xx = (int)(pix % W);
-    const long long t = pix / W;
-    const int yy = (int)(t % H), b = (int)(t / H);
+  const int in_row = blockIdx.x * 256 + threadIdx.x;
+  if (in_row >= W * q4) return;
+  const int xx = in_row / q4, q = in_row - xx * q4;
+  for (int row = blockIdx.y; row < B * H; row += gridDim.y) {
+    const int b = row / H, yy = row - b * H;
+    const long long pix = (long long)row * W + xx;
     float4 acc = bias ? *reinterpret_cast<const float4*>(bias + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap) {
@@ -605,8 +606,8 @@ bool conv3x3_first_supported(int cin, int cout) {
 int launch_conv3x3_first(const float* x_nchw, int cin, const float* w, int kp, const float* bias, int relu, int cout, int B,
                          int H, int W, float* y, int ldy, cudaStream_t s) {
   IRB_REQUIRE(conv3x3_first_supported(cin, cout) && ldy % 4 == 0, "conv3x3_first: unsupported shape");
-  const long long total = (long long)B * H * W * (cout / 4);
-  const int blocks = (int)std::min<long long>(cdivll(total, 256), 148LL * 32);
+  IRB_REQUIRE((long long)B * H < (1LL << 31), "conv3x3_first: too many image rows");
+  const dim3 blocks(cdiv(W * (cout / 4), 256), (unsigned)std::min<long long>((long long)B * H, 65535));
   const size_t smem = (size_t)cout * 9 * cin * sizeof(float);
   const double pix = (double)B * H * W;
   ProfScope prof(TAG_CONV3, 4.0 * pix * (cin + cout), 2.0 * 9.0 * pix * cin * cout, s);
