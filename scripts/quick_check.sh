@@ -1,5 +1,6 @@
 #!/bin/bash
-# GPU-box pass for the fused GDFN kernel: block parity, model parity, benches in both modes (+ optional unfused A/B).
+# Quick GPU-box pass after a kernel change: block parity, full parity suite, benches in both modes with per-launch
+# CUDA-event dumps (+ optional A/B against the multi-kernel GDFN).  Usage (under gpurun): bash scripts/check_ffn_fused.sh <tag>
 TAG=${1:-ff}
 OUT=gpurun_out
 mkdir -p $OUT
