@@ -497,11 +497,21 @@ __global__ void __launch_bounds__(256) conv3x3_small_kernel(const float* __restr
         if (!cok || y2 < 0 || y2 >= H || x < 0 || x >= W) return make_float4(0.f, 0.f, 0.f, 0.f);
         return *reinterpret_cast<const float4*>(in + (((long long)b * H + y2) * W + x) * ld + 4 * c4);
       };
+      // the column two steps ahead is already in flight when a pixel is computed (the loop is a load -> FMA -> reduce
+      // chain per pixel; without the extra column every step waited a full L2 round trip)
+      float4 nxt[3];
 #pragma unroll
-      for (int ry = 0; ry < 3; ++ry) { win[ry][1] = ldv(ry, x0 - 1); win[ry][2] = ldv(ry, x0); }
+      for (int ry = 0; ry < 3; ++ry) { win[ry][1] = ldv(ry, x0 - 1); win[ry][2] = ldv(ry, x0); nxt[ry] = ldv(ry, x0 + 1); }
+      // single-output case (gray images): the lane's 9 taps live in registers for the whole segment
+      float4 kreg[COUT == 1 ? 9 : 1];
+      if constexpr (COUT == 1) {
+#pragma unroll
+        for (int t = 0; t < 9; ++t)
+          kreg[t] = cok ? *reinterpret_cast<const float4*>(wsm + t * cin + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
       for (int j = 0; j < 32 && x0 + j < W; ++j) {
 #pragma unroll
-        for (int ry = 0; ry < 3; ++ry) { win[ry][0] = win[ry][1]; win[ry][1] = win[ry][2]; win[ry][2] = ldv(ry, x0 + j + 1); }
+        for (int ry = 0; ry < 3; ++ry) { win[ry][0] = win[ry][1]; win[ry][1] = win[ry][2]; win[ry][2] = nxt[ry]; nxt[ry] = ldv(ry, x0 + j + 2); }
         float acc[COUT];
 #pragma unroll
         for (int co = 0; co < COUT; ++co) acc[co] = 0.f;
@@ -513,7 +523,9 @@ __global__ void __launch_bounds__(256) conv3x3_small_kernel(const float* __restr
               const float4 v = win[ry][dx];
 #pragma unroll
               for (int co = 0; co < COUT; ++co) {
-                const float4 k = *reinterpret_cast<const float4*>(wsm + (co * 9 + ry * 3 + dx) * cin + 4 * c4);
+                float4 k;
+                if constexpr (COUT == 1) k = kreg[ry * 3 + dx];
+                else k = *reinterpret_cast<const float4*>(wsm + (co * 9 + ry * 3 + dx) * cin + 4 * c4);
                 acc[co] = fmaf(v.x, k.x, fmaf(v.y, k.y, fmaf(v.z, k.z, fmaf(v.w, k.w, acc[co]))));
               }
             }
@@ -607,7 +619,9 @@ int launch_conv3x3_first(const float* x_nchw, int cin, const float* w, int kp, c
                          int H, int W, float* y, int ldy, cudaStream_t s) {
   IRB_REQUIRE(conv3x3_first_supported(cin, cout) && ldy % 4 == 0, "conv3x3_first: unsupported shape");
   IRB_REQUIRE((long long)B * H < (1LL << 31), "conv3x3_first: too many image rows");
-  const dim3 blocks(cdiv(W * (cout / 4), 256), (unsigned)std::min<long long>((long long)B * H, 65535));
+  // ~8 resident blocks per SM in total; each walks many image rows, so the per-block weight staging is amortised
+  const int gx = cdiv(W * (cout / 4), 256);
+  const dim3 blocks(gx, (unsigned)std::max<long long>(1, std::min<long long>((long long)B * H, cdiv(148 * 8, gx))));
   const size_t smem = (size_t)cout * 9 * cin * sizeof(float);
   const double pix = (double)B * H * W;
   ProfScope prof(TAG_CONV3, 4.0 * pix * (cin + cout), 2.0 * 9.0 * pix * cin * cout, s);
