@@ -30,8 +30,9 @@ METRIC = "restormer_fwd_mpix_per_s"
 DTYPES = {
     # arithmetic the path computes in; both modes accumulate in fp32 and keep the residual stream, LayerNorm
     # statistics, softmax and GELU in fp32, and both meet the north-star parity bar (max-abs <= 1e-3, dPSNR <= 0.01 dB)
-    "fp32": "fp32 activations, tf32 tensor-core operands (fp16 operands and an on-chip fp16 hidden tensor inside the "
-            "fused GDFN kernel), fp32 accumulate",
+    "fp32": "fp32 residual stream / qkv / accumulators, tf32 tensor-core operands; fp16 (same 10-bit mantissa) where a "
+            "tensor is only ever a tensor-core operand (norm2 output, v, folded attention matrix) and for the fused "
+            "GDFN's on-chip hidden tensor",
     "half": "fp16 intermediates + fp16 tensor-core operands, fp32 accumulate and fp32 residual stream",
 }
 UNIT = "Mpix/s"
