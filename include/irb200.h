@@ -40,7 +40,9 @@ typedef enum IrStatus {
 /* Arithmetic mode of the tensor-core contractions.  Accumulation is always fp32, and the
  * residual stream, LayerNorm statistics, softmax and GELU are always fp32. */
 typedef enum IrMode {
-  IR_MODE_FP32 = 0,        /* fp32 activations, tf32 tensor-core operands (fp32 parity mode) */
+  IR_MODE_FP32 = 0,        /* fp32 residual stream / qkv, tf32 tensor-core operands; tensors that are only ever tensor-core
+                              operands (norm2 output, v, folded attention matrix) and the fused GDFN's on-chip hidden
+                              tensor are fp16 -- the same 10-bit mantissa (fp32 parity mode) */
   IR_MODE_HALF = 1,        /* fp16 intermediates + fp16 operands (same 10-bit mantissa as tf32) */
   IR_MODE_FP32_SIMT = 2    /* every contraction on CUDA cores in exact fp32: the on-device second oracle of the
                               tensor-core kernels (tests / bisecting only; several times slower) */
