@@ -357,7 +357,7 @@ int launch_gram_ref(const GramParams& p, cudaStream_t s) {
 //   W_eff[b][n][h*ch + j] = sum_i W_proj[n][h*ch + i] * softmax_j(S[i][j] / (|q_i| |k_j|) * T_h)
 // grid (heads, B); dynamic smem: ch*ch + 2*ch floats
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) fold_kernel(const FoldParams p) {
+__global__ void __launch_bounds__(1024) fold_kernel(const FoldParams p) {
   extern __shared__ float sm[];
   const int head = blockIdx.x, b = blockIdx.y;
   const int ch = p.C / p.heads;
@@ -453,7 +453,9 @@ int launch_fold(const FoldParams& p, cudaStream_t s) {
   const int zb = std::max(1, std::min(8, cdiv(2 * 148, p.heads * p.B)));
   dim3 grid(p.heads, p.B, zb);
   ProfScope prof(TAG_FOLD, 4.0 * (double)p.B * p.C * p.C, 2.0 * (double)p.B * p.C * p.C * ch, s);
-  fold_kernel<<<grid, 256, smem, s>>>(p);
+  // 1024 threads: the kernel is a chain of L2 round trips (partials -> softmax -> products) over a 48x48 .. 96x96 matrix;
+  // four times the threads is a quarter of the trips per thread
+  fold_kernel<<<grid, 1024, smem, s>>>(p);
   IRB_LAUNCH_CHECK();
   return IR_OK;
 }
