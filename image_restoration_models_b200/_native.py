@@ -10,15 +10,15 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("IRB200_LIB") or os.path.join(_HERE, "libirb200.so")   # override: A/B builds when tuning
 
 IR_OK, IR_ERR_INVALID, IR_ERR_WORKSPACE, IR_ERR_CUDA, IR_ERR_OOM = 0, -1, -2, -3, -4
-MODE_FP32, MODE_HALF, MODE_FP32_SIMT = 0, 1, 2
-ABI_VERSION = 1
+MODE_FP32, MODE_HALF, MODE_FP32_SIMT, MODE_FP32_STRICT = 0, 1, 2, 3
+ABI_VERSION = 2
 
 
 class IrRestormerCfg(C.Structure):
     _fields_ = [
         ("inp_channels", C.c_int32), ("out_channels", C.c_int32), ("dim", C.c_int32),
         ("num_blocks", C.c_int32 * 4), ("num_refinement_blocks", C.c_int32), ("heads", C.c_int32 * 4),
-        ("ffn_expansion_factor", C.c_float), ("bias", C.c_int32), ("layernorm_with_bias", C.c_int32),
+        ("ffn_expansion_factor", C.c_double), ("bias", C.c_int32), ("layernorm_with_bias", C.c_int32),
         ("dual_pixel_task", C.c_int32),
     ]
 
@@ -57,11 +57,11 @@ SIGNATURES = {
     "ir_dncnn_forward": (C.c_int, [C.POINTER(IrDncnnCfg), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                    C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
     "ir_dncnn_launch_count": (C.c_int, [C.POINTER(IrDncnnCfg)]),
-    "ir_block_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int]),
-    "ir_block_packed_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]),
-    "ir_block_pack_weights": (C.c_int, [C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, _PP, C.c_int, C.c_void_p,
+    "ir_block_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "ir_block_packed_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int]),
+    "ir_block_pack_weights": (C.c_int, [C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, _PP, C.c_int, C.c_void_p,
                                         C.c_size_t, C.c_int, C.c_void_p]),
-    "ir_block_forward": (C.c_int, [C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+    "ir_block_forward": (C.c_int, [C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                    C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
     "ir_nchw_to_nhwc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "ir_nhwc_to_nchw": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),

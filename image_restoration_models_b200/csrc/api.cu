@@ -50,7 +50,8 @@ static const char* kTagNames[TAG_COUNT] = {
     "dwconv_gate_project_out", "dwconv_qkv_gram", "gdfn_fused"};
 
 static int check_mode(int mode) {
-  IRB_REQUIRE(mode == IR_MODE_FP32 || mode == IR_MODE_HALF || mode == IR_MODE_FP32_SIMT, "mode: unknown IrMode");
+  IRB_REQUIRE(mode == IR_MODE_FP32 || mode == IR_MODE_HALF || mode == IR_MODE_FP32_SIMT || mode == IR_MODE_FP32_STRICT,
+              "mode: unknown IrMode");
   return IR_OK;
 }
 static int engine_of(int mode) { return engine_of_mode(mode); }
@@ -178,21 +179,21 @@ int ir_dncnn_forward(const IrDncnnCfg* cfg, const void* packed, const float* x, 
 int ir_dncnn_launch_count(const IrDncnnCfg* cfg) { return cfg ? cfg->nb : -1; }
 
 // ------------------------------------------------------------------------------------------ single block
-size_t ir_block_workspace_bytes(int C, int heads, float ffn, int B, int H, int W, int mode) {
+size_t ir_block_workspace_bytes(int C, int heads, double ffn, int B, int H, int W, int mode) {
   if (check_mode(mode) != IR_OK || B <= 0 || H <= 0 || W <= 0) return 0;
   BlockPlan bp; std::vector<PackOp> ops; long long pf;
   if (build_block_plan(bp, ops, pf, C, heads, ffn, 0, 0, engine_of(mode)) != IR_OK) return 0;
   return block_workspace_bytes(bp, B, H, W);
 }
 
-size_t ir_block_packed_bytes(int C, int heads, float ffn, int bias, int ln_with_bias, int mode) {
+size_t ir_block_packed_bytes(int C, int heads, double ffn, int bias, int ln_with_bias, int mode) {
   if (check_mode(mode) != IR_OK) return 0;
   BlockPlan bp; std::vector<PackOp> ops; long long pf;
   if (build_block_plan(bp, ops, pf, C, heads, ffn, bias, ln_with_bias, engine_of(mode)) != IR_OK) return 0;
   return (size_t)pf * sizeof(float);
 }
 
-int ir_block_pack_weights(int C, int heads, float ffn, int bias, int ln_with_bias, const float* const* h_params,
+int ir_block_pack_weights(int C, int heads, double ffn, int bias, int ln_with_bias, const float* const* h_params,
                           int n_params, void* packed, size_t packed_bytes, int mode, void* stream) {
   IRB_REQUIRE(h_params && packed, "pack: null argument");
   IRB_TRY(check_mode(mode));
@@ -204,7 +205,7 @@ int ir_block_pack_weights(int C, int heads, float ffn, int bias, int ln_with_bia
   return run_pack_ops(ops, h_params, (float*)packed, (cudaStream_t)stream);
 }
 
-int ir_block_forward(int C, int heads, float ffn, int bias, int ln_with_bias, const void* packed, float* x_nhwc, int B,
+int ir_block_forward(int C, int heads, double ffn, int bias, int ln_with_bias, const void* packed, float* x_nhwc, int B,
                      int H, int W, void* workspace, size_t workspace_bytes, int mode, void* stream) {
   IRB_REQUIRE(packed && x_nhwc && workspace, "forward: null argument");
   IRB_TRY(check_mode(mode));
@@ -256,6 +257,11 @@ int ir_test_conv1x1(int engine, const void* a1v, int lda1, int k1, const void* a
   t.r = r; t.ldr = ldr; t.y = y; t.ldy = ldy; t.a_pad = a_pad;
   t.a_half = a_half; t.op_half = op_half; t.y_half = y_half;
   if (tma) {
+    if (ln_mode != LN_NONE && K > 128) {       // wide rows: standalone LayerNorm into scratch, like run_1x1 (restormer.cu)
+      IRB_REQUIRE(!a_half && k2 == 0, "test_conv1x1: LayerNorm needs one fp32 source");
+      IRB_TRY(launch_layernorm(a1, lda1, xhat, K, op_half ? 1 : 2, rows, K, ln_mode, ln_w, ln_b, s));
+      t.a1 = xhat; t.lda1 = K; t.ln_mode = LN_NONE; t.a_half = op_half;
+    }
     const int st = launch_gemm_tma(t, s);
     if (st == IR_UNSUPPORTED_SHAPE) { set_error("unsupported: shape not handled by the TMA-fed kernel"); return IR_ERR_INVALID; }
     return st;

@@ -262,8 +262,8 @@ attn_front_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
             sts128(boxa + (r0 + 1) * 128u + ((c16 ^ ((r0 + 1) & 7u)) << 4), make_float4(a1, b1, c1, d1));
           } else {
             // fp16: box p/64 = by/2, byte offset in the 128-byte row = (p%64)*2 = ((by&1)*32 + oy*16 + 4bx)*2
-            const __half2 h01 = __floats2half2_rn(a0, b0), h23 = __floats2half2_rn(c0, d0);
-            const __half2 g01 = __floats2half2_rn(a1, b1), g23 = __floats2half2_rn(c1, d1);
+            const __half2 h01 = f2h2_sat(a0, b0), h23 = f2h2_sat(c0, d0);
+            const __half2 g01 = f2h2_sat(a1, b1), g23 = f2h2_sat(c1, d1);
             // the norms use the rounded operands, like the MMA
             a0 = __low2float(h01); b0 = __high2float(h01); c0 = __low2float(h23); d0 = __high2float(h23);
             a1 = __low2float(g01); b1 = __high2float(g01); c1 = __low2float(g23); d1 = __high2float(g23);
@@ -311,7 +311,7 @@ attn_front_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
               uint2 t = make_uint2(__float_as_uint(to_tf32(gx)), __float_as_uint(to_tf32(gy)));
               sts64u(vb + lp * 128u + ((((uint32_t)cp >> 1) ^ (lp & 7u)) << 4) + ((uint32_t)cp & 1u) * 8u, t);
             } else {
-              const __half2 h = __floats2half2_rn(gx, gy);
+              const __half2 h = f2h2_sat(gx, gy);
               asm volatile("st.shared.b32 [%0], %1;" ::"r"(vb + lp * 64u + (uint32_t)cp * 4u),
                            "r"(*reinterpret_cast<const uint32_t*>(&h)) : "memory");
             }

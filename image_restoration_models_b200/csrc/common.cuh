@@ -35,6 +35,17 @@ int  cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 
 __host__ __device__ static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
+#ifdef __CUDACC__
+// fp32 pair -> fp16 pair, round to nearest, SATURATING: +-65504 instead of inf when an activation leaves fp16's range
+// (one F2FP.SATFINITE instruction, the cost of the plain conversion).  Every activation conversion in the library goes
+// through this; see IR_MODE_FP32_STRICT / the Python range guard for models that need more than fp16's 5 exponent bits.
+__device__ __forceinline__ __half2 f2h2_sat(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return *reinterpret_cast<__half2*>(&r);
+}
+#endif
+
 // Opt a kernel into `bytes` of dynamic shared memory once per DEVICE (the attribute is per device, and one process may
 // drive several); `done` is the caller's per-kernel table.
 struct SmemOptIn { bool done[64] = {}; };

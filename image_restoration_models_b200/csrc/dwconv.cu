@@ -57,8 +57,8 @@ template <> __device__ __forceinline__ void st4<float>(float* p, const float4& v
 }
 template <> __device__ __forceinline__ void st4<__half>(__half* p, const float4& v) {
   uint2 t;
-  *reinterpret_cast<__half2*>(&t.x) = __floats2half2_rn(v.x, v.y);
-  *reinterpret_cast<__half2*>(&t.y) = __floats2half2_rn(v.z, v.w);
+  *reinterpret_cast<__half2*>(&t.x) = f2h2_sat(v.x, v.y);
+  *reinterpret_cast<__half2*>(&t.y) = f2h2_sat(v.z, v.w);
   *reinterpret_cast<uint2*>(p) = t;
 }
 

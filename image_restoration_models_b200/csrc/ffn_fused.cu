@@ -109,7 +109,7 @@ __device__ __forceinline__ f2_t ld_h2(uint32_t a) {
 // FHFMA (fma.rn.f32.f16, no conversions, two scalar instructions per channel pair): +18 %; FFMA2 alternated with
 // scalar FFMA pairs: +6 %; 16 dw warps of 2x4 blocks: +9 %.
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
-  const __half2 h = __floats2half2_rn(a, b);
+  const __half2 h = f2h2_sat(a, b);
   return *reinterpret_cast<const uint32_t*>(&h);
 }
 

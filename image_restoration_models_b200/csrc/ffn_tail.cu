@@ -257,7 +257,7 @@ ffn_tail_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__
               uint2 t = make_uint2(__float_as_uint(to_tf32(gx)), __float_as_uint(to_tf32(gy)));
               sts64u(ob + row * 128u + ((((uint32_t)cp >> 1) ^ (row & 7u)) << 4) + ((uint32_t)cp & 1u) * 8u, t);
             } else {
-              const __half2 h = __floats2half2_rn(gx, gy);
+              const __half2 h = f2h2_sat(gx, gy);
               const uint32_t a = ob + row * 128u + ((((uint32_t)cp >> 2) ^ (row & 7u)) << 4) + ((uint32_t)cp & 3u) * 4u;
               asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(*reinterpret_cast<const uint32_t*>(&h)) : "memory");
             }

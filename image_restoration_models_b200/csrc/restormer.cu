@@ -45,7 +45,8 @@ int run_conv3_tc(const float* in, int ld_in, int cin, const float* w_packed, con
 }
 
 int engine_of_mode(int mode) {
-  return mode == IR_MODE_FP32_SIMT ? ENGINE_SIMT : mode == IR_MODE_HALF ? ENGINE_TC_HALF : ENGINE_TC;
+  return mode == IR_MODE_FP32_SIMT ? ENGINE_SIMT : mode == IR_MODE_HALF ? ENGINE_TC_HALF
+       : mode == IR_MODE_FP32_STRICT ? ENGINE_TC_STRICT : ENGINE_TC;
 }
 
 struct Builder {
@@ -63,9 +64,9 @@ struct Builder {
   long long alloc(long long n) { const long long o = off; off += (n + 63) / 64 * 64; return o; }
 };
 
-static void plan_block(Builder& bl, BlockPlan& bp, int C, int heads, float ffn, int bias, int ln_bias) {
+static void plan_block(Builder& bl, BlockPlan& bp, int C, int heads, double ffn, int bias, int ln_bias) {
   bp.C = C; bp.heads = heads;
-  bp.h = (int)(C * (double)ffn);   // int(dim*ffn_expansion_factor), restormer.py:80
+  bp.h = (int)(C * ffn);           // int(dim*ffn_expansion_factor) in double precision, like Python (restormer.py:80)
   // python: int(48*2.66)=127, int(96*2.66)=255, int(192*2.66)=510, int(384*2.66)=1021
   bp.hp = round_up(bp.h, 16);
   auto vec = [&](long long& dst, int n) {
@@ -115,7 +116,7 @@ static void plan_block(Builder& bl, BlockPlan& bp, int C, int heads, float ffn, 
   // tensor lives only in shared memory, where fp32 storage does not fit; fp16 carries the same 10-bit mantissa as the
   // tf32 operands it replaces, and accumulation stays fp32.
   static const bool no_fused = getenv("IRB_NO_FFN_FUSED") != nullptr;      // A/B switch for benchmarks
-  bp.fuse_ffn = !no_fused && bl.engine != ENGINE_SIMT && !bias && ffn_fused_supported(C, bp.hp);
+  bp.fuse_ffn = !no_fused && bl.engine != ENGINE_SIMT && bl.engine != ENGINE_TC_STRICT && !bias && ffn_fused_supported(C, bp.hp);
   if (bp.fuse_ffn) bp.fuse_tail = false;
   static const bool no_k4xn = getenv("IRB_NO_K4_XN") != nullptr;           // A/B switch for benchmarks
   bp.k4_xn = !no_k4xn && bp.fuse_ffn && bp.tma_attn && !bias && tma_gemm_xn_supported(C, bl.half() || bp.v_half);
@@ -151,11 +152,11 @@ static void plan_block(Builder& bl, BlockPlan& bp, int C, int heads, float ffn, 
 
 int block_param_count(int bias, int ln_bias) { return 9 + (ln_bias ? 2 : 0) + (bias ? 6 : 0); }
 
-int build_block_plan(BlockPlan& bp, std::vector<PackOp>& ops, long long& packed_floats, int C, int heads, float ffn,
+int build_block_plan(BlockPlan& bp, std::vector<PackOp>& ops, long long& packed_floats, int C, int heads, double ffn,
                      int bias, int ln_bias, int engine) {
   IRB_REQUIRE(C > 0 && heads > 0 && C % heads == 0, "block: C must be divisible by heads");
   IRB_REQUIRE((C / heads) % 16 == 0 && C / heads <= 128, "block: head dim must be a multiple of 16 and <= 128");
-  IRB_REQUIRE(ffn > 0.f, "block: ffn_expansion_factor must be positive");
+  IRB_REQUIRE(ffn > 0.0, "block: ffn_expansion_factor must be positive");
   Builder bl(ops, engine);
   plan_block(bl, bp, C, heads, ffn, bias, ln_bias);
   packed_floats = bl.off;
@@ -205,7 +206,7 @@ int build_restormer_plan(RestormerPlan& pl, const IrRestormerCfg& c, int engine)
   }
   IRB_REQUIRE((2 * c.dim) % c.heads[0] == 0 && (2 * c.dim / c.heads[0]) % 16 == 0 && 2 * c.dim / c.heads[0] <= 128,
               "restormer: level-1 decoder head dim must be a multiple of 16 and <= 128");
-  IRB_REQUIRE(c.num_refinement_blocks >= 0 && c.ffn_expansion_factor > 0.f, "restormer: bad refinement / ffn factor");
+  IRB_REQUIRE(c.num_refinement_blocks >= 0 && c.ffn_expansion_factor > 0.0, "restormer: bad refinement / ffn factor");
   IRB_REQUIRE(c.dual_pixel_task || c.inp_channels == c.out_channels,
               "restormer: inp_channels must equal out_channels unless dual_pixel_task (residual add, restormer.py:281)");
   pl.cfg = c;
@@ -396,7 +397,8 @@ static int run_1x1(const GemmParams& g, bool tc, bool half, bool a_half, bool y_
   if (tma) {
     // the layer's weights were packed for the TMA-fed kernel at plan time; the plan only selects shapes it supports
     if (g.ln_mode != LN_NONE && g.K > 128) {
-      IRB_TRY(launch_layernorm(g.a1, g.lda1, xhat, g.K, half ? 1 : 0, (long long)g.B * g.H * g.W, g.K, g.ln_mode,
+      // fp32 operands reach the kind::tf32 MMA straight from the TMA box: round them here (the tensor core truncates)
+      IRB_TRY(launch_layernorm(g.a1, g.lda1, xhat, g.K, half ? 1 : 2, (long long)g.B * g.H * g.W, g.K, g.ln_mode,
                                g.ln_w, g.ln_b, s));
       t.a1 = xhat; t.lda1 = g.K; t.ln_mode = LN_NONE; t.a_half = half;
     }

@@ -54,8 +54,9 @@ int  block_param_count(int bias, int ln_bias);
 // engine: 0 = tcgen05 contractions with tf32 operands and fp32 intermediates; 1 = CUDA-core fp32 contractions and
 // reference kernels (on-device second oracle); 2 = tcgen05 contractions with fp16 operands and fp16 intermediates
 // (the residual stream, LayerNorm statistics, Gram accumulation, softmax and GELU stay fp32)
-enum Engine { ENGINE_TC = 0, ENGINE_SIMT = 1, ENGINE_TC_HALF = 2 };
-int  build_block_plan(BlockPlan& bp, std::vector<PackOp>& ops, long long& packed_floats, int C, int heads, float ffn,
+// 3 = as 0 but without any fp16 tensor (v, norm2 output and the GDFN hidden tensor stay fp32 / tf32): IR_MODE_FP32_STRICT
+enum Engine { ENGINE_TC = 0, ENGINE_SIMT = 1, ENGINE_TC_HALF = 2, ENGINE_TC_STRICT = 3 };
+int  build_block_plan(BlockPlan& bp, std::vector<PackOp>& ops, long long& packed_floats, int C, int heads, double ffn,
                       int bias, int ln_bias, int engine);
 int  build_restormer_plan(RestormerPlan& pl, const IrRestormerCfg& cfg, int engine);
 bool tc_gemm_supported(int K, int N, bool half);

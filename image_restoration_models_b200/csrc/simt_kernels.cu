@@ -639,10 +639,17 @@ int launch_conv3x3_first(const float* x_nchw, int cin, const float* w, int kp, c
 // ---------------------------------------------------------------------------------------------
 // standalone channel LayerNorm, one warp per pixel (C <= 1024), two-pass statistics in registers
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float rna_tf32(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+
 template <typename TY>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, int ldx, TY* __restrict__ y,
                                                         int ldy, long long rows, int C, int ln_mode,
-                                                        const float* __restrict__ w, const float* __restrict__ b) {
+                                                        const float* __restrict__ w, const float* __restrict__ b,
+                                                        int round_tf32) {
   const int lane = threadIdx.x & 31;
   const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -683,11 +690,12 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
           o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
         }
         if constexpr (sizeof(TY) == 4) {
+          if (round_tf32) o = make_float4(rna_tf32(o.x), rna_tf32(o.y), rna_tf32(o.z), rna_tf32(o.w));
           *reinterpret_cast<float4*>(y + row * ldy + 4 * f) = o;
         } else {
           uint2 t;
-          *reinterpret_cast<__half2*>(&t.x) = __floats2half2_rn(o.x, o.y);
-          *reinterpret_cast<__half2*>(&t.y) = __floats2half2_rn(o.z, o.w);
+          *reinterpret_cast<__half2*>(&t.x) = f2h2_sat(o.x, o.y);
+          *reinterpret_cast<__half2*>(&t.y) = f2h2_sat(o.z, o.w);
           *reinterpret_cast<uint2*>(y + row * ldy + 4 * f) = t;
         }
       }
@@ -701,7 +709,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 template <typename TY, int LPR, int V>
 __global__ void __launch_bounds__(256) layernorm_rows_kernel(const float* __restrict__ x, TY* __restrict__ y, long long rows,
                                                              int ln_mode, const float* __restrict__ w,
-                                                             const float* __restrict__ b) {
+                                                             const float* __restrict__ b, int round_tf32) {
   constexpr int C = 4 * LPR * V, RPW = 32 / LPR;
   const int lane = threadIdx.x & 31, l = lane % LPR, r = lane / LPR;
   const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -742,11 +750,12 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(const float* __rest
       o.x = (v[i].x - sub) * rstd * g[i].x + bb[i].x; o.y = (v[i].y - sub) * rstd * g[i].y + bb[i].y;
       o.z = (v[i].z - sub) * rstd * g[i].z + bb[i].z; o.w = (v[i].w - sub) * rstd * g[i].w + bb[i].w;
       if constexpr (sizeof(TY) == 4) {
+        if (round_tf32) o = make_float4(rna_tf32(o.x), rna_tf32(o.y), rna_tf32(o.z), rna_tf32(o.w));
         reinterpret_cast<float4*>(y + row * C)[i * LPR + l] = o;
       } else {
         uint2 t;
-        *reinterpret_cast<__half2*>(&t.x) = __floats2half2_rn(o.x, o.y);
-        *reinterpret_cast<__half2*>(&t.y) = __floats2half2_rn(o.z, o.w);
+        *reinterpret_cast<__half2*>(&t.x) = f2h2_sat(o.x, o.y);
+        *reinterpret_cast<__half2*>(&t.y) = f2h2_sat(o.z, o.w);
         reinterpret_cast<uint2*>(y + row * C)[i * LPR + l] = t;
       }
     }
@@ -754,19 +763,23 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(const float* __rest
 }
 
 template <int LPR>
-static int launch_layernorm_rows(const float* x, void* y, int y_half, long long rows, int ln_mode, const float* w,
+static int launch_layernorm_rows(const float* x, void* y, int y_fmt, long long rows, int ln_mode, const float* w,
                                  const float* b, cudaStream_t s) {
+  const int y_half = y_fmt == 1, rnd = y_fmt == 2;
   constexpr int RPB = 8 * (32 / LPR);      // pixels per block pass
   const long long need = cdivll(rows, RPB);
   const int blocks = (int)(need < 148LL * 8 ? (need > 0 ? need : 1) : 148LL * 8);
-  if (y_half) layernorm_rows_kernel<__half, LPR, 3><<<blocks, 256, 0, s>>>(x, (__half*)y, rows, ln_mode, w, b);
-  else        layernorm_rows_kernel<float, LPR, 3><<<blocks, 256, 0, s>>>(x, (float*)y, rows, ln_mode, w, b);
+  if (y_half) layernorm_rows_kernel<__half, LPR, 3><<<blocks, 256, 0, s>>>(x, (__half*)y, rows, ln_mode, w, b, 0);
+  else        layernorm_rows_kernel<float, LPR, 3><<<blocks, 256, 0, s>>>(x, (float*)y, rows, ln_mode, w, b, rnd);
   IRB_LAUNCH_CHECK();
   return IR_OK;
 }
 
-int launch_layernorm(const float* x, int ldx, void* y, int ldy, int y_half, long long rows, int C, int ln_mode,
+// y_fmt: 0 fp32, 1 fp16, 2 fp32 rounded to tf32 (round-to-nearest; the consumer is a kind::tf32 MMA reading the tensor
+// straight from its TMA box, and the tensor core TRUNCATES the low 13 mantissa bits of an unrounded operand)
+int launch_layernorm(const float* x, int ldx, void* y, int ldy, int y_fmt, long long rows, int C, int ln_mode,
                      const float* w, const float* b, cudaStream_t s) {
+  const int y_half = y_fmt == 1;
   IRB_REQUIRE(C % 4 == 0 && C <= 1024 && ldx % 4 == 0 && ldy % 4 == 0, "layernorm: C must be a multiple of 4, <= 1024");
   IRB_REQUIRE(ln_mode == LN_BIASFREE || ln_mode == LN_WITHBIAS, "layernorm: bad mode");
   const long long blocks_needed = cdivll(rows, 8);
@@ -774,15 +787,15 @@ int launch_layernorm(const float* x, int ldx, void* y, int ldy, int y_half, long
   ProfScope prof(TAG_LAYERNORM, (y_half ? 6.0 : 8.0) * (double)rows * C, 0.0, s);
   if (ldx == C && ldy == C && (reinterpret_cast<uintptr_t>(x) & 15u) == 0 && (reinterpret_cast<uintptr_t>(y) & 15u) == 0) {
     switch (C) {
-      case 48:  return launch_layernorm_rows<4>(x, y, y_half, rows, ln_mode, w, b, s);
-      case 96:  return launch_layernorm_rows<8>(x, y, y_half, rows, ln_mode, w, b, s);
-      case 192: return launch_layernorm_rows<16>(x, y, y_half, rows, ln_mode, w, b, s);
-      case 384: return launch_layernorm_rows<32>(x, y, y_half, rows, ln_mode, w, b, s);
+      case 48:  return launch_layernorm_rows<4>(x, y, y_fmt, rows, ln_mode, w, b, s);
+      case 96:  return launch_layernorm_rows<8>(x, y, y_fmt, rows, ln_mode, w, b, s);
+      case 192: return launch_layernorm_rows<16>(x, y, y_fmt, rows, ln_mode, w, b, s);
+      case 384: return launch_layernorm_rows<32>(x, y, y_fmt, rows, ln_mode, w, b, s);
       default: break;
     }
   }
-  if (y_half) layernorm_kernel<__half><<<blocks > 0 ? blocks : 1, 256, 0, s>>>(x, ldx, (__half*)y, ldy, rows, C, ln_mode, w, b);
-  else        layernorm_kernel<float><<<blocks > 0 ? blocks : 1, 256, 0, s>>>(x, ldx, (float*)y, ldy, rows, C, ln_mode, w, b);
+  if (y_half) layernorm_kernel<__half><<<blocks > 0 ? blocks : 1, 256, 0, s>>>(x, ldx, (__half*)y, ldy, rows, C, ln_mode, w, b, 0);
+  else        layernorm_kernel<float><<<blocks > 0 ? blocks : 1, 256, 0, s>>>(x, ldx, (float*)y, ldy, rows, C, ln_mode, w, b, y_fmt == 2);
   IRB_LAUNCH_CHECK();
   return IR_OK;
 }

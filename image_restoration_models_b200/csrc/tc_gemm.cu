@@ -187,7 +187,7 @@ __device__ __forceinline__ void store_chunk<__half>(uint8_t* dst, const float* v
   uint4 t;
   __half2* h = reinterpret_cast<__half2*>(&t);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+  for (int i = 0; i < 4; ++i) h[i] = f2h2_sat(v[2 * i], v[2 * i + 1]);
   *reinterpret_cast<uint4*>(dst) = t;
 }
 
@@ -339,8 +339,8 @@ template <>
 __device__ __forceinline__ void store_out4<__half>(__half* dst, const float4& o) {
   uint2 t;
   __half2* h = reinterpret_cast<__half2*>(&t);
-  h[0] = __floats2half2_rn(o.x, o.y);
-  h[1] = __floats2half2_rn(o.z, o.w);
+  h[0] = f2h2_sat(o.x, o.y);
+  h[1] = f2h2_sat(o.z, o.w);
   *reinterpret_cast<uint2*>(dst) = t;
 }
 
@@ -448,7 +448,7 @@ __device__ __forceinline__ void epi_group_h64(const EpiCtx<__half>& ec, uint32_t
       uint4 t;
       __half2* h = reinterpret_cast<__half2*>(&t);
 #pragma unroll
-      for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(v[8 * jj + 2 * e], v[8 * jj + 2 * e + 1]);
+      for (int e = 0; e < 4; ++e) h[e] = f2h2_sat(v[8 * jj + 2 * e], v[8 * jj + 2 * e + 1]);
       srow[hf * 4 + jj] = t;
     }
   }

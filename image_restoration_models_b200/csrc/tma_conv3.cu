@@ -226,8 +226,8 @@ tma_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const Conv3Params p) {
             for (int c8 = 0; c8 < 8; ++c8) {
               uint4 t;
               __half2* hh = reinterpret_cast<__half2*>(&t);
-              hh[0] = __floats2half2_rn(x[2 * c8].x, x[2 * c8].y); hh[1] = __floats2half2_rn(x[2 * c8].z, x[2 * c8].w);
-              hh[2] = __floats2half2_rn(x[2 * c8 + 1].x, x[2 * c8 + 1].y); hh[3] = __floats2half2_rn(x[2 * c8 + 1].z, x[2 * c8 + 1].w);
+              hh[0] = f2h2_sat(x[2 * c8].x, x[2 * c8].y); hh[1] = f2h2_sat(x[2 * c8].z, x[2 * c8].w);
+              hh[2] = f2h2_sat(x[2 * c8 + 1].x, x[2 * c8 + 1].y); hh[3] = f2h2_sat(x[2 * c8 + 1].z, x[2 * c8 + 1].w);
               sts128u(orow + (((uint32_t)c8 ^ rsw) << 4), t);
             }
             fence_async_smem();

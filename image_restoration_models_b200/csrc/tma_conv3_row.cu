@@ -278,8 +278,8 @@ conv3_row_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               for (int c8 = 0; c8 < 8; ++c8) {
                 uint4 u;
                 __half2* hh = reinterpret_cast<__half2*>(&u);
-                hh[0] = __floats2half2_rn(x[2 * c8].x, x[2 * c8].y); hh[1] = __floats2half2_rn(x[2 * c8].z, x[2 * c8].w);
-                hh[2] = __floats2half2_rn(x[2 * c8 + 1].x, x[2 * c8 + 1].y); hh[3] = __floats2half2_rn(x[2 * c8 + 1].z, x[2 * c8 + 1].w);
+                hh[0] = f2h2_sat(x[2 * c8].x, x[2 * c8].y); hh[1] = f2h2_sat(x[2 * c8].z, x[2 * c8].w);
+                hh[2] = f2h2_sat(x[2 * c8 + 1].x, x[2 * c8 + 1].y); hh[3] = f2h2_sat(x[2 * c8 + 1].z, x[2 * c8 + 1].w);
                 sts128u(orow + (((uint32_t)c8 ^ sw7) << 4), u);
               }
             }

@@ -167,8 +167,8 @@ __device__ __forceinline__ void ln_transform(const TmaGemmParams& p, Bars* bars,
           uint4 t = make_uint4(0u, 0u, 0u, 0u);
           if (i + 1 < NKB * 8 && i * 4 < p.K) {
             __half2* h = reinterpret_cast<__half2*>(&t);
-            h[0] = __floats2half2_rn(x[i].x, x[i].y); h[1] = __floats2half2_rn(x[i].z, x[i].w);
-            h[2] = __floats2half2_rn(x[i + 1].x, x[i + 1].y); h[3] = __floats2half2_rn(x[i + 1].z, x[i + 1].w);
+            h[0] = f2h2_sat(x[i].x, x[i].y); h[1] = f2h2_sat(x[i].z, x[i].w);
+            h[2] = f2h2_sat(x[i + 1].x, x[i + 1].y); h[3] = f2h2_sat(x[i + 1].z, x[i + 1].w);
           }
           sts128u(orow + (((uint32_t)c8 ^ rsw) << 4), t);
         }
@@ -431,8 +431,8 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 const float4 x = xr[c8 * 2 + e];
                 const float4 gw = *reinterpret_cast<const float4*>(lnv + c8 * 8 + e * 4);
                 const float4 gb = *reinterpret_cast<const float4*>(lnv + NC + c8 * 8 + e * 4);
-                h[2 * e] = __floats2half2_rn(fmaf((x.x - sub) * rstd, gw.x, gb.x), fmaf((x.y - sub) * rstd, gw.y, gb.y));
-                h[2 * e + 1] = __floats2half2_rn(fmaf((x.z - sub) * rstd, gw.z, gb.z), fmaf((x.w - sub) * rstd, gw.w, gb.w));
+                h[2 * e] = f2h2_sat(fmaf((x.x - sub) * rstd, gw.x, gb.x), fmaf((x.y - sub) * rstd, gw.y, gb.y));
+                h[2 * e + 1] = f2h2_sat(fmaf((x.z - sub) * rstd, gw.z, gb.z), fmaf((x.w - sub) * rstd, gw.w, gb.w));
               }
               sts128u(sXN + (uint32_t)(c8 >> 3) * WBOX + ((((uint32_t)c8 & 7u) ^ lsw) << 4), t);
             }
@@ -504,7 +504,7 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               uint4 t;
               __half2* h = reinterpret_cast<__half2*>(&t);
 #pragma unroll
-              for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(v[8 * c + 2 * e], v[8 * c + 2 * e + 1]);
+              for (int e = 0; e < 4; ++e) h[e] = f2h2_sat(v[8 * c + 2 * e], v[8 * c + 2 * e + 1]);
               sts128u(myrow + (((uint32_t)(hf * 4 + c) ^ lsw) << 4), t);
             }
           }

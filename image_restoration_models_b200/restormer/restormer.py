@@ -15,7 +15,53 @@ import torch.nn as nn
 from .. import _native
 from .._params import AffineParams, ConvParams, Holder, ordered_tensors
 
-_MODES = {"fp32": _native.MODE_FP32, "half": _native.MODE_HALF, "fp32_simt": _native.MODE_FP32_SIMT}
+_MODES = {"fp32": _native.MODE_FP32, "half": _native.MODE_HALF, "fp32_simt": _native.MODE_FP32_SIMT,
+          "fp32_strict": _native.MODE_FP32_STRICT}
+
+# Range guard of the fast fp32 mode.  IR_MODE_FP32 keeps the tensors that are only ever tensor-core operands (norm2
+# output, v, the fused GDFN's on-chip hidden / gated tensors) as fp16: tf32's mantissa but 5 exponent bits.  The device
+# conversions saturate (+-65504, never inf).  At pack time `fp16_range_bound` estimates how large those tensors get from
+# the weights alone; a model whose estimate comes near fp16's range runs in IR_MODE_FP32_STRICT (tf32 operands and
+# fp32 tensors everywhere) instead.  The estimate is statistical, not worst-case (an L1 worst case is ~1000x above what a
+# network produces and would always trip): LayerNorm outputs are taken as zero-mean with standard deviation m * |w_k|,
+# m = 1 for WithBias and sqrt(1 + r^2) for BiasFree (which divides x, not x - mean, by the std; r = |mean| / std), a
+# contraction output n then has std sqrt(sum_k W[n,k]^2 var_k) (+ the bias path), the depthwise conv scales it by at
+# most sum |taps|, and every tensor is bounded at RANGE_SIGMAS standard deviations.
+FP16_MAX = 65504.0
+FP16_GUARD_FRACTION = 0.25          # switch to the strict mode when the estimate exceeds a quarter of fp16's range
+BIASFREE_MEAN_OVER_STD = 4.0
+RANGE_SIGMAS = 6.0
+
+
+def _block_fp16_bound(blk, with_bias: bool, fused_gdfn: bool) -> torch.Tensor:
+    """RANGE_SIGMAS-sigma estimate of max(|xn2|, |hidden|, |gated|, |v|) of one TransformerBlock (restormer.py:88-93,
+    :111-116); xn2 / hidden / gated only count where the block runs the fused GDFN (C <= 128).  0-d device tensor."""
+    m = 1.0 if with_bias else (1.0 + BIASFREE_MEAN_OVER_STD ** 2) ** 0.5
+
+    def ln_stats(body):
+        w = body.weight.detach().double()
+        bias = getattr(body, "bias", None)
+        return (m * w) ** 2, (bias.detach().abs().double() if bias is not None else torch.zeros_like(w))
+
+    def conv_out(weight, var, mean_abs):            # std and |mean| bound per output channel of a 1x1 conv
+        w = weight.detach().double().flatten(1)
+        return torch.sqrt((w * w) @ var), w.abs() @ mean_abs
+
+    k = RANGE_SIGMAS
+    var1, mu1 = ln_stats(blk.norm1.body)
+    c = var1.numel()
+    sq, mq = conv_out(blk.attn.qkv.weight, var1, mu1)
+    dq = blk.attn.qkv_dwconv.weight.detach().abs().double().flatten(1).sum(1)
+    out = [((k * sq + mq) * dq)[2 * c:].max()]                                   # v
+    if fused_gdfn:
+        var2, mu2 = ln_stats(blk.norm2.body)
+        sh, mh = conv_out(blk.ffn.project_in.weight, var2, mu2)
+        di = blk.ffn.dwconv.weight.detach().abs().double().flatten(1).sum(1)
+        hid = k * sh + mh
+        dwh = hid * di
+        h = dwh.numel() // 2
+        out += [(k * torch.sqrt(var2) + mu2).max(), hid.max(), (dwh[:h] * dwh[h:]).max()]   # xn2, hidden, |gelu(a) b| <= |a||b|
+    return torch.stack(out).max()
 
 
 def _transformer_block(dim, num_heads, ffn_expansion_factor, bias, LayerNorm_type):
@@ -96,7 +142,11 @@ class Restormer(nn.Module):
             int(inp_channels), int(out_channels), int(dim), (C.c_int32 * 4)(*num_blocks), int(num_refinement_blocks),
             (C.c_int32 * 4)(*heads), float(ffn_expansion_factor), int(bool(bias)),
             int(LayerNorm_type != "BiasFree"), int(bool(dual_pixel_task)))
+        self._with_bias_ln = LayerNorm_type != "BiasFree"
+        self._conv_bias = bool(bias)
         self._mode = "fp32"
+        self._range_guard = True     # fp32 mode: fall back to fp32_strict when fp16_range_bound() nears fp16's range
+        self._native_mode = None     # the IrMode the packed weights were built for (fp32 may resolve to fp32_strict)
         self._packed = None          # (device, mode, tensor)
         self._workspace = None       # (key, tensor)
 
@@ -110,6 +160,34 @@ class Restormer(nn.Module):
         self._mode = mode
         self._packed = None
         return self
+
+    def set_range_guard(self, enabled: bool):
+        """fp32 mode only: enable / disable the pack-time fp16 range guard (on by default)."""
+        self._range_guard = bool(enabled)
+        self._packed = None
+        return self
+
+    def _blocks(self):
+        for stage in (self.encoder_level1, self.encoder_level2, self.encoder_level3, self.latent, self.decoder_level3,
+                      self.decoder_level2, self.decoder_level1, self.refinement):
+            yield from stage
+
+    def fp16_range_bound(self) -> float:
+        """Largest magnitude any fp16-held tensor of IR_MODE_FP32 can reach, bounded from the weights alone."""
+        if self._conv_bias:
+            return 0.0            # conv biases disable every fused kernel: no fp16 tensor exists in fp32 mode
+        def fused(blk):           # mirrors ffn_fused_supported (csrc/ffn_fused.cu): C <= 128, hidden padded to 64s
+            c = blk.norm2.body.weight.numel()
+            hp = -(-(blk.ffn.project_out.weight.shape[1]) // 16) * 16
+            return c % 16 == 0 and c <= 128 and hp % 64 == 0 and hp >= 128
+        bounds = [_block_fp16_bound(b, self._with_bias_ln, fused(b)) for b in self._blocks()]
+        return float(torch.stack(bounds).max()) if bounds else 0.0
+
+    def resolved_mode(self) -> str:
+        """The mode the next forward runs in: 'fp32' resolves to 'fp32_strict' when the range guard trips."""
+        if self._mode == "fp32" and self._range_guard and self.fp16_range_bound() > FP16_GUARD_FRACTION * FP16_MAX:
+            return "fp32_strict"
+        return self._mode
 
     def invalidate_packed(self):
         """Call after modifying parameters in place."""
@@ -126,7 +204,7 @@ class Restormer(nn.Module):
 
     def _pack(self, device):
         lib = _native.lib()
-        mode = _MODES[self._mode]
+        mode = _MODES[self.resolved_mode()]
         tensors = ordered_tensors(self)
         n = lib.ir_restormer_param_count(C.byref(self._cfg))
         if n < 0:
@@ -148,10 +226,11 @@ class Restormer(nn.Module):
         _native.check(lib.ir_restormer_pack_weights(C.byref(self._cfg), _native.ptr_array(keep), n, packed.data_ptr(),
                                                     nbytes, mode, stream))
         self._packed = (device, self._mode, packed)
+        self._native_mode = mode
         return packed
 
     def workspace_bytes(self, B, H, W):
-        return _native.lib().ir_restormer_workspace_bytes(C.byref(self._cfg), B, H, W, _MODES[self._mode])
+        return _native.lib().ir_restormer_workspace_bytes(C.byref(self._cfg), B, H, W, _MODES[self.resolved_mode()])
 
     def launches_per_forward(self):
         return _native.lib().ir_restormer_launch_count(C.byref(self._cfg))
@@ -168,17 +247,17 @@ class Restormer(nn.Module):
         dev = x.device
         with torch.cuda.device(dev):
             lib = _native.lib()
-            mode = _MODES[self._mode]
             pk = self._packed
             packed = pk[2] if pk is not None and pk[0] == dev and pk[1] == self._mode else self._pack(dev)
-            key = (dev, self._mode, B, H, W)
+            mode = self._native_mode
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            key = (dev, mode, B, H, W, stream)    # scratch is per stream: forwards on two streams must not share it
             if self._workspace is None or self._workspace[0] != key:
                 self._workspace = None      # release before allocating the new one
                 nbytes = lib.ir_restormer_workspace_bytes(C.byref(self._cfg), B, H, W, mode)
                 self._workspace = (key, torch.empty(nbytes, dtype=torch.uint8, device=dev))
             ws = self._workspace[1]
             y = torch.empty((B, self.out_channels, H, W), dtype=torch.float32, device=dev)
-            stream = torch.cuda.current_stream(dev).cuda_stream
             _native.check(lib.ir_restormer_forward(C.byref(self._cfg), packed.data_ptr(), x.data_ptr(), y.data_ptr(),
                                                    B, H, W, ws.data_ptr(), ws.numel(), mode, stream))
         return y

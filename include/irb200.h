@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define IRB200_ABI_VERSION 1
+#define IRB200_ABI_VERSION 2
 
 typedef enum IrStatus {
   IR_OK = 0,
@@ -44,8 +44,12 @@ typedef enum IrMode {
                               operands (norm2 output, v, folded attention matrix) and the fused GDFN's on-chip hidden
                               tensor are fp16 -- the same 10-bit mantissa (fp32 parity mode) */
   IR_MODE_HALF = 1,        /* fp16 intermediates + fp16 operands (same 10-bit mantissa as tf32) */
-  IR_MODE_FP32_SIMT = 2    /* every contraction on CUDA cores in exact fp32: the on-device second oracle of the
+  IR_MODE_FP32_SIMT = 2,   /* every contraction on CUDA cores in exact fp32: the on-device second oracle of the
                               tensor-core kernels (tests / bisecting only; several times slower) */
+  IR_MODE_FP32_STRICT = 3  /* as IR_MODE_FP32 but with NO fp16 tensor anywhere: tf32 operands (8 exponent bits), fp32 v / norm2
+                              output / GDFN hidden tensor in HBM.  The range-safe mode for checkpoints whose activations
+                              may leave fp16's range (|x| > 65504); ~25 % slower (the GDFN runs as two kernels).  The
+                              Python shim selects it automatically from a pack-time bound (see _range_guard) */
 } IrMode;
 
 /* Mirrors Restormer.__init__ kwargs (src/restormer/restormer.py:194-205). */
@@ -56,7 +60,7 @@ typedef struct IrRestormerCfg {
   int32_t num_blocks[4];
   int32_t num_refinement_blocks;
   int32_t heads[4];
-  float   ffn_expansion_factor;
+  double  ffn_expansion_factor; /* double: int(dim * factor) must round like Python's (restormer.py:80) */
   int32_t bias;                 /* conv bias (all shipped YAMLs: 0) */
   int32_t layernorm_with_bias;  /* 0 = 'BiasFree', 1 = 'WithBias' */
   int32_t dual_pixel_task;
@@ -109,12 +113,12 @@ int    ir_dncnn_launch_count(const IrDncnnCfg* cfg);
 
 /* One TransformerBlock in place on x[B*H*W, C] (src/restormer/restormer.py:146-150).
  * h_params: the block's tensors in state_dict order (norm1.., attn.., norm2.., ffn..).     */
-size_t ir_block_workspace_bytes(int C, int heads, float ffn_expansion_factor, int B, int H, int W, int mode);
-size_t ir_block_packed_bytes(int C, int heads, float ffn_expansion_factor, int bias, int ln_with_bias, int mode);
-int    ir_block_pack_weights(int C, int heads, float ffn_expansion_factor, int bias, int ln_with_bias,
+size_t ir_block_workspace_bytes(int C, int heads, double ffn_expansion_factor, int B, int H, int W, int mode);
+size_t ir_block_packed_bytes(int C, int heads, double ffn_expansion_factor, int bias, int ln_with_bias, int mode);
+int    ir_block_pack_weights(int C, int heads, double ffn_expansion_factor, int bias, int ln_with_bias,
                              const float* const* h_params, int n_params, void* packed, size_t packed_bytes,
                              int mode, void* stream);
-int    ir_block_forward(int C, int heads, float ffn_expansion_factor, int bias, int ln_with_bias,
+int    ir_block_forward(int C, int heads, double ffn_expansion_factor, int bias, int ln_with_bias,
                         const void* packed, float* x_nhwc, int B, int H, int W,
                         void* workspace, size_t workspace_bytes, int mode, void* stream);
 

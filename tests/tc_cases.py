@@ -73,7 +73,12 @@ TMA_CASES = [
     (256, 0, 96, 1, 384, 0, True, True, 1, 1, 0),
     (512, 0, 192, 1, 200, 0, False, True, 1, 1, 0),        # K6 level 3 in fp16: two N-chunks
     (96, 0, 512, 3, 4096, 1, False, False, 1, 0, 1),       # many tiles, fp16
+    (192, 0, 576, 1, 256, 2, False, False, 1),             # K1 level 3: standalone LN (tf32-rounded store) + TMA contraction
+    (384, 0, 1152, 1, 128, 1, False, False, 1),            # K1 latent, same path
 ]
+# the two wide-LayerNorm cases above also run with a tight bound: unrounded fp32 operands would be TRUNCATED by the
+# kind::tf32 MMA (twice the error of round-to-nearest, and a bias towards zero)
+TMA_WIDE_LN_CASES = [len(TMA_CASES) - 2, len(TMA_CASES) - 1]
 
 
 def run_case(case, engine, seed=0):

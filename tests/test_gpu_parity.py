@@ -210,6 +210,109 @@ def test_dncnn_config1_full_size():
         check_parity(f"config1_dncnn_{act}", y, y_ref, oracle.synth_image((1, 1, 256, 256), 93, None).numpy())
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# Parity AT the benchmarked sizes: MDTA's Gram is a reduction over all H*W pixels
+# (restormer.py:121-125), so the rounding error of the tensor-core operands could grow with the image; these cases
+# compare a full 512x512 forward with the CPU oracle (fp32, ~7 s each on the host; its own noise is ~3e-7).
+# ---------------------------------------------------------------------------------------------------------------
+_ORACLE_CACHE = {}
+
+
+def oracle_512(task, wseed, xseed, sigma, batch_index=None):
+    key = (task, wseed, xseed, sigma, batch_index)
+    if key not in _ORACLE_CACHE:
+        kw = oracle.RESTORMER_TASKS[task]
+        sd = oracle.synth_state_dict(oracle.restormer_schema(**kw), wseed)
+        n = kw["inp_channels"]
+        if batch_index is None:
+            x = oracle.synth_image((1, n, 512, 512), xseed, sigma)
+        else:
+            x = oracle.synth_image((8, n, 512, 512), xseed, sigma)[batch_index:batch_index + 1]
+        _ORACLE_CACHE[key] = oracle.restormer_forward(sd, x).numpy()
+    return _ORACLE_CACHE[key]
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("task,wseed,xseed,sigma", [
+    ("gray_denoise", 85, 95, 25.0),      # BASELINE config 2 element: 1 x 1 x 512 x 512, BiasFree
+    ("motion_deblur", 86, 96, None),     # config 4 tile: 1 x 3 x 512 x 512, WithBias
+    ("defocus_dual", 87, 97, None),      # config 5 tile: 1 x 6 x 512 x 512 dual-pixel
+])
+def test_restormer_512_vs_oracle(task, wseed, xseed, sigma, mode):
+    kw = oracle.RESTORMER_TASKS[task]
+    y_ref = oracle_512(task, wseed, xseed, sigma)
+    m = build_restormer(kw, wseed, mode)
+    x = oracle.synth_image((1, kw["inp_channels"], 512, 512), xseed, sigma)
+    y = m(x.cuda()).cpu().numpy()
+    clean = oracle.synth_image((1, kw["inp_channels"], 512, 512), xseed, None).numpy()[:, : y.shape[1]]
+    check_parity(f"size512_{task}[{mode}]", y, y_ref, clean)
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_config2_batch_element_vs_oracle(mode):
+    """One image taken out of a real 8 x 512 x 512 batch (the bench workload) against the oracle on that image."""
+    kw = oracle.RESTORMER_TASKS["gray_denoise"]
+    y_ref = oracle_512("gray_denoise", 81, 91, 25.0, batch_index=5)
+    m = build_restormer(kw, 81, mode)
+    x = oracle.synth_image((8, 1, 512, 512), 91, 25.0)
+    y = m(x.cuda())[5:6].cpu().numpy()
+    clean = oracle.synth_image((8, 1, 512, 512), 91, None).numpy()[5:6]
+    check_parity(f"config2_batch8_element5[{mode}]", y, y_ref, clean)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# fp16 range (VERDICT r01 "What's weak"): IR_MODE_FP32 holds operand-only tensors as fp16.  Scaled LayerNorm gains
+# push v / the GDFN hidden tensor towards fp16's limits; the pack-time guard must move such a model to
+# IR_MODE_FP32_STRICT, the device conversions must saturate instead of producing inf, and below the guard's threshold
+# the fast mode must still meet the bar (relative to the output's scale).
+# ---------------------------------------------------------------------------------------------------------------
+def scaled_ln_state_dict(kw, wseed, gain):
+    sd = oracle.synth_state_dict(oracle.restormer_schema(**kw), wseed)
+    return {k: (v * gain if (".norm1." in k or ".norm2." in k) and k.endswith("weight") else v) for k, v in sd.items()}
+
+
+@pytest.mark.parametrize("task,gain,expect", [
+    ("gray_denoise", 2.0, "fp32"),            # BiasFree, below the guard: fast mode
+    ("motion_deblur", 4.0, "fp32"),           # WithBias, below the guard
+    ("gray_denoise", 50.0, "fp32_strict"),    # the guard trips: tf32 operands / fp32 tensors everywhere
+    ("motion_deblur", 50.0, "fp32_strict"),
+    ("motion_deblur", 3000.0, "fp32_strict"), # hidden really leaves fp16's range (> 65504)
+])
+def test_fp16_range_guard_and_strict_mode(task, gain, expect):
+    kw = oracle.RESTORMER_TASKS[task]
+    sd = scaled_ln_state_dict(kw, 88, gain)
+    x = oracle.synth_image((1, kw["inp_channels"], 64, 64), 98, 25.0)
+    y_ref = oracle.restormer_forward({k: v.double() for k, v in sd.items()}, x.double()).numpy()
+    m = M.Restormer(**kw, bias=False).eval()
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda()
+    assert m.resolved_mode() == expect, (m.fp16_range_bound(), expect)
+    y = m(x.cuda()).cpu().numpy()
+    scale = max(1.0, float(np.abs(y_ref).max()))
+    rel = float(np.abs(y - y_ref).max()) / scale
+    record(f"range_{task}_gain{gain:g}", mode=m.resolved_mode(), bound=m.fp16_range_bound(), rel_err=rel, out_scale=scale)
+    assert np.isfinite(y).all()
+    assert rel <= TOL_MAXABS, (task, gain, rel)
+    if expect == "fp32_strict":
+        # the fast mode on the same weights (guard off): saturating conversions keep every value finite
+        yf = m.set_range_guard(False)(x.cuda()).cpu().numpy()
+        assert m.resolved_mode() == "fp32"
+        record(f"range_{task}_gain{gain:g}_guard_off", rel_err=float(np.abs(yf - y_ref).max()) / scale)
+        assert np.isfinite(yf).all()
+
+
+def test_strict_mode_parity_on_goldens():
+    """IR_MODE_FP32_STRICT (no fp16 tensor anywhere) against the reference goldens, same bar."""
+    for name in golden_names("restormer")[:3]:
+        meta, z = load_golden(name)
+        kw = oracle.RESTORMER_TASKS[meta["task"]]
+        m = build_restormer(kw, meta["wseed"], "fp32_strict")
+        x = oracle.synth_image(meta["shape"], meta["xseed"], meta["sigma"])
+        clean = oracle.synth_image(meta["shape"], meta["xseed"], None).numpy()
+        y = m(x.cuda()).cpu().numpy()
+        check_parity(f"{name}[fp32_strict]", y, z["y64"], clean[:, : y.shape[1]])
+
+
 def test_native_library_is_the_loaded_code():
     """The forward must run from the in-tree .so (no silent PyTorch path)."""
     maps = open("/proc/self/maps").read()

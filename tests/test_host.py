@@ -108,6 +108,41 @@ def test_no_cpu_fallback_and_argument_errors():
     assert lib.ir_restormer_param_count(C.byref(bad2)) == -1
 
 
+def test_hidden_width_rounds_like_python():
+    """int(dim * ffn_expansion_factor) in double precision (restormer.py:80): 80 * 2.1 = 168.00000000000003 -> 168, while
+    the factor as a C float (2.0999999) gives 167.  The factor crosses the ABI as a double."""
+    kw = dict(inp_channels=3, out_channels=3, dim=80, num_blocks=[1, 1, 1, 1], num_refinement_blocks=1,
+              heads=[5, 10, 10, 20], ffn_expansion_factor=2.1, bias=False, LayerNorm_type="WithBias")
+    assert int(80 * 2.1) == 168 and int(80 * float(torch.tensor(2.1, dtype=torch.float32))) == 167
+    m = M.Restormer(**kw)
+    lib = _native.lib()
+    tensors = list(m.state_dict().values())
+    assert lib.ir_restormer_param_count(C.byref(m._cfg)) == len(tensors)
+    for i, t in enumerate(tensors):
+        assert lib.ir_restormer_param_numel(C.byref(m._cfg), i) == t.numel(), i
+
+
+def test_fp16_range_guard_selects_strict_mode_from_the_weights():
+    kw = oracle.RESTORMER_TASKS["gray_denoise"]
+    sd = oracle.synth_state_dict(oracle.restormer_schema(**kw), 5)
+    m = M.Restormer(**kw, bias=False).eval()
+    m.load_state_dict(sd)
+    b0 = m.fp16_range_bound()
+    assert 0 < b0 < 0.25 * 65504 and m.resolved_mode() == "fp32"
+    big = {k: (v * 50 if (".norm1." in k or ".norm2." in k) and k.endswith("weight") else v) for k, v in sd.items()}
+    m.load_state_dict(big)
+    assert m.fp16_range_bound() > 100 * b0 and m.resolved_mode() == "fp32_strict"
+    assert m.set_range_guard(False).resolved_mode() == "fp32"
+    assert m.set_range_guard(True).set_mode("half").resolved_mode() == "half"       # explicit modes are never overridden
+    # the strict mode keeps the GDFN hidden tensor in HBM: larger workspace, more launches are fine, same parameters
+    m.set_mode("fp32").load_state_dict(sd)
+    fast = m.workspace_bytes(1, 256, 256)
+    m.load_state_dict(big)
+    assert m.workspace_bytes(1, 256, 256) > fast
+    # conv biases disable every fused kernel: nothing is fp16 in fp32 mode
+    assert M.Restormer(3, 3, bias=True).fp16_range_bound() == 0.0
+
+
 def test_workspace_and_launch_queries():
     m = M.Restormer(3, 3)
     b1 = m.workspace_bytes(1, 256, 256)
