@@ -317,9 +317,9 @@ int ir_probe_shifted_descriptor(const float* a, const float* w, float* d, int sh
 }
 
 int ir_tile_gather(const void* img, int dtype, float divisor, int H, int W, int C, const int* tile_xy, int T, int th,
-                   int tw, int TH, int TW, float* out, void* stream) {
+                   int tw, int TH, int TW, const double* noise_hwc, float* out, void* stream) {
   IRB_REQUIRE(img && tile_xy && out && H > 0 && W > 0 && C > 0 && T > 0, "tile_gather: bad argument");
-  return launch_tile_gather(img, dtype, divisor, H, W, C, tile_xy, T, th, tw, TH, TW, out, (cudaStream_t)stream);
+  return launch_tile_gather(img, dtype, divisor, H, W, C, tile_xy, T, th, tw, TH, TW, noise_hwc, out, (cudaStream_t)stream);
 }
 
 int ir_tile_blend(const float* pred, const int* tile_xy, int T, int th, int tw, int TH, int TW, const float* window,

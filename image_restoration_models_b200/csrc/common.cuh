@@ -159,7 +159,7 @@ int launch_nhwc_to_nchw(const float* src, float* dst, int B, int C, int H, int W
 
 // device-side tiling / blending of the inference harness (tiling.cu)
 int launch_tile_gather(const void* img, int dtype, float divisor, int H, int W, int C, const int* tile_xy, int T, int th,
-                       int tw, int TH, int TW, float* out, cudaStream_t s);
+                       int tw, int TH, int TW, const double* noise, float* out, cudaStream_t s);
 int launch_tile_blend(const float* pred, const int* tile_xy, int T, int th, int tw, int TH, int TW, const float* window,
                       int win_ld, int H, int W, int C, void* out, int dtype, float scale, float lo, float hi,
                       cudaStream_t s);

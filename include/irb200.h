@@ -150,9 +150,12 @@ int    ir_nhwc_to_nchw(const float* src, float* dst, int B, int C, int H, int W,
 /* ---- tiled inference harness on the device (replaces the numpy tile loop of run_model_inference,
  *      src/utils.py:353-454; bit-exact with it given the same tile predictions) ----
  * dtype: 0 uint8, 1 uint16, 2 float32 (HWC image).  tile_xy: device int32 [T][2] = (h_idx, w_idx) in the reference's
- * loop order.  Tiles are th x tw pixels, reflect-padded to TH x TW (multiples of 8) for the model.               */
+ * loop order.  Tiles are th x tw pixels, reflect-padded to TH x TW (multiples of 8) for the model.
+ * noise_hwc (nullable): float64 [th][tw][C] field added to every normalised tile before the pad, then clipped to [0,1]
+ * (add_gaussian_noise, src/utils.py:29-36; the reference reseeds per tile, so one field serves every tile).        */
 int    ir_tile_gather(const void* img, int dtype, float divisor /* 255, 65535, max or 1 */, int H, int W, int C,
-                      const int* tile_xy, int T, int th, int tw, int TH, int TW, float* out_nchw_tiles, void* stream);
+                      const int* tile_xy, int T, int th, int tw, int TH, int TW, const double* noise_hwc,
+                      float* out_nchw_tiles, void* stream);
 int    ir_tile_blend(const float* pred_nchw_tiles, const int* tile_xy, int T, int th, int tw, int TH, int TW,
                      const float* window /* [.][win_ld] fp32, get_gaussian_weights */, int win_ld, int H, int W, int C,
                      void* out_img, int dtype, float scale, float lo, float hi, void* stream);

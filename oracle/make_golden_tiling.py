@@ -29,6 +29,12 @@ CASES = [
     ("tiling_u8_color_33x47_nopad", "uint8", 33, 47, 3, 20, 4, False, 4),
     ("tiling_f32_color_40x40_p64", "float32", 40, 40, 3, 64, 16, True, 5),
 ]
+# synthetic degradation (need_degradation=True, noise_level=sigma): (name, dtype, H, W, C, patch, overlap, use_pad, seed, sigma)
+NOISE_CASES = [
+    ("tiling_noise25_u8_color_70x90_p32", "uint8", 70, 90, 3, 32, 8, True, 6, 25),
+    ("tiling_noise15_u8_gray_50x37_p24", "uint8", 50, 37, 1, 24, 6, True, 7, 15),
+    ("tiling_noise50_u8_gray_33x47_nopad", "uint8", 33, 47, 1, 20, 4, False, 8, 50),
+]
 
 
 class StandIn(torch.nn.Module):
@@ -84,6 +90,15 @@ def main():
                                            pad=utils.pad if use_pad else None)
         meta = dict(kind="tiling", dtype=dtype, shape=[h, w, c], patch_size=ps, patch_overlap=ov, use_pad=use_pad,
                     seed=seed)
+        np.savez(os.path.join(OUT, name + ".npz"), meta=json.dumps(meta), out=out)
+        print(name, out.dtype, out.shape, int(out.astype(np.float64).sum()))
+    for name, dtype, h, w, c, ps, ov, use_pad, seed, sigma in NOISE_CASES:
+        img = make_image(dtype, h, w, c, seed)
+        out, _ = utils.run_model_inference(model, img, torch.device("cpu"), patch_size=ps, patch_overlap=ov,
+                                           need_degradation=True, noise_level=sigma,
+                                           pad=utils.pad if use_pad else None)
+        meta = dict(kind="tiling_noise", dtype=dtype, shape=[h, w, c], patch_size=ps, patch_overlap=ov, use_pad=use_pad,
+                    seed=seed, sigma=sigma)
         np.savez(os.path.join(OUT, name + ".npz"), meta=json.dumps(meta), out=out)
         print(name, out.dtype, out.shape, int(out.astype(np.float64).sum()))
     np.save(os.path.join(OUT, "gaussian_window_24.npy"), utils.get_gaussian_weights(24, 24, 1))

@@ -1,8 +1,8 @@
 """CPU restatement of the reference's tiled-inference harness (TEST INFRASTRUCTURE, see oracle/__init__.py).
 
 Restates /root/reference/src/utils.py: normalize :159-171, pad :174-181, get_gaussian_weights :314-350 and
-run_model_inference :353-454 (noise injection :408-409 and postprocess hooks omitted: they are not on the Restormer /
-DnCNN path of SURVEY.md §8(f) rows 1-2).  ``model`` is any callable NCHW float32 torch tensor -> tensor.
+run_model_inference :353-454 with the noise injection of add_gaussian_noise :29-36 (:408-409); the postprocess hooks are
+omitted (DeblurGANv2 only).  ``model`` is any callable NCHW float32 torch tensor -> tensor.
 """
 from __future__ import annotations
 
@@ -53,7 +53,19 @@ def tile_grid(h: int, w: int, patch_size, patch_overlap: int):
     return h_idx, w_idx, patch_size
 
 
-def run_model_inference(model, input_img: np.ndarray, patch_size=None, patch_overlap: int = 32, use_pad: bool = True):
+def add_gaussian_noise(img: np.ndarray, sigma=15):
+    """utils.add_gaussian_noise :29-36: global numpy generator reseeded with 0, float64 noise added in place to the
+    float32 patch (numpy computes the sum in double and rounds to float32), clip to [0, 1]."""
+    if img.dtype != np.float32 and img.dtype != np.float64:
+        img = img.astype(np.float32) / 255.
+    rs = np.random.RandomState(0)            # == np.random.seed(0) followed by np.random.normal, without the side effect
+    img += rs.normal(0, sigma / 255., img.shape)
+    img = np.clip(img, 0, 1)
+    return img.astype(np.float32)
+
+
+def run_model_inference(model, input_img: np.ndarray, patch_size=None, patch_overlap: int = 32, use_pad: bool = True,
+                        need_degradation=False, noise_level=None):
     """run_model_inference :353-454 (returns the restored image only)."""
     with torch.no_grad():
         img = normalize(input_img)
@@ -66,6 +78,8 @@ def run_model_inference(model, input_img: np.ndarray, patch_size=None, patch_ove
         for hi in h_idx:
             for wi in w_idx:
                 patch = img[hi:hi + ps, wi:wi + ps, :].copy()
+                if need_degradation and noise_level is not None:
+                    patch = add_gaussian_noise(patch, noise_level)
                 x = torch.from_numpy(patch.transpose(2, 0, 1)).unsqueeze(0)
                 if use_pad:
                     hp, wp = x.shape[-2:]

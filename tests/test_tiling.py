@@ -14,7 +14,7 @@ import torch
 
 import oracle
 from oracle import tiling_ref
-from oracle.make_golden_tiling import CASES, StandIn, make_image
+from oracle.make_golden_tiling import CASES, NOISE_CASES, StandIn, make_image
 from image_restoration_models_b200 import tiling
 from conftest import GOLDEN, ROOT, load_golden
 
@@ -25,17 +25,21 @@ class NumpyBackend:
     def upload(self, a):
         return torch.from_numpy(np.ascontiguousarray(a))
 
-    def gather(self, img, code, divisor, H, W, C, xy, T, th, tw, TH, TW):
+    def gather(self, img, code, divisor, H, W, C, xy, T, th, tw, TH, TW, noise=None):
         x = img.numpy().astype(np.float32)
         if divisor != 1.0:
             x = x / np.float32(divisor)
         out = []
         for h0, w0 in xy.numpy():
-            t = torch.from_numpy(x[h0:h0 + th, w0:w0 + tw].transpose(2, 0, 1).copy()).unsqueeze(0)
+            patch = x[h0:h0 + th, w0:w0 + tw].copy()
+            if noise is not None:
+                patch += noise.numpy()
+                patch = np.clip(patch, 0, 1).astype(np.float32)
+            t = torch.from_numpy(patch.transpose(2, 0, 1).copy()).unsqueeze(0)
             out.append(torch.nn.functional.pad(t, (0, TW - tw, 0, TH - th), "reflect") if (TH > th or TW > tw) else t)
         return torch.cat(out, 0)
 
-    def blend(self, pred, xy, T, th, tw, TH, TW, window, H, W, C, out_dtype, code, scale, lo, hi):
+    def blend(self, pred, xy, T, th, tw, TH, TW, window, H, W, C, out_dtype, code, scale, lo, hi, out=None):
         out = np.zeros((H, W, C), np.float32)
         wm = np.zeros((H, W, C), np.float32)
         win = np.repeat(window.numpy()[:th, :tw, None], C, axis=2)
@@ -64,10 +68,63 @@ def test_tiling_host_logic_matches_reference_harness(case):
     name, dtype, h, w, c, ps, ov, use_pad, seed = case
     meta, z = load_golden(name)
     img = make_image(dtype, h, w, c, seed)
-    out, ms = tiling.run_model_inference(StandIn().eval(), img, "cpu", ps, ov, pad=use_pad, tile_batch=3,
-                                         backend=NumpyBackend())
+    out, ms = tiling.run_model_inference(StandIn().eval(), img, "cpu", patch_size=ps, patch_overlap=ov,
+                                         pad=tiling.pad if use_pad else None, tile_batch=3, backend=NumpyBackend())
     assert out.dtype == z["out"].dtype and np.array_equal(out, z["out"])
     assert ms >= 0.0
+
+
+@pytest.mark.parametrize("case", NOISE_CASES, ids=[c[0] for c in NOISE_CASES])
+def test_noise_injection_oracle_and_host_logic_match_reference_harness(case):
+    """need_degradation=True: add_gaussian_noise (src/utils.py:29-36, :408-409) reseeds numpy per tile, so one float64
+    field per tile shape reproduces it; goldens from the unmodified reference harness."""
+    name, dtype, h, w, c, ps, ov, use_pad, seed, sigma = case
+    meta, z = load_golden(name)
+    img = make_image(dtype, h, w, c, seed)
+    ref = tiling_ref.run_model_inference(StandIn().eval(), img, ps, ov, use_pad, need_degradation=True, noise_level=sigma)
+    assert np.array_equal(ref, z["out"])
+    before = np.random.get_state()[1].copy()
+    out, _ = tiling.run_model_inference(StandIn().eval(), img, "cpu", patch_size=ps, patch_overlap=ov,
+                                        need_degradation=True, noise_level=sigma,
+                                        pad=tiling.pad if use_pad else None, tile_batch=2, backend=NumpyBackend())
+    assert np.array_equal(out, z["out"])
+    assert np.array_equal(before, np.random.get_state()[1])          # the package does not reseed the global generator
+    # need_degradation without a level, or a level without the flag, adds nothing (:408)
+    clean, _ = tiling.run_model_inference(StandIn().eval(), img, "cpu", patch_size=ps, patch_overlap=ov,
+                                          need_degradation=False, noise_level=sigma,
+                                          pad=tiling.pad if use_pad else None, backend=NumpyBackend())
+    assert not np.array_equal(clean, z["out"])
+
+
+def test_called_exactly_like_get_model_prediction():
+    """The reference's caller (src/utils.py:294-302) passes pad=pad, patch_size=, patch_overlap=, need_degradation=,
+    noise_level= and progress_bar= by keyword after three positionals; the DnCNN branch (:303-310) passes no pad."""
+    class Bar:
+        def __init__(self): self.total, self.n = None, 0
+        def tqdm(self, it, desc=None, total=None): self.total = total; return self
+        def update(self): self.n += 1
+    name, dtype, h, w, c, ps, ov, use_pad, seed = CASES[0]
+    meta, z = load_golden(name)
+    img = make_image(dtype, h, w, c, seed)
+    bar = Bar()
+    restored, ms = tiling.run_model_inference(StandIn().eval(), img, "cpu", pad=tiling.pad, patch_size=ps,
+                                              patch_overlap=ov, need_degradation=False, noise_level=None,
+                                              progress_bar=bar, backend=NumpyBackend())
+    assert np.array_equal(restored, z["out"]) and bar.total == bar.n == 12
+    # DnCNN branch: no pad argument -> pad=None -> tiles are NOT padded (H, W need not be multiples of 8)
+    name, dtype, h, w, c, ps, ov, use_pad, seed = CASES[3]
+    meta, z = load_golden(name)
+    restored, _ = tiling.run_model_inference(StandIn().eval(), make_image(dtype, h, w, c, seed), "cpu", patch_size=ps,
+                                             patch_overlap=ov, need_degradation=False, noise_level=None,
+                                             progress_bar=None, backend=NumpyBackend())
+    assert np.array_equal(restored, z["out"])
+    # the fourth positional argument is `normalize`, as in the reference; only the default one is on this path
+    tiling.run_model_inference(StandIn().eval(), make_image(dtype, h, w, c, seed), "cpu", tiling.normalize, ps, ov,
+                               backend=NumpyBackend())
+    with pytest.raises(NotImplementedError):
+        tiling.run_model_inference(StandIn().eval(), img, "cpu", lambda a: a, backend=NumpyBackend())
+    with pytest.raises(NotImplementedError):
+        tiling.run_model_inference(StandIn().eval(), img, "cpu", postprocess=lambda a: a, backend=NumpyBackend())
 
 
 def test_tile_grid_window_and_partition():
@@ -87,6 +144,7 @@ def test_tile_grid_window_and_partition():
         assert max(sizes) - min(sizes) <= 1
     with pytest.raises(ValueError):
         tiling.run_model_inference(lambda x: x, np.zeros((4, 4), np.uint8), "cpu", backend=NumpyBackend())
+    np.testing.assert_array_equal(tiling.normalize(np.array([[[0, 255]]], np.uint8)), np.array([[[0.0, 1.0]]], np.float32))
 
 
 def _worker(rank, world, port, case, out_dir):
@@ -96,22 +154,24 @@ def _worker(rank, world, port, case, out_dir):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     name, dtype, h, w, c, ps, ov, use_pad, seed = case
     img = make_image(dtype, h, w, c, seed)
-    out, _ = tiling.run_model_inference(StandIn().eval(), img, "cpu", ps, ov, pad=use_pad, tile_batch=2,
-                                        backend=NumpyBackend())
-    np.save(os.path.join(out_dir, f"rank{rank}.npy"), out)
+    out, _ = tiling.run_model_inference(StandIn().eval(), img, "cpu", patch_size=ps, patch_overlap=ov,
+                                        pad=tiling.pad if use_pad else None, tile_batch=2, backend=NumpyBackend(), dst=1)
+    if out is not None:
+        np.save(os.path.join(out_dir, f"rank{rank}.npy"), out)
     dist.destroy_process_group()
 
 
 @pytest.mark.parametrize("case", [CASES[0], CASES[2]], ids=[CASES[0][0], CASES[2][0]])
 def test_two_ranks_split_tiles_and_agree_with_single_rank(case, tmp_path):
-    """World size 2 over gloo: ranks take contiguous tile slices, all-gather the predictions and blend in the
-    reference order -> every rank's image is bit-identical to the single-rank (and the reference's) result."""
+    """World size 2 over gloo: ranks take contiguous tile slices, the predictions are gathered to ONE rank (dst = 1 here)
+    which blends in the reference order -> its image is bit-identical to the single-rank (and the reference's) result;
+    the other rank returns None and blends nothing."""
     import torch.multiprocessing as mp
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     mp.spawn(_worker, args=(2, port, case, str(tmp_path)), nprocs=2, join=True)
     meta, z = load_golden(case[0])
-    for r in range(2):
-        assert np.array_equal(np.load(tmp_path / f"rank{r}.npy"), z["out"])
+    assert not (tmp_path / "rank0.npy").exists()
+    assert np.array_equal(np.load(tmp_path / "rank1.npy"), z["out"])
 
 
 @pytest.mark.gpu
@@ -120,8 +180,41 @@ def test_tiling_cuda_kernels_bit_exact_vs_reference_harness(case):
     name, dtype, h, w, c, ps, ov, use_pad, seed = case
     meta, z = load_golden(name)
     img = make_image(dtype, h, w, c, seed)
-    out, _ = tiling.run_model_inference(StandIn().eval().cuda(), img, "cuda", ps, ov, pad=use_pad, tile_batch=4)
+    out, _ = tiling.run_model_inference(StandIn().eval().cuda(), img, "cuda", patch_size=ps, patch_overlap=ov,
+                                        pad=tiling.pad if use_pad else None, tile_batch=4)
     assert out.dtype == z["out"].dtype and np.array_equal(out, z["out"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", NOISE_CASES, ids=[c[0] for c in NOISE_CASES])
+def test_noise_injection_cuda_kernel_bit_exact_vs_reference_harness(case):
+    name, dtype, h, w, c, ps, ov, use_pad, seed, sigma = case
+    meta, z = load_golden(name)
+    img = make_image(dtype, h, w, c, seed)
+    out, _ = tiling.run_model_inference(StandIn().eval().cuda(), img, "cuda", patch_size=ps, patch_overlap=ov,
+                                        need_degradation=True, noise_level=sigma, pad=tiling.pad if use_pad else None,
+                                        tile_batch=4)
+    assert np.array_equal(out, z["out"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", [CASES[0], CASES[2]], ids=[CASES[0][0], CASES[2][0]])
+def test_frame_pipeline_is_bit_identical_to_single_frame_path(case):
+    """FramePipeline (streams, pinned double buffers, events) over 5 distinct frames == run_model_inference per frame,
+    and frame 0 == the reference golden."""
+    name, dtype, h, w, c, ps, ov, use_pad, seed = case
+    meta, z = load_golden(name)
+    frames = [make_image(dtype, h, w, c, seed + 40 * i) for i in range(5)]
+    model = StandIn().eval().cuda()
+    pipe = tiling.FramePipeline(model, "cuda", frames[0].shape, frames[0].dtype, patch_size=ps, patch_overlap=ov,
+                                pad=tiling.pad if use_pad else None, tile_batch=5)
+    outs = pipe.run(frames)
+    assert np.array_equal(outs[0], z["out"])
+    for f, o in zip(frames, outs):
+        single, _ = tiling.run_model_inference(model, f, "cuda", patch_size=ps, patch_overlap=ov,
+                                               pad=tiling.pad if use_pad else None)
+        assert np.array_equal(o, single)
+    assert pipe.run(frames[:3], copy_out=False) is None
 
 
 @pytest.mark.gpu
@@ -135,7 +228,7 @@ def test_tiled_restormer_matches_oracle_harness():
     ref = tiling_ref.run_model_inference(lambda x: oracle.restormer_forward(sd, x), img, 64, 16, True)
     m = M.Restormer(**kw, bias=False).eval()
     m.load_state_dict(sd, strict=True)
-    out, _ = tiling.run_model_inference(m.cuda(), img, "cuda", 64, 16, pad=True, tile_batch=8)
+    out, _ = tiling.run_model_inference(m.cuda(), img, "cuda", patch_size=64, patch_overlap=16, pad=tiling.pad, tile_batch=8)
     diff = np.abs(out.astype(np.int32) - ref.astype(np.int32))
     assert diff.max() <= 1 and (diff > 0).mean() < 0.02
 
@@ -152,8 +245,8 @@ def test_dual_pixel_six_channel_input_three_channel_output_host_logic():
     channels (src/utils.py:394-395,405); uint16 in, uint16 out."""
     img = make_image("uint16", 45, 64, 6, 77)
     ref = tiling_ref.run_model_inference(DualStandIn().eval(), img, 40, 12, True)
-    out, _ = tiling.run_model_inference(DualStandIn().eval(), img, "cpu", 40, 12, pad=True, tile_batch=2,
-                                        backend=NumpyBackend())
+    out, _ = tiling.run_model_inference(DualStandIn().eval(), img, "cpu", patch_size=40, patch_overlap=12, pad=True,
+                                        tile_batch=2, backend=NumpyBackend())
     assert out.shape == (45, 64, 3) and out.dtype == np.uint16 and np.array_equal(out, ref)
 
 
@@ -161,5 +254,6 @@ def test_dual_pixel_six_channel_input_three_channel_output_host_logic():
 def test_dual_pixel_six_channel_input_cuda_kernels_bit_exact():
     img = make_image("uint16", 45, 64, 6, 77)
     ref = tiling_ref.run_model_inference(DualStandIn().eval(), img, 40, 12, True)
-    out, _ = tiling.run_model_inference(DualStandIn().eval().cuda(), img, "cuda", 40, 12, pad=True, tile_batch=4)
+    out, _ = tiling.run_model_inference(DualStandIn().eval().cuda(), img, "cuda", patch_size=40, patch_overlap=12, pad=True,
+                                        tile_batch=4)
     assert out.shape == (45, 64, 3) and np.array_equal(out, ref)
