@@ -410,11 +410,10 @@ def main():
         # FMA-equivalents per gated element for the erf gate.  Reported against 128 FMA/clk/SM x 148
         # SMs x the SM clock sampled in this run; `bound` says so instead of naming a roofline the kernel is not on.
         hp_total = 0.0      # sum over launches of pixels * hp  ==  flops term 36*hp*pix / 36
-        kw_cfg = kw
-        d = kw_cfg["dim"]
-        nb, nr = kw_cfg["num_blocks"], kw_cfg["num_refinement_blocks"]
+        d = kw.get("dim", 48)
+        nb, nr = kw.get("num_blocks", [4, 6, 6, 8]), kw.get("num_refinement_blocks", 4)
         pix = BATCH * HEIGHT * WIDTH
-        hp_of = lambda c: -(-int(c * kw_cfg["ffn_expansion_factor"]) // 16) * 16
+        hp_of = lambda c: -(-int(c * kw.get("ffn_expansion_factor", 2.66)) // 16) * 16
         launches_cfg = [(d, pix, nb[0]), (2 * d, pix // 4, 2 * nb[1]), (2 * d, pix, nb[0] + nr)]   # (C, pixels, launches)
         fma = sum(n * p * (18.0 + 12.0) * hp_of(c) for c, p, n in launches_cfg)
         clk = (clocks or {}).get("sm_mhz") if rank == 0 else None

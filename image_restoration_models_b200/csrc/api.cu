@@ -47,7 +47,7 @@ ProfScope::~ProfScope() {
 static const char* kTagNames[TAG_COUNT] = {
     "other", "ln_qkv_1x1", "dwconv3x3_qkv", "mdta_gram", "softmax_fold", "attn_out_1x1", "ln_project_in_1x1",
     "dwconv3x3_gelu_gate", "ffn_project_out_1x1", "conv3x3", "reduce_chan_1x1", "concat_copy", "layernorm",
-    "dwconv_gate_project_out", "dwconv_qkv_gram", "gdfn_fused"};
+    "dwconv_gate_project_out", "dwconv_qkv_gram", "gdfn_fused", "mdta_fused_front"};
 
 static int check_mode(int mode) {
   IRB_REQUIRE(mode == IR_MODE_FP32 || mode == IR_MODE_HALF || mode == IR_MODE_FP32_SIMT || mode == IR_MODE_FP32_STRICT,

@@ -66,7 +66,7 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 // ---------------------------------------------------------------------------------------------
 enum KernelTag {
   TAG_OTHER = 0, TAG_LN_QKV, TAG_DW_QKV, TAG_GRAM, TAG_FOLD, TAG_ATTN_OUT, TAG_LN_PIN, TAG_DW_GATE, TAG_FFN_OUT,
-  TAG_CONV3, TAG_REDUCE, TAG_COPY, TAG_LAYERNORM, TAG_FFN_TAIL, TAG_ATTN_FRONT, TAG_FFN_FUSED, TAG_COUNT
+  TAG_CONV3, TAG_REDUCE, TAG_COPY, TAG_LAYERNORM, TAG_FFN_TAIL, TAG_ATTN_FRONT, TAG_FFN_FUSED, TAG_ATTN_FUSED, TAG_COUNT
 };
 struct ProfScope {
   ProfScope(int tag, double bytes, double flops, cudaStream_t s);

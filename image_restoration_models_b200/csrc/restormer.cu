@@ -8,6 +8,7 @@
 #include "ffn_tail.cuh"
 #include "attn_front.cuh"
 #include "ffn_fused.cuh"
+#include "attn_fused.cuh"
 
 #include <algorithm>
 #include <cstdlib>
@@ -120,10 +121,20 @@ static void plan_block(Builder& bl, BlockPlan& bp, int C, int heads, double ffn,
   if (bp.fuse_ffn) bp.fuse_tail = false;
   static const bool no_k4xn = getenv("IRB_NO_K4_XN") != nullptr;           // A/B switch for benchmarks
   bp.k4_xn = !no_k4xn && bp.fuse_ffn && bp.tma_attn && !bias && tma_gemm_xn_supported(C, bl.half() || bp.v_half);
+  // the whole MDTA front in one kernel (attn_fused.cu): its v output and the attention-output contraction's operands are
+  // fp16 (as with v_half), its qkv weights the fp16 operand image padded to whole 32-channel units
+  static const bool no_attn_fused = getenv("IRB_NO_ATTN_FUSED") != nullptr;   // A/B switch for benchmarks
+  bp.fuse_attn = !no_attn_fused && bp.fuse_front && !bias && attn_fused_supported(C, heads) &&
+                 (bl.engine == ENGINE_TC ? bp.v_half : bl.half()) && bp.tma_attn;
   vec(bp.ln1_w, C);
   if (ln_bias) vec(bp.ln1_b, C);
   vec(bp.temp, heads);
-  mat(bp.qkv_w, 3 * C, 3 * C, 1, C, C, bp.tc_qkv, bp.tma_qkv);
+  if (bp.fuse_attn) {
+    const int np = attn_fused_wrows(C);
+    mat(bp.qkv_w, 3 * C, np, 1, C, C, true, false, true);
+  } else {
+    mat(bp.qkv_w, 3 * C, 3 * C, 1, C, C, bp.tc_qkv, bp.tma_qkv);
+  }
   if (bias) vec(bp.qkv_b, 3 * C);
   if (bp.fuse_front) {
     const int cpad = round_up(3 * C, 32);
@@ -307,10 +318,12 @@ static int gram_parts(int B, int heads, int HW) {
 void block_scratch_need(BlockScratchNeed& n, const BlockPlan& bp, int B, int H, int W) {
   const long long P = (long long)B * H * W;
   const int ch = bp.C / bp.heads;
-  n.qkv = std::max(n.qkv, P * 3 * bp.C);
+  if (bp.fuse_attn) n.v16 = std::max(n.v16, P * bp.C);      // qkv stays on chip; only v (fp16) is written
+  else n.qkv = std::max(n.qkv, P * 3 * bp.C);
   if (!bp.fuse_ffn) n.hidden = std::max(n.hidden, P * 2 * bp.hp);            // fused GDFN: the hidden tensor stays on chip
   if (!bp.fuse_ffn && !bp.fuse_tail) n.gated = std::max(n.gated, P * bp.hp);
-  const int parts = bp.fuse_front ? attn_front_parts(B, H, W, bp.C, bp.heads) : gram_parts(B, bp.heads, H * W);
+  const int parts = bp.fuse_attn ? attn_fused_parts(B, H, W)
+                  : bp.fuse_front ? attn_front_parts(B, H, W, bp.C, bp.heads) : gram_parts(B, bp.heads, H * W);
   n.s_part = std::max(n.s_part, (long long)B * bp.heads * parts * ch * ch);
   n.n_part = std::max(n.n_part, (long long)B * bp.heads * parts * 2 * ch);
   n.w_eff = std::max(n.w_eff, (long long)B * bp.C * bp.kp_attn);
@@ -333,7 +346,7 @@ void carve_block_scratch(Carver& cv, BlockScratch& bs, const BlockScratchNeed& n
   // intermediates are fp32 or fp16 (n.es bytes per element); take() counts in floats
   auto elems = [&](long long e) { return (e * n.es + 3) / 4; };
   bs.qkv = cv.take(elems(n.qkv));
-  bs.qkv_dw = cv.take(elems(n.qkv));
+  bs.qkv_dw = cv.take(std::max(elems(n.qkv), (n.v16 + 1) / 2));
   bs.hidden = cv.take(elems(n.hidden));
   bs.gated = cv.take(elems(n.gated));
   bs.s_part = cv.take(n.s_part);
@@ -430,8 +443,9 @@ int run_block(const BlockPlan& bp, const float* packed, const float* x_in, float
   const size_t es = hf ? 2 : 4;
   auto P = [&](long long off) -> const float* { return off >= 0 ? packed + off : nullptr; };
 
-  // (1) norm1 + qkv 1x1   (restormer.py:147 norm1, :114 qkv)
   GemmParams g{};
+  if (!bp.fuse_attn) {
+  // (1) norm1 + qkv 1x1   (restormer.py:147 norm1, :114 qkv)
   g.a1 = x_in; g.lda1 = C; g.k1 = C; g.a2 = nullptr; g.lda2 = 0; g.k2 = 0; g.a_mode = A_PLAIN;
   g.B = B; g.H = H; g.W = W;
   g.w = P(bp.qkv_w); g.w_bstride = 0; g.N = 3 * C; g.K = C; g.Kp = C; g.bias = P(bp.qkv_b);
@@ -439,12 +453,24 @@ int run_block(const BlockPlan& bp, const float* packed, const float* x_in, float
   g.relu = 0; g.r = nullptr; g.ldr = 0; g.acc_sign = 1.f;
   g.y = (float*)bs.qkv; g.ldy = 3 * C; g.o_mode = O_NHWC; g.tag = TAG_LN_QKV;
   IRB_TRY(run_1x1(g, bp.tc_qkv, hf, false, hf, bs.xhat, s, bp.tma_qkv));
+  }
 
   DwParams dwp{};
   GramParams gp{};
   const void* v_ptr = (const char*)bs.qkv_dw + (size_t)2 * C * es;
   int v_ld = 3 * C;
-  if (bp.fuse_front) {
+  if (bp.fuse_attn) {
+    // (1+2+3) norm1 + qkv 1x1 + depthwise 3x3 + q.k^T Gram partials + squared norms in one kernel; only v (fp16) is
+    // written (:147, :114-115, :121-124)
+    AttnFusedArgs fa{};
+    fa.x = x_in; fa.ln_w = P(bp.ln1_w); fa.ln_b = P(bp.ln1_b); fa.ln_mode = ln;
+    fa.w_qkv = P(bp.qkv_w); fa.dw_chunked = P(bp.qkvdw_w); fa.v = bs.qkv_dw;
+    fa.s_part = bs.s_part; fa.n_part = bs.n_part; fa.parts = attn_fused_parts(B, H, W);
+    fa.B = B; fa.H = H; fa.W = W; fa.C = C; fa.heads = bp.heads;
+    IRB_TRY(launch_attn_fused(fa, s));
+    gp.nparts = fa.parts;
+    v_ptr = bs.qkv_dw; v_ld = C;
+  } else if (bp.fuse_front) {
     // (2+3) depthwise 3x3 + q.k^T Gram partials + squared norms; only v is written (:114-115, :121-124)
     AttnFrontArgs fa{};
     fa.qkv = bs.qkv; fa.half = hf; fa.v_half = bp.v_half; fa.v = bs.qkv_dw; fa.dw_chunked = P(bp.qkvdw_w);
@@ -593,7 +619,7 @@ int restormer_launch_count(const RestormerPlan& pl) {
   int n = 0;
   auto blocks = [&](const std::vector<BlockPlan>& v) {
     for (const auto& bp : v) {
-      n += 8 - (bp.fuse_tail || bp.fuse_ffn ? 1 : 0) - (bp.fuse_front ? 1 : 0) - (bp.k4_xn ? 1 : 0);
+      n += 8 - (bp.fuse_tail || bp.fuse_ffn ? 1 : 0) - (bp.fuse_front ? 1 : 0) - (bp.k4_xn ? 1 : 0) - (bp.fuse_attn ? 1 : 0);
       // standalone LayerNorm where the contraction cannot take it as a prologue (the wide levels)
       auto ln_standalone = [&](bool tc, bool tma, int N) {
         if (!tc) return false;
@@ -603,7 +629,7 @@ int restormer_launch_count(const RestormerPlan& pl) {
         t.a_half = 0; t.op_half = bp.half; t.y_half = bp.half;
         return tc_gemm_configure(t) == 0;
       };
-      n += (ln_standalone(bp.tc_qkv, bp.tma_qkv, 3 * bp.C) ? 1 : 0) + (ln_standalone(bp.tc_pin, bp.tma_pin, 2 * bp.hp) ? 1 : 0);
+      n += (!bp.fuse_attn && ln_standalone(bp.tc_qkv, bp.tma_qkv, 3 * bp.C) ? 1 : 0) + (ln_standalone(bp.tc_pin, bp.tma_pin, 2 * bp.hp) ? 1 : 0);
     }
   };
   for (int l = 0; l < 4; ++l) blocks(pl.enc[l]);

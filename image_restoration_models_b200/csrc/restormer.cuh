@@ -25,6 +25,7 @@ struct BlockPlan {     // one TransformerBlock (restormer.py:137-150); offsets i
   bool tc_qkv, tc_attn, tc_pin, tc_pout;   // which 1x1 contractions run on the tcgen05 kernel
   bool tma_qkv, tma_attn, tma_pin, tma_pout;   // ... and of those, which on the TMA-fed kernel (tma_gemm.cu; weights in its layout)
   bool fuse_front;                         // qkv dwconv + Gram + norms + v store in one kernel (attn_front.cu)
+  bool fuse_attn;                          // norm1 + qkv 1x1 + all of the above in one kernel (attn_fused.cu): qkv never exists in HBM
   bool fuse_tail;                          // dwconv + gate + project_out + residual in one kernel (ffn_tail.cu)
   bool fuse_ffn;                           // the whole GDFN in one kernel behind a standalone LayerNorm (ffn_fused.cu)
   bool v_half;                             // fp32 mode: v and the folded attention matrix are fp16 operands (same mantissa as tf32)
@@ -46,7 +47,7 @@ struct RestormerPlan {
   std::vector<BlockPlan> enc[4], dec[3], refine;
 };
 
-struct BlockScratchNeed { long long qkv = 0, hidden = 0, gated = 0, s_part = 0, n_part = 0, w_eff = 0, xhat = 0; int es = 4; };
+struct BlockScratchNeed { long long qkv = 0, hidden = 0, gated = 0, s_part = 0, n_part = 0, w_eff = 0, xhat = 0, v16 = 0; int es = 4; };   // v16: fp16 elements of v where the fused front writes it
 struct BlockScratch { void *qkv, *qkv_dw, *hidden, *gated; float *s_part, *n_part; void *w_eff, *xhat; };
 struct RestormerWs { float* e[4]; float* e1_in; float* d[3]; float* up_tmp; BlockScratch bs; };
 
