@@ -47,6 +47,30 @@ def find_nvcc():
     return nvcc
 
 
+def build_variant(out_path: str, extra_flags, objdir: str) -> str:
+    """A/B build of the library with extra nvcc flags (e.g. -DIRB_FUSED_EXPERIMENTS) next to the shipped one; select it at
+    run time with IRB200_LIB=<out_path>.  Tuning only: never the product."""
+    nvcc = find_nvcc()
+    os.makedirs(objdir, exist_ok=True)
+    procs, objs = [], []
+    for src in _sources():
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        procs.append((src, subprocess.Popen([nvcc, *NVCC_FLAGS, *extra_flags, "-c", src, "-o", obj],
+                                            stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(obj)
+    for src, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            sys.stderr.write(out)
+            raise RuntimeError(f"nvcc failed on {src}")
+    r = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out_path, *objs,
+                        "-Xlinker", "--no-undefined"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout)
+        raise RuntimeError("CUDA link failed")
+    return out_path
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     fp = _fingerprint()
     if not force and os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == fp:
@@ -85,4 +109,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--experiments" in sys.argv:
+        root = os.path.dirname(HERE)
+        os.makedirs(os.path.join(root, "build_ab"), exist_ok=True)
+        print(build_variant(os.path.join(root, "build_ab", "libirb200_dbg.so"), ["-DIRB_FUSED_EXPERIMENTS"],
+                            os.path.join(root, "build_ab", "obj_dbg")))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

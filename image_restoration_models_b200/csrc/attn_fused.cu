@@ -11,17 +11,22 @@
 // only, exactly as ffn_fused.cu does for the GDFN.  Per pixel the kernel reads 4C bytes of x (1.4 x with the halo, served
 // by L2) and writes 2C bytes of v.
 //
-// One persistent CTA per SM, bound to one image (the Gram accumulates per image), 20 warps; the pipeline unit is 32 qkv
-// channels:
+// One persistent CTA per SM, bound to one image (the Gram accumulates per image), 20 warps.  The pipeline unit of the
+// CUDA-core roles is 32 qkv channels; the tensor core works in GROUPS of three units (N = 96): with one MMA1 per unit the
+// single issuing warp -- ~33 instructions of descriptor / uniform-register traffic per tcgen05.mma, 116 of them per tile --
+// paced the whole kernel (ncu: every other role waiting on it, whatever else was removed; profiles/r02_attn_fused_*).
 //
 //   LayerNorm (4 warps)   per tile: the fp32 x halo rows straight from global memory (C/12 lanes per pixel, 16-byte
 //                         loads), two-pass statistics, fp16 xn rows into the [192 px][128 B] SWIZZLE_128B operand boxes
 //                         (double-buffered: tile j+1 is normalised while tile j computes).  Pixels outside the image
 //                         are written as ZERO rows: the qkv conv has no bias, so qkv = 0 there, which IS the depthwise
 //                         conv's zero padding (also with a WithBias LayerNorm, whose output on a zero row is not zero)
-//   producer (1 thread)   per unit: the unit's 32 rows of W_qkv (fp16 operand image, bulk copies)
-//   MMA (1 warp)          MMA1: D1[192 px][32] = xn_patch . W_unit^T as two M = 128 instructions (patch rows 0-127 and
-//                         64-191) into a double-buffered TMEM accumulator, issued two units ahead;
+//                         A bulk-tensor L2 PREFETCH of the x halo box runs two tiles ahead, so that these register loads
+//                         see L2 latency instead of HBM latency (a lane holds only 9 x 16 bytes in flight)
+//   producer (1 thread)   once: all of W_qkv (fp16 operand image, 20 / 74 KB) into shared memory, where it stays
+//   MMA (1 warp)          MMA1: D1[192 px][96] = xn_patch . W_group^T as two M = 128 instructions per K step (patch rows
+//                         0-127 and 64-191) into a double-buffered TMEM accumulator; everything about the issue loop is
+//                         a compile-time constant (descriptors are a base plus a constant);
 //                         Gram: S[i][j] += sum_p q_i[p] k_j[p] with A = the q rows and B = the k rows of the X tile
 //   convert (4 + 2 warps) tcgen05.ld of D1 -> fp16 -> qkv patch [180 px][80 B] in shared memory
 //   dw warps (8)          thread = 2 channels x a 2 x 4 pixel block, packed FFMA2 taps.  q / k units are written
@@ -36,6 +41,8 @@
 #include "tmap.cuh"
 
 #include <algorithm>
+#include <cstdlib>
+#include <type_traits>
 
 namespace irb {
 
@@ -51,23 +58,27 @@ constexpr int ABOX = AROWS * 128;              // one 64-channel box of the xn p
 constexpr int UC = 32;                         // qkv channels per unit
 constexpr int HROW = 80;                       // qkv patch row pitch: 64 B of channels + 16 B pad (conflict-free 16-byte stores)
 constexpr int HSTAGE = HPIX * HROW;
-constexpr int WBOX = UC * 128;                 // one 64-channel K box of a unit's W_qkv rows
+
 constexpr int CP = 16, BH = 2, BW = 4;         // dw thread: channel pair x 2x4 pixel block; 16 x 16 = 256 threads
-constexpr int CVA_WARPS = 4, DW_WARPS = 8, CVB_WARPS = 2, LN_WARPS = 4;
+constexpr int CVA_WARPS = 4, DW_WARPS = 8, CVB_WARPS = 2;
 constexpr int WARP_DW = CVA_WARPS, WARP_MMA = WARP_DW + DW_WARPS, WARP_PROD = WARP_MMA + 1, WARP_CVB = WARP_PROD + 1,
               WARP_LN = WARP_CVB + CVB_WARPS;
-constexpr int NWARPS = WARP_LN + LN_WARPS, NTHREADS = NWARPS * 32;
+template <int LNW> constexpr int nthreads() { return (WARP_LN + LNW) * 32; }
 static_assert((WARP_CVB & 3) == 2, "the two extra convert warps must own TMEM lane quarters 2 and 3");
-constexpr int D1_COLS = 2 * UC;                // per buffer: rows 0-127 in columns [0, 32), rows 64-191 in [32, 64)
-constexpr int S_COL0 = 2 * D1_COLS;            // the Gram accumulator
-constexpr int TMEM_COLS = 256;
+constexpr int GU = 3;                          // units per MMA1 group
+constexpr int GN = GU * UC;                    // 96 accumulator columns per group and row half
+constexpr int D1_COLS = 2 * GN;                // per buffer: rows 0-127 in columns [0, 96), rows 64-191 in [96, 192)
+constexpr int ND = 2;                          // D1 group accumulators in TMEM
+constexpr int S_COL0 = ND * D1_COLS;           // the Gram accumulator (<= 96 columns)
+constexpr int TMEM_COLS = 512;
+constexpr int NHMAX = 4;                       // qkv patch stages (at most)
 constexpr int VBOXB = TM * UC * 2;             // v staging bytes per buffer (all 8 warps)
 
 struct Bars {
   unsigned long long a_full[2], a_empty[2];
-  unsigned long long w_full[2], w_empty[2];
-  unsigned long long d1_full[2], d1_empty[2];
-  unsigned long long h_full[2], h_empty[2];
+  unsigned long long w_full;
+  unsigned long long d1_full[ND], d1_empty[ND];
+  unsigned long long h_full[NHMAX], h_empty[NHMAX];
   unsigned long long x_ready, x_empty, acc_done;
   uint32_t tmem_base;
 };
@@ -82,11 +93,32 @@ struct FusedFrontParams {
   float* n_part;           // [B][heads][parts][2][ch]
   int ln_mode;
   int B, H, W, C, heads, parts;
-  int nkb, ks_last;        // 64-channel K boxes of xn / W_qkv; K steps (16 channels) in the last box
-  int nqk, nv, nunits, NP; // units of q|k, of v; NP = padded rows of W_qkv
+  int nv, NP;              // units of v; NP = padded rows of W_qkv
   int tiles_x, tiles_y, tiles_per_img;
   int xrows;
-  uint32_t a_bytes, w_bytes, off_a, off_w, off_h, off_x, off_v, off_bars;
+  uint32_t off_a, off_w, off_h, off_x, off_v, off_bars;
+};
+
+// compile-time geometry of one channel width
+template <int CW> struct Geo {
+  static constexpr int NKB = (CW + 63) / 64;                 // 64-channel K boxes of xn / W_qkv
+  static constexpr int KS_LAST = (CW - 64 * (NKB - 1)) / 16; // K steps (16 channels) in the last box
+  static constexpr int NUNITS = (3 * CW + UC - 1) / UC;      // 5 / 9
+  static constexpr int NQK = 2 * CW / UC;                    // 3 / 6 units of q|k
+  static constexpr int NG = (NUNITS + GU - 1) / GU;          // 2 / 3 MMA1 groups
+  static constexpr int NP = NUNITS * UC;                     // rows of the W_qkv image
+  static constexpr int NA = CW <= 48 ? 2 : 1;                // xn patch buffers (C = 96: the patch retires a third into its
+                                                             // tile, once the last group's MMA1 has read it)
+  static constexpr int NH = CW <= 48 ? 4 : 2;                // qkv patch stages
+  static constexpr int LNW = CW <= 48 ? 4 : 8;               // LayerNorm warps (C = 96: single xn buffer, LayerNorm of the next
+                                                             // tile is on the critical path -> twice the warps; 80 registers)
+  static constexpr int NTHREADS = nthreads<LNW>();
+  // where the MMA warp issues the Gram of a tile: behind the tile's own groups (C = 48: measured 0.47 vs 0.55 ms), or in
+  // front of the NEXT tile's last group (C = 96, single xn buffer: 1.00 vs 1.14 ms)
+  static constexpr bool GRAM_LATE = CW > 48;
+  static constexpr uint32_t A_BYTES = NKB * ABOX;
+  static constexpr uint32_t W_BYTES = NKB * NP * 128;
+  __host__ __device__ static constexpr int group_units(int grp) { return grp == NG - 1 ? NUNITS - GU * (NG - 1) : GU; }
 };
 
 typedef unsigned long long f2_t;
@@ -111,43 +143,69 @@ struct TileIter {
   __device__ int x0() const { return (t % tx_n) * TW; }
 };
 
-// D1 -> fp16 qkv patch for the 32 patch rows this warp owns (TMEM lane quarter `q`, rows row0 .. row0 + 31)
-__device__ __forceinline__ void convert_unit(Bars* bars, uint32_t g, uint32_t tmem_base, int q, int col_off, int row0,
-                                             uint32_t sH, int lane) {
-  const uint32_t s = g & 1u, ph = (g >> 1) & 1u;
-  mbar_wait(smem_u32(&bars->d1_full[s]), ph);
-  tc_fence_after();
-  float v[32];
-  tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + s * D1_COLS + (uint32_t)col_off, v);
-  tmem_ld_wait();
-  tc_fence_before();
-  __syncwarp();
-  if (lane == 0) mbar_arrive(smem_u32(&bars->d1_empty[s]));
-  mbar_wait(smem_u32(&bars->h_empty[s]), ph ^ 1u);
+// D1 -> fp16 qkv patch for the 32 patch rows this warp owns (TMEM lane quarter `q`, rows row0 .. row0 + 31), one MMA1 group
+// (up to three units) at a time; `half_off` selects the row half's accumulator columns
+template <int CW>
+__device__ __forceinline__ void convert_tiles(Bars* bars, const FusedFrontParams& p, uint32_t tmem_base, int q, int half_off,
+                                              int row0, uint32_t sH, int lane) {
+  using G = Geo<CW>;
   const int row = row0 + lane;
-  if (row < HPIX) {
-    const uint32_t dst = sH + s * HSTAGE + (uint32_t)row * HROW;
+  uint32_t g = 0, gg = 0;
+  for (TileIter ti(p); ti.valid(); ti.next()) {
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      uint4 u;
-      u.x = h2_bits(f2h2_sat(v[8 * c + 0], v[8 * c + 1]));
-      u.y = h2_bits(f2h2_sat(v[8 * c + 2], v[8 * c + 3]));
-      u.z = h2_bits(f2h2_sat(v[8 * c + 4], v[8 * c + 5]));
-      u.w = h2_bits(f2h2_sat(v[8 * c + 6], v[8 * c + 7]));
-      sts128u(dst + c * 16, u);
+    for (int grp = 0; grp < G::NG; ++grp, ++gg) {
+      const uint32_t sd = gg & 1u;
+      mbar_wait(smem_u32(&bars->d1_full[sd]), (gg >> 1) & 1u);
+      tc_fence_after();
+#pragma unroll
+      for (int ug = 0; ug < G::group_units(grp); ++ug, ++g) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + sd * D1_COLS + (uint32_t)(half_off + ug * UC), v);
+        tmem_ld_wait();
+        if (ug == G::group_units(grp) - 1) {                  // the group's accumulator is free again
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&bars->d1_empty[sd]));
+        }
+        const uint32_t s = g % G::NH;
+        mbar_wait(smem_u32(&bars->h_empty[s]), ((g / G::NH) & 1u) ^ 1u);
+        if (row < HPIX) {
+          const uint32_t dst = sH + s * HSTAGE + (uint32_t)row * HROW;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint4 u;
+            u.x = h2_bits(f2h2_sat(v[8 * c + 0], v[8 * c + 1]));
+            u.y = h2_bits(f2h2_sat(v[8 * c + 2], v[8 * c + 3]));
+            u.z = h2_bits(f2h2_sat(v[8 * c + 4], v[8 * c + 5]));
+            u.w = h2_bits(f2h2_sat(v[8 * c + 6], v[8 * c + 7]));
+            sts128u(dst + c * 16, u);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bars->h_full[s]));
+      }
     }
   }
-  __syncwarp();
-  if (lane == 0) mbar_arrive(smem_u32(&bars->h_full[s]));
 }
 
-// depthwise 3x3 of one unit for this thread's 2 channels x (2 x 4) pixels; taps straight from L1 / L2 (10 KB in all)
-__device__ __forceinline__ void dw_unit(uint32_t patch, const float* __restrict__ taps, f2_t (&acc)[BH][BW]) {
-  f2_t w[9];
+// this thread's taps of one unit, straight from L1 / L2 (10 KB in all); issued BEFORE the wait for the unit's patch
+__device__ __forceinline__ void load_taps(const float* __restrict__ taps, f2_t (&w)[9]) {
 #pragma unroll
   for (int t = 0; t < 9; ++t) {
     const float2 f = __ldg(reinterpret_cast<const float2*>(taps + t * UC));
     w[t] = pack2(f.x, f.y);
+  }
+}
+
+// depthwise 3x3 of one unit for this thread's 2 channels x (2 x 4) pixels
+template <int DBG>
+__device__ __forceinline__ void dw_unit(uint32_t patch, const f2_t (&w)[9], f2_t (&acc)[BH][BW]) {
+  if (DBG & 2) {
+#pragma unroll
+    for (int oy = 0; oy < BH; ++oy)
+#pragma unroll
+      for (int ox = 0; ox < BW; ++ox) acc[oy][ox] = w[oy * 4 + ox];
+    return;
   }
 #pragma unroll
   for (int iy = 0; iy < BH + 2; ++iy) {
@@ -170,10 +228,13 @@ __device__ __forceinline__ void dw_unit(uint32_t patch, const float* __restrict_
 }
 
 // CW: channel count (48 or 96).  NQK = 2C/32 q|k units per tile.
-template <int CW>
-__global__ void __launch_bounds__(NTHREADS, 1)
-attn_fused_kernel(const __grid_constant__ CUtensorMap tmV, const FusedFrontParams p) {
-  constexpr int NQK = 2 * CW / UC;
+// DBG != 0: timing experiments only (results are garbage): 1 LayerNorm without its global loads, 2 no depthwise taps,
+// 8 no MMA1 instructions (compiled with -DIRB_FUSED_EXPERIMENTS, selected by IRB_AF_DBG)
+template <int CW, int DBG>
+__global__ void __launch_bounds__(Geo<CW>::NTHREADS, 1)
+attn_fused_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmX, const FusedFrontParams p) {
+  using G = Geo<CW>;
+  constexpr int NQK = G::NQK, NH = G::NH, NA = G::NA;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
@@ -184,18 +245,20 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmV, const FusedFrontParam
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.y, part = blockIdx.x;
-  const uint32_t nunits = (uint32_t)p.nunits;
 
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) {
-      mbar_init(smem_u32(&bars->a_full[s]), LN_WARPS);
+      mbar_init(smem_u32(&bars->a_full[s]), G::LNW);
       mbar_init(smem_u32(&bars->a_empty[s]), 1);
-      mbar_init(smem_u32(&bars->w_full[s]), 1);
-      mbar_init(smem_u32(&bars->w_empty[s]), 1);
-      mbar_init(smem_u32(&bars->d1_full[s]), 1);
-      mbar_init(smem_u32(&bars->d1_empty[s]), CVA_WARPS + CVB_WARPS);
+    }
+    for (int s = 0; s < NHMAX; ++s) {
       mbar_init(smem_u32(&bars->h_full[s]), CVA_WARPS + CVB_WARPS);
       mbar_init(smem_u32(&bars->h_empty[s]), DW_WARPS);
+    }
+    mbar_init(smem_u32(&bars->w_full), 1);
+    for (int s = 0; s < ND; ++s) {
+      mbar_init(smem_u32(&bars->d1_full[s]), 1);
+      mbar_init(smem_u32(&bars->d1_empty[s]), CVA_WARPS + CVB_WARPS);
     }
     mbar_init(smem_u32(&bars->x_ready), DW_WARPS);
     mbar_init(smem_u32(&bars->x_empty), 1);
@@ -217,7 +280,7 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmV, const FusedFrontParam
   if (warp >= WARP_LN) {
     // =============================== LayerNorm: x halo rows -> fp16 operand boxes ===============================
     constexpr int LPR = CW / 12, RPW = 32 / LPR;           // lanes per pixel row (3 float4 each), rows per warp pass
-    constexpr int RPP = RPW * LN_WARPS;                    // rows per pass of the four warps (32 / 16)
+    constexpr int RPP = RPW * G::LNW;                      // rows per pass of all LayerNorm warps (32)
     constexpr int NPASS = AROWS / RPP;                     // 6 / 12: rows 180 .. 191 are written as zeros
     constexpr int GP = 3;                                  // passes in flight (loads issued before the arithmetic)
     static_assert(AROWS % RPP == 0 && NPASS % GP == 0, "pass geometry");
@@ -229,16 +292,22 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmV, const FusedFrontParam
       gb[i] = p.ln_mode == LN_WITHBIAS ? __ldg(reinterpret_cast<const float4*>(p.ln_b) + i * LPR + l)
                                        : make_float4(0.f, 0.f, 0.f, 0.f);
     }
+    // L2 prefetch of the x halo boxes, two tiles ahead of the tile being normalised
+    TileIter tp(p);
+    const bool pf = lw == 0 && lane == 0 && !(DBG & 1);
+    if (pf) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmX)) : "memory");
+      for (int k = 0; k < 2 && tp.valid(); ++k, tp.next()) tma_prefetch_l2_4d(&tmX, 0, tp.x0() - 1, tp.y0() - 1, b);
+    }
     uint32_t j = 0;
     for (TileIter ti(p); ti.valid(); ti.next(), ++j) {
       const int y0 = ti.y0(), x0 = ti.x0();
-      const uint32_t ab = j & 1u;
-      mbar_wait(smem_u32(&bars->a_empty[ab]), ((j >> 1) & 1u) ^ 1u);
-      const uint32_t abase = sA + ab * p.a_bytes;
-#pragma unroll 1
-      for (int pg = 0; pg < NPASS; pg += GP) {
-        float4 v[GP][3];
-        bool inside[GP];
+      if (pf && tp.valid()) { tma_prefetch_l2_4d(&tmX, 0, tp.x0() - 1, tp.y0() - 1, b); tp.next(); }
+      const uint32_t ab = j % NA;
+      const uint32_t abase = sA + ab * G::A_BYTES;
+      float4 v[GP][3];
+      bool inside[GP];
+      auto load_group = [&](int pg) {
 #pragma unroll
         for (int q = 0; q < GP; ++q) {
           const int row = (pg + q) * RPP + lw * RPW + r;
@@ -247,8 +316,12 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmV, const FusedFrontParam
           inside[q] = row < HPIX && gy >= 0 && gy < p.H && gx >= 0 && gx < p.W;
           const float4* src = reinterpret_cast<const float4*>(p.x + (((long long)b * p.H + gy) * p.W + gx) * CW);
 #pragma unroll
-          for (int i = 0; i < 3; ++i) v[q][i] = inside[q] ? __ldg(src + i * LPR + l) : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int i = 0; i < 3; ++i)
+            v[q][i] = (DBG & 1) ? make_float4(0.5f * l, 1.f, -1.f, 0.25f * i)
+                                : inside[q] ? __ldg(src + i * LPR + l) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
+      };
+      auto compute_group = [&](int pg) {
 #pragma unroll
         for (int q = 0; q < GP; ++q) {
           const int row = (pg + q) * RPP + lw * RPW + r;
@@ -282,82 +355,97 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmV, const FusedFrontParam
             sts64u(abase + kb * ABOX + (uint32_t)row * 128u + (((kk >> 3) ^ ((uint32_t)row & 7u)) << 4) + (kk & 7u) * 2u, t);
           }
         }
+      };
+      // the first group's loads go out BEFORE the wait for the buffer: their latency hides behind it
+      load_group(0);
+      mbar_wait(smem_u32(&bars->a_empty[ab]), ((j / NA) & 1u) ^ 1u);
+      compute_group(0);
+#pragma unroll 1
+      for (int pg = GP; pg < NPASS; pg += GP) {
+        load_group(pg);
+        compute_group(pg);
       }
       fence_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&bars->a_full[ab]));
     }
   } else if (warp == WARP_PROD) {
-    // =============================== producer: the units' W_qkv rows ===============================
+    // =============================== producer: W_qkv, once ===============================
     if (lane == 0) {
-      uint32_t g = 0;
-      for (TileIter ti(p); ti.valid(); ti.next()) {
-        for (uint32_t u = 0; u < nunits; ++u, ++g) {
-          const uint32_t s = g & 1u, fb = smem_u32(&bars->w_full[s]);
-          mbar_wait(smem_u32(&bars->w_empty[s]), ((g >> 1) & 1u) ^ 1u);
-          mbar_expect_tx(fb, (uint32_t)p.nkb * WBOX);
-          for (int kb = 0; kb < p.nkb; ++kb)
-            bulk_load(sW + s * p.w_bytes + (uint32_t)kb * WBOX, p.w_qkv + ((size_t)kb * p.NP + (size_t)u * UC) * 128, WBOX, fb);
-        }
-      }
+      const uint32_t fb = smem_u32(&bars->w_full);
+      mbar_expect_tx(fb, G::W_BYTES);
+      constexpr uint32_t CHUNK = 8192;
+      for (uint32_t o = 0; o < G::W_BYTES; o += CHUNK)
+        bulk_load(sW + o, p.w_qkv + o, (G::W_BYTES - o) < CHUNK ? (G::W_BYTES - o) : CHUNK, fb);
     }
   } else if (warp == WARP_MMA) {
     // =============================== MMA issuer ===============================
-    const uint32_t idesc1 = make_idesc<__half>(UC), idescS = make_idesc<__half>(CW);
-    uint32_t ntl = 0;
-    for (TileIter ti(p); ti.valid(); ti.next()) ++ntl;
-    const uint32_t G = ntl * nunits;
-    auto issue1 = [&](uint32_t g) {
-      const uint32_t j = g / nunits, u = g - j * nunits, s = g & 1u, ph = (g >> 1) & 1u, ab = j & 1u;
-      if (u == 0) mbar_wait(smem_u32(&bars->a_full[ab]), (j >> 1) & 1u);
-      mbar_wait(smem_u32(&bars->w_full[s]), ph);
-      mbar_wait(smem_u32(&bars->d1_empty[s]), ph ^ 1u);
+    // Issue order: the groups of tile j with the Gram of tile j-1 in front of the LAST group.  (Groups of tile j, then
+    // Gram j, left a bubble at every tile boundary: the first group of tile j+1 sat behind the wait for tile j's q | k rows.
+    // The last group cannot go earlier anyway: its accumulator is freed by converts whose qkv patch stages wait for dw
+    // warps that wait for this very Gram.  A polling event loop over both conditions was measured 20-100 % slower.)
+    const uint32_t idescS = make_idesc<__half>(CW);
+    const uint64_t wdesc = sw128_desc(sW), xdesc = sw128_desc(sX);
+    mbar_wait(smem_u32(&bars->w_full), 0);
+    auto issue_group = [&](auto grp_tag, uint32_t gg, uint32_t jg) {
+      constexpr int grp = decltype(grp_tag)::value;
+      const uint32_t idesc1 = make_idesc<__half>(G::group_units(grp) * UC);
+      const uint32_t sd = gg & 1u, ab = jg % NA;
       tc_fence_after();
-      const uint32_t d = tmem_base + s * D1_COLS;
-      for (int kb = 0; kb < p.nkb; ++kb) {
-        const uint32_t a_addr = sA + ab * p.a_bytes + (uint32_t)kb * ABOX;
-        const uint32_t w_addr = sW + s * p.w_bytes + (uint32_t)kb * WBOX;
-        const int ks = kb == p.nkb - 1 ? p.ks_last : 4;
-        for (int kk = 0; kk < ks; ++kk) {
+      const uint32_t d = tmem_base + sd * D1_COLS;
+      const uint64_t adesc = sw128_desc(sA + ab * G::A_BYTES);
+#pragma unroll
+      for (int kb = 0; kb < G::NKB; ++kb) {
+#pragma unroll
+        for (int kk = 0; kk < (kb == G::NKB - 1 ? G::KS_LAST : 4); ++kk) {
+          if (DBG & 8) continue;
           const uint32_t acc = (kb > 0 || kk > 0) ? 1u : 0u;
-          const uint64_t bd = sw128_desc(w_addr + kk * 32);
-          umma_elect<__half>(d, sw128_desc(a_addr + kk * 32), bd, idesc1, acc);
-          umma_elect<__half>(d + UC, sw128_desc(a_addr + 64 * 128 + kk * 32), bd, idesc1, acc);
+          // descriptors: base + (byte offset >> 4); the whole offset is a compile-time constant
+          const uint64_t bd = wdesc + (uint64_t)((kb * G::NP * 128 + grp * GU * UC * 128 + kk * 32) >> 4);
+          const uint64_t ad = adesc + (uint64_t)((kb * ABOX + kk * 32) >> 4);
+          umma_elect<__half>(d, ad, bd, idesc1, acc);
+          umma_elect<__half>(d + GN, ad + (uint64_t)((64 * 128) >> 4), bd, idesc1, acc);
         }
       }
-      umma_commit_elect(smem_u32(&bars->d1_full[s]));
-      umma_commit_elect(smem_u32(&bars->w_empty[s]));
-      if (u == nunits - 1) umma_commit_elect(smem_u32(&bars->a_empty[ab]));
+      umma_commit_elect(smem_u32(&bars->d1_full[sd]));
+      if (grp == G::NG - 1) umma_commit_elect(smem_u32(&bars->a_empty[ab]));
       __syncwarp();
     };
-    auto gram = [&](uint32_t j) {
-      mbar_wait(smem_u32(&bars->x_ready), j & 1u);
+    auto gram = [&](uint32_t jx) {
+      mbar_wait(smem_u32(&bars->x_ready), jx & 1u);          // the dw warps have written tile jx's q | k rows
       tc_fence_after();
 #pragma unroll
-      for (int a = 0; a < 2; ++a)                          // X boxes: 64 pixels (fp16) each
+      for (int a = 0; a < 2; ++a)                            // X boxes: 64 pixels (fp16) each
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
-          const uint32_t qa = sX + (uint32_t)a * xbox + kk * 32;            // q rows start at row 0
-          const uint32_t ka = qa + (uint32_t)CW * 128u;                     // k rows start at row C
-          umma_elect<__half>(tmem_base + S_COL0, sw128_desc(qa), sw128_desc(ka), idescS, (j > 0 || a > 0 || kk > 0) ? 1u : 0u);
+          const uint64_t qa = xdesc + (uint64_t)((a * (int)xbox + kk * 32) >> 4);   // q rows start at row 0
+          const uint64_t ka = qa + (uint64_t)((CW * 128) >> 4);                     // k rows start at row C
+          umma_elect<__half>(tmem_base + S_COL0, qa, ka, idescS, (jx > 0 || a > 0 || kk > 0) ? 1u : 0u);
         }
       umma_commit_elect(smem_u32(&bars->x_empty));
       __syncwarp();
     };
-    if (G > 0) issue1(0);
-    if (G > 1) issue1(1);
-    for (uint32_t g = 0; g < G; ++g) {
-      if (g + 2 < G) issue1(g + 2);
-      const uint32_t j = g / nunits, u = g - j * nunits;
-      if (u == (uint32_t)NQK + 1u) gram(j);                // the dw warps finished unit NQK-1 about two units ago
+    uint32_t gg = 0, j = 0;
+    for (TileIter ti(p); ti.valid(); ti.next(), ++j) {
+      auto one = [&](auto grp_tag) {
+        constexpr int grp = decltype(grp_tag)::value;
+        if (G::GRAM_LATE && grp == G::NG - 1 && j > 0) gram(j - 1);
+        if (grp == 0) mbar_wait(smem_u32(&bars->a_full[j % NA]), (j / NA) & 1u);
+        mbar_wait(smem_u32(&bars->d1_empty[gg & 1u]), ((gg >> 1) & 1u) ^ 1u);
+        issue_group(grp_tag, gg, j);
+        ++gg;
+      };
+      one(std::integral_constant<int, 0>{});
+      if (G::NG > 2) one(std::integral_constant<int, 1>{});
+      one(std::integral_constant<int, G::NG - 1>{});
+      if (!G::GRAM_LATE) gram(j);
     }
+    if (G::GRAM_LATE && j > 0) gram(j - 1);
     umma_commit_elect(smem_u32(&bars->acc_done));
   } else if (warp >= WARP_CVB) {
     // =============================== convert: patch rows 128 .. 179 (second MMA, TMEM lanes 64 .. 127) ===============================
     const int q = warp & 3;
-    uint32_t g = 0;
-    for (TileIter ti(p); ti.valid(); ti.next())
-      for (uint32_t u = 0; u < nunits; ++u, ++g) convert_unit(bars, g, tmem_base, q, UC, 128 + (q - 2) * 32, sH, lane);
+    convert_tiles<CW>(bars, p, tmem_base, q, GN, 128 + (q - 2) * 32, sH, lane);
   } else if (warp >= WARP_DW) {
     // =============================== depthwise 3x3 -> X tile (q, k) / v staging ===============================
     const int ctid = tid - WARP_DW * 32;
@@ -385,10 +473,12 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmV, const FusedFrontParam
       mbar_wait(smem_u32(&bars->x_empty), (j & 1u) ^ 1u);
 #pragma unroll
       for (int ch = 0; ch < NQK; ++ch, ++g) {
-        const uint32_t s = g & 1u;
-        mbar_wait(smem_u32(&bars->h_full[s]), (g >> 1) & 1u);
+        const uint32_t s = g % NH;
+        f2_t w[9];
+        load_taps(p.dw + (size_t)(ch * 9) * UC + cp * 2, w);
+        mbar_wait(smem_u32(&bars->h_full[s]), (g / NH) & 1u);
         f2_t acc[BH][BW];
-        dw_unit(sH + s * HSTAGE + win0, p.dw + (size_t)(ch * 9) * UC + cp * 2, acc);
+        dw_unit<DBG>(sH + s * HSTAGE + win0, w, acc);
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&bars->h_empty[s]));
         // transposed store: rows = channels ch*32 + 2cp (+1), columns = the block's pixels (4 consecutive per row)
@@ -427,10 +517,12 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmV, const FusedFrontParam
       // ---- v units: each warp stages its own 2 x 8 pixel region ([pixel][channel], 64-byte rows) and stores it with its
       //      own bulk-tensor copy: no block-wide barrier on the path ----
       for (int ch = 0; ch < p.nv; ++ch, ++vc, ++g) {
-        const uint32_t s = g & 1u;
-        mbar_wait(smem_u32(&bars->h_full[s]), (g >> 1) & 1u);
+        const uint32_t s = g % NH;
+        f2_t w[9];
+        load_taps(p.dw + (size_t)((NQK + ch) * 9) * UC + cp * 2, w);
+        mbar_wait(smem_u32(&bars->h_full[s]), (g / NH) & 1u);
         f2_t acc[BH][BW];
-        dw_unit(sH + s * HSTAGE + win0, p.dw + (size_t)((NQK + ch) * 9) * UC + cp * 2, acc);
+        dw_unit<DBG>(sH + s * HSTAGE + win0, w, acc);
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&bars->h_empty[s]));
         const uint32_t vb = vwarp + (vc & 1u) * (16u * 64u);
@@ -479,12 +571,8 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmV, const FusedFrontParam
   } else {
     // =============================== convert (patch rows 0 .. 127), then the CTA's partial Gram ===============================
     const int q = warp;
-    uint32_t g = 0;
-    bool any = false;
-    for (TileIter ti(p); ti.valid(); ti.next()) {
-      any = true;
-      for (uint32_t u = 0; u < nunits; ++u, ++g) convert_unit(bars, g, tmem_base, q, 0, q * 32, sH, lane);
-    }
+    const bool any = TileIter(p).valid();
+    convert_tiles<CW>(bars, p, tmem_base, q, 0, q * 32, sH, lane);
     const int chd = CW / p.heads;
     const int i = warp * 32 + lane;                         // TMEM lane == q channel
     if (any) {
@@ -520,36 +608,37 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmV, const FusedFrontParam
 }
 
 struct FusedFrontCfg {
-  int nkb, ks_last, xrows, nunits;
-  uint32_t a_bytes, w_bytes, off_a, off_w, off_h, off_x, off_v, off_bars;
+  int xrows;
+  uint32_t off_a, off_w, off_h, off_x, off_v, off_bars;
   size_t smem;
 };
 
-bool configure(int C, int heads, FusedFrontCfg& c) {
-  if ((C != 48 && C != 96) || heads <= 0 || C % heads != 0) return false;
-  c.nkb = (C + 63) / 64;
-  c.ks_last = (C - 64 * (c.nkb - 1)) / 16;
-  c.nunits = (3 * C + UC - 1) / UC;
-  c.xrows = std::max(2 * C, 128);                       // A reads 128 rows from row 0 (M = 128), B reads C rows from row C
-  c.a_bytes = (uint32_t)c.nkb * ABOX;
-  c.w_bytes = (uint32_t)c.nkb * WBOX;
+template <int CW>
+bool configure_w(int heads, FusedFrontCfg& c) {
+  using G = Geo<CW>;
+  if (heads <= 0 || CW % heads != 0) return false;
+  c.xrows = std::max(2 * CW, 128);                      // A reads 128 rows from row 0 (M = 128), B reads C rows from row C
   size_t off = 0;
-  c.off_a = (uint32_t)off; off += 2 * (size_t)c.a_bytes;
-  c.off_w = (uint32_t)off; off += 2 * (size_t)c.w_bytes;
+  c.off_a = (uint32_t)off; off += (size_t)G::NA * G::A_BYTES;
+  c.off_w = (uint32_t)off; off += align_up((size_t)G::W_BYTES, 1024);
   c.off_x = (uint32_t)off; off += (size_t)2 * c.xrows * 128;
   c.off_v = (uint32_t)off; off += (size_t)2 * VBOXB;
-  c.off_h = (uint32_t)off; off += 2 * (size_t)HSTAGE;
+  c.off_h = (uint32_t)off; off += (size_t)G::NH * HSTAGE;
   off = align_up(off, 16);
   c.off_bars = (uint32_t)off; off += sizeof(Bars);
   c.smem = off + 1024;          // alignment slack
-  return c.smem <= 227 * 1024 && (size_t)16 * 2 * C * 4 <= (size_t)2 * VBOXB;
+  return c.smem <= 227 * 1024 && (size_t)16 * 2 * CW * 4 <= (size_t)2 * VBOXB;
 }
 
-template <int CW>
-int launch_inst(const CUtensorMap& tV, const FusedFrontParams& p, dim3 grid, size_t smem, cudaStream_t s) {
+bool configure(int C, int heads, FusedFrontCfg& c) {
+  return C == 48 ? configure_w<48>(heads, c) : C == 96 ? configure_w<96>(heads, c) : false;
+}
+
+template <int CW, int DBG = 0>
+int launch_inst(const CUtensorMap& tV, const CUtensorMap& tX, const FusedFrontParams& p, dim3 grid, size_t smem, cudaStream_t s) {
   static SmemOptIn optin;
-  IRB_TRY(opt_in_smem(attn_fused_kernel<CW>, optin));
-  attn_fused_kernel<CW><<<grid, NTHREADS, smem, s>>>(tV, p);
+  IRB_TRY(opt_in_smem(attn_fused_kernel<CW, DBG>, optin));
+  attn_fused_kernel<CW, DBG><<<grid, Geo<CW>::NTHREADS, smem, s>>>(tV, tX, p);
   IRB_LAUNCH_CHECK();
   return IR_OK;
 }
@@ -574,12 +663,19 @@ int launch_attn_fused(const AttnFusedArgs& a, cudaStream_t s) {
   IRB_REQUIRE(a.B > 0 && a.H > 0 && a.W > 0 && a.B <= 65535, "attn_fused: bad extent");
   IRB_REQUIRE(a.ln_mode == LN_BIASFREE || a.ln_mode == LN_WITHBIAS, "attn_fused: bad LayerNorm mode");
   IRB_REQUIRE((reinterpret_cast<uintptr_t>(a.x) & 15u) == 0, "attn_fused: x must be 16-byte aligned");
-  CUtensorMap tV;
+  CUtensorMap tV, tX;
   {
     cuuint64_t d[4] = {(cuuint64_t)a.C, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.B};
     cuuint64_t st[3] = {(cuuint64_t)a.C * 2, (cuuint64_t)a.C * 2 * a.W, (cuuint64_t)a.C * 2 * a.W * a.H};
     cuuint32_t box[4] = {UC, 8, 2, 1};                 // one dw warp's region
     IRB_TRY(make_tmap(&tV, a.v, true, 4, d, st, box, false));
+  }
+  {
+    // the x halo box of a tile, for the L2 prefetch only (never a shared-memory destination)
+    cuuint64_t d[4] = {(cuuint64_t)a.C, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.B};
+    cuuint64_t st[3] = {(cuuint64_t)a.C * 4, (cuuint64_t)a.C * 4 * a.W, (cuuint64_t)a.C * 4 * a.W * a.H};
+    cuuint32_t box[4] = {(cuuint32_t)a.C, PW, TH + 2, 1};
+    IRB_TRY(make_tmap(&tX, a.x, false, 4, d, st, box, false));
   }
   FusedFrontParams p{};
   p.x = a.x; p.ln_w = a.ln_w; p.ln_b = a.ln_b; p.ln_mode = a.ln_mode;
@@ -588,11 +684,9 @@ int launch_attn_fused(const AttnFusedArgs& a, cudaStream_t s) {
   p.B = a.B; p.H = a.H; p.W = a.W; p.C = a.C; p.heads = a.heads;
   p.parts = attn_fused_parts(a.B, a.H, a.W);
   IRB_REQUIRE(p.parts == a.parts, "attn_fused: partial count mismatch");
-  p.nkb = c.nkb; p.ks_last = c.ks_last;
-  p.nqk = 2 * a.C / UC; p.nv = cdiv(a.C, UC); p.nunits = c.nunits; p.NP = c.nunits * UC;
+  p.nv = cdiv(a.C, UC); p.NP = attn_fused_wrows(a.C);
   p.tiles_x = cdiv(a.W, TW); p.tiles_y = cdiv(a.H, TH); p.tiles_per_img = p.tiles_x * p.tiles_y;
   p.xrows = c.xrows;
-  p.a_bytes = c.a_bytes; p.w_bytes = c.w_bytes;
   p.off_a = c.off_a; p.off_w = c.off_w; p.off_h = c.off_h; p.off_x = c.off_x; p.off_v = c.off_v; p.off_bars = c.off_bars;
   dim3 grid(p.parts, a.B, 1);
   const size_t smem = std::max<size_t>(c.smem, 120 * 1024);     // one CTA per SM
@@ -600,7 +694,20 @@ int launch_attn_fused(const AttnFusedArgs& a, cudaStream_t s) {
   // algorithmic bytes: x read (fp32) + v write (fp16); flops: qkv 1x1 + depthwise + Gram
   ProfScope prof(TAG_ATTN_FUSED, pix * (4.0 * a.C + 2.0 * a.C),
                  pix * (2.0 * 3 * a.C * a.C + 2.0 * 9 * 3 * a.C + 2.0 * a.C * (a.C / a.heads)), s);
-  return a.C == 48 ? launch_inst<48>(tV, p, grid, smem, s) : launch_inst<96>(tV, p, grid, smem, s);
+#ifdef IRB_FUSED_EXPERIMENTS
+  static const int dbg = getenv("IRB_AF_DBG") ? atoi(getenv("IRB_AF_DBG")) : 0;
+  if (a.C == 96) {
+    switch (dbg) {
+      case 1: return launch_inst<96, 1>(tV, tX, p, grid, smem, s);
+      case 2: return launch_inst<96, 2>(tV, tX, p, grid, smem, s);
+      case 3: return launch_inst<96, 3>(tV, tX, p, grid, smem, s);
+      case 8: return launch_inst<96, 8>(tV, tX, p, grid, smem, s);
+      case 11: return launch_inst<96, 11>(tV, tX, p, grid, smem, s);
+      default: break;
+    }
+  }
+#endif
+  return a.C == 48 ? launch_inst<48>(tV, tX, p, grid, smem, s) : launch_inst<96>(tV, tX, p, grid, smem, s);
 }
 
 }  // namespace irb

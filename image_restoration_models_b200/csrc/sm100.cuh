@@ -73,6 +73,12 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, uint32_t src
                ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                : "memory");
 }
+// L2 prefetch of a tensor box (no shared-memory destination, no barrier): later loads of the box hit L2
+__device__ __forceinline__ void tma_prefetch_l2_4d(const CUtensorMap* tm, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
+               ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
 // bulk-tensor reduction: global[tile] += smem[tile] (element type from the tensor map), out-of-range elements skipped
 __device__ __forceinline__ void tma_reduce_add_4d(const CUtensorMap* tm, uint32_t src, int c0, int c1, int c2, int c3) {
   asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
