@@ -47,6 +47,11 @@ SIGNATURES = {
     "ir_restormer_workspace_bytes": (C.c_size_t, [C.POINTER(IrRestormerCfg), C.c_int, C.c_int, C.c_int, C.c_int]),
     "ir_restormer_forward": (C.c_int, [C.POINTER(IrRestormerCfg), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                        C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
+    "ir_restormer_graph_workspace_bytes": (C.c_size_t, [C.POINTER(IrRestormerCfg), C.c_int, C.c_int, C.c_int, C.c_int]),
+    "ir_restormer_forward_graph": (C.c_int, [C.POINTER(IrRestormerCfg), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                             C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
+    "ir_graph_cache_clear": (C.c_int, []),
+    "ir_graph_cache_stats": (C.c_int, [C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
     "ir_restormer_launch_count": (C.c_int, [C.POINTER(IrRestormerCfg)]),
     "ir_dncnn_param_count": (C.c_int, [C.POINTER(IrDncnnCfg)]),
     "ir_dncnn_param_numel": (C.c_longlong, [C.POINTER(IrDncnnCfg), C.c_int]),
@@ -56,6 +61,9 @@ SIGNATURES = {
     "ir_dncnn_workspace_bytes": (C.c_size_t, [C.POINTER(IrDncnnCfg), C.c_int, C.c_int, C.c_int, C.c_int]),
     "ir_dncnn_forward": (C.c_int, [C.POINTER(IrDncnnCfg), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                    C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
+    "ir_dncnn_graph_workspace_bytes": (C.c_size_t, [C.POINTER(IrDncnnCfg), C.c_int, C.c_int, C.c_int, C.c_int]),
+    "ir_dncnn_forward_graph": (C.c_int, [C.POINTER(IrDncnnCfg), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                         C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
     "ir_dncnn_launch_count": (C.c_int, [C.POINTER(IrDncnnCfg)]),
     "ir_block_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int]),
     "ir_block_packed_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int]),

@@ -4,6 +4,9 @@
 #include "tc_gemm.cuh"
 
 #include <cstdlib>
+#include <cstring>
+#include <list>
+#include <map>
 #include <mutex>
 
 namespace irb {
@@ -48,6 +51,75 @@ static const char* kTagNames[TAG_COUNT] = {
     "other", "ln_qkv_1x1", "dwconv3x3_qkv", "mdta_gram", "softmax_fold", "attn_out_1x1", "ln_project_in_1x1",
     "dwconv3x3_gelu_gate", "ffn_project_out_1x1", "conv3x3", "reduce_chan_1x1", "concat_copy", "layernorm",
     "dwconv_gate_project_out", "dwconv_qkv_gram", "gdfn_fused", "mdta_fused_front"};
+
+// ---- CUDA-graph cache of whole forwards ----------------------------------------------------------
+// The reference harness calls the model once per 256x256 / 512x512 tile with batch 1 (src/utils.py:403-419): ~280 launches of
+// kernels that take 5-30 us each, i.e. a launch-bound host loop (plan construction + ~600 cuTensorMapEncodeTiled calls per
+// forward).  ir_*_forward_graph captures the launch sequence of one (configuration, mode, shape, buffers) ONCE and replays it.
+// Input and output go through staging slots at the end of the workspace so that the captured addresses never change.
+// First call of a key: plain launches (lazy per-kernel initialisation must not happen under capture); second call:
+// capture + instantiate + launch; then replays.  Least-recently-used entries are destroyed beyond GRAPH_CAP.
+struct GraphEntry { cudaGraphExec_t exec = nullptr; };
+static std::mutex g_graph_mu;
+static std::map<std::string, GraphEntry> g_graphs;
+static std::list<std::string> g_graph_lru;               // front = most recent
+static const size_t GRAPH_CAP = 32;
+static long long g_graph_replays = 0, g_graph_captures = 0;
+
+static void graph_touch(const std::string& key) {
+  g_graph_lru.remove(key);
+  g_graph_lru.push_front(key);
+  while (g_graph_lru.size() > GRAPH_CAP) {
+    auto it = g_graphs.find(g_graph_lru.back());
+    if (it != g_graphs.end()) { if (it->second.exec) cudaGraphExecDestroy(it->second.exec); g_graphs.erase(it); }
+    g_graph_lru.pop_back();
+  }
+}
+
+template <typename T> static void key_add(std::string& k, const T& v) { k.append(reinterpret_cast<const char*>(&v), sizeof(T)); }
+
+template <typename F>
+static int run_graph_cached(const std::string& key, cudaStream_t s, F&& launch_all) {
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  IRB_CUDA(cudaStreamIsCapturing(s, &cs));
+  if (g_prof_on || cs != cudaStreamCaptureStatusNone) return launch_all(s);  // profiling / caller-side capture: plain launches
+  std::unique_lock<std::mutex> lk(g_graph_mu);
+  auto it = g_graphs.find(key);
+  if (it == g_graphs.end()) {                 // first sight of this key: plain launches, remember it
+    g_graphs[key] = GraphEntry{};
+    graph_touch(key);
+    lk.unlock();
+    return launch_all(s);
+  }
+  graph_touch(key);
+  if (it->second.exec == nullptr) {
+    // captured on a private stream: the caller's may be the legacy default stream, which cannot capture; the graph does
+    // not remember where it was recorded and is launched on the caller's stream
+    int dev = 0;
+    IRB_CUDA(cudaGetDevice(&dev));
+    static cudaStream_t cap_streams[64] = {};
+    IRB_REQUIRE(dev >= 0 && dev < 64, "graph cache: device ordinal out of range");
+    if (!cap_streams[dev]) IRB_CUDA(cudaStreamCreateWithFlags(&cap_streams[dev], cudaStreamNonBlocking));
+    cudaStream_t cap = cap_streams[dev];
+    IRB_CUDA(cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
+    const int st = launch_all(cap);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(cap, &graph);
+    if (st != IR_OK) { if (graph) cudaGraphDestroy(graph); return st; }
+    if (e != cudaSuccess) return cuda_fail(e, "cudaStreamEndCapture", __FILE__, __LINE__);
+    cudaGraphExec_t exec = nullptr;
+    const cudaError_t e2 = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e2 != cudaSuccess) return cuda_fail(e2, "cudaGraphInstantiate", __FILE__, __LINE__);
+    it->second.exec = exec;
+    ++g_graph_captures;
+  }
+  ++g_graph_replays;
+  IRB_CUDA(cudaGraphLaunch(it->second.exec, s));
+  return IR_OK;
+}
+
+static size_t stage_bytes(long long elems) { return align_up((size_t)elems * sizeof(float), 256); }
 
 static int check_mode(int mode) {
   IRB_REQUIRE(mode == IR_MODE_FP32 || mode == IR_MODE_HALF || mode == IR_MODE_FP32_SIMT || mode == IR_MODE_FP32_STRICT,
@@ -119,6 +191,40 @@ int ir_restormer_forward(const IrRestormerCfg* cfg, const void* packed, const fl
   return restormer_forward(pl, (const float*)packed, x, y, B, H, W, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
+size_t ir_restormer_graph_workspace_bytes(const IrRestormerCfg* cfg, int B, int H, int W, int mode) {
+  const size_t base = ir_restormer_workspace_bytes(cfg, B, H, W, mode);
+  if (base == 0) return 0;
+  const long long P = (long long)B * H * W;
+  return align_up(base, 256) + stage_bytes(P * cfg->inp_channels) + stage_bytes(P * cfg->out_channels);
+}
+
+int ir_restormer_forward_graph(const IrRestormerCfg* cfg, const void* packed, const float* x, float* y, int B, int H, int W,
+                               void* workspace, size_t workspace_bytes, int mode, void* stream) {
+  IRB_REQUIRE(cfg && packed && x && y && workspace, "forward: null argument");
+  IRB_TRY(check_mode(mode));
+  IRB_REQUIRE(B > 0 && H > 0 && W > 0, "restormer: empty input");
+  RestormerPlan pl;
+  IRB_TRY(build_restormer_plan(pl, *cfg, engine_of(mode)));
+  const size_t base = align_up(restormer_workspace_bytes(pl, B, H, W), 256);
+  const long long P = (long long)B * H * W;
+  const size_t xin = stage_bytes(P * cfg->inp_channels), yout = stage_bytes(P * cfg->out_channels);
+  if (workspace_bytes < base + xin + yout) { set_error("workspace too small"); return IR_ERR_WORKSPACE; }
+  float* xs = reinterpret_cast<float*>((char*)workspace + base);
+  float* ys = reinterpret_cast<float*>((char*)workspace + base + xin);
+  cudaStream_t s = (cudaStream_t)stream;
+  int dev = 0;
+  IRB_CUDA(cudaGetDevice(&dev));
+  std::string key("R");
+  key_add(key, *cfg); key_add(key, mode); key_add(key, B); key_add(key, H); key_add(key, W); key_add(key, dev);
+  key_add(key, packed); key_add(key, workspace);
+  IRB_CUDA(cudaMemcpyAsync(xs, x, (size_t)P * cfg->inp_channels * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  IRB_TRY(run_graph_cached(key, s, [&](cudaStream_t ls) {
+    return restormer_forward(pl, (const float*)packed, xs, ys, B, H, W, workspace, base, ls);
+  }));
+  IRB_CUDA(cudaMemcpyAsync(y, ys, (size_t)P * cfg->out_channels * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  return IR_OK;
+}
+
 int ir_restormer_launch_count(const IrRestormerCfg* cfg) {
   if (!cfg) return -1;
   RestormerPlan pl;
@@ -174,6 +280,56 @@ int ir_dncnn_forward(const IrDncnnCfg* cfg, const void* packed, const float* x, 
   DncnnPlan pl;
   IRB_TRY(build_dncnn_plan(pl, *cfg, engine_of(mode)));
   return dncnn_forward(pl, (const float*)packed, x, y, B, H, W, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+size_t ir_dncnn_graph_workspace_bytes(const IrDncnnCfg* cfg, int B, int H, int W, int mode) {
+  const size_t base = ir_dncnn_workspace_bytes(cfg, B, H, W, mode);
+  if (base == 0) return 0;
+  const long long P = (long long)B * H * W;
+  return align_up(base, 256) + stage_bytes(P * cfg->in_nc) + stage_bytes(P * cfg->out_nc);
+}
+
+int ir_dncnn_forward_graph(const IrDncnnCfg* cfg, const void* packed, const float* x, float* y, int B, int H, int W,
+                           void* workspace, size_t workspace_bytes, int mode, void* stream) {
+  IRB_REQUIRE(cfg && packed && x && y && workspace, "forward: null argument");
+  IRB_TRY(check_mode(mode));
+  IRB_REQUIRE(B > 0 && H > 0 && W > 0, "dncnn: empty input");
+  DncnnPlan pl;
+  IRB_TRY(build_dncnn_plan(pl, *cfg, engine_of(mode)));
+  const size_t base = align_up(dncnn_workspace_bytes(pl, B, H, W), 256);
+  const long long P = (long long)B * H * W;
+  const size_t xin = stage_bytes(P * cfg->in_nc), yout = stage_bytes(P * cfg->out_nc);
+  if (workspace_bytes < base + xin + yout) { set_error("workspace too small"); return IR_ERR_WORKSPACE; }
+  float* xs = reinterpret_cast<float*>((char*)workspace + base);
+  float* ys = reinterpret_cast<float*>((char*)workspace + base + xin);
+  cudaStream_t s = (cudaStream_t)stream;
+  int dev = 0;
+  IRB_CUDA(cudaGetDevice(&dev));
+  std::string key("D");
+  key_add(key, *cfg); key_add(key, mode); key_add(key, B); key_add(key, H); key_add(key, W); key_add(key, dev);
+  key_add(key, packed); key_add(key, workspace);
+  IRB_CUDA(cudaMemcpyAsync(xs, x, (size_t)P * cfg->in_nc * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  IRB_TRY(run_graph_cached(key, s, [&](cudaStream_t ls) {
+    return dncnn_forward(pl, (const float*)packed, xs, ys, B, H, W, workspace, base, ls);
+  }));
+  IRB_CUDA(cudaMemcpyAsync(y, ys, (size_t)P * cfg->out_nc * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  return IR_OK;
+}
+
+int ir_graph_cache_clear(void) {
+  std::lock_guard<std::mutex> lk(g_graph_mu);
+  for (auto& kv : g_graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  g_graphs.clear();
+  g_graph_lru.clear();
+  return IR_OK;
+}
+
+int ir_graph_cache_stats(long long* h_entries, long long* h_captures, long long* h_replays) {
+  std::lock_guard<std::mutex> lk(g_graph_mu);
+  if (h_entries) *h_entries = (long long)g_graphs.size();
+  if (h_captures) *h_captures = g_graph_captures;
+  if (h_replays) *h_replays = g_graph_replays;
+  return IR_OK;
 }
 
 int ir_dncnn_launch_count(const IrDncnnCfg* cfg) { return cfg ? cfg->nb : -1; }

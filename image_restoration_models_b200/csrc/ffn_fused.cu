@@ -31,6 +31,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <type_traits>
 
 namespace irb {
 
@@ -151,7 +152,11 @@ __device__ __forceinline__ void convert_unit(Bars* bars, uint32_t g, uint32_t tm
 
 // DBG != 0: timing experiments only (results are garbage): 1 no W_in reloads, 2 no xn patch reloads, 4 no depthwise taps,
 // 8 no W_out reloads
-template <int BH, int DBG>
+// CW: channel count when it is one of the shipped widths (48 / 96), else 0 (generic: runtime K loops).  With CW known the
+// MMA warp's issue loop is straight-line code: descriptors are a base plus a compile-time constant and the unit / chunk /
+// tile counters advance by compare-and-wrap.  (ncu on attn_fused.cu: ~33 instructions of descriptor and uniform-register
+// traffic per tcgen05.mma when the loop bounds are runtime values, and the issuing warp paced the kernel.)
+template <int BH, int DBG, int CW>
 __global__ void __launch_bounds__(Roles<BH>::NWARPS * 32, 1)
 ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmY, const FusedParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -263,44 +268,65 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint32_t ntl = 0;
     for (TileIter ti(p); ti.valid(); ti.next()) ++ntl;
     const uint32_t G = ntl * nunits;
+    const uint64_t adesc0 = sw128_desc(sA), wdesc0 = sw128_desc(sWin), opdesc = sw128_desc(sOP), wodesc0 = sw128_desc(sWout);
+    // MMA1 of unit g: (tile j1, unit u1) advance with it
+    uint32_t j1 = 0, u1 = 0;
     auto issue1 = [&](uint32_t g) {
-      const uint32_t j = g / nunits, u = g - j * nunits, s = g & 1u, ph = (g >> 1) & 1u, ab = j & 1u;
-      if (u == 0) mbar_wait(smem_u32(&bars->a_full[ab]), (j >> 1) & 1u);
+      const uint32_t s = g & 1u, ph = (g >> 1) & 1u, ab = j1 & 1u;
+      if (u1 == 0) mbar_wait(smem_u32(&bars->a_full[ab]), (j1 >> 1) & 1u);
       mbar_wait(smem_u32(&bars->w1_full[s]), ph);
       mbar_wait(smem_u32(&bars->d1_empty[s]), ph ^ 1u);
       tc_fence_after();
       const uint32_t d = tmem_base + s * D1_COLS;
-      for (int kb = 0; kb < p.nkb; ++kb) {
-        const uint32_t a_addr = sA + ab * p.a_bytes + (uint32_t)kb * ABOX;
-        const uint32_t w_addr = sWin + s * p.win_bytes + (uint32_t)kb * WINBOX;
-        const int ks = kb == p.nkb - 1 ? p.ks_last : 4;
-        for (int kk = 0; kk < ks; ++kk) {
-          const uint32_t acc = (kb > 0 || kk > 0) ? 1u : 0u;
-          const uint64_t bd = sw128_desc(w_addr + kk * 32);
-          umma_elect<__half>(d, sw128_desc(a_addr + kk * 32), bd, idesc1, acc);
-          umma_elect<__half>(d + 64, sw128_desc(a_addr + 64 * 128 + kk * 32), bd, idesc1, acc);
+      const uint64_t ad = adesc0 + (uint64_t)((ab * p.a_bytes) >> 4), wd = wdesc0 + (uint64_t)((s * p.win_bytes) >> 4);
+      if constexpr (CW > 0) {
+        constexpr int NKB = (CW + 63) / 64, KS_LAST = (CW - 64 * (NKB - 1)) / 16;
+#pragma unroll
+        for (int kb = 0; kb < NKB; ++kb)
+#pragma unroll
+          for (int kk = 0; kk < (kb == NKB - 1 ? KS_LAST : 4); ++kk) {
+            const uint32_t acc = (kb > 0 || kk > 0) ? 1u : 0u;
+            const uint64_t bd = wd + (uint64_t)((kb * WINBOX + kk * 32) >> 4);
+            const uint64_t a0 = ad + (uint64_t)((kb * ABOX + kk * 32) >> 4);
+            umma_elect<__half>(d, a0, bd, idesc1, acc);
+            umma_elect<__half>(d + 64, a0 + (uint64_t)((64 * 128) >> 4), bd, idesc1, acc);
+          }
+      } else {
+        for (int kb = 0; kb < p.nkb; ++kb) {
+          const int ks = kb == p.nkb - 1 ? p.ks_last : 4;
+          for (int kk = 0; kk < ks; ++kk) {
+            const uint32_t acc = (kb > 0 || kk > 0) ? 1u : 0u;
+            const uint64_t bd = wd + (uint64_t)((kb * WINBOX + kk * 32) >> 4);
+            const uint64_t a0 = ad + (uint64_t)((kb * ABOX + kk * 32) >> 4);
+            umma_elect<__half>(d, a0, bd, idesc1, acc);
+            umma_elect<__half>(d + 64, a0 + (uint64_t)((64 * 128) >> 4), bd, idesc1, acc);
+          }
         }
       }
       umma_commit_elect(smem_u32(&bars->d1_full[s]));
       umma_commit_elect(smem_u32(&bars->w1_empty[s]));
-      if (u == nunits - 1) umma_commit_elect(smem_u32(&bars->a_empty[ab]));
+      if (u1 == nunits - 1) umma_commit_elect(smem_u32(&bars->a_empty[ab]));
       __syncwarp();
+      if (++u1 == nunits) { u1 = 0; ++j1; }
     };
+    // MMA2 of chunk cc: (tile j2, chunk c2) advance with it
+    uint32_t j2 = 0, c2 = 0;
     auto issue2 = [&](uint32_t cc) {
-      const uint32_t j = cc / (uint32_t)p.nchunk, c = cc - j * (uint32_t)p.nchunk, slot = j & 1u, s = cc & 1u;
-      if (c == 0) mbar_wait(smem_u32(&bars->acc_empty[slot]), ((j >> 1) & 1u) ^ 1u);
+      const uint32_t slot = j2 & 1u, s = cc & 1u;
+      if (c2 == 0) mbar_wait(smem_u32(&bars->acc_empty[slot]), ((j2 >> 1) & 1u) ^ 1u);
       mbar_wait(smem_u32(&bars->w2_full[s]), (cc >> 1) & 1u);
       mbar_wait(smem_u32(&bars->op_ready), cc & 1u);
       tc_fence_after();
       const uint32_t d = tmem_base + D2_COL0 + slot * (uint32_t)p.acc_stride;
-      const uint32_t w_addr = sWout + s * p.wout_bytes;
+      const uint64_t wd = wodesc0 + (uint64_t)((s * p.wout_bytes) >> 4);
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk)
-        umma_elect<__half>(d, sw128_desc(sOP + kk * 32), sw128_desc(w_addr + kk * 32), idesc2, (c > 0 || kk > 0) ? 1u : 0u);
+        umma_elect<__half>(d, opdesc + (uint64_t)((kk * 32) >> 4), wd + (uint64_t)((kk * 32) >> 4), idesc2, (c2 > 0 || kk > 0) ? 1u : 0u);
       umma_commit_elect(smem_u32(&bars->op_empty));
       umma_commit_elect(smem_u32(&bars->w2_empty[s]));
-      if (c == (uint32_t)p.nchunk - 1) umma_commit_elect(smem_u32(&bars->acc_full[slot]));
+      if (c2 == (uint32_t)p.nchunk - 1) umma_commit_elect(smem_u32(&bars->acc_full[slot]));
       __syncwarp();
+      if (++c2 == (uint32_t)p.nchunk) { c2 = 0; ++j2; }
     };
     if (G > 0) issue1(0);
     if (G > 1) issue1(1);
@@ -512,24 +538,31 @@ int launch_ffn_fused(const FfnFusedArgs& a, cudaStream_t s) {
   const double pix = (double)a.B * a.H * a.W;
   // algorithmic bytes: xn read (fp16) + x read-modify-write (fp32); flops: project_in + depthwise + project_out
   ProfScope prof(TAG_FFN_FUSED, pix * (2.0 * a.C + 8.0 * a.C), pix * (4.0 * a.hp * a.C + 36.0 * a.hp + 2.0 * a.hp * a.C), s);
-  auto go = [&](auto kernel) -> int {
-    static SmemOptIn optin;      // one per instantiation of this lambda's template, i.e. per kernel
+  // one opt-in table per KERNEL: keyed by an integer tag, because every instantiation has the same function-pointer type
+  // (a table in a generic lambda would be shared by all of them and only the first kernel would ever be opted in)
+  auto go = [&](auto kernel, auto tag) -> int {
+    static SmemOptIn optin;      // one per (lambda instantiation == tag type)
+    (void)tag;
     IRB_TRY(opt_in_smem(kernel, optin));
     kernel<<<grid, Roles<4>::NWARPS * 32, smem, s>>>(tA, tY, p);
     return IR_OK;
   };
+#define IRB_GO(DBG_, CW_) go(ffn_fused_kernel<4, DBG_, CW_>, std::integral_constant<int, (DBG_) * 1000 + (CW_)>{})
 #ifdef IRB_FUSED_EXPERIMENTS
   static const int dbg = getenv("IRB_FUSED_DBG") ? atoi(getenv("IRB_FUSED_DBG")) : 0;
   switch (dbg) {
-    case 0: IRB_TRY(go(ffn_fused_kernel<4, 0>)); break;
-    case 1: IRB_TRY(go(ffn_fused_kernel<4, 1>)); break;
-    case 3: IRB_TRY(go(ffn_fused_kernel<4, 3>)); break;
-    case 4: IRB_TRY(go(ffn_fused_kernel<4, 4>)); break;
-    case 11: IRB_TRY(go(ffn_fused_kernel<4, 11>)); break;
-    default: IRB_TRY(go(ffn_fused_kernel<4, 15>)); break;
+    case 0: IRB_TRY(IRB_GO(0, 0)); break;
+    case 1: IRB_TRY(IRB_GO(1, 0)); break;
+    case 3: IRB_TRY(IRB_GO(3, 0)); break;
+    case 4: IRB_TRY(IRB_GO(4, 0)); break;
+    case 11: IRB_TRY(IRB_GO(11, 0)); break;
+    default: IRB_TRY(IRB_GO(15, 0)); break;
   }
 #else
-  IRB_TRY(go(ffn_fused_kernel<4, 0>));
+  static const bool generic = getenv("IRB_FFN_GENERIC_ISSUE") != nullptr;      // A/B switch for benchmarks
+  if (a.C == 96 && !generic) IRB_TRY(IRB_GO(0, 96));
+  else if (a.C == 48 && !generic) IRB_TRY(IRB_GO(0, 48));
+  else IRB_TRY(IRB_GO(0, 0));
 #endif
   IRB_LAUNCH_CHECK();
   return IR_OK;

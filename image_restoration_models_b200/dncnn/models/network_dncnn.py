@@ -53,8 +53,17 @@ class DnCNN(nn.Module):
         self.in_nc, self.out_nc = int(in_nc), int(out_nc)
         self._cfg = _native.IrDncnnCfg(int(in_nc), int(out_nc), int(nc), int(nb), int(has_bn))
         self._mode = "fp32"
+        self._graphs = "auto"        # CUDA-graph replay of the 17-20 launches: "auto" (inputs up to 1 Mpix), True, False
         self._packed = None
         self._workspace = None
+
+    def set_cuda_graphs(self, enabled="auto"):
+        """Replay the forward from a cached CUDA graph (ir_dncnn_forward_graph); see Restormer.set_cuda_graphs."""
+        if enabled not in ("auto", True, False):
+            raise ValueError("enabled must be 'auto', True or False")
+        self._graphs = enabled
+        self._workspace = None
+        return self
 
     def set_mode(self, mode: str):
         if mode not in _MODES:
@@ -126,14 +135,17 @@ class DnCNN(nn.Module):
             mode = _MODES[self._mode]
             pk = self._packed
             packed = pk[2] if pk is not None and pk[0] == dev and pk[1] == self._mode else self._pack(dev)
-            key = (dev, self._mode, B, H, W)
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            graph = self._graphs is True or (self._graphs == "auto" and B * H * W <= (1 << 20))
+            key = (dev, self._mode, B, H, W, stream, graph)   # scratch is per stream
             if self._workspace is None or self._workspace[0] != key:
                 self._workspace = None
-                nbytes = lib.ir_dncnn_workspace_bytes(C.byref(self._cfg), B, H, W, mode)
+                size_fn = lib.ir_dncnn_graph_workspace_bytes if graph else lib.ir_dncnn_workspace_bytes
+                nbytes = size_fn(C.byref(self._cfg), B, H, W, mode)
                 self._workspace = (key, torch.empty(nbytes, dtype=torch.uint8, device=dev))
             ws = self._workspace[1]
             y = torch.empty((B, self.out_nc, H, W), dtype=torch.float32, device=dev)
-            stream = torch.cuda.current_stream(dev).cuda_stream
-            _native.check(lib.ir_dncnn_forward(C.byref(self._cfg), packed.data_ptr(), xin.data_ptr(), y.data_ptr(),
-                                               B, H, W, ws.data_ptr(), ws.numel(), mode, stream))
+            fwd = lib.ir_dncnn_forward_graph if graph else lib.ir_dncnn_forward
+            _native.check(fwd(C.byref(self._cfg), packed.data_ptr(), xin.data_ptr(), y.data_ptr(), B, H, W, ws.data_ptr(),
+                              ws.numel(), mode, stream))
         return y

@@ -146,6 +146,7 @@ class Restormer(nn.Module):
         self._conv_bias = bool(bias)
         self._mode = "fp32"
         self._range_guard = True     # fp32 mode: fall back to fp32_strict when fp16_range_bound() nears fp16's range
+        self._graphs = "auto"        # CUDA-graph replay of the launch sequence: "auto" (small inputs), True, False
         self._native_mode = None     # the IrMode the packed weights were built for (fp32 may resolve to fp32_strict)
         self._packed = None          # (device, mode, tensor)
         self._workspace = None       # (key, tensor)
@@ -160,6 +161,21 @@ class Restormer(nn.Module):
         self._mode = mode
         self._packed = None
         return self
+
+    GRAPH_AUTO_MAX_PIXELS = 1 << 20
+
+    def set_cuda_graphs(self, enabled="auto"):
+        """Replay the forward's ~280 launches from a cached CUDA graph (ir_restormer_forward_graph).  "auto" (default): for
+        inputs of at most GRAPH_AUTO_MAX_PIXELS pixels per call -- the launch-bound regime of the reference harness, which
+        feeds one 256x256 / 512x512 tile at a time (src/utils.py:403-419).  Results are bit-identical either way."""
+        if enabled not in ("auto", True, False):
+            raise ValueError("enabled must be 'auto', True or False")
+        self._graphs = enabled
+        self._workspace = None
+        return self
+
+    def _use_graph(self, B, H, W):
+        return self._graphs is True or (self._graphs == "auto" and B * H * W <= self.GRAPH_AUTO_MAX_PIXELS)
 
     def set_range_guard(self, enabled: bool):
         """fp32 mode only: enable / disable the pack-time fp16 range guard (on by default)."""
@@ -251,13 +267,16 @@ class Restormer(nn.Module):
             packed = pk[2] if pk is not None and pk[0] == dev and pk[1] == self._mode else self._pack(dev)
             mode = self._native_mode
             stream = torch.cuda.current_stream(dev).cuda_stream
-            key = (dev, mode, B, H, W, stream)    # scratch is per stream: forwards on two streams must not share it
+            graph = self._use_graph(B, H, W)
+            key = (dev, mode, B, H, W, stream, graph)   # scratch is per stream: forwards on two streams must not share it
             if self._workspace is None or self._workspace[0] != key:
                 self._workspace = None      # release before allocating the new one
-                nbytes = lib.ir_restormer_workspace_bytes(C.byref(self._cfg), B, H, W, mode)
+                size_fn = lib.ir_restormer_graph_workspace_bytes if graph else lib.ir_restormer_workspace_bytes
+                nbytes = size_fn(C.byref(self._cfg), B, H, W, mode)
                 self._workspace = (key, torch.empty(nbytes, dtype=torch.uint8, device=dev))
             ws = self._workspace[1]
             y = torch.empty((B, self.out_channels, H, W), dtype=torch.float32, device=dev)
-            _native.check(lib.ir_restormer_forward(C.byref(self._cfg), packed.data_ptr(), x.data_ptr(), y.data_ptr(),
-                                                   B, H, W, ws.data_ptr(), ws.numel(), mode, stream))
+            fwd = lib.ir_restormer_forward_graph if graph else lib.ir_restormer_forward
+            _native.check(fwd(C.byref(self._cfg), packed.data_ptr(), x.data_ptr(), y.data_ptr(), B, H, W, ws.data_ptr(),
+                              ws.numel(), mode, stream))
         return y

@@ -93,6 +93,18 @@ size_t ir_restormer_workspace_bytes(const IrRestormerCfg* cfg, int B, int H, int
 int    ir_restormer_forward(const IrRestormerCfg* cfg, const void* packed, const float* x, float* y,
                             int B, int H, int W, void* workspace, size_t workspace_bytes, int mode,
                             void* stream);
+/* The same forward through a CUDA-graph cache: the ~280 launches of one (cfg, mode, B, H, W, packed, workspace) are captured
+ * on the second call and replayed afterwards -- the launch-bound regime of the reference harness, which calls the model
+ * once per tile with batch 1 (src/utils.py:403-419).  x and y may change from call to call (they are copied through
+ * staging slots at the end of the workspace, whose size ir_restormer_graph_workspace_bytes includes); packed and
+ * workspace identify the cached graph.  The library owns the instantiated graphs (ir_graph_cache_clear releases them;
+ * at most 32 are kept, least recently used first out).  Results are bit-identical to ir_restormer_forward. */
+size_t ir_restormer_graph_workspace_bytes(const IrRestormerCfg* cfg, int B, int H, int W, int mode);
+int    ir_restormer_forward_graph(const IrRestormerCfg* cfg, const void* packed, const float* x, float* y,
+                                  int B, int H, int W, void* workspace, size_t workspace_bytes, int mode,
+                                  void* stream);
+int    ir_graph_cache_clear(void);
+int    ir_graph_cache_stats(long long* h_entries, long long* h_captures, long long* h_replays);
 /* Number of kernel launches one ir_restormer_forward issues (for bench.py's gpu_launches). */
 int    ir_restormer_launch_count(const IrRestormerCfg* cfg);
 
@@ -106,6 +118,10 @@ size_t ir_dncnn_workspace_bytes(const IrDncnnCfg* cfg, int B, int H, int W, int 
 int    ir_dncnn_forward(const IrDncnnCfg* cfg, const void* packed, const float* x, float* y,
                         int B, int H, int W, void* workspace, size_t workspace_bytes, int mode,
                         void* stream);
+size_t ir_dncnn_graph_workspace_bytes(const IrDncnnCfg* cfg, int B, int H, int W, int mode);
+int    ir_dncnn_forward_graph(const IrDncnnCfg* cfg, const void* packed, const float* x, float* y,
+                              int B, int H, int W, void* workspace, size_t workspace_bytes, int mode,
+                              void* stream);
 int    ir_dncnn_launch_count(const IrDncnnCfg* cfg);
 
 /* ---- single-stage entry points (unit tests and ncu hit each kernel in isolation) ----

@@ -388,6 +388,38 @@ def test_guard_zones_stay_intact(task, shape, mode):
                                     ws.data_ptr(), ws_bytes - 1, native_mode, stream) == _native.IR_ERR_WORKSPACE
 
 
+def test_cuda_graph_replay_is_bit_identical_and_reused():
+    """ir_*_forward_graph: plain launches on the first call of a key, capture on the second, replay afterwards; inputs
+    change between calls (staging slots), results must equal the un-captured path bit for bit."""
+    lib = _native.lib()
+    lib.ir_graph_cache_clear()
+    kw = oracle.RESTORMER_TASKS["color_denoise"]
+    m = build_restormer(kw, 67, "fp32").set_cuda_graphs(True)
+    ref = build_restormer(kw, 67, "fp32").set_cuda_graphs(False)
+    xs = [oracle.synth_image((1, 3, 64, 80), 300 + i, 25.0).cuda() for i in range(4)]
+    for x in xs:
+        assert torch.equal(m(x), ref(x))
+    e, c, r = (C.c_longlong(), C.c_longlong(), C.c_longlong())
+    c0 = c.value
+    lib.ir_graph_cache_stats(C.byref(e), C.byref(c), C.byref(r))
+    assert e.value == 1 and r.value >= 3          # one key: call 1 plain, call 2 capture + launch, calls 3-4 replays
+    # a second shape is a second key; "auto" picks the graph path for tile-sized inputs
+    auto = build_restormer(kw, 67, "fp32")
+    assert auto._use_graph(1, 512, 512) and not auto._use_graph(8, 512, 512)
+    x2 = oracle.synth_image((2, 3, 32, 32), 310, 25.0).cuda()
+    for _ in range(3):
+        assert torch.equal(m(x2), ref(x2))
+    d = M.DnCNN(1, 1, 64, 17, "R").eval()
+    d.load_state_dict(oracle.synth_state_dict(oracle.dncnn_schema(1, 1, 64, 17, "R"), 8), strict=True)
+    d = d.cuda()
+    dx = oracle.synth_image((1, 1, 48, 56), 9, 25.0).cuda()
+    y_plain = d.set_cuda_graphs(False)(dx)
+    d.set_cuda_graphs(True)
+    for _ in range(3):
+        assert torch.equal(d(dx), y_plain)
+    assert lib.ir_graph_cache_clear() == 0
+
+
 def test_native_library_is_the_loaded_code():
     """The forward must run from the in-tree .so (no silent PyTorch path)."""
     maps = open("/proc/self/maps").read()
