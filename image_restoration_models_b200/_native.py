@@ -86,6 +86,9 @@ SIGNATURES = {
     "ir_tile_blend": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
                                 C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float,
                                 C.c_void_p]),
+    "ir_image_metrics_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "ir_image_metrics": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p,
+                                   C.c_void_p, C.c_size_t, C.c_void_p]),
     "ir_profile_begin": (C.c_int, []),
     "ir_profile_end": (C.c_int, [C.POINTER(IrKernelStat), C.c_int]),
     "ir_profile_tag_name": (C.c_char_p, [C.c_int]),

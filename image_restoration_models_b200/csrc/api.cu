@@ -485,6 +485,15 @@ int ir_tile_blend(const float* pred, const int* tile_xy, int T, int th, int tw, 
                            (cudaStream_t)stream);
 }
 
+size_t ir_image_metrics_workspace_bytes(int H, int W, int C) { return image_metrics_workspace_bytes(H, W, C); }
+
+int ir_image_metrics(const void* pred, const void* target, int dtype, int H, int W, int C, double data_range,
+                     double* out, void* workspace, size_t workspace_bytes, void* stream) {
+  IRB_REQUIRE(pred && target && out && workspace, "image_metrics: null pointer");
+  return launch_image_metrics(pred, target, dtype, H, W, C, data_range, out, workspace, workspace_bytes,
+                              (cudaStream_t)stream);
+}
+
 int ir_profile_begin(void) {
   std::lock_guard<std::mutex> lk(g_prof_mu);
   for (auto& r : g_prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }

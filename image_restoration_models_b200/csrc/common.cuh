@@ -164,6 +164,11 @@ int launch_tile_blend(const float* pred, const int* tile_xy, int T, int th, int 
                       int win_ld, int H, int W, int C, void* out, int dtype, float scale, float lo, float hi,
                       cudaStream_t s);
 
+// PSNR / SSIM of an HWC image pair (metrics.cu): out = {psnr, ssim, mse} as float64
+size_t image_metrics_workspace_bytes(int H, int W, int C);
+int launch_image_metrics(const void* pred, const void* target, int dtype, int H, int W, int C, double data_range,
+                         double* out, void* ws, size_t ws_bytes, cudaStream_t s);
+
 // weight packing (pack.cu)
 struct PackMat {
   const float* src; float* dst;

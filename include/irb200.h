@@ -176,6 +176,15 @@ int    ir_tile_blend(const float* pred_nchw_tiles, const int* tile_xy, int T, in
                      const float* window /* [.][win_ld] fp32, get_gaussian_weights */, int win_ld, int H, int W, int C,
                      void* out_img, int dtype, float scale, float lo, float hi, void* stream);
 
+/* ---- PSNR / SSIM on the device (replaces calculate_metrics, src/utils.py:134-156; scikit-image's
+ *      peak_signal_noise_ratio and structural_similarity with their defaults: 7x7 uniform window, K1 0.01, K2 0.03,
+ *      sample covariance, float64, 3-pixel border cropped, mean over channels) ----
+ * pred / target: HWC images of the same dtype (0 uint8, 1 uint16, 2 float32), C = 1 or 3, H, W >= 7.
+ * out: device float64 [3] = {psnr_dB, ssim, mse}.  workspace >= ir_image_metrics_workspace_bytes(H, W, C).        */
+size_t ir_image_metrics_workspace_bytes(int H, int W, int C);
+int    ir_image_metrics(const void* pred, const void* target, int dtype, int H, int W, int C, double data_range,
+                        double* out, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- per-kernel device timing (bench.py roofline; off by default, adds two events per launch) ----
  * ir_profile_begin() starts recording every launch the calling process issues through this library;
  * ir_profile_end() synchronises the recorded events and returns one aggregate row per kernel family. */
