@@ -327,7 +327,7 @@ void block_scratch_need(BlockScratchNeed& n, const BlockPlan& bp, int B, int H, 
   n.s_part = std::max(n.s_part, (long long)B * bp.heads * parts * ch * ch);
   n.n_part = std::max(n.n_part, (long long)B * bp.heads * parts * 2 * ch);
   n.w_eff = std::max(n.w_eff, (long long)B * bp.C * bp.kp_attn);
-  if (bp.C > 128 || bp.fuse_ffn) n.xhat = std::max(n.xhat, P * bp.C);
+  if (bp.C > 128 || bp.fuse_ffn || bp.fuse_attn) n.xhat = std::max(n.xhat, P * bp.C);
   n.es = bp.half ? 2 : 4;
 }
 
@@ -467,7 +467,15 @@ int run_block(const BlockPlan& bp, const float* packed, const float* x_in, float
     fa.w_qkv = P(bp.qkv_w); fa.dw_chunked = P(bp.qkvdw_w); fa.v = bs.qkv_dw;
     fa.s_part = bs.s_part; fa.n_part = bs.n_part; fa.parts = attn_fused_parts(B, H, W);
     fa.B = B; fa.H = H; fa.W = W; fa.C = C; fa.heads = bp.heads;
-    IRB_TRY(launch_attn_fused(fa, s));
+    static const bool attn_v1 = getenv("IRB_ATTN_FUSED_V1") != nullptr;      // A/B switch for benchmarks
+    if (attn_v1 && attn_fused_v1_supported(C, bp.heads)) {
+      IRB_TRY(launch_attn_fused_v1(fa, s));
+    } else {
+      // norm1 as an fp16 tensor (bs.xhat; the attention-output kernel overwrites it with norm2 afterwards)
+      IRB_TRY(launch_layernorm(x_in, C, bs.xhat, C, 1, (long long)B * H * W, C, ln, P(bp.ln1_w), P(bp.ln1_b), s));
+      fa.xn = bs.xhat;
+      IRB_TRY(launch_attn_fused(fa, s));
+    }
     gp.nparts = fa.parts;
     v_ptr = bs.qkv_dw; v_ld = C;
   } else if (bp.fuse_front) {
@@ -619,7 +627,8 @@ int restormer_launch_count(const RestormerPlan& pl) {
   int n = 0;
   auto blocks = [&](const std::vector<BlockPlan>& v) {
     for (const auto& bp : v) {
-      n += 8 - (bp.fuse_tail || bp.fuse_ffn ? 1 : 0) - (bp.fuse_front ? 1 : 0) - (bp.k4_xn ? 1 : 0) - (bp.fuse_attn ? 1 : 0);
+      // (the fused MDTA front replaces LN + qkv and the front kernel by a LayerNorm pass and itself)
+      n += 8 - (bp.fuse_tail || bp.fuse_ffn ? 1 : 0) - (bp.fuse_front ? 1 : 0) - (bp.k4_xn ? 1 : 0);
       // standalone LayerNorm where the contraction cannot take it as a prologue (the wide levels)
       auto ln_standalone = [&](bool tc, bool tma, int N) {
         if (!tc) return false;

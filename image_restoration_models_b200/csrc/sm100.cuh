@@ -38,6 +38,23 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// Spinning wait (no suspend-time hint, no NANOSLEEP): for roles on the critical path of a tight ping-pong.  With the hint a
+// wait that outlasts the hardware's own try_wait window falls into a sleep whose wake-up was measured at ~1 us
+// (attn_fused.cu timing experiments: the kernel got SLOWER when work was removed from the waiting role).
+__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t it = 0; !done; ++it) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (it > (1u << 26)) __trap();
+  }
+}
+
 // non-blocking probe of a phase (producer-side polling)
 __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
   uint32_t done;
