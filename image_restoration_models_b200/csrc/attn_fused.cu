@@ -22,13 +22,13 @@
 //   drops the halo patch into the MMA's SWIZZLE_128B operand boxes; the zero fill outside the image IS the depthwise conv's
 //   zero padding (the qkv conv has no bias: xn = 0 gives qkv = 0).
 //
-// One persistent CTA per SM, bound to one image (the Gram accumulates per image), 9 warps:
+// One persistent CTA per SM, bound to one image (the Gram accumulates per image), 10 warps:
 //
 //   depthwise (8 warps)   warp w owns TMEM lane quarter w & 3 (32 channels) and output columns 8 (w >> 2) .. +7 of the tile.
 //                         q / k channels: fp16 rows of the X tile ([channel][pixel], one 16-byte store per output row),
-//                         squared norms of the rounded values in a register; v channels: fp16 straight to global memory
+//                         squared norms in a register; v channels: fp16 straight to global memory
 //                         (a warp writes 64 contiguous bytes per pixel); at the end TMEM -> the CTA's partial S
-//   MMA / producer (1 warp)  once: W_qkv (fp16 operand image) into shared memory, where it stays.  Per tile: the xn patch
+//   producer + MMA (2 warps) once: W_qkv (fp16 operand image) into shared memory, where it stays.  Per tile: the xn patch
 //                         load of the tile after next, MMA1 in groups of 128 channels (A = 128 rows of W from a row offset,
 //                         B = the xn patch, N = 192) into a double-buffered accumulator, and the Gram S += q . k^T of the
 //                         PREVIOUS tile (A = the q rows, B = the k rows of the X tile)
@@ -64,8 +64,8 @@ constexpr int ABOX = AROWS * 128;              // one 64-channel box of the xn p
 constexpr int UC = 32;                         // channels per unit (one warp's TMEM lane quarter)
 
 constexpr int DW_WARPS = 8;
-constexpr int WARP_MMA = DW_WARPS;
-constexpr int NTHREADS = (WARP_MMA + 1) * 32;
+constexpr int WARP_MMA = DW_WARPS, WARP_PROD = WARP_MMA + 1;
+constexpr int NTHREADS = (WARP_PROD + 1) * 32;
 constexpr int D1_COLS = AROWS;                 // accumulator columns per group
 constexpr int ND = 2;                          // group accumulators in TMEM
 constexpr int S_COL0 = ND * D1_COLS;           // the Gram accumulator (<= 96 columns)
@@ -164,29 +164,28 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const FusedFrontParam
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
 
-  if (warp == WARP_MMA) {
-    // =============================== W_qkv once, xn patches, the MMA issue loop ===============================
-    TileIter ta(p);
-    uint32_t ja = 0;
-    auto load_a = [&]() {             // lane 0 only
-      const uint32_t buf = ja % NA, fb = smem_u32(&bars->a_full[buf]);
-      mbar_expect_tx(fb, G::A_TX);
-#pragma unroll
-      for (int kb = 0; kb < G::NKB; ++kb)
-        tma_load_4d(&tmA, fb, sA + buf * G::A_BYTES + (uint32_t)kb * ABOX, kb * 64, ta.x0() - 1, ta.y0() - 1, b);
-      ta.next();
-      ++ja;
-    };
+  if (warp == WARP_PROD) {
+    // =============================== producer: W_qkv once, the xn patches ===============================
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
-      const uint32_t fb = smem_u32(&bars->w_full);
-      mbar_expect_tx(fb, G::W_BYTES);
+      const uint32_t fw = smem_u32(&bars->w_full);
+      mbar_expect_tx(fw, G::W_BYTES);
       constexpr uint32_t CHUNK = 8192;
       for (uint32_t o = 0; o < G::W_BYTES; o += CHUNK)
-        bulk_load(sW + o, p.w_qkv + o, (G::W_BYTES - o) < CHUNK ? (G::W_BYTES - o) : CHUNK, fb);
-      for (int k = 0; k < NA && ta.valid(); ++k) load_a();            // the buffers start free
+        bulk_load(sW + o, p.w_qkv + o, (G::W_BYTES - o) < CHUNK ? (G::W_BYTES - o) : CHUNK, fw);
+      uint32_t ja = 0;
+      for (TileIter ta(p); ta.valid(); ta.next(), ++ja) {
+        const uint32_t buf = ja % NA, fb = smem_u32(&bars->a_full[buf]);
+        // the buffer is free once the last group's MMAs of the tile that used it have completed
+        mbar_wait_spin(smem_u32(&bars->a_empty[buf]), ((ja / NA) & 1u) ^ 1u);
+        mbar_expect_tx(fb, G::A_TX);
+#pragma unroll
+        for (int kb = 0; kb < G::NKB; ++kb)
+          tma_load_4d(&tmA, fb, sA + buf * G::A_BYTES + (uint32_t)kb * ABOX, kb * 64, ta.x0() - 1, ta.y0() - 1, b);
+      }
     }
-    __syncwarp();
+  } else if (warp == WARP_MMA) {
+    // =============================== the MMA issue loop ===============================
     const uint32_t idesc1 = make_idesc<__half>(AROWS);
     const uint32_t idescS = make_idesc<__half>(CW);
     const uint64_t wdesc = sw128_desc(sW), xdesc = sw128_desc(sX);
@@ -236,12 +235,6 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const FusedFrontParam
         issue_group(grp_tag, gg, j);
         ++gg;
       };
-      // the patch buffer of tile j-1 is free once its last group's MMAs have completed: refill it with tile j+1's patch
-      if (j >= 1 && lane == 0 && ta.valid()) {
-        mbar_wait_spin(smem_u32(&bars->a_empty[(j - 1) % NA]), ((j - 1) / NA) & 1u);
-        load_a();
-      }
-      __syncwarp();
       // group 0 of this tile goes out BEFORE the Gram of the previous one: its accumulator is ready when the depthwise
       // warps come back from the previous tile's last group
       one(std::integral_constant<int, 0>{});
@@ -281,7 +274,7 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const FusedFrontParam
         if (active) {
           const uint32_t taddr = tlane + sd * D1_COLS;
           if (u * UC < 2 * CW) {
-            // ---- q | k unit: row `ch` of the X tile, 8 fp16 pixels per output row; norms of the rounded values ----
+            // ---- q | k unit: row `ch` of the X tile, 8 fp16 pixels per output row; squared norms ----
             f2_t n = dwt::pack2(0.f, 0.f);
             const uint32_t xrow = sX + (uint32_t)ch * 128u + (uint32_t)(h << 4), sw = ((uint32_t)ch & 7u) << 4;
             dwt::unit(taddr, w, [&](int oy, const f2_t (&acc)[4]) {
@@ -299,11 +292,12 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const FusedFrontParam
               // pixel (oy, 8h + e) of the tile: X box oy / 4, 16-byte chunk (oy % 4) * 2 + h of the channel's 128-byte row
               sts128u((xrow + (uint32_t)(oy >> 2) * xbox + (uint32_t)((oy & 3) << 5)) ^ sw,
                       make_uint4(h2_bits(h0), h2_bits(h1), h2_bits(h2), h2_bits(h3)));
-              const float2 f0 = __half22float2(h0), f1 = __half22float2(h1), f2 = __half22float2(h2), f3 = __half22float2(h3);
-              n = dwt::fma2(dwt::pack2(f0.x, f0.y), dwt::pack2(f0.x, f0.y), n);
-              n = dwt::fma2(dwt::pack2(f1.x, f1.y), dwt::pack2(f1.x, f1.y), n);
-              n = dwt::fma2(dwt::pack2(f2.x, f2.y), dwt::pack2(f2.x, f2.y), n);
-              n = dwt::fma2(dwt::pack2(f3.x, f3.y), dwt::pack2(f3.x, f3.y), n);
+              // the norms take the unrounded fp32 values: against the fp16 operands the Gram sees, each term differs by a
+              // mean-zero rounding error of 2^-11, which averages out over the H * W pixels of the sum
+              n = dwt::fma2(dwt::pack2(a[0], a[1]), dwt::pack2(a[0], a[1]), n);
+              n = dwt::fma2(dwt::pack2(a[2], a[3]), dwt::pack2(a[2], a[3]), n);
+              n = dwt::fma2(dwt::pack2(a[4], a[5]), dwt::pack2(a[4], a[5]), n);
+              n = dwt::fma2(dwt::pack2(a[6], a[7]), dwt::pack2(a[6], a[7]), n);
             });
             float n0, n1;
             dwt::unpack2(n, n0, n1);

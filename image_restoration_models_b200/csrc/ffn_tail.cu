@@ -250,7 +250,7 @@ ffn_tail_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__
 #pragma unroll
           for (int ox = 0; ox < BW; ++ox) {
             float gx, gy;
-            unpack2(gelu_gate2(acc[0][oy][ox], acc[1][oy][ox]), gx, gy);
+            unpack2(gelu_gate2e(acc[0][oy][ox], acc[1][oy][ox]), gx, gy);
             const uint32_t row = (uint32_t)((BH * by + oy) * TW + BW * bx + ox);
             if constexpr (std::is_same<TH_, float>::value) {
               // 2 tf32 values = 8 bytes: 16-byte chunk cp/2 of the row, swizzled by the row

@@ -48,6 +48,35 @@ __device__ __forceinline__ f2_t gelu_gate2(f2_t x, f2_t gate) {
   return mul2(fma2(hx, ys, hx), gate);                   // 0.5 x (1 + erf(x / sqrt 2)) * gate
 }
 
+// gelu(x) * gate with ONE special-function instruction per element.  For a = |x| the tail of the Gaussian is
+// erfc(a / sqrt 2) = 2^(-Q(a)) with Q smooth and Q(0) = 0, and
+//     gelu(x) = max(x, 0) - |x| * 0.5 erfc(|x| / sqrt 2) = max(x, 0) - a * 2^(-(Q(a) + 1))
+// (x > 0: x - 0.5 x erfc; x <= 0: 0.5 x erfc).  Q is a degree-6 polynomial without constant term: six packed FMAs (the last
+// one adds the 1 that halves the result), one MUFU.EX2, no reciprocal, no select.  The error of the polynomial is weighted by
+// erfc itself, i.e. it vanishes where gelu is large.  Fit: scripts/fit_gelu_exp2.py (weighted minimax on [0, 6], |x| clamped
+// to 6 where erfc < 2e-9): max |gelu error| 3.1e-7 in fp32 arithmetic, the rounding level of the subtraction itself.  The A&S
+// form above costs two MUFU per element (rcp + ex2) and four more packed operations.
+__device__ __forceinline__ f2_t gelu_gate2e(f2_t x, f2_t gate) {
+  const f2_t C6 = pack2(-2.992467082811e-05f, -2.992467082811e-05f), C5 = pack2(7.398781788458e-04f, 7.398781788458e-04f),
+             C4 = pack2(-7.977474556594e-03f, -7.977474556594e-03f), C3 = pack2(5.323820251441e-02f, 5.323820251441e-02f),
+             C2 = pack2(4.589156769318e-01f, 4.589156769318e-01f), C1 = pack2(1.151147084379f, 1.151147084379f),
+             ONE = pack2(1.0f, 1.0f), NEG1 = pack2(-1.0f, -1.0f);
+  float xx, xy;
+  unpack2(x, xx, xy);
+  const f2_t a = pack2(fminf(fabsf(xx), 6.0f), fminf(fabsf(xy), 6.0f));
+  f2_t q = fma2(C6, a, C5);
+  q = fma2(q, a, C4);
+  q = fma2(q, a, C3);
+  q = fma2(q, a, C2);
+  q = fma2(q, a, C1);
+  q = fma2(q, a, ONE);                                          // Q(a) + 1
+  float qx, qy;
+  unpack2(q, qx, qy);
+  const f2_t t = mul2(a, pack2(ex2_approx(-qx), ex2_approx(-qy)));   // |x| * 0.5 erfc(|x| / sqrt 2)
+  const f2_t g = fma2(t, NEG1, pack2(fmaxf(xx, 0.f), fmaxf(xy, 0.f)));
+  return mul2(g, gate);
+}
+
 // Measured on ffn_fused.cu: alternating packed FFMA2 with pairs of scalar FFMA (to use both halves of the FP32 datapath)
 // is 6 % slower than packed-only -- FFMA with three register operands issues every second cycle, so two scalar
 // instructions cost what one FFMA2 costs and take twice the issue slots.

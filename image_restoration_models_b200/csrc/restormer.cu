@@ -531,7 +531,8 @@ int run_block(const BlockPlan& bp, const float* packed, const float* x_in, float
     FfnFusedArgs fa{};
     fa.xn = bs.xhat; fa.x = x_out; fa.w_in = P(bp.pin_w); fa.w_out = P(bp.pout_w); fa.dw_chunked = P(bp.ffdw_w);
     fa.B = B; fa.H = H; fa.W = W; fa.C = C; fa.hp = hp;
-    return launch_ffn_fused(fa, s);
+    static const bool ffn_v1 = getenv("IRB_FFN_FUSED_V1") != nullptr;         // A/B switch for benchmarks
+    return ffn_v1 && ffn_fused_v1_supported(C, hp) ? launch_ffn_fused_v1(fa, s) : launch_ffn_fused(fa, s);
   }
 
   // (6) norm2 + project_in 1x1 (:148, :89)
