@@ -10,8 +10,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("IRB200_LIB") or os.path.join(_HERE, "libirb200.so")   # override: A/B builds when tuning
 
 IR_OK, IR_ERR_INVALID, IR_ERR_WORKSPACE, IR_ERR_CUDA, IR_ERR_OOM = 0, -1, -2, -3, -4
-MODE_FP32, MODE_HALF, MODE_FP32_SIMT, MODE_FP32_STRICT = 0, 1, 2, 3
-ABI_VERSION = 2
+MODE_FP32, MODE_HALF, MODE_FP32_SIMT, MODE_FP32_STRICT, MODE_BF16 = 0, 1, 2, 3, 4
+ABI_VERSION = 3
 
 
 class IrRestormerCfg(C.Structure):

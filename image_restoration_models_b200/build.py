@@ -24,15 +24,33 @@ NVCC_FLAGS = [
 ]
 
 
+# Sources compiled a second time as the bf16 flavour (csrc/bf16_build.h is force-included: float16 -> bfloat16, namespace
+# irb -> irb_bf16, mode-taking entry points renamed; IR_MODE_BF16 of the primary build forwards to them).  Left out: kernels
+# without a 16-bit path that the flavour never calls.
+BF16_SKIP = {"probe_desc.cu", "tiling.cu", "metrics.cu"}
+BF16_FLAGS = ["-include", os.path.join(CSRC, "bf16_build.h")]
+
+
 def _sources():
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
+
+
+def _jobs(objdir, extra_flags=()):
+    """(source, object, flags) of both flavours."""
+    jobs = []
+    for src in _sources():
+        base = os.path.basename(src)
+        jobs.append((src, os.path.join(objdir, base[:-3] + ".o"), [*NVCC_FLAGS, *extra_flags]))
+        if base not in BF16_SKIP:
+            jobs.append((src, os.path.join(objdir, base[:-3] + "_bf16.o"), [*NVCC_FLAGS, *extra_flags, *BF16_FLAGS]))
+    return jobs
 
 
 def _fingerprint():
     h = hashlib.sha256()
     for root in (CSRC, os.path.join(os.path.dirname(HERE), "include")):
         for f in sorted(os.listdir(root)):
-            if f.endswith((".cu", ".cuh", ".h")):
+            if f.endswith((".cu", ".cuh", ".h")):  # incl. bf16_build.h
                 with open(os.path.join(root, f), "rb") as fh:
                     h.update(f.encode())
                     h.update(fh.read())
@@ -53,9 +71,8 @@ def build_variant(out_path: str, extra_flags, objdir: str) -> str:
     nvcc = find_nvcc()
     os.makedirs(objdir, exist_ok=True)
     procs, objs = [], []
-    for src in _sources():
-        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
-        procs.append((src, subprocess.Popen([nvcc, *NVCC_FLAGS, *extra_flags, "-c", src, "-o", obj],
+    for src, obj, flags in _jobs(objdir, extra_flags):
+        procs.append((src, subprocess.Popen([nvcc, *flags, "-c", src, "-o", obj],
                                             stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     for src, p in procs:
@@ -80,9 +97,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
     procs = []
-    for src in _sources():
-        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-c", src, "-o", obj]
+    for src, obj, flags in _jobs(objdir):
+        cmd = [nvcc, *flags, "-c", src, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

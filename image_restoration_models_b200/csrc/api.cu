@@ -11,46 +11,50 @@
 
 namespace irb {
 
+#ifndef IRB_BF16_BUILD
 int probe_shifted_descriptor(const float* a, const float* w, float* d, int shift, int base_off, cudaStream_t s);
+#endif
 
+// ---- process state shared by the two flavours of the library (fp16 = primary build, bf16 = second compilation of every
+// source, bf16_build.h): the last-error string and the launch profiler live in the primary build; the bf16 flavour reaches
+// them through these C-linkage trampolines (hidden: they are not part of the ABI)
+extern "C" {
+void irb200_shared_set_error(const char* msg);
+int irb200_shared_prof_open(int tag, double bytes, double flops, void* stream);
+void irb200_shared_prof_close(int idx, void* stream);
+int irb200_shared_prof_active(void);
+}
+
+#ifndef IRB_BF16_BUILD
 static thread_local std::string g_err;
+struct ProfRec { int tag; double bytes, flops; cudaEvent_t e0, e1; };
+static std::mutex g_prof_mu;
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+#endif
 
-void set_error(const std::string& msg) { g_err = msg; }
+void set_error(const std::string& msg) { irb200_shared_set_error(msg.c_str()); }
 
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
   char buf[512];
   snprintf(buf, sizeof(buf), "CUDA error: %s (%s) at %s:%d [%s]", cudaGetErrorString(e), cudaGetErrorName(e), file,
            line, what);
-  g_err = buf;
-  if (e == cudaErrorMemoryAllocation) { g_err = std::string("CUDA out of memory: ") + buf; return IR_ERR_OOM; }
+  if (e == cudaErrorMemoryAllocation) { set_error(std::string("CUDA out of memory: ") + buf); return IR_ERR_OOM; }
+  set_error(buf);
   return IR_ERR_CUDA;
 }
 
 // ---- per-launch timing -------------------------------------------------------------------------
-struct ProfRec { int tag; double bytes, flops; cudaEvent_t e0, e1; };
-static std::mutex g_prof_mu;
-static bool g_prof_on = false;
-static std::vector<ProfRec> g_prof;
+ProfScope::ProfScope(int tag, double bytes, double flops, cudaStream_t s)
+    : idx(irb200_shared_prof_open(tag, bytes, flops, (void*)s)), stream(s) {}
+ProfScope::~ProfScope() { if (idx >= 0) irb200_shared_prof_close(idx, (void*)stream); }
 
-ProfScope::ProfScope(int tag, double bytes, double flops, cudaStream_t s) : idx(-1), stream(s) {
-  if (!g_prof_on) return;
-  std::lock_guard<std::mutex> lk(g_prof_mu);
-  ProfRec r{tag, bytes, flops, nullptr, nullptr};
-  if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return;
-  cudaEventRecord(r.e0, s);
-  g_prof.push_back(r);
-  idx = (int)g_prof.size() - 1;
-}
-ProfScope::~ProfScope() {
-  if (idx < 0) return;
-  std::lock_guard<std::mutex> lk(g_prof_mu);
-  if (idx < (int)g_prof.size()) cudaEventRecord(g_prof[idx].e1, stream);
-}
-
+#ifndef IRB_BF16_BUILD
 static const char* kTagNames[TAG_COUNT] = {
     "other", "ln_qkv_1x1", "dwconv3x3_qkv", "mdta_gram", "softmax_fold", "attn_out_1x1", "ln_project_in_1x1",
     "dwconv3x3_gelu_gate", "ffn_project_out_1x1", "conv3x3", "reduce_chan_1x1", "concat_copy", "layernorm",
     "dwconv_gate_project_out", "dwconv_qkv_gram", "gdfn_fused", "mdta_fused_front"};
+#endif
 
 // ---- CUDA-graph cache of whole forwards ----------------------------------------------------------
 // The reference harness calls the model once per 256x256 / 512x512 tile with batch 1 (src/utils.py:403-419): ~280 launches of
@@ -82,7 +86,7 @@ template <typename F>
 static int run_graph_cached(const std::string& key, cudaStream_t s, F&& launch_all) {
   cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
   IRB_CUDA(cudaStreamIsCapturing(s, &cs));
-  if (g_prof_on || cs != cudaStreamCaptureStatusNone) return launch_all(s);  // profiling / caller-side capture: plain launches
+  if (irb200_shared_prof_active() || cs != cudaStreamCaptureStatusNone) return launch_all(s);  // profiling / caller-side capture: plain launches
   std::unique_lock<std::mutex> lk(g_graph_mu);
   auto it = g_graphs.find(key);
   if (it == g_graphs.end()) {                 // first sight of this key: plain launches, remember it
@@ -122,6 +126,7 @@ static int run_graph_cached(const std::string& key, cudaStream_t s, F&& launch_a
 static size_t stage_bytes(long long elems) { return align_up((size_t)elems * sizeof(float), 256); }
 
 static int check_mode(int mode) {
+  // (IR_MODE_BF16 never arrives here: the primary build's entry points forward it to the bf16 flavour as IR_MODE_HALF)
   IRB_REQUIRE(mode == IR_MODE_FP32 || mode == IR_MODE_HALF || mode == IR_MODE_FP32_SIMT || mode == IR_MODE_FP32_STRICT,
               "mode: unknown IrMode");
   return IR_OK;
@@ -133,12 +138,55 @@ static int engine_of(int mode) { return engine_of_mode(mode); }
 using namespace irb;
 
 extern "C" {
+#ifndef IRB_BF16_BUILD
+// ---- shared-state trampolines (hidden) -----------------------------------------------------------
+void irb200_shared_set_error(const char* msg) { g_err = msg ? msg : ""; }
+int irb200_shared_prof_open(int tag, double bytes, double flops, void* stream) {
+  if (!g_prof_on) return -1;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  ProfRec r{tag, bytes, flops, nullptr, nullptr};
+  if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return -1;
+  cudaEventRecord(r.e0, (cudaStream_t)stream);
+  g_prof.push_back(r);
+  return (int)g_prof.size() - 1;
+}
+int irb200_shared_prof_active(void) { return g_prof_on ? 1 : 0; }
+void irb200_shared_prof_close(int idx, void* stream) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (idx >= 0 && idx < (int)g_prof.size()) cudaEventRecord(g_prof[idx].e1, (cudaStream_t)stream);
+}
+
+// ---- the bf16 flavour of the mode-taking entry points (second compilation of this file, bf16_build.h) ----
+size_t ir_restormer_packed_bytes__bf16(const IrRestormerCfg*, int);
+int ir_restormer_pack_weights__bf16(const IrRestormerCfg*, const float* const*, int, void*, size_t, int, void*);
+size_t ir_restormer_workspace_bytes__bf16(const IrRestormerCfg*, int, int, int, int);
+int ir_restormer_forward__bf16(const IrRestormerCfg*, const void*, const float*, float*, int, int, int, void*, size_t, int, void*);
+size_t ir_restormer_graph_workspace_bytes__bf16(const IrRestormerCfg*, int, int, int, int);
+int ir_restormer_forward_graph__bf16(const IrRestormerCfg*, const void*, const float*, float*, int, int, int, void*, size_t, int, void*);
+size_t ir_dncnn_packed_bytes__bf16(const IrDncnnCfg*, int);
+int ir_dncnn_pack_weights__bf16(const IrDncnnCfg*, const float* const*, int, void*, size_t, int, void*);
+size_t ir_dncnn_workspace_bytes__bf16(const IrDncnnCfg*, int, int, int, int);
+int ir_dncnn_forward__bf16(const IrDncnnCfg*, const void*, const float*, float*, int, int, int, void*, size_t, int, void*);
+size_t ir_dncnn_graph_workspace_bytes__bf16(const IrDncnnCfg*, int, int, int, int);
+int ir_dncnn_forward_graph__bf16(const IrDncnnCfg*, const void*, const float*, float*, int, int, int, void*, size_t, int, void*);
+size_t ir_block_workspace_bytes__bf16(int, int, double, int, int, int, int);
+size_t ir_block_packed_bytes__bf16(int, int, double, int, int, int);
+int ir_block_pack_weights__bf16(int, int, double, int, int, const float* const*, int, void*, size_t, int, void*);
+int ir_block_forward__bf16(int, int, double, int, int, const void*, float*, int, int, int, void*, size_t, int, void*);
+int ir_graph_cache_clear__bf16(void);
+int ir_graph_cache_stats__bf16(long long*, long long*, long long*);
+// IR_MODE_BF16 is the half mode of the bf16 flavour
+#define IRB_FWD_BF16(fn, ...) if (mode == IR_MODE_BF16) return fn##__bf16(__VA_ARGS__)
 #pragma GCC visibility push(default)
 
 int ir_abi_version(void) { return IRB200_ABI_VERSION; }
 const char* ir_last_error(void) { return g_err.c_str(); }
+#else
+#define IRB_FWD_BF16(fn, ...) (void)0
+#endif
 
 // ------------------------------------------------------------------------------------------ Restormer
+#ifndef IRB_BF16_BUILD
 int ir_restormer_param_count(const IrRestormerCfg* cfg) {
   if (!cfg) { set_error("invalid argument: null cfg"); return -1; }
   RestormerPlan pl;
@@ -155,8 +203,10 @@ long long ir_restormer_param_numel(const IrRestormerCfg* cfg, int index) {
   set_error("invalid argument: parameter index out of range");
   return -1;
 }
+#endif
 
 size_t ir_restormer_packed_bytes(const IrRestormerCfg* cfg, int mode) {
+  IRB_FWD_BF16(ir_restormer_packed_bytes, cfg, IR_MODE_HALF);
   if (!cfg || check_mode(mode) != IR_OK) return 0;
   RestormerPlan pl;
   if (build_restormer_plan(pl, *cfg, engine_of(mode)) != IR_OK) return 0;
@@ -165,6 +215,7 @@ size_t ir_restormer_packed_bytes(const IrRestormerCfg* cfg, int mode) {
 
 int ir_restormer_pack_weights(const IrRestormerCfg* cfg, const float* const* h_params, int n_params, void* packed,
                               size_t packed_bytes, int mode, void* stream) {
+  IRB_FWD_BF16(ir_restormer_pack_weights, cfg, h_params, n_params, packed, packed_bytes, IR_MODE_HALF, stream);
   IRB_REQUIRE(cfg && h_params && packed, "pack: null argument");
   IRB_TRY(check_mode(mode));
   RestormerPlan pl;
@@ -176,6 +227,7 @@ int ir_restormer_pack_weights(const IrRestormerCfg* cfg, const float* const* h_p
 }
 
 size_t ir_restormer_workspace_bytes(const IrRestormerCfg* cfg, int B, int H, int W, int mode) {
+  IRB_FWD_BF16(ir_restormer_workspace_bytes, cfg, B, H, W, IR_MODE_HALF);
   if (!cfg || check_mode(mode) != IR_OK || B <= 0 || H <= 0 || W <= 0) return 0;
   RestormerPlan pl;
   if (build_restormer_plan(pl, *cfg, engine_of(mode)) != IR_OK) return 0;
@@ -184,6 +236,7 @@ size_t ir_restormer_workspace_bytes(const IrRestormerCfg* cfg, int B, int H, int
 
 int ir_restormer_forward(const IrRestormerCfg* cfg, const void* packed, const float* x, float* y, int B, int H, int W,
                          void* workspace, size_t workspace_bytes, int mode, void* stream) {
+  IRB_FWD_BF16(ir_restormer_forward, cfg, packed, x, y, B, H, W, workspace, workspace_bytes, IR_MODE_HALF, stream);
   IRB_REQUIRE(cfg && packed && x && y && workspace, "forward: null argument");
   IRB_TRY(check_mode(mode));
   RestormerPlan pl;
@@ -192,6 +245,7 @@ int ir_restormer_forward(const IrRestormerCfg* cfg, const void* packed, const fl
 }
 
 size_t ir_restormer_graph_workspace_bytes(const IrRestormerCfg* cfg, int B, int H, int W, int mode) {
+  IRB_FWD_BF16(ir_restormer_graph_workspace_bytes, cfg, B, H, W, IR_MODE_HALF);
   const size_t base = ir_restormer_workspace_bytes(cfg, B, H, W, mode);
   if (base == 0) return 0;
   const long long P = (long long)B * H * W;
@@ -200,6 +254,7 @@ size_t ir_restormer_graph_workspace_bytes(const IrRestormerCfg* cfg, int B, int 
 
 int ir_restormer_forward_graph(const IrRestormerCfg* cfg, const void* packed, const float* x, float* y, int B, int H, int W,
                                void* workspace, size_t workspace_bytes, int mode, void* stream) {
+  IRB_FWD_BF16(ir_restormer_forward_graph, cfg, packed, x, y, B, H, W, workspace, workspace_bytes, IR_MODE_HALF, stream);
   IRB_REQUIRE(cfg && packed && x && y && workspace, "forward: null argument");
   IRB_TRY(check_mode(mode));
   IRB_REQUIRE(B > 0 && H > 0 && W > 0, "restormer: empty input");
@@ -225,14 +280,17 @@ int ir_restormer_forward_graph(const IrRestormerCfg* cfg, const void* packed, co
   return IR_OK;
 }
 
+#ifndef IRB_BF16_BUILD
 int ir_restormer_launch_count(const IrRestormerCfg* cfg) {
   if (!cfg) return -1;
   RestormerPlan pl;
   if (build_restormer_plan(pl, *cfg, ENGINE_TC) != IR_OK) return -1;
   return restormer_launch_count(pl);
 }
+#endif
 
 // ------------------------------------------------------------------------------------------ DnCNN
+#ifndef IRB_BF16_BUILD
 int ir_dncnn_param_count(const IrDncnnCfg* cfg) {
   if (!cfg) { set_error("invalid argument: null cfg"); return -1; }
   DncnnPlan pl;
@@ -246,8 +304,10 @@ long long ir_dncnn_param_numel(const IrDncnnCfg* cfg, int index) {
   if (build_dncnn_plan(pl, *cfg, ENGINE_TC) != IR_OK) return -1;
   return dncnn_param_numel(pl, index);
 }
+#endif
 
 size_t ir_dncnn_packed_bytes(const IrDncnnCfg* cfg, int mode) {
+  IRB_FWD_BF16(ir_dncnn_packed_bytes, cfg, IR_MODE_HALF);
   if (!cfg || check_mode(mode) != IR_OK) return 0;
   DncnnPlan pl;
   if (build_dncnn_plan(pl, *cfg, engine_of(mode)) != IR_OK) return 0;
@@ -256,6 +316,7 @@ size_t ir_dncnn_packed_bytes(const IrDncnnCfg* cfg, int mode) {
 
 int ir_dncnn_pack_weights(const IrDncnnCfg* cfg, const float* const* h_params, int n_params, void* packed,
                           size_t packed_bytes, int mode, void* stream) {
+  IRB_FWD_BF16(ir_dncnn_pack_weights, cfg, h_params, n_params, packed, packed_bytes, IR_MODE_HALF, stream);
   IRB_REQUIRE(cfg && h_params && packed, "pack: null argument");
   IRB_TRY(check_mode(mode));
   DncnnPlan pl;
@@ -267,6 +328,7 @@ int ir_dncnn_pack_weights(const IrDncnnCfg* cfg, const float* const* h_params, i
 }
 
 size_t ir_dncnn_workspace_bytes(const IrDncnnCfg* cfg, int B, int H, int W, int mode) {
+  IRB_FWD_BF16(ir_dncnn_workspace_bytes, cfg, B, H, W, IR_MODE_HALF);
   if (!cfg || check_mode(mode) != IR_OK || B <= 0 || H <= 0 || W <= 0) return 0;
   DncnnPlan pl;
   if (build_dncnn_plan(pl, *cfg, engine_of(mode)) != IR_OK) return 0;
@@ -275,6 +337,7 @@ size_t ir_dncnn_workspace_bytes(const IrDncnnCfg* cfg, int B, int H, int W, int 
 
 int ir_dncnn_forward(const IrDncnnCfg* cfg, const void* packed, const float* x, float* y, int B, int H, int W,
                      void* workspace, size_t workspace_bytes, int mode, void* stream) {
+  IRB_FWD_BF16(ir_dncnn_forward, cfg, packed, x, y, B, H, W, workspace, workspace_bytes, IR_MODE_HALF, stream);
   IRB_REQUIRE(cfg && packed && x && y && workspace, "forward: null argument");
   IRB_TRY(check_mode(mode));
   DncnnPlan pl;
@@ -283,6 +346,7 @@ int ir_dncnn_forward(const IrDncnnCfg* cfg, const void* packed, const float* x, 
 }
 
 size_t ir_dncnn_graph_workspace_bytes(const IrDncnnCfg* cfg, int B, int H, int W, int mode) {
+  IRB_FWD_BF16(ir_dncnn_graph_workspace_bytes, cfg, B, H, W, IR_MODE_HALF);
   const size_t base = ir_dncnn_workspace_bytes(cfg, B, H, W, mode);
   if (base == 0) return 0;
   const long long P = (long long)B * H * W;
@@ -291,6 +355,7 @@ size_t ir_dncnn_graph_workspace_bytes(const IrDncnnCfg* cfg, int B, int H, int W
 
 int ir_dncnn_forward_graph(const IrDncnnCfg* cfg, const void* packed, const float* x, float* y, int B, int H, int W,
                            void* workspace, size_t workspace_bytes, int mode, void* stream) {
+  IRB_FWD_BF16(ir_dncnn_forward_graph, cfg, packed, x, y, B, H, W, workspace, workspace_bytes, IR_MODE_HALF, stream);
   IRB_REQUIRE(cfg && packed && x && y && workspace, "forward: null argument");
   IRB_TRY(check_mode(mode));
   IRB_REQUIRE(B > 0 && H > 0 && W > 0, "dncnn: empty input");
@@ -317,6 +382,9 @@ int ir_dncnn_forward_graph(const IrDncnnCfg* cfg, const void* packed, const floa
 }
 
 int ir_graph_cache_clear(void) {
+#ifndef IRB_BF16_BUILD
+  ir_graph_cache_clear__bf16();                            // each flavour keeps its own cache
+#endif
   std::lock_guard<std::mutex> lk(g_graph_mu);
   for (auto& kv : g_graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   g_graphs.clear();
@@ -325,17 +393,24 @@ int ir_graph_cache_clear(void) {
 }
 
 int ir_graph_cache_stats(long long* h_entries, long long* h_captures, long long* h_replays) {
+  long long e2 = 0, c2 = 0, r2 = 0;
+#ifndef IRB_BF16_BUILD
+  ir_graph_cache_stats__bf16(&e2, &c2, &r2);
+#endif
   std::lock_guard<std::mutex> lk(g_graph_mu);
-  if (h_entries) *h_entries = (long long)g_graphs.size();
-  if (h_captures) *h_captures = g_graph_captures;
-  if (h_replays) *h_replays = g_graph_replays;
+  if (h_entries) *h_entries = (long long)g_graphs.size() + e2;
+  if (h_captures) *h_captures = g_graph_captures + c2;
+  if (h_replays) *h_replays = g_graph_replays + r2;
   return IR_OK;
 }
 
+#ifndef IRB_BF16_BUILD
 int ir_dncnn_launch_count(const IrDncnnCfg* cfg) { return cfg ? cfg->nb : -1; }
+#endif
 
 // ------------------------------------------------------------------------------------------ single block
 size_t ir_block_workspace_bytes(int C, int heads, double ffn, int B, int H, int W, int mode) {
+  IRB_FWD_BF16(ir_block_workspace_bytes, C, heads, ffn, B, H, W, IR_MODE_HALF);
   if (check_mode(mode) != IR_OK || B <= 0 || H <= 0 || W <= 0) return 0;
   BlockPlan bp; std::vector<PackOp> ops; long long pf;
   if (build_block_plan(bp, ops, pf, C, heads, ffn, 0, 0, engine_of(mode)) != IR_OK) return 0;
@@ -343,6 +418,7 @@ size_t ir_block_workspace_bytes(int C, int heads, double ffn, int B, int H, int 
 }
 
 size_t ir_block_packed_bytes(int C, int heads, double ffn, int bias, int ln_with_bias, int mode) {
+  IRB_FWD_BF16(ir_block_packed_bytes, C, heads, ffn, bias, ln_with_bias, IR_MODE_HALF);
   if (check_mode(mode) != IR_OK) return 0;
   BlockPlan bp; std::vector<PackOp> ops; long long pf;
   if (build_block_plan(bp, ops, pf, C, heads, ffn, bias, ln_with_bias, engine_of(mode)) != IR_OK) return 0;
@@ -351,6 +427,7 @@ size_t ir_block_packed_bytes(int C, int heads, double ffn, int bias, int ln_with
 
 int ir_block_pack_weights(int C, int heads, double ffn, int bias, int ln_with_bias, const float* const* h_params,
                           int n_params, void* packed, size_t packed_bytes, int mode, void* stream) {
+  IRB_FWD_BF16(ir_block_pack_weights, C, heads, ffn, bias, ln_with_bias, h_params, n_params, packed, packed_bytes, IR_MODE_HALF, stream);
   IRB_REQUIRE(h_params && packed, "pack: null argument");
   IRB_TRY(check_mode(mode));
   BlockPlan bp; std::vector<PackOp> ops; long long pf;
@@ -363,6 +440,7 @@ int ir_block_pack_weights(int C, int heads, double ffn, int bias, int ln_with_bi
 
 int ir_block_forward(int C, int heads, double ffn, int bias, int ln_with_bias, const void* packed, float* x_nhwc, int B,
                      int H, int W, void* workspace, size_t workspace_bytes, int mode, void* stream) {
+  IRB_FWD_BF16(ir_block_forward, C, heads, ffn, bias, ln_with_bias, packed, x_nhwc, B, H, W, workspace, workspace_bytes, IR_MODE_HALF, stream);
   IRB_REQUIRE(packed && x_nhwc && workspace, "forward: null argument");
   IRB_TRY(check_mode(mode));
   BlockPlan bp; std::vector<PackOp> ops; long long pf;
@@ -371,6 +449,7 @@ int ir_block_forward(int C, int heads, double ffn, int bias, int ln_with_bias, c
                        (cudaStream_t)stream);
 }
 
+#ifndef IRB_BF16_BUILD
 int ir_nchw_to_nhwc(const float* src, float* dst, int B, int C, int H, int W, void* stream) {
   IRB_REQUIRE(src && dst && B > 0 && C > 0 && H > 0 && W > 0, "layout: bad argument");
   return launch_nchw_to_nhwc(src, dst, B, C, H, W, (cudaStream_t)stream);
@@ -535,4 +614,5 @@ int ir_profile_end(IrKernelStat* h_out, int max_rows) {
 const char* ir_profile_tag_name(int tag) { return (tag >= 0 && tag < TAG_COUNT) ? kTagNames[tag] : "invalid"; }
 
 #pragma GCC visibility pop
+#endif
 }  // extern "C"

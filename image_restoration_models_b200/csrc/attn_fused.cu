@@ -5,7 +5,7 @@
 //     S[b]   += q . k^T over the pixels, |q_i|^2, |k_j|^2     (Gram + the norms F.normalize needs :121-124)
 //     v      -> HBM (fp16)                                    (the only tensor written)
 //
-// As in the first version (attn_fused_v1.cu) the 1x1 contraction is recomputed per 8 x 16 pixel tile over the (8+2) x (16+2)
+// As in the first version (git history: attn_fused.cu before the TMEM-direct rewrite) the 1x1 contraction is recomputed per 8 x 16 pixel tile over the (8+2) x (16+2)
 // halo the depthwise conv needs and the 3C-wide qkv tensor never exists in HBM.  What changed:
 //
 // * the orientation of that contraction: D^T[channel][patch pixel] = W_qkv . xn_patch^T -- the WEIGHTS are the MMA's A

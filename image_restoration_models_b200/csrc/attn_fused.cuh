@@ -1,15 +1,11 @@
-// Whole MDTA front (attn_fused.cu): LayerNorm + qkv 1x1 + depthwise 3x3 + q.k^T Gram partials + squared norms + v store.
+// Whole MDTA front (attn_fused.cu) behind norm1: qkv 1x1 + depthwise 3x3 + q.k^T Gram partials + squared norms + v store.
 #pragma once
 #include "common.cuh"
 
 namespace irb {
 
 struct AttnFusedArgs {
-  const void* xn;          // [B*H*W][C] fp16: norm1(x) (second version; the first normalises x itself)
-  const float* x;          // [B*H*W][C] fp32 residual stream (read only; first version)
-  const float* ln_w;       // norm1 weight [C]
-  const float* ln_b;       // norm1 bias [C] (WithBias) or nullptr
-  int ln_mode;             // LN_BIASFREE / LN_WITHBIAS
+  const void* xn;          // [B*H*W][C] fp16: norm1(x)
   const void* w_qkv;       // qkv 1x1, fp16 SWIZZLE_128B operand image (PackMat fmt 4): [Kpad/64][attn_fused_wrows(C)][128 B]
   const float* dw_chunked; // taps [ceil(3C/32)][9][32] (launch_pack_dw_chunked with one set)
   void* v;                 // [B*H*W][C] fp16: depthwise-convolved v
@@ -23,8 +19,5 @@ bool attn_fused_supported(int C, int heads);
 int  attn_fused_wrows(int C);                 // rows of the packed W_qkv image (3C rounded up to whole 32-channel units)
 int  attn_fused_parts(int B, int H, int W);
 int  launch_attn_fused(const AttnFusedArgs& a, cudaStream_t s);
-// first version (qkv patch through shared memory as fp16; kept for A/B timing, IRB_ATTN_FUSED_V1=1)
-bool attn_fused_v1_supported(int C, int heads);
-int  launch_attn_fused_v1(const AttnFusedArgs& a, cudaStream_t s);
 
 }  // namespace irb

@@ -41,7 +41,11 @@ __host__ __device__ static inline int cdiv(int a, int b) { return (a + b - 1) / 
 // through this; see IR_MODE_FP32_STRICT / the Python range guard for models that need more than fp16's 5 exponent bits.
 __device__ __forceinline__ __half2 f2h2_sat(float lo, float hi) {
   uint32_t r;
+#ifdef IRB_BF16_BUILD
+  asm("cvt.rn.satfinite.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+#else
   asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+#endif
   return *reinterpret_cast<__half2*>(&r);
 }
 #endif

@@ -3,7 +3,7 @@
 //
 //     x[pixel, :] += W_out . ( gelu(dw3x3(W_in . xn)[pixel, 0:hp]) * dw3x3(W_in . xn)[pixel, hp:2hp] )
 //
-// xn = LayerNorm(x) (norm2) arrives as an fp16 tensor.  As in the first version (ffn_fused_v1.cu) project_in is recomputed per
+// xn = LayerNorm(x) (norm2) arrives as an fp16 tensor.  As in the first version (git history) project_in is recomputed per
 // 8 x 16 pixel tile over the (8+2) x (16+2) halo the depthwise conv needs and the 2*hp-wide hidden tensor never exists in
 // HBM.  What changed is the orientation of project_in: D^T[hidden channel][patch pixel] = W_in . xn_patch^T -- 128 rows of
 // W_in are the MMA's A operand (128 TMEM lanes), the fp16 xn patch the B operand (N = 192 >= 180 patch pixels = TMEM

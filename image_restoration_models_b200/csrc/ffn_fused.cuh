@@ -15,8 +15,5 @@ struct FfnFusedArgs {
 
 bool ffn_fused_supported(int C, int hp);
 int  launch_ffn_fused(const FfnFusedArgs& a, cudaStream_t s);
-// first version (hidden patch through shared memory as fp16; kept for A/B timing, IRB_FFN_FUSED_V1=1)
-bool ffn_fused_v1_supported(int C, int hp);
-int  launch_ffn_fused_v1(const FfnFusedArgs& a, cudaStream_t s);
 
 }  // namespace irb

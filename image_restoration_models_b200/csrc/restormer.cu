@@ -463,19 +463,13 @@ int run_block(const BlockPlan& bp, const float* packed, const float* x_in, float
     // (1+2+3) norm1 + qkv 1x1 + depthwise 3x3 + q.k^T Gram partials + squared norms in one kernel; only v (fp16) is
     // written (:147, :114-115, :121-124)
     AttnFusedArgs fa{};
-    fa.x = x_in; fa.ln_w = P(bp.ln1_w); fa.ln_b = P(bp.ln1_b); fa.ln_mode = ln;
     fa.w_qkv = P(bp.qkv_w); fa.dw_chunked = P(bp.qkvdw_w); fa.v = bs.qkv_dw;
     fa.s_part = bs.s_part; fa.n_part = bs.n_part; fa.parts = attn_fused_parts(B, H, W);
     fa.B = B; fa.H = H; fa.W = W; fa.C = C; fa.heads = bp.heads;
-    static const bool attn_v1 = getenv("IRB_ATTN_FUSED_V1") != nullptr;      // A/B switch for benchmarks
-    if (attn_v1 && attn_fused_v1_supported(C, bp.heads)) {
-      IRB_TRY(launch_attn_fused_v1(fa, s));
-    } else {
-      // norm1 as an fp16 tensor (bs.xhat; the attention-output kernel overwrites it with norm2 afterwards)
-      IRB_TRY(launch_layernorm(x_in, C, bs.xhat, C, 1, (long long)B * H * W, C, ln, P(bp.ln1_w), P(bp.ln1_b), s));
-      fa.xn = bs.xhat;
-      IRB_TRY(launch_attn_fused(fa, s));
-    }
+    // norm1 as an fp16 tensor (bs.xhat; the attention-output kernel overwrites it with norm2 afterwards)
+    IRB_TRY(launch_layernorm(x_in, C, bs.xhat, C, 1, (long long)B * H * W, C, ln, P(bp.ln1_w), P(bp.ln1_b), s));
+    fa.xn = bs.xhat;
+    IRB_TRY(launch_attn_fused(fa, s));
     gp.nparts = fa.parts;
     v_ptr = bs.qkv_dw; v_ld = C;
   } else if (bp.fuse_front) {
@@ -531,8 +525,7 @@ int run_block(const BlockPlan& bp, const float* packed, const float* x_in, float
     FfnFusedArgs fa{};
     fa.xn = bs.xhat; fa.x = x_out; fa.w_in = P(bp.pin_w); fa.w_out = P(bp.pout_w); fa.dw_chunked = P(bp.ffdw_w);
     fa.B = B; fa.H = H; fa.W = W; fa.C = C; fa.hp = hp;
-    static const bool ffn_v1 = getenv("IRB_FFN_FUSED_V1") != nullptr;         // A/B switch for benchmarks
-    return ffn_v1 && ffn_fused_v1_supported(C, hp) ? launch_ffn_fused_v1(fa, s) : launch_ffn_fused(fa, s);
+    return launch_ffn_fused(fa, s);
   }
 
   // (6) norm2 + project_in 1x1 (:148, :89)

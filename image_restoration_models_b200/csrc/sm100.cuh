@@ -127,7 +127,11 @@ __device__ __forceinline__ uint64_t sw128_desc(uint32_t addr) {
 
 template <typename TOp>
 __device__ __forceinline__ uint32_t make_idesc(int n) {
+#ifdef IRB_BF16_BUILD
+  const uint32_t fmt = sizeof(TOp) == 4 ? 2u : 1u;      // TF32 = 2, BF16 = 1; accumulator F32
+#else
   const uint32_t fmt = sizeof(TOp) == 4 ? 2u : 0u;      // TF32 = 2, F16 = 0; accumulator F32
+#endif
   return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 

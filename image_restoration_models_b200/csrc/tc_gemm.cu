@@ -88,7 +88,11 @@ template <typename TOp>
 __device__ __forceinline__ uint32_t make_idesc(int n) {
   // c_format F32 (bits 4-5 = 1); a/b format at bits 7-9 / 10-12: TF32 = 2, F16 = 0; both K-major;
   // N>>3 at bit 17, M>>4 at bit 24
-  const uint32_t fmt = sizeof(TOp) == 4 ? 2u : 0u;
+#ifdef IRB_BF16_BUILD
+  const uint32_t fmt = sizeof(TOp) == 4 ? 2u : 1u;      // TF32 = 2, BF16 = 1; accumulator F32
+#else
+  const uint32_t fmt = sizeof(TOp) == 4 ? 2u : 0u;      // TF32 = 2, F16 = 0; accumulator F32
+#endif
   return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
 }
 

@@ -17,7 +17,8 @@ import torch.nn as nn
 from ... import _native
 from ..._params import ConvParams, Holder, ordered_tensors
 
-_MODES = {"fp32": _native.MODE_FP32, "half": _native.MODE_HALF, "fp32_simt": _native.MODE_FP32_SIMT}
+_MODES = {"fp32": _native.MODE_FP32, "half": _native.MODE_HALF, "fp32_simt": _native.MODE_FP32_SIMT,
+          "bf16": _native.MODE_BF16}
 
 
 class _BatchNormParams(nn.Module):

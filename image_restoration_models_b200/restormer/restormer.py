@@ -16,7 +16,7 @@ from .. import _native
 from .._params import AffineParams, ConvParams, Holder, ordered_tensors
 
 _MODES = {"fp32": _native.MODE_FP32, "half": _native.MODE_HALF, "fp32_simt": _native.MODE_FP32_SIMT,
-          "fp32_strict": _native.MODE_FP32_STRICT}
+          "fp32_strict": _native.MODE_FP32_STRICT, "bf16": _native.MODE_BF16}
 
 # Range guard of the fast fp32 mode.  IR_MODE_FP32 keeps the tensors that are only ever tensor-core operands (norm2
 # output, v, the fused GDFN's on-chip hidden / gated tensors) as fp16: tf32's mantissa but 5 exponent bits.  The device
@@ -155,7 +155,9 @@ class Restormer(nn.Module):
     def set_mode(self, mode: str):
         """'fp32': tf32 tensor-core operands, fp32 intermediates.  'half': fp16 tensor-core operands and fp16
         intermediates (same 10-bit mantissa as tf32; residual stream, statistics and accumulation stay fp32).
-        'fp32_simt': every contraction on CUDA cores in exact fp32 (the on-device reference used by the tests)."""
+        'fp32_simt': every contraction on CUDA cores in exact fp32 (the on-device reference used by the tests).
+        'bf16': the half mode with bfloat16 instead of float16 (IR_MODE_BF16; 8 mantissa bits: outside the 1e-3 parity
+        bar, reported separately)."""
         if mode not in _MODES:
             raise ValueError(f"mode must be one of {sorted(_MODES)}")
         self._mode = mode

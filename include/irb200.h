@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define IRB200_ABI_VERSION 2
+#define IRB200_ABI_VERSION 3
 
 typedef enum IrStatus {
   IR_OK = 0,
@@ -46,10 +46,13 @@ typedef enum IrMode {
   IR_MODE_HALF = 1,        /* fp16 intermediates + fp16 operands (same 10-bit mantissa as tf32) */
   IR_MODE_FP32_SIMT = 2,   /* every contraction on CUDA cores in exact fp32: the on-device second oracle of the
                               tensor-core kernels (tests / bisecting only; several times slower) */
-  IR_MODE_FP32_STRICT = 3  /* as IR_MODE_FP32 but with NO fp16 tensor anywhere: tf32 operands (8 exponent bits), fp32 v / norm2
+  IR_MODE_FP32_STRICT = 3, /* as IR_MODE_FP32 but with NO fp16 tensor anywhere: tf32 operands (8 exponent bits), fp32 v / norm2
                               output / GDFN hidden tensor in HBM.  The range-safe mode for checkpoints whose activations
                               may leave fp16's range (|x| > 65504); ~25 % slower (the GDFN runs as two kernels).  The
                               Python shim selects it automatically from a pack-time bound (see _range_guard) */
+  IR_MODE_BF16 = 4         /* IR_MODE_HALF with bfloat16 instead of float16 for the 16-bit intermediates and the tensor-core operands
+                              (BASELINE config 3's "fp32 and bf16").  8 mantissa bits: OUTSIDE the 1e-3 parity bar (measured
+                              max-abs ~3e-3), reported separately; same bytes and speed as IR_MODE_HALF, no range limit */
 } IrMode;
 
 /* Mirrors Restormer.__init__ kwargs (src/restormer/restormer.py:194-205). */
