@@ -70,6 +70,13 @@ constexpr int D1_COLS = AROWS;                 // accumulator columns per group
 constexpr int ND = 2;                          // group accumulators in TMEM
 constexpr int S_COL0 = ND * D1_COLS;           // the Gram accumulator (<= 96 columns)
 constexpr int TMEM_COLS = 512;
+#ifndef IRB_PROD_POLL_NS
+#define IRB_PROD_POLL_NS 200
+#endif
+#ifndef IRB_MMA_POLL_NS
+#define IRB_MMA_POLL_NS 32
+#endif
+constexpr int PROD_POLL_NS = IRB_PROD_POLL_NS, MMA_POLL_NS = IRB_MMA_POLL_NS;   // sleep between barrier probes of the one-thread roles
 constexpr int NA = 2;                          // xn patch buffers
 
 struct Bars {
@@ -177,7 +184,7 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const FusedFrontParam
       for (TileIter ta(p); ta.valid(); ta.next(), ++ja) {
         const uint32_t buf = ja % NA, fb = smem_u32(&bars->a_full[buf]);
         // the buffer is free once the last group's MMAs of the tile that used it have completed
-        mbar_wait_spin(smem_u32(&bars->a_empty[buf]), ((ja / NA) & 1u) ^ 1u);
+        mbar_wait_poll<PROD_POLL_NS>(smem_u32(&bars->a_empty[buf]), ((ja / NA) & 1u) ^ 1u);
         mbar_expect_tx(fb, G::A_TX);
 #pragma unroll
         for (int kb = 0; kb < G::NKB; ++kb)
@@ -189,7 +196,7 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const FusedFrontParam
     const uint32_t idesc1 = make_idesc<__half>(AROWS);
     const uint32_t idescS = make_idesc<__half>(CW);
     const uint64_t wdesc = sw128_desc(sW), xdesc = sw128_desc(sX);
-    mbar_wait_spin(smem_u32(&bars->w_full), 0);
+    mbar_wait_poll<MMA_POLL_NS>(smem_u32(&bars->w_full), 0);
     // MMA1 of one group: D^T[128 channels][192 patch pixels] = W[start_row ..][K] . xn_patch[192][K]^T
     auto issue_group = [&](auto grp_tag, uint32_t gg, uint32_t jg) {
       constexpr int grp = decltype(grp_tag)::value;
@@ -213,7 +220,7 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const FusedFrontParam
       __syncwarp();
     };
     auto gram = [&](uint32_t jx) {
-      mbar_wait_spin(smem_u32(&bars->x_ready), jx & 1u);          // the depthwise warps have written tile jx's q | k rows
+      mbar_wait_poll<MMA_POLL_NS>(smem_u32(&bars->x_ready), jx & 1u);          // the depthwise warps have written tile jx's q | k rows
       tc_fence_after();
 #pragma unroll
       for (int a = 0; a < 2; ++a)                            // X boxes: 64 pixels (fp16) each
@@ -230,8 +237,8 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const FusedFrontParam
     for (TileIter ti(p); ti.valid(); ti.next(), ++j) {
       auto one = [&](auto grp_tag) {
         constexpr int grp = decltype(grp_tag)::value;
-        if (grp == 0) mbar_wait_spin(smem_u32(&bars->a_full[j % NA]), (j / NA) & 1u);
-        mbar_wait_spin(smem_u32(&bars->d1_empty[gg & 1u]), ((gg >> 1) & 1u) ^ 1u);
+        if (grp == 0) mbar_wait_poll<MMA_POLL_NS>(smem_u32(&bars->a_full[j % NA]), (j / NA) & 1u);
+        mbar_wait_poll<MMA_POLL_NS>(smem_u32(&bars->d1_empty[gg & 1u]), ((gg >> 1) & 1u) ^ 1u);
         issue_group(grp_tag, gg, j);
         ++gg;
       };

@@ -81,7 +81,11 @@ __device__ __forceinline__ void row_taps(const Row& r, const f2_t (&w)[9], f2_t 
 //   emit  : emit(oy, acc) with acc[j] = output pixels (8h + 2j, 8h + 2j + 1) of row oy, called for oy = 0 .. 7 in order
 // The loads of patch row R+1 are in flight while row R's taps execute.
 template <typename Emit>
-__device__ __forceinline__ void unit(uint32_t taddr, const f2_t (&w)[9], Emit&& emit) {
+__device__ __forceinline__ void unit(uint32_t taddr_in, const f2_t (&w)[9], Emit&& emit) {
+  // tcgen05.ld takes its address from a UNIFORM register.  The address is warp-uniform but derived from the warp index, so
+  // ptxas keeps it in a vector register and emits one R2UR per load (two per LDTM in the first build: 8 % of the depthwise
+  // instruction stream).  A warp reduction returns its result in a uniform register; OR of equal values is the value.
+  const uint32_t taddr = __reduce_or_sync(0xffffffffu, taddr_in);
   f2_t acc[3][4];
   Row ra, rb;
   ld_row(taddr, ra);

@@ -61,6 +61,13 @@ constexpr int NTHREADS = (WARP_PROD + 1) * 32;
 constexpr int D1_COLS = AROWS;                 // accumulator A at column 0, B at 192
 constexpr int D2_COL0 = 2 * D1_COLS;           // D2[128 px][C] at column 384
 constexpr int TMEM_COLS = 512;
+#ifndef IRB_PROD_POLL_NS
+#define IRB_PROD_POLL_NS 200
+#endif
+#ifndef IRB_MMA_POLL_NS
+#define IRB_MMA_POLL_NS 32
+#endif
+constexpr int PROD_POLL_NS = IRB_PROD_POLL_NS, MMA_POLL_NS = IRB_MMA_POLL_NS;   // sleep between barrier probes of the one-thread roles
 
 struct Bars {
   unsigned long long a_full[2], a_empty[2];
@@ -169,7 +176,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t ja = 0, gl = 0, cl = 0;
       auto load_a = [&]() {
         const uint32_t buf = ja % NA, fb = smem_u32(&bars->a_full[buf]);
-        mbar_wait_spin(smem_u32(&bars->a_empty[buf]), ((ja / NA) & 1u) ^ 1u);
+        mbar_wait_poll<PROD_POLL_NS>(smem_u32(&bars->a_empty[buf]), ((ja / NA) & 1u) ^ 1u);
         if ((DBG & 128) && ja >= (uint32_t)NA) {
           mbar_arrive(fb);
         } else {
@@ -184,7 +191,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       auto load_win = [&]() {           // group gl = (chunk c, set) of its tile
         const uint32_t s = gl & 1u, fb = smem_u32(&bars->w1_full[s]);
         const uint32_t gi = gl % (2u * NC), c = gi >> 1, set = gi & 1u;
-        mbar_wait_spin(smem_u32(&bars->w1_empty[s]), ((gl >> 1) & 1u) ^ 1u);
+        mbar_wait_poll<PROD_POLL_NS>(smem_u32(&bars->w1_empty[s]), ((gl >> 1) & 1u) ^ 1u);
         if ((DBG & 32) && gl >= 2) {
           mbar_arrive(fb);
         } else {
@@ -198,7 +205,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       };
       auto load_wout = [&]() {          // chunk cl
         const uint32_t fb = smem_u32(&bars->w2_full);
-        mbar_wait_spin(smem_u32(&bars->w2_empty), (cl & 1u) ^ 1u);
+        mbar_wait_poll<PROD_POLL_NS>(smem_u32(&bars->w2_empty), (cl & 1u) ^ 1u);
         if ((DBG & 64) && cl >= 1) {
           mbar_arrive(fb);
         } else {
@@ -225,9 +232,9 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // MMA1 of group gg (tile j, first group of the tile when `first`, last when `last`) into accumulator gg & 1
     auto issue1 = [&](uint32_t j, bool first, bool last) {
       const uint32_t s = gg & 1u, ph = (gg >> 1) & 1u, ab = j % NA;
-      if (first) mbar_wait_spin(smem_u32(&bars->a_full[ab]), (j / NA) & 1u);
-      mbar_wait_spin(smem_u32(&bars->w1_full[s]), ph);
-      mbar_wait_spin(smem_u32(&bars->d1_empty[s]), ph ^ 1u);
+      if (first) mbar_wait_poll<MMA_POLL_NS>(smem_u32(&bars->a_full[ab]), (j / NA) & 1u);
+      mbar_wait_poll<MMA_POLL_NS>(smem_u32(&bars->w1_full[s]), ph);
+      mbar_wait_poll<MMA_POLL_NS>(smem_u32(&bars->d1_empty[s]), ph ^ 1u);
       tc_fence_after();
       const uint32_t d = tmem_base + s * D1_COLS;
       const uint64_t pd0 = adesc0 + (uint64_t)((ab * G::A_BYTES) >> 4), wd0 = wdesc0 + (uint64_t)((s * G::WIN_BYTES) >> 4);
@@ -248,9 +255,9 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // MMA2 of chunk cc (chunk c of tile j)
     auto issue2 = [&](uint32_t cc) {
       const uint32_t c = cc % NC, j = cc / NC;
-      if (c == 0) mbar_wait_spin(smem_u32(&bars->acc_empty), (j & 1u) ^ 1u);
-      mbar_wait_spin(smem_u32(&bars->w2_full), cc & 1u);
-      mbar_wait_spin(smem_u32(&bars->op_ready), cc & 1u);
+      if (c == 0) mbar_wait_poll<MMA_POLL_NS>(smem_u32(&bars->acc_empty), (j & 1u) ^ 1u);
+      mbar_wait_poll<MMA_POLL_NS>(smem_u32(&bars->w2_full), cc & 1u);
+      mbar_wait_poll<MMA_POLL_NS>(smem_u32(&bars->op_ready), cc & 1u);
       tc_fence_after();
       const uint32_t d = tmem_base + D2_COL0;
 #pragma unroll

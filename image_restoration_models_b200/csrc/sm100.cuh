@@ -55,6 +55,27 @@ __device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
   }
 }
 
+// Polling wait with a short sleep between probes: for the one-thread roles (producer, MMA issuer) of a kernel whose other
+// warps are issue-bound.  A bare spin loop shares its scheduler with two working warps and took ~20 % of that scheduler's
+// issue slots (ncu on ffn_fused.cu: 19 % of all executed instructions were TRYWAIT / BRA of the two waiting warps); NS bounds
+// the extra wake-up latency.
+template <int NS>
+__device__ __forceinline__ void mbar_wait_poll(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t it = 0; ; ++it) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    __nanosleep(NS);
+    if (it > (1u << 24)) __trap();
+  }
+}
+
 // non-blocking probe of a phase (producer-side polling)
 __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
   uint32_t done;
