@@ -21,6 +21,7 @@ NVCC_FLAGS = [
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC,-fvisibility=hidden",
     "--expt-relaxed-constexpr",
+    "-DIRB200_TESTING",          # per-kernel test hooks + hardware probe (include/irb200_testing.h); drop for deployment
 ]
 
 

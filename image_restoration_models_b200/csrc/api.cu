@@ -1,4 +1,5 @@
 // extern "C" boundary (include/irb200.h).  Plain pointers and sizes only; no torch types.
+#include "../../include/irb200_testing.h"
 #include "dncnn.cuh"
 #include "restormer.cuh"
 #include "tc_gemm.cuh"
@@ -11,7 +12,7 @@
 
 namespace irb {
 
-#ifndef IRB_BF16_BUILD
+#if !defined(IRB_BF16_BUILD) && defined(IRB200_TESTING)
 int probe_shifted_descriptor(const float* a, const float* w, float* d, int shift, int base_off, cudaStream_t s);
 #endif
 
@@ -459,6 +460,7 @@ int ir_nhwc_to_nchw(const float* src, float* dst, int B, int C, int H, int W, vo
   return launch_nhwc_to_nchw(src, dst, B, C, H, W, (cudaStream_t)stream);
 }
 
+#ifdef IRB200_TESTING
 int ir_test_conv1x1(int engine, const void* a1v, int lda1, int k1, const void* a2v, int lda2, int k2,
                     const float* w_rowmajor, const float* bias, int ln_mode, const float* ln_w, const float* ln_b,
                     const float* r, int ldr, void* y, int ldy, int B, int HW, int N, int a_pad, int a_half,
@@ -550,6 +552,8 @@ int ir_probe_shifted_descriptor(const float* a, const float* w, float* d, int sh
   IRB_REQUIRE(a && w && d && shift >= 0 && shift <= 32, "probe: bad argument");
   return probe_shifted_descriptor(a, w, d, shift, base_off, (cudaStream_t)stream);
 }
+
+#endif  // IRB200_TESTING
 
 int ir_tile_gather(const void* img, int dtype, float divisor, int H, int W, int C, const int* tile_xy, int T, int th,
                    int tw, int TH, int TW, const double* noise_hwc, float* out, void* stream) {

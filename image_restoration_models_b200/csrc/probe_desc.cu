@@ -2,6 +2,7 @@
 // start address is shifted by whole 128-byte rows inside a TMA-written box address the rows the same way TMA wrote
 // them, and what must the descriptor's base-offset field hold?  One CTA: TMA-load A[160][32] and W[32][32] (fp32,
 // SWIZZLE_128B boxes), D[128][32] = A[shift : shift + 128] . W^T with kind::tf32, store D.
+#ifdef IRB200_TESTING
 #include "common.cuh"
 #include "sm100.cuh"
 #include "tmap.cuh"
@@ -75,3 +76,5 @@ int probe_shifted_descriptor(const float* a, const float* w, float* d, int shift
   return IR_OK;
 }
 }  // namespace irb
+
+#endif  // IRB200_TESTING

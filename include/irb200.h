@@ -127,7 +127,8 @@ int    ir_dncnn_forward_graph(const IrDncnnCfg* cfg, const void* packed, const f
                               void* stream);
 int    ir_dncnn_launch_count(const IrDncnnCfg* cfg);
 
-/* ---- single-stage entry points (unit tests and ncu hit each kernel in isolation) ----
+/* ---- single-stage entry points (unit tests and ncu hit each kernel in isolation; the per-kernel test hooks and the
+ *      hardware probe are declared in irb200_testing.h, outside the product ABI) ----
  * Activations here are channels-last: a[pixel * ld + channel], pixel = (b*H + y)*W + x.    */
 
 /* One TransformerBlock in place on x[B*H*W, C] (src/restormer/restormer.py:146-150).
@@ -140,27 +141,6 @@ int    ir_block_pack_weights(int C, int heads, double ffn_expansion_factor, int 
 int    ir_block_forward(int C, int heads, double ffn_expansion_factor, int bias, int ln_with_bias,
                         const void* packed, float* x_nhwc, int B, int H, int W,
                         void* workspace, size_t workspace_bytes, int mode, void* stream);
-
-/* One 1x1 convolution y[pix, n] = sum_k LN?(a)[pix, k] * w[n, k] (+bias) (+r) on channels-last rows, with the
- * reference's row-major weight [N][K] (K = k1 + k2, second source = channel concat).  engine 0 = tcgen05
- * kernel, 1 = CUDA-core fp32 kernel.  ln_mode: 0 none, 1 BiasFree, 2 WithBias.  scratch >= (N*K + B*HW*K)*4 bytes. */
-int    ir_test_conv1x1(int engine, const void* a1, int lda1, int k1, const void* a2, int lda2, int k2,
-                       const float* w_rowmajor, const float* bias, int ln_mode, const float* ln_w, const float* ln_b,
-                       const float* r, int ldr, void* y, int ldy, int B, int HW, int N, int a_pad,
-                       int a_half, int op_half, int y_half,   /* element types: a1/a2, tensor-core operands, y */
-                       void* scratch, size_t scratch_bytes, void* stream);
-
-/* One 3x3 convolution (stride 1, zero padding 1, PyTorch [cout][cin][3][3] weight) on channels-last fp32 rows.
- * o_mode: 0 plain rows y[pix*ldy + n]; 1 PixelUnshuffle(2) folded into the store; 2 PixelShuffle(2) folded into the
- * store (restormer.py:176,186).  engine 0 = tcgen05 implicit GEMM, 1 = CUDA-core fp32.  scratch >= cout*9*cin*4 B. */
-int    ir_test_conv3x3(int engine, const float* x_nhwc, int ldx, int cin, const float* w_oihw, const float* bias,
-                       int cout, int B, int H, int W, float* y, int ldy, int o_mode, int relu, int op_half,
-                       void* scratch, size_t scratch_bytes, void* stream);
-
-/* Hardware probe (bring-up): D[128][32] = A[shift : shift+128][32] . W[32][32]^T with the A operand descriptor's start
- * address shifted by `shift` rows inside one TMA-written SWIZZLE_128B box and `base_off` in its base-offset field. */
-int    ir_probe_shifted_descriptor(const float* a /* [160][32] */, const float* w /* [32][32] */, float* d /* [128][32] */,
-                                   int shift, int base_off, void* stream);
 
 /* Layout helpers used at the boundary of unit tests (NCHW fp32 <-> channels-last fp32). */
 int    ir_nchw_to_nhwc(const float* src, float* dst, int B, int C, int H, int W, void* stream);

@@ -1,0 +1,62 @@
+#!/usr/bin/env python
+"""Copy the evidence of one GPU pass (scripts/r02_gpu_final.sh <tag>) from gpurun_out/ into profiles/ and fill the
+measured numbers into DESIGN.md (from scripts/DESIGN.md.tmpl).  Usage: collect_profiles.py <tag>"""
+import json, os, shutil, subprocess, sys
+
+tag = sys.argv[1]
+R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G, P = os.path.join(R, "gpurun_out"), os.path.join(R, "profiles")
+
+
+def cp(src, dst):
+    s = os.path.join(G, src)
+    if os.path.exists(s):
+        shutil.copy(s, os.path.join(P, dst))
+    else:
+        print("missing", src)
+
+
+cp(f"bench_{tag}.json", f"{tag}_bench_fp32.json")
+cp(f"bench_half_{tag}.json", f"{tag}_bench_half.json")
+cp(f"bench_ref_{tag}.json", f"{tag}_bench_reference_arm.json")
+cp(f"parity_{tag}.json", "r02_parity.json")
+cp(f"latency_{tag}.json", f"{tag}_latency.json")
+cp(f"configs_{tag}.json", f"{tag}_configs.json")
+cp(f"blocks_{tag}.log", f"{tag}_block_kernels.log")
+cp(f"status_{tag}.txt", f"{tag}_status.txt")
+cp(f"gpu_{tag}.txt", f"{tag}_gpu.txt")
+cp(f"launches_{tag}_fp32.csv", f"{tag}_ncu_launches_fp32.csv")
+cp(f"traffic_{tag}_fp32.json", "traffic_fp32.json")
+cp(f"launch_fp32_{tag}.csv", f"{tag}_launches_fp32_events.csv")
+cp(f"ncu_summary_{tag}.csv", "r02_fused_ncu_summary.csv")
+cp(f"ncu_details_{tag}.csv", f"{tag}_fused_ncu_details.csv")
+if os.path.exists(os.path.join(G, f"pytest_{tag}.log")):
+    open(os.path.join(P, f"{tag}_pytest_gpu.txt"), "w").write(open(os.path.join(G, f"pytest_{tag}.log")).read()[-600:])
+
+d = json.load(open(os.path.join(G, f"bench_{tag}.json")))
+lat = json.load(open(os.path.join(G, f"latency_{tag}.json")))
+fam = []
+peaks = {"fp32_pipe": "FP32 pipe", "hbm": "HBM"}
+for k in d["kernels"]:
+    name, ms = k["name"], k["ms"]
+    if name == d["roofline"]["kernel"]:
+        fam.append(f"{name} {ms:.1f} ms ({d['roofline']['frac']:.2f} of the FP32 pipe, {k['hbm_frac']:.2f} HBM)")
+    else:
+        which = "HBM" if k["hbm_frac"] >= k["tensor_frac"] else "tensor"
+        fam.append(f"{name} {ms:.1f} ms ({k['best_frac']:.2f} {which})")
+t = d["tiled_config4"]
+sub = {
+    "@FP32@": f"{d['value']:.1f}", "@FP32MS@": f"{d['ms_per_step']:.1f}", "@HALF@": f"{d['other_mode']['value']:.1f}",
+    "@BF16@": f"{d['bf16_mode']['value']:.1f}", "@E2E@": f"{d['e2e']['value']:.1f}",
+    "@TILED@": f"{t['value']:.1f}", "@TILEDC@": f"{t['computed_tile_mpix_per_s']:.1f}",
+    "@LAT256@": f"{lat['restormer_color_denoise_1x3x256x256']['graph']['device_ms']:.2f}",
+    "@LAT512@": f"{lat['restormer_color_denoise_1x3x512x512']['graph']['device_ms']:.2f}",
+    "@FAMILIES@": "; ".join(fam) + f".  Step: {d['step_algorithmic_GB']:.0f} GB algorithmic, {d['step_TFLOP']:.2f} TFLOP; "
+                  f"{100 * d['roofline']['step_share_at_0p6']:.0f} % of the step time is spent in kernels at >= 0.6 of their roofline.",
+    "r02z_": f"{tag}_",
+}
+s = open(os.path.join(R, "scripts", "DESIGN.md.tmpl")).read()
+for a, b in sub.items():
+    s = s.replace(a, b)
+open(os.path.join(R, "DESIGN.md"), "w").write(s)
+print("DESIGN.md written;", d["value"], "Mpix/s")
