@@ -76,6 +76,7 @@ struct Bars {
   unsigned long long d1_full[2], d1_empty[2];
   unsigned long long op_ready, op_empty;
   unsigned long long acc_full, acc_empty;
+  unsigned long long xs_full, xs_empty;      // NEXT: the tile's residual rows have landed in / been stored from the staging boxes
   uint32_t tmem_base;
 };
 
@@ -83,6 +84,10 @@ struct FusedParams {
   const uint8_t* w_in;     // fp16 SWIZZLE_128B image [nkb][2 hp][128 B]
   const uint8_t* w_out;    // [hp / 64][C][128 B]
   const float* dw;         // taps [hp / 64][2][9][64]
+  __half* xn_next;         // NEXT: [B][H][W][C] fp16, LayerNorm of the updated residual stream (the next block's norm1)
+  const float* lnw;        // NEXT: that LayerNorm's weight / bias
+  const float* lnb;
+  int ln_mode;
   int B, H, W;
   int tiles_x, tiles_y, ntiles;
   uint32_t off_a, off_win, off_wout, off_op, off_stg, off_bars;
@@ -119,7 +124,10 @@ __device__ __forceinline__ void sts16(uint32_t a, uint32_t v) {
 // DBG != 0: timing experiments only (results are garbage; compiled with -DIRB_FUSED_EXPERIMENTS, selected by IRB_FUSED_DBG):
 // 2 depthwise warps without TMEM loads / taps, 4 plain product instead of the GELU gate, 8 no MMA instructions,
 // 16 no operand stores, 32 W_in loaded only twice, 64 W_out loaded only once, 128 xn patches loaded only NA times
-template <int CW, int DBG>
+// NEXT: the epilogue LOADS the tile's residual rows (bulk-tensor load into the staging boxes), adds, stores, and also
+// writes LayerNorm(x_new) as the fp16 operand tensor of the next block's attention front: the next block's norm1 pass (4C
+// read + 2C written per pixel, one launch) disappears.  Without NEXT the residual is reduced in L2 and never loaded.
+template <int CW, int DBG, bool NEXT>
 __global__ void __launch_bounds__(NTHREADS, 1)
 ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmY, const FusedParams p) {
   using G = Geo<CW>;
@@ -147,7 +155,9 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     mbar_init(smem_u32(&bars->op_ready), DW_WARPS);
     mbar_init(smem_u32(&bars->op_empty), 1);
     mbar_init(smem_u32(&bars->acc_full), 1);
-    mbar_init(smem_u32(&bars->acc_empty), DW_WARPS);
+    mbar_init(smem_u32(&bars->acc_empty), NEXT ? 4 : DW_WARPS);
+    mbar_init(smem_u32(&bars->xs_full), 1);
+    mbar_init(smem_u32(&bars->xs_empty), 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -214,7 +224,21 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         ++cl;
       };
+      // NEXT: residual rows of tile jx into the staging boxes, once the previous tile's stores have read them
+      TileIter tx(p);
+      uint32_t jx = 0;
+      auto load_x = [&]() {
+        const uint32_t fb = smem_u32(&bars->xs_full);
+        mbar_wait_poll<PROD_POLL_NS>(smem_u32(&bars->xs_empty), (jx & 1u) ^ 1u);
+        mbar_expect_tx(fb, (uint32_t)G::NGRP * OPBOX);
+        for (int gi = 0; gi < G::NGRP; ++gi)
+          for (int q = 0; q < 4; ++q)
+            tma_load_4d(&tmY, fb, sStg + (uint32_t)gi * OPBOX + (uint32_t)q * 4096u, gi * 32, tx.x0(), tx.y0() + 2 * q, tx.img());
+        tx.next();
+        ++jx;
+      };
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+      if (NEXT) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmY)) : "memory");
       for (int k = 0; k < NA && ta.valid(); ++k) load_a();
       for (int k = 0; k < 2 && gl < NGT; ++k) load_win();
       for (uint32_t cc = 0; cc < NCT; ++cc) {
@@ -222,6 +246,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (gl < NGT) load_win();
         if (cc % NC == NC - 1 && ta.valid()) load_a();
         load_wout();
+        if (NEXT && cc % NC == 0) load_x();                  // (tile jx's epilogue runs a tile later)
       }
     }
   } else if (warp == WARP_MMA) {
@@ -300,6 +325,73 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
     // D2 of tile j -> staging -> x += : lanes = the 32 pixels of tile rows 2q, 2q+1; this warp's 32-channel groups
     auto epilogue = [&](uint32_t j, int b, int y0, int x0) {
+      if (NEXT) {
+        // ---- x_new = x + ffn for this quarter's 32 pixels (all C channels per lane), stored back; norm1 of the next block ----
+        if (h != (int)(j & 1u)) return;                      // the two warps of a quarter take turns
+        mbar_wait_spin(smem_u32(&bars->acc_full), j & 1u);
+        tc_fence_after();
+        mbar_wait_spin(smem_u32(&bars->xs_full), j & 1u);    // the residual rows have landed in the staging boxes
+        float xr[G::NGRP * 32];
+#pragma unroll
+        for (int gi = 0; gi < G::NGRP; ++gi) {
+          float v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + D2_COL0 + (uint32_t)(gi * 32), v);
+          tmem_ld_wait();
+          const uint32_t stg = sStg + (uint32_t)gi * OPBOX + (uint32_t)q * 4096u + (uint32_t)lane * 128u;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const uint32_t a = stg + (((uint32_t)c ^ lsw) << 4);
+            const float4 x4 = lds128(a);
+            const float4 o = make_float4(x4.x + v[4 * c], x4.y + v[4 * c + 1], x4.z + v[4 * c + 2], x4.w + v[4 * c + 3]);
+            sts128(a, o);
+            xr[gi * 32 + 4 * c] = o.x; xr[gi * 32 + 4 * c + 1] = o.y; xr[gi * 32 + 4 * c + 2] = o.z; xr[gi * 32 + 4 * c + 3] = o.w;
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty));
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          for (int gi = 0; gi < G::NGRP; ++gi)
+            tma_store_4d(&tmY, sStg + (uint32_t)gi * OPBOX + (uint32_t)q * 4096u, gi * 32, x0, y0 + 2 * q, b);
+          bulk_commit();
+        }
+        // LayerNorm over the lane's CW channels (two-pass statistics in registers, restormer.py:25-57)
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < CW; ++i) sum += xr[i];
+        const float mu = sum * (1.0f / CW);
+        float ss = 0.f;
+#pragma unroll
+        for (int i = 0; i < CW; ++i) { const float d = xr[i] - mu; ss = fmaf(d, d, ss); }
+        const float rstd = 1.0f / sqrtf(ss * (1.0f / CW) + 1e-5f);
+        const bool wb = p.ln_mode == LN_WITHBIAS;
+        const float sub = wb ? mu : 0.f;
+        const int py = y0 + 2 * q + (lane >> 4), px = x0 + (lane & 15);
+        if (py < p.H && px < p.W) {
+          uint4* dst = reinterpret_cast<uint4*>(p.xn_next + (((long long)b * p.H + py) * p.W + px) * CW);
+#pragma unroll
+          for (int c8 = 0; c8 < CW / 8; ++c8) {
+            const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.lnw) + 2 * c8), w1 = __ldg(reinterpret_cast<const float4*>(p.lnw) + 2 * c8 + 1);
+            float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+            if (wb) { b0 = __ldg(reinterpret_cast<const float4*>(p.lnb) + 2 * c8); b1 = __ldg(reinterpret_cast<const float4*>(p.lnb) + 2 * c8 + 1); }
+            const float* xv = xr + 8 * c8;
+            uint4 u;
+            u.x = h2_bits(f2h2_sat(fmaf((xv[0] - sub) * rstd, w0.x, b0.x), fmaf((xv[1] - sub) * rstd, w0.y, b0.y)));
+            u.y = h2_bits(f2h2_sat(fmaf((xv[2] - sub) * rstd, w0.z, b0.z), fmaf((xv[3] - sub) * rstd, w0.w, b0.w)));
+            u.z = h2_bits(f2h2_sat(fmaf((xv[4] - sub) * rstd, w1.x, b1.x), fmaf((xv[5] - sub) * rstd, w1.y, b1.y)));
+            u.w = h2_bits(f2h2_sat(fmaf((xv[6] - sub) * rstd, w1.z, b1.z), fmaf((xv[7] - sub) * rstd, w1.w, b1.w)));
+            dst[c8] = u;
+          }
+        }
+        if (lane == 0) {
+          bulk_wait_read<0>();                               // the stores have read the staging boxes
+          mbar_arrive(smem_u32(&bars->xs_empty));
+        }
+        __syncwarp();
+        return;
+      }
       mbar_wait_spin(smem_u32(&bars->acc_full), j & 1u);
       tc_fence_after();
       if (lane == 0) bulk_wait_read<0>();                    // the previous tile's reductions have read the staging boxes
@@ -358,7 +450,8 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (lane == 0) mbar_arrive(smem_u32(&bars->d1_empty[0]));
         }
         // the previous tile's output, while this tile's x2 accumulator is (long) ready and its MMA2 has long retired
-        if (c == 0 && j > 0) epilogue(j - 1, pb, py0, px0);
+        // (NEXT: behind phase 2 instead -- the epilogue then holds the pixel's whole row in registers, r1 must be dead)
+        if (!NEXT && c == 0 && j > 0) epilogue(j - 1, pb, py0, px0);
         // ---- phase 2: depthwise taps of x2 (accumulator B), gate, fp16 operand rows ----
         {
           f2_t w[9];
@@ -395,6 +488,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&bars->op_ready));
         }
+        if (NEXT && c == 0 && j > 0) epilogue(j - 1, pb, py0, px0);
       }
       pb = ti.img(); py0 = ti.y0(); px0 = ti.x0();
     }
@@ -434,11 +528,11 @@ bool configure(int C, int hp, FusedCfg& c) {
   return C == 48 ? configure_w<48>(hp, c) : C == 96 ? configure_w<96>(hp, c) : false;
 }
 
-template <int CW, int DBG = 0>
+template <int CW, int DBG = 0, bool NEXT = false>
 int launch_inst(const CUtensorMap& tA, const CUtensorMap& tY, const FusedParams& p, int grid, size_t smem, cudaStream_t s) {
   static SmemOptIn optin;
-  IRB_TRY(opt_in_smem(ffn_fused_kernel<CW, DBG>, optin));
-  ffn_fused_kernel<CW, DBG><<<grid, NTHREADS, smem, s>>>(tA, tY, p);
+  IRB_TRY(opt_in_smem(ffn_fused_kernel<CW, DBG, NEXT>, optin));
+  ffn_fused_kernel<CW, DBG, NEXT><<<grid, NTHREADS, smem, s>>>(tA, tY, p);
   IRB_LAUNCH_CHECK();
   return IR_OK;
 }
@@ -471,6 +565,9 @@ int launch_ffn_fused(const FfnFusedArgs& a, cudaStream_t s) {
   p.w_in = reinterpret_cast<const uint8_t*>(a.w_in);
   p.w_out = reinterpret_cast<const uint8_t*>(a.w_out);
   p.dw = a.dw_chunked;
+  p.xn_next = reinterpret_cast<__half*>(a.xn_next); p.lnw = a.ln_w_next; p.lnb = a.ln_b_next; p.ln_mode = a.ln_mode_next;
+  IRB_REQUIRE(a.xn_next == nullptr || (a.ln_w_next != nullptr && (a.ln_mode_next == LN_BIASFREE ||
+              (a.ln_mode_next == LN_WITHBIAS && a.ln_b_next != nullptr))), "ffn_fused: bad LayerNorm of the next block");
   p.B = a.B; p.H = a.H; p.W = a.W;
   p.tiles_x = cdiv(a.W, TW); p.tiles_y = cdiv(a.H, TH); p.ntiles = p.tiles_x * p.tiles_y * a.B;
   p.off_a = c.off_a; p.off_win = c.off_win; p.off_wout = c.off_wout; p.off_op = c.off_op; p.off_stg = c.off_stg;
@@ -479,7 +576,7 @@ int launch_ffn_fused(const FfnFusedArgs& a, cudaStream_t s) {
   const size_t smem = std::max<size_t>(c.smem, 120 * 1024);     // one CTA per SM: the kernel owns all 512 TMEM columns
   const double pix = (double)a.B * a.H * a.W;
   // algorithmic bytes: xn read (fp16) + x read-modify-write (fp32); flops: project_in + depthwise + project_out
-  ProfScope prof(TAG_FFN_FUSED, pix * (2.0 * a.C + 8.0 * a.C), pix * (4.0 * a.hp * a.C + 36.0 * a.hp + 2.0 * a.hp * a.C), s);
+  ProfScope prof(TAG_FFN_FUSED, pix * (2.0 * a.C + 8.0 * a.C + (a.xn_next ? 2.0 * a.C : 0.0)), pix * (4.0 * a.hp * a.C + 36.0 * a.hp + 2.0 * a.hp * a.C), s);
 #ifdef IRB_FUSED_EXPERIMENTS
   static const int dbg = getenv("IRB_FUSED_DBG") ? atoi(getenv("IRB_FUSED_DBG")) : 0;
   if (a.C == 96) {
@@ -498,6 +595,8 @@ int launch_ffn_fused(const FfnFusedArgs& a, cudaStream_t s) {
     }
   }
 #endif
+  if (a.xn_next != nullptr)
+    return a.C == 48 ? launch_inst<48, 0, true>(tA, tY, p, grid, smem, s) : launch_inst<96, 0, true>(tA, tY, p, grid, smem, s);
   return a.C == 48 ? launch_inst<48>(tA, tY, p, grid, smem, s) : launch_inst<96>(tA, tY, p, grid, smem, s);
 }
 

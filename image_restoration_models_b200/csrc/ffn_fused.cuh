@@ -11,6 +11,12 @@ struct FfnFusedArgs {
   const void* w_out;       // project_out, fmt 4: [hp/64][C][128 B]
   const float* dw_chunked; // depthwise taps [hp/64][2][9][64] (launch_pack_dw_chunked, kc = 64)
   int B, H, W, C, hp;
+  // optional: also write LayerNorm(x_new) -- the NEXT block's norm1 (restormer.py:147) -- as an fp16 tensor; the epilogue then
+  // loads the residual instead of reducing into it
+  void* xn_next = nullptr;          // [B*H*W][C] fp16
+  const float* ln_w_next = nullptr; // [C]
+  const float* ln_b_next = nullptr; // [C] (WithBias) or nullptr
+  int ln_mode_next = 0;             // LN_BIASFREE / LN_WITHBIAS
 };
 
 bool ffn_fused_supported(int C, int hp);

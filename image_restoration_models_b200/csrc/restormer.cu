@@ -327,7 +327,8 @@ void block_scratch_need(BlockScratchNeed& n, const BlockPlan& bp, int B, int H, 
   n.s_part = std::max(n.s_part, (long long)B * bp.heads * parts * ch * ch);
   n.n_part = std::max(n.n_part, (long long)B * bp.heads * parts * 2 * ch);
   n.w_eff = std::max(n.w_eff, (long long)B * bp.C * bp.kp_attn);
-  if (bp.C > 128 || bp.fuse_ffn || bp.fuse_attn) n.xhat = std::max(n.xhat, P * bp.C);
+  if (bp.C > 128 || bp.fuse_ffn) n.xhat = std::max(n.xhat, P * bp.C);
+  if (bp.fuse_attn) n.xhat2 = std::max(n.xhat2, (P * bp.C + 1) / 2);      // fp16 norm1 output, counted in floats
   n.es = bp.half ? 2 : 4;
 }
 
@@ -353,6 +354,7 @@ void carve_block_scratch(Carver& cv, BlockScratch& bs, const BlockScratchNeed& n
   bs.n_part = cv.take(n.n_part);
   bs.w_eff = cv.take(elems(n.w_eff));
   bs.xhat = cv.take(elems(n.xhat));
+  bs.xhat2 = cv.take(n.xhat2);
 }
 
 size_t block_workspace_bytes(const BlockPlan& bp, int B, int H, int W) {
@@ -435,14 +437,24 @@ static int run_1x1(const GemmParams& g, bool tc, bool half, bool a_half, bool y_
 // -----------------------------------------------------------------------------------------------
 // one TransformerBlock: x_out = block(x_in)   (x_in may equal x_out)
 // -----------------------------------------------------------------------------------------------
+bool block_chains_norm1(const BlockPlan& bp, const BlockPlan& next) {
+  // OFF by default.  Measured (profiles/r02_norm1_chain_ab.json): the LayerNorm passes it removes cost 2.3 ms per step, the
+  // heavier epilogue -- one warp per lane quarter holds the pixel's whole row, on the critical path of the lock-step
+  // depthwise phases -- costs the GDFN 3.6 ms.  IRB_NORM1_CHAIN=1 turns it on (parity-tested either way).
+  static const bool on = getenv("IRB_NORM1_CHAIN") != nullptr;
+  return on && bp.fuse_ffn && next.fuse_attn && bp.C == next.C;
+}
+
 int run_block(const BlockPlan& bp, const float* packed, const float* x_in, float* x_out, int B, int H, int W,
-              const BlockScratch& bs, int ln_with_bias, cudaStream_t s) {
+              const BlockScratch& bs, int ln_with_bias, cudaStream_t s, const BlockPlan* next, bool* xn1_ready) {
   const int C = bp.C, hp = bp.hp;
   const int ln = ln_with_bias ? LN_WITHBIAS : LN_BIASFREE;
   const bool hf = bp.half;                 // fp16 intermediates: qkv, qkv_dw (v), hidden, gated, W_eff
   const size_t es = hf ? 2 : 4;
   auto P = [&](long long off) -> const float* { return off >= 0 ? packed + off : nullptr; };
 
+  const bool xn1_in = xn1_ready && *xn1_ready;
+  if (xn1_ready) *xn1_ready = false;        // consumed below; set again if this block's GDFN emits the next norm1
   GemmParams g{};
   if (!bp.fuse_attn) {
   // (1) norm1 + qkv 1x1   (restormer.py:147 norm1, :114 qkv)
@@ -466,9 +478,10 @@ int run_block(const BlockPlan& bp, const float* packed, const float* x_in, float
     fa.w_qkv = P(bp.qkv_w); fa.dw_chunked = P(bp.qkvdw_w); fa.v = bs.qkv_dw;
     fa.s_part = bs.s_part; fa.n_part = bs.n_part; fa.parts = attn_fused_parts(B, H, W);
     fa.B = B; fa.H = H; fa.W = W; fa.C = C; fa.heads = bp.heads;
-    // norm1 as an fp16 tensor (bs.xhat; the attention-output kernel overwrites it with norm2 afterwards)
-    IRB_TRY(launch_layernorm(x_in, C, bs.xhat, C, 1, (long long)B * H * W, C, ln, P(bp.ln1_w), P(bp.ln1_b), s));
-    fa.xn = bs.xhat;
+    // norm1 as an fp16 tensor (bs.xhat2): written by the previous block's GDFN epilogue, else by a LayerNorm pass
+    if (!xn1_in)
+      IRB_TRY(launch_layernorm(x_in, C, bs.xhat2, C, 1, (long long)B * H * W, C, ln, P(bp.ln1_w), P(bp.ln1_b), s));
+    fa.xn = bs.xhat2;
     IRB_TRY(launch_attn_fused(fa, s));
     gp.nparts = fa.parts;
     v_ptr = bs.qkv_dw; v_ld = C;
@@ -525,6 +538,11 @@ int run_block(const BlockPlan& bp, const float* packed, const float* x_in, float
     FfnFusedArgs fa{};
     fa.xn = bs.xhat; fa.x = x_out; fa.w_in = P(bp.pin_w); fa.w_out = P(bp.pout_w); fa.dw_chunked = P(bp.ffdw_w);
     fa.B = B; fa.H = H; fa.W = W; fa.C = C; fa.hp = hp;
+    if (next && xn1_ready && block_chains_norm1(bp, *next)) {
+      // the next block's norm1 from this kernel's epilogue (the attention front of THIS block has long read bs.xhat2)
+      fa.xn_next = bs.xhat2; fa.ln_w_next = P(next->ln1_w); fa.ln_b_next = P(next->ln1_b); fa.ln_mode_next = ln;
+      *xn1_ready = true;
+    }
     return launch_ffn_fused(fa, s);
   }
 
@@ -576,15 +594,22 @@ int block_forward(const BlockPlan& bp, const float* packed, float* x, int B, int
   return run_block(bp, packed, x, x, B, H, W, bs, ln_with_bias, s);
 }
 
+// after: the first block of the stage that follows on the same tensor (refinement behind decoder level 1) or nullptr;
+// xn1_ready: carried from / to that neighbouring stage
 static int run_stage(const std::vector<BlockPlan>& blocks, const float* packed, const float* x_in, float* x_out, int B,
-                     int H, int W, int C, const BlockScratch& bs, int lnb, cudaStream_t s) {
+                     int H, int W, int C, const BlockScratch& bs, int lnb, cudaStream_t s, const BlockPlan* after = nullptr,
+                     bool* xn1_ready = nullptr) {
+  bool local = false;
+  bool* ready = xn1_ready ? xn1_ready : &local;
   if (blocks.empty()) {   // nn.Sequential() of zero blocks is the identity
     if (x_in != x_out) IRB_TRY(launch_copy_channels(x_in, C, x_out, C, (long long)B * H * W, C, s));
+    *ready = false;
     return IR_OK;
   }
   const float* cur = x_in;
-  for (const auto& bp : blocks) {
-    IRB_TRY(run_block(bp, packed, cur, x_out, B, H, W, bs, lnb, s));
+  for (size_t i = 0; i < blocks.size(); ++i) {
+    const BlockPlan* next = i + 1 < blocks.size() ? &blocks[i + 1] : after;
+    IRB_TRY(run_block(blocks[i], packed, cur, x_out, B, H, W, bs, lnb, s, next, ready));
     cur = x_out;
   }
   return IR_OK;
@@ -619,10 +644,13 @@ static int conv3(const ConvPlan& cp, const float* packed, const float* in, int l
 
 int restormer_launch_count(const RestormerPlan& pl) {
   int n = 0;
-  auto blocks = [&](const std::vector<BlockPlan>& v) {
+  // chain: blocks that follow each other on one tensor; `prev` = the block before the first one of `v` (or nullptr)
+  auto blocks = [&](const std::vector<BlockPlan>& v, const BlockPlan* prev) {
     for (const auto& bp : v) {
-      // (the fused MDTA front replaces LN + qkv and the front kernel by a LayerNorm pass and itself)
+      // (the fused MDTA front replaces LN + qkv and the front kernel by a LayerNorm pass and itself; that pass disappears
+      // when the previous block's GDFN emits norm1 from its epilogue)
       n += 8 - (bp.fuse_tail || bp.fuse_ffn ? 1 : 0) - (bp.fuse_front ? 1 : 0) - (bp.k4_xn ? 1 : 0);
+      if (prev && bp.fuse_attn && block_chains_norm1(*prev, bp)) n -= 1;
       // standalone LayerNorm where the contraction cannot take it as a prologue (the wide levels)
       auto ln_standalone = [&](bool tc, bool tma, int N) {
         if (!tc) return false;
@@ -633,11 +661,13 @@ int restormer_launch_count(const RestormerPlan& pl) {
         return tc_gemm_configure(t) == 0;
       };
       n += (!bp.fuse_attn && ln_standalone(bp.tc_qkv, bp.tma_qkv, 3 * bp.C) ? 1 : 0) + (ln_standalone(bp.tc_pin, bp.tma_pin, 2 * bp.hp) ? 1 : 0);
+      prev = &bp;
     }
   };
-  for (int l = 0; l < 4; ++l) blocks(pl.enc[l]);
-  for (int l = 0; l < 3; ++l) blocks(pl.dec[l]);
-  blocks(pl.refine);
+  for (int l = 0; l < 4; ++l) blocks(pl.enc[l], nullptr);
+  for (int l = 2; l >= 1; --l) blocks(pl.dec[l], nullptr);
+  blocks(pl.dec[0], nullptr);
+  blocks(pl.refine, pl.dec[0].empty() ? nullptr : &pl.dec[0].back());
   // patch_embed, 3 down, 3 up, 2 reduce, 1 concat copy, output (+ skip_conv)
   return n + 11 + (pl.cfg.dual_pixel_task ? 1 : 0);
 }
@@ -685,8 +715,10 @@ int restormer_forward(const RestormerPlan& pl, const float* packed, const float*
   // level 1 (:269-273): up2_1 writes channels [0,dim) of the 2*dim-wide stream, the skip fills [dim,2dim)
   IRB_TRY(conv3(pl.up[0], packed, below, 2 * d, A_IM2COL_NHWC, B, H / 2, W / 2, ws.d[0], 2 * d, O_SHUFFLE, nullptr, pl.half, s));
   IRB_TRY(launch_copy_channels(ws.e[0], d, ws.d[0] + d, 2 * d, (long long)B * H * W, d, s));
-  IRB_TRY(run_stage(pl.dec[0], packed, ws.d[0], ws.d[0], B, H, W, 2 * d, ws.bs, lnb, s));
-  IRB_TRY(run_stage(pl.refine, packed, ws.d[0], ws.d[0], B, H, W, 2 * d, ws.bs, lnb, s));
+  bool xn1 = false;     // refinement continues on decoder level 1's tensor: its first norm1 comes from the last decoder GDFN
+  IRB_TRY(run_stage(pl.dec[0], packed, ws.d[0], ws.d[0], B, H, W, 2 * d, ws.bs, lnb, s,
+                    pl.refine.empty() ? nullptr : &pl.refine[0], &xn1));
+  IRB_TRY(run_stage(pl.refine, packed, ws.d[0], ws.d[0], B, H, W, 2 * d, ws.bs, lnb, s, nullptr, &xn1));
   if (dual) {
     // out += skip_conv(patch_embed output) (:276-277), then output conv without image residual (:278)
     GemmParams g{};

@@ -47,8 +47,8 @@ struct RestormerPlan {
   std::vector<BlockPlan> enc[4], dec[3], refine;
 };
 
-struct BlockScratchNeed { long long qkv = 0, hidden = 0, gated = 0, s_part = 0, n_part = 0, w_eff = 0, xhat = 0, v16 = 0; int es = 4; };   // v16: fp16 elements of v where the fused front writes it
-struct BlockScratch { void *qkv, *qkv_dw, *hidden, *gated; float *s_part, *n_part; void *w_eff, *xhat; };
+struct BlockScratchNeed { long long qkv = 0, hidden = 0, gated = 0, s_part = 0, n_part = 0, w_eff = 0, xhat = 0, xhat2 = 0, v16 = 0; int es = 4; };   // v16: fp16 elements of v where the fused front writes it
+struct BlockScratch { void *qkv, *qkv_dw, *hidden, *gated; float *s_part, *n_part; void *w_eff, *xhat, *xhat2; };   // xhat: norm2 / wide-level LayerNorm output, xhat2: fp16 norm1 output of the fused MDTA front
 struct RestormerWs { float* e[4]; float* e1_in; float* d[3]; float* up_tmp; BlockScratch bs; };
 
 int  block_param_count(int bias, int ln_bias);
@@ -71,8 +71,14 @@ int  run_pack_ops(const std::vector<PackOp>& ops, const float* const* params, fl
 size_t block_workspace_bytes(const BlockPlan& bp, int B, int H, int W);
 int  engine_of_mode(int mode);
 size_t restormer_workspace_bytes(const RestormerPlan& pl, int B, int H, int W);
+// next: the block that consumes x_out (same C, same extent) or nullptr; when both blocks are fused, this block's GDFN also
+// writes the next block's norm1 output (bs.xhat2) and *xn1_ready is set for the next call.  xn1_ready (in): bs.xhat2
+// already holds norm1(x_in).
 int  run_block(const BlockPlan& bp, const float* packed, const float* x_in, float* x_out, int B, int H, int W,
-               const BlockScratch& bs, int ln_with_bias, cudaStream_t s);
+               const BlockScratch& bs, int ln_with_bias, cudaStream_t s, const BlockPlan* next = nullptr,
+               bool* xn1_ready = nullptr);
+// true when `bp`'s GDFN can emit norm1 of `next` (both on the fused kernels, same width)
+bool block_chains_norm1(const BlockPlan& bp, const BlockPlan& next);
 int  block_forward(const BlockPlan& bp, const float* packed, float* x, int B, int H, int W, void* workspace,
                    size_t workspace_bytes, int ln_with_bias, cudaStream_t s);
 int  restormer_launch_count(const RestormerPlan& pl);
