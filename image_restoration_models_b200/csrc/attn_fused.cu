@@ -260,8 +260,9 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const FusedFrontParam
       const int y0 = ti.y0(), x0 = ti.x0();
       const int vy = min(TH, p.H - y0), vx = max(0, min(8, p.W - (x0 + 8 * h)));   // valid output rows / columns of this half
       const bool partial = vy < TH || vx < 8;
-      // the Gram MMA of the previous tile has read the X tile
-      mbar_wait_spin(smem_u32(&bars->x_empty), (j & 1u) ^ 1u);
+      // The Gram MMA of the previous tile must have read the X tile before this tile's first q | k row is stored: the wait
+      // sits in front of that store (first output row of the tile's first q | k unit), behind the taps of three patch rows
+      bool xwait = true;
 #pragma unroll 1
       for (int grp = 0; grp < G::NG; ++grp, ++gg) {
         const int u = unit_of(grp, q);
@@ -285,6 +286,7 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const FusedFrontParam
             f2_t n = dwt::pack2(0.f, 0.f);
             const uint32_t xrow = sX + (uint32_t)ch * 128u + (uint32_t)(h << 4), sw = ((uint32_t)ch & 7u) << 4;
             dwt::unit(taddr, w, [&](int oy, const f2_t (&acc)[4]) {
+              if (oy == 0 && xwait) { mbar_wait_spin(smem_u32(&bars->x_empty), (j & 1u) ^ 1u); xwait = false; }
               if (DBG & 32) { n = dwt::add2(n, dwt::add2(dwt::add2(acc[0], acc[1]), dwt::add2(acc[2], acc[3]))); return; }
               float a[8];
 #pragma unroll
