@@ -30,9 +30,9 @@ METRIC = "restormer_fwd_mpix_per_s"
 DTYPES = {
     # arithmetic the path computes in; both modes accumulate in fp32 and keep the residual stream, LayerNorm
     # statistics, softmax and GELU in fp32, and both meet the north-star parity bar (max-abs <= 1e-3, dPSNR <= 0.01 dB)
-    "fp32": "fp32 residual stream / qkv / accumulators, tf32 tensor-core operands; fp16 (same 10-bit mantissa) where a "
-            "tensor is only ever a tensor-core operand (norm2 output, v, folded attention matrix) and for the fused "
-            "GDFN's on-chip hidden tensor",
+    "fp32": "fp32 residual stream / accumulators / statistics / softmax / GELU, tf32 operands in the 3x3 convolutions; fp16 (same "
+            "10-bit mantissa) where a tensor is only ever a tensor-core operand (norm1 / norm2 output, v, folded attention "
+            "matrix, the fused kernels' on-chip operands) and for the intermediates of the two low-resolution levels (C > 128)",
     "half": "fp16 intermediates + fp16 tensor-core operands, fp32 accumulate and fp32 residual stream",
     "bf16": "bf16 intermediates + bf16 tensor-core operands, fp32 accumulate and fp32 residual stream (outside the 1e-3 "
             "parity bar: reported separately)",

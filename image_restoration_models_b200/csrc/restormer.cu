@@ -65,7 +65,23 @@ struct Builder {
   long long alloc(long long n) { const long long o = off; off += (n + 63) / 64 * 64; return o; }
 };
 
+static void plan_block_engine(Builder& bl, BlockPlan& bp, int C, int heads, double ffn, int bias, int ln_bias);
+
+// IR_MODE_FP32 at the two low-resolution levels (C > 128: 1/16 and 1/64 of the pixels, 13 % of the bytes, but 28 % of the
+// step as fp32 tensors): the block runs the 16-bit plan -- qkv, v, the GDFN hidden / gated tensors and the LayerNorm outputs
+// are fp16 (tf32's mantissa), the contractions take fp16 operands; the residual stream, statistics, softmax, GELU and every
+// accumulator stay fp32 as in every mode.  The high-resolution levels already keep those tensors on chip.  The pack-time
+// range guard covers these tensors (restormer.py _block_fp16_bound); IR_MODE_FP32_STRICT keeps fp32 everywhere.
 static void plan_block(Builder& bl, BlockPlan& bp, int C, int heads, double ffn, int bias, int ln_bias) {
+  static const bool no_wide16 = getenv("IRB_NO_WIDE16") != nullptr;           // A/B switch for benchmarks
+  const bool wide16 = !no_wide16 && bl.engine == ENGINE_TC && C > 128 && !bias;
+  if (wide16) bl.engine = ENGINE_TC_HALF;
+  plan_block_engine(bl, bp, C, heads, ffn, bias, ln_bias);
+  if (wide16) bl.engine = ENGINE_TC;
+  bp.wide16 = wide16;
+}
+
+static void plan_block_engine(Builder& bl, BlockPlan& bp, int C, int heads, double ffn, int bias, int ln_bias) {
   bp.C = C; bp.heads = heads;
   bp.h = (int)(C * ffn);           // int(dim*ffn_expansion_factor) in double precision, like Python (restormer.py:80)
   // python: int(48*2.66)=127, int(96*2.66)=255, int(192*2.66)=510, int(384*2.66)=1021
@@ -171,7 +187,7 @@ int build_block_plan(BlockPlan& bp, std::vector<PackOp>& ops, long long& packed_
   Builder bl(ops, engine);
   plan_block(bl, bp, C, heads, ffn, bias, ln_bias);
   packed_floats = bl.off;
-  IRB_REQUIRE(!bp.half || (bp.tc_qkv && bp.tc_attn && bp.tc_pin && bp.tc_pout),
+  IRB_REQUIRE(!bp.half || bp.wide16 || (bp.tc_qkv && bp.tc_attn && bp.tc_pin && bp.tc_pout),
               "half mode: channel widths must be multiples of 16 (tensor-core operand granularity)");
   return IR_OK;
 }
@@ -318,18 +334,20 @@ static int gram_parts(int B, int heads, int HW) {
 void block_scratch_need(BlockScratchNeed& n, const BlockPlan& bp, int B, int H, int W) {
   const long long P = (long long)B * H * W;
   const int ch = bp.C / bp.heads;
+  // intermediates are fp32 or 16-bit PER BLOCK (the wide levels of the fp32 mode run the 16-bit plan): sizes in floats
+  const long long es = bp.half ? 2 : 4;
+  auto fl = [&](long long elems) { return (elems * es + 3) / 4; };
   if (bp.fuse_attn) n.v16 = std::max(n.v16, P * bp.C);      // qkv stays on chip; only v (fp16) is written
-  else n.qkv = std::max(n.qkv, P * 3 * bp.C);
-  if (!bp.fuse_ffn) n.hidden = std::max(n.hidden, P * 2 * bp.hp);            // fused GDFN: the hidden tensor stays on chip
-  if (!bp.fuse_ffn && !bp.fuse_tail) n.gated = std::max(n.gated, P * bp.hp);
+  else n.qkv = std::max(n.qkv, fl(P * 3 * bp.C));
+  if (!bp.fuse_ffn) n.hidden = std::max(n.hidden, fl(P * 2 * bp.hp));        // fused GDFN: the hidden tensor stays on chip
+  if (!bp.fuse_ffn && !bp.fuse_tail) n.gated = std::max(n.gated, fl(P * bp.hp));
   const int parts = bp.fuse_attn ? attn_fused_parts(B, H, W)
                   : bp.fuse_front ? attn_front_parts(B, H, W, bp.C, bp.heads) : gram_parts(B, bp.heads, H * W);
   n.s_part = std::max(n.s_part, (long long)B * bp.heads * parts * ch * ch);
   n.n_part = std::max(n.n_part, (long long)B * bp.heads * parts * 2 * ch);
-  n.w_eff = std::max(n.w_eff, (long long)B * bp.C * bp.kp_attn);
-  if (bp.C > 128 || bp.fuse_ffn) n.xhat = std::max(n.xhat, P * bp.C);
+  n.w_eff = std::max(n.w_eff, fl((long long)B * bp.C * bp.kp_attn));
+  if (bp.C > 128 || bp.fuse_ffn) n.xhat = std::max(n.xhat, fl(P * bp.C));
   if (bp.fuse_attn) n.xhat2 = std::max(n.xhat2, (P * bp.C + 1) / 2);      // fp16 norm1 output, counted in floats
-  n.es = bp.half ? 2 : 4;
 }
 
 struct Carver {
@@ -344,16 +362,15 @@ struct Carver {
 };
 
 void carve_block_scratch(Carver& cv, BlockScratch& bs, const BlockScratchNeed& n) {
-  // intermediates are fp32 or fp16 (n.es bytes per element); take() counts in floats
-  auto elems = [&](long long e) { return (e * n.es + 3) / 4; };
-  bs.qkv = cv.take(elems(n.qkv));
-  bs.qkv_dw = cv.take(std::max(elems(n.qkv), (n.v16 + 1) / 2));
-  bs.hidden = cv.take(elems(n.hidden));
-  bs.gated = cv.take(elems(n.gated));
+  // sizes are in floats already (block_scratch_need)
+  bs.qkv = cv.take(n.qkv);
+  bs.qkv_dw = cv.take(std::max(n.qkv, (n.v16 + 1) / 2));
+  bs.hidden = cv.take(n.hidden);
+  bs.gated = cv.take(n.gated);
   bs.s_part = cv.take(n.s_part);
   bs.n_part = cv.take(n.n_part);
-  bs.w_eff = cv.take(elems(n.w_eff));
-  bs.xhat = cv.take(elems(n.xhat));
+  bs.w_eff = cv.take(n.w_eff);
+  bs.xhat = cv.take(n.xhat);
   bs.xhat2 = cv.take(n.xhat2);
 }
 

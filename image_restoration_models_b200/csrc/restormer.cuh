@@ -32,7 +32,8 @@ struct BlockPlan {     // one TransformerBlock (restormer.py:137-150); offsets i
   bool k4_xn;                              // the attention-output contraction also emits norm2(x) as the fused GDFN's fp16 operand
   int kp_attn;                             // K pitch of the folded attention matrix W_eff (padded for the TMA kernel)
   bool ref_kernels;                        // ENGINE_SIMT: reference CUDA-core kernels everywhere
-  bool half;                               // ENGINE_TC_HALF: fp16 intermediates (qkv, v, hidden, gated) and fp16 operands
+  bool half;                               // 16-bit plan: fp16 intermediates (qkv, v, hidden, gated) and fp16 operands
+  bool wide16 = false;                     // ... chosen for this block by IR_MODE_FP32 (C > 128), not by the mode
 };
 
 struct ConvPlan { int cout, cin, k, kp; long long w, b; bool tc; int cout_p; bool tma = false; };   // cout_p: rows in the packed weight (>= cout, zero rows)
@@ -47,7 +48,7 @@ struct RestormerPlan {
   std::vector<BlockPlan> enc[4], dec[3], refine;
 };
 
-struct BlockScratchNeed { long long qkv = 0, hidden = 0, gated = 0, s_part = 0, n_part = 0, w_eff = 0, xhat = 0, xhat2 = 0, v16 = 0; int es = 4; };   // v16: fp16 elements of v where the fused front writes it
+struct BlockScratchNeed { long long qkv = 0, hidden = 0, gated = 0, s_part = 0, n_part = 0, w_eff = 0, xhat = 0, xhat2 = 0, v16 = 0; };   // floats (v16: fp16 elements)   // v16: fp16 elements of v where the fused front writes it
 struct BlockScratch { void *qkv, *qkv_dw, *hidden, *gated; float *s_part, *n_part; void *w_eff, *xhat, *xhat2; };   // xhat: norm2 / wide-level LayerNorm output, xhat2: fp16 norm1 output of the fused MDTA front
 struct RestormerWs { float* e[4]; float* e1_in; float* d[3]; float* up_tmp; BlockScratch bs; };
 

@@ -18,8 +18,9 @@ from .._params import AffineParams, ConvParams, Holder, ordered_tensors
 _MODES = {"fp32": _native.MODE_FP32, "half": _native.MODE_HALF, "fp32_simt": _native.MODE_FP32_SIMT,
           "fp32_strict": _native.MODE_FP32_STRICT, "bf16": _native.MODE_BF16}
 
-# Range guard of the fast fp32 mode.  IR_MODE_FP32 keeps the tensors that are only ever tensor-core operands (norm2
-# output, v, the fused GDFN's on-chip hidden / gated tensors) as fp16: tf32's mantissa but 5 exponent bits.  The device
+# Range guard of the fast fp32 mode.  IR_MODE_FP32 keeps the tensors that are only ever tensor-core operands (norm1 / norm2
+# output, v, the fused kernels' on-chip operands) as fp16, and runs the two low-resolution levels (C > 128) on the 16-bit
+# plan (qkv, hidden, gated as fp16): tf32's mantissa but 5 exponent bits.  The device
 # conversions saturate (+-65504, never inf).  At pack time `fp16_range_bound` estimates how large those tensors get from
 # the weights alone; a model whose estimate comes near fp16's range runs in IR_MODE_FP32_STRICT (tf32 operands and
 # fp32 tensors everywhere) instead.  The estimate is statistical, not worst-case (an L1 worst case is ~1000x above what a
@@ -33,9 +34,11 @@ BIASFREE_MEAN_OVER_STD = 4.0
 RANGE_SIGMAS = 6.0
 
 
-def _block_fp16_bound(blk, with_bias: bool, fused_gdfn: bool) -> torch.Tensor:
+def _block_fp16_bound(blk, with_bias: bool, fused_gdfn: bool, wide: bool = False) -> torch.Tensor:
     """RANGE_SIGMAS-sigma estimate of max(|xn2|, |hidden|, |gated|, |v|) of one TransformerBlock (restormer.py:88-93,
-    :111-116); xn2 / hidden / gated only count where the block runs the fused GDFN (C <= 128).  0-d device tensor."""
+    :111-116); xn2 / hidden / gated count where the block keeps them as fp16: under the fused GDFN (C <= 128) and at the
+    wide levels (C > 128), which IR_MODE_FP32 runs on the 16-bit plan -- there qkv before and after its depthwise conv
+    and norm1's output count too.  0-d device tensor."""
     m = 1.0 if with_bias else (1.0 + BIASFREE_MEAN_OVER_STD ** 2) ** 0.5
 
     def ln_stats(body):
@@ -53,7 +56,9 @@ def _block_fp16_bound(blk, with_bias: bool, fused_gdfn: bool) -> torch.Tensor:
     sq, mq = conv_out(blk.attn.qkv.weight, var1, mu1)
     dq = blk.attn.qkv_dwconv.weight.detach().abs().double().flatten(1).sum(1)
     out = [((k * sq + mq) * dq)[2 * c:].max()]                                   # v
-    if fused_gdfn:
+    if wide:
+        out += [(k * torch.sqrt(var1) + mu1).max(), (k * sq + mq).max(), ((k * sq + mq) * dq).max()]   # xn1, qkv, dw(qkv)
+    if fused_gdfn or wide:
         var2, mu2 = ln_stats(blk.norm2.body)
         sh, mh = conv_out(blk.ffn.project_in.weight, var2, mu2)
         di = blk.ffn.dwconv.weight.detach().abs().double().flatten(1).sum(1)
@@ -198,7 +203,8 @@ class Restormer(nn.Module):
             c = blk.norm2.body.weight.numel()
             hp = -(-(blk.ffn.project_out.weight.shape[1]) // 16) * 16
             return c % 16 == 0 and c <= 128 and hp % 64 == 0 and hp >= 128
-        bounds = [_block_fp16_bound(b, self._with_bias_ln, fused(b)) for b in self._blocks()]
+        wide = lambda blk: blk.norm2.body.weight.numel() > 128      # mirrors plan_block (csrc/restormer.cu): 16-bit plan
+        bounds = [_block_fp16_bound(b, self._with_bias_ln, fused(b), wide(b)) for b in self._blocks()]
         return float(torch.stack(bounds).max()) if bounds else 0.0
 
     def resolved_mode(self) -> str:

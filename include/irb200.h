@@ -40,9 +40,11 @@ typedef enum IrStatus {
 /* Arithmetic mode of the tensor-core contractions.  Accumulation is always fp32, and the
  * residual stream, LayerNorm statistics, softmax and GELU are always fp32. */
 typedef enum IrMode {
-  IR_MODE_FP32 = 0,        /* fp32 residual stream / qkv, tf32 tensor-core operands; tensors that are only ever tensor-core
-                              operands (norm2 output, v, folded attention matrix) and the fused GDFN's on-chip hidden
-                              tensor are fp16 -- the same 10-bit mantissa (fp32 parity mode) */
+  IR_MODE_FP32 = 0,        /* fp32 residual stream, fp32 accumulation / statistics / softmax / GELU, tf32 operands in the 3x3
+                              convolutions; tensors that are only ever tensor-core operands (norm1 / norm2 output, v, folded
+                              attention matrix, the fused kernels' on-chip operands) are fp16 -- the same 10-bit mantissa --
+                              and the two low-resolution levels (C > 128) run the 16-bit plan of IR_MODE_HALF (qkv, hidden,
+                              gated as fp16).  The default (parity) mode: max-abs <= 1e-3 */
   IR_MODE_HALF = 1,        /* fp16 intermediates + fp16 operands (same 10-bit mantissa as tf32) */
   IR_MODE_FP32_SIMT = 2,   /* every contraction on CUDA cores in exact fp32: the on-device second oracle of the
                               tensor-core kernels (tests / bisecting only; several times slower) */
