@@ -372,7 +372,10 @@ def main():
     f16_peak = tpeaks["fp16_tflops_sustained"] if tpeaks else bf16_peak
     tpeak_src = ("profiles/tensor_peaks.json (torch.matmul 8192^3, sustained)" if tpeaks else
                  "MEASURED_PEAKS.json bf16 sustained (tf32 taken as half of it: no measured tf32 peak on file)")
-    F16_FAMILIES = {"gdfn_fused", "dwconv_qkv_gram", "attn_out_1x1", "mdta_fused_front"}
+    # (fp32 mode: everything but the 3x3 convolutions and reduce_chan takes fp16 operands -- the fused kernels, the attention
+    # output, and the 16-bit plan of the two low-resolution levels)
+    F16_FAMILIES = {"gdfn_fused", "dwconv_qkv_gram", "attn_out_1x1", "mdta_fused_front", "ln_qkv_1x1", "ln_project_in_1x1",
+                    "ffn_project_out_1x1", "dwconv_gate_project_out", "dwconv3x3_gelu_gate"}
     step_ms_sum = sum(r["ms"] for r in rows)
     kernels = []
     for r in rows:

@@ -45,7 +45,14 @@ for k in d["kernels"]:
         which = "HBM" if k["hbm_frac"] >= k["tensor_frac"] else "tensor"
         fam.append(f"{name} {ms:.1f} ms ({k['best_frac']:.2f} {which})")
 t = d["tiled_config4"]
+par = json.load(open(os.path.join(G, f"parity_{tag}.json")))
+e = lambda k: f"{par[k]['max_abs']:.1e}" if k in par else "n/a"
+p512 = lambda m: " / ".join(e(f"size512_{t}[{m}]") for t in ("gray_denoise", "motion_deblur", "defocus_dual"))
+b8 = max((v["max_abs"] for k, v in par.items() if k.startswith("config2_batch8_element") and "[fp32]" in k), default=float("nan"))
+gold = lambda m: max(v["max_abs"] for k, v in par.items() if k.startswith("restormer_") and k.endswith(f"[{m}]"))
 sub = {
+    "@GOLDF@": f"{gold('fp32'):.1e}", "@GOLDH@": f"{gold('half'):.1e}",
+    "@P512F@": p512("fp32"), "@P512H@": p512("half"), "@PB8@": f"≤ {b8:.1e}",
     "@FP32@": f"{d['value']:.1f}", "@FP32MS@": f"{d['ms_per_step']:.1f}", "@HALF@": f"{d['other_mode']['value']:.1f}",
     "@BF16@": f"{d['bf16_mode']['value']:.1f}", "@E2E@": f"{d['e2e']['value']:.1f}",
     "@TILED@": f"{t['value']:.1f}", "@TILEDC@": f"{t['computed_tile_mpix_per_s']:.1f}",
