@@ -33,10 +33,11 @@
 //                         B = the xn patch, N = 192) into a double-buffered accumulator, and the Gram S += q . k^T of the
 //                         PREVIOUS tile (A = the q rows, B = the k rows of the X tile)
 //
-// Channel groups.  3C = 288 (144) channels are 9 (4.5) units of 32; the accumulator has 128 lanes.  Group 0 = W rows 0..127
-// (units 0-3 on quarters 0-3), group 1 = rows 128..255 (unit 4 on quarter 0; at C = 96 the other quarters hold units 5-7,
-// which group 2 computes again and nobody reads here), group 2 (C = 96) = rows 160..287 (units 5-8).  Rows of D^T are
-// independent, so lanes fed by rows past the weight image hold garbage that is never read.
+// Channel groups.  3C = 288 (144) channels are 9 (4.5) units of 32 = 4 n + 1; the accumulator has 128 lanes.  Full groups:
+// W rows 128 g .. 128 g + 127 (units 4 g .. 4 g + 3 on quarters 0-3; they hold every q | k channel).  The last group is the
+// LONE unit (the last 32 channels of v): tile j puts it on lane quarter j & 3 by starting its 128-row window 32 (j & 3) rows
+// early.  Rows of D^T are independent, so lanes fed by other rows (or by rows past the weight image) hold values that are
+// never read.  The quarter with three units thus changes from tile to tile, and the others run ahead into the next tile.
 //
 // fold_kernel then reduces the partials in a fixed order (deterministic, no atomics).
 #include "attn_fused.cuh"
@@ -110,10 +111,18 @@ template <int CW> struct Geo {
   static constexpr uint32_t A_TX = NKB * HPIX * 128;         // bytes one patch load delivers
   static constexpr uint32_t W_BYTES = NKB * NP * 128;
   // first W row of a group
-  __host__ __device__ static constexpr int start_row(int g) { return g == 0 ? 0 : g == 1 ? 128 : 160; }
+  // first W row of a full group (the last group is the lone unit, see lone_start_row)
+  __host__ __device__ static constexpr int start_row(int g) { return g * 128; }
+  // the LAST group holds one unit only (the last 32 channels of v: 3C is 4 n + 1 units at both widths).  Tile j places it on
+  // lane quarter j & 3 (its 128-row window starts 32 * (j & 3) rows early; the other lanes get rows nobody reads), so that the
+  // quarter with three units changes from tile to tile while the others run ahead into the next tile's first group
+  __host__ __device__ static constexpr int lone_start_row(int r) { return (NUNITS - 1 - r) * UC; }
 };
 // the unit lane quarter q reads from group g (-1: nothing new in that quarter)
-__device__ __forceinline__ int unit_of(int g, int q) { return g == 0 ? q : g == 1 ? (q == 0 ? 4 : -1) : 5 + q; }
+// the unit lane quarter q reads from group g of `ng` (-1: nothing new in that quarter); r = the lone unit's quarter
+__device__ __forceinline__ int unit_of(int g, int ng, int nunits, int q, int r) {
+  return g < ng - 1 ? 4 * g + q : (q == r ? nunits - 1 : -1);
+}
 
 struct TileIter {
   int t, step, end, tx_n;
@@ -204,13 +213,16 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const FusedFrontParam
       tc_fence_after();
       const uint32_t d = tmem_base + sd * D1_COLS;
       const uint64_t pdesc = sw128_desc(sA + ab * G::A_BYTES);
+      // the lone unit's window moves with the tile (the only runtime term of the descriptors)
+      const uint64_t wbase = wdesc + (grp == G::NG - 1 ? (uint64_t)((G::lone_start_row((int)(jg & 3u)) * 128) >> 4)
+                                                       : (uint64_t)((G::start_row(grp) * 128) >> 4));
 #pragma unroll
       for (int kb = 0; kb < G::NKB; ++kb) {
 #pragma unroll
         for (int kk = 0; kk < (kb == G::NKB - 1 ? G::KS_LAST : 4); ++kk) {
           if (DBG & 8) continue;
           // descriptors: base + (byte offset >> 4); the whole offset is a compile-time constant
-          const uint64_t wd = wdesc + (uint64_t)((kb * G::NP * 128 + G::start_row(grp) * 128 + kk * 32) >> 4);
+          const uint64_t wd = wbase + (uint64_t)((kb * G::NP * 128 + kk * 32) >> 4);
           const uint64_t pd = pdesc + (uint64_t)((kb * ABOX + kk * 32) >> 4);
           umma_elect<__half>(d, wd, pd, idesc1, (kb > 0 || kk > 0) ? 1u : 0u);
         }
@@ -265,7 +277,7 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const FusedFrontParam
       bool xwait = true;
 #pragma unroll 1
       for (int grp = 0; grp < G::NG; ++grp, ++gg) {
-        const int u = unit_of(grp, q);
+        const int u = unit_of(grp, G::NG, G::NUNITS, q, (int)(j & 3u));
         const bool active = u >= 0 && u < G::NUNITS && !(DBG & 2);
         const int ch = u * UC + lane;                        // this thread's qkv channel
         f2_t w[9];
@@ -339,10 +351,13 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const FusedFrontParam
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&bars->d1_empty[sd]));
+        if (grp == G::NG - 2) {
+          // every q | k unit lives in the full groups: the X tile is complete, the Gram can go (the lone v unit is still ahead)
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&bars->x_ready));
+        }
       }
-      fence_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&bars->x_ready));
     }
     // ---- squared-norm partials: the two column halves of every q | k channel ----
     asm volatile("bar.sync 1, %0;" ::"n"(DW_WARPS * 32) : "memory");
