@@ -157,6 +157,7 @@ attn_front_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
+  pdl_sync();   // set-up done under the previous kernel's tail; from here on global memory is ours (common.cuh)
 
   if (warp == WARP_H) {
     // =============================== patch / tap producer ===============================
@@ -416,8 +417,7 @@ template <typename TH_, int NQK, bool VH>
 int launch_inst(const CUtensorMap& tH, const CUtensorMap& tV, const FrontParams& p, dim3 grid, size_t smem, cudaStream_t s) {
   static SmemOptIn optin;
   IRB_TRY(opt_in_smem(attn_front_kernel<TH_, NQK, VH>, optin));
-  attn_front_kernel<TH_, NQK, VH><<<grid, NTHREADS, smem, s>>>(tH, tV, p);
-  IRB_LAUNCH_CHECK();
+  IRB_CUDA(launch_pdl(attn_front_kernel<TH_, NQK, VH>, grid, dim3(NTHREADS), smem, s, tH, tV, p));
   return IR_OK;
 }
 

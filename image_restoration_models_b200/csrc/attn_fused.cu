@@ -179,6 +179,7 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const FusedFrontParam
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
+  pdl_sync();   // set-up done under the previous kernel's tail; from here on global memory is ours (common.cuh)
 
   if (warp == WARP_PROD) {
     // =============================== producer: W_qkv once, the xn patches ===============================
@@ -437,8 +438,7 @@ template <int CW, int DBG = 0>
 int launch_inst(const CUtensorMap& tA, const FusedFrontParams& p, dim3 grid, size_t smem, cudaStream_t s) {
   static SmemOptIn optin;
   IRB_TRY(opt_in_smem(attn_fused_kernel<CW, DBG>, optin));
-  attn_fused_kernel<CW, DBG><<<grid, NTHREADS, smem, s>>>(tA, p);
-  IRB_LAUNCH_CHECK();
+  IRB_CUDA(launch_pdl(attn_fused_kernel<CW, DBG>, grid, dim3(NTHREADS), smem, s, tA, p));
   return IR_OK;
 }
 

@@ -5,6 +5,7 @@
 #include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string>
 
 #include "../../include/irb200.h"
@@ -47,6 +48,40 @@ __device__ __forceinline__ __half2 f2h2_sat(float lo, float hi) {
   asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
 #endif
   return *reinterpret_cast<__half2*>(&r);
+}
+#endif
+
+#ifdef __CUDACC__
+// ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch (opt-in, see pdl_enabled).  Every kernel of the forward can be launched with the
+// programmatic-stream-serialisation attribute (launch_pdl) and follows ONE rule: its set-up (barrier initialisation, tensor-memory allocation, tensor-map
+// prefetch: nothing that reads or writes global memory another kernel of the forward touches) runs first, then
+// pdl_wait() -- which returns once the preceding grid has completed and flushed -- and only then the first global access.
+// pdl_trigger() sits next to it: the next grid's blocks may then take an SM the moment this grid's block leaves it and run
+// their own set-up under this grid's tail.  Both instructions are no-ops in a launch without the attribute.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_sync() { pdl_wait(); pdl_trigger(); }
+
+// OFF by default: measured on B200 (profiles/r02_pdl_ab.json) it shortens back-to-back plain launches of batch-1 forwards
+// (256x256 tile 5.31 -> 4.82 ms) but not the CUDA-graph replay the latency path uses (4.73 ms either way), and at batch 8 the
+// step is 0.1-0.8 % SLOWER (the early-resident blocks of the next grid cost more than the set-up they hide).  IRB_PDL=1 turns it on.
+static inline bool pdl_enabled() {
+  static const bool on = getenv("IRB_PDL") != nullptr;
+  return on;
+}
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                                     Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 #endif
 

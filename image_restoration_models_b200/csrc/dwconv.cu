@@ -88,6 +88,7 @@ __global__ void __launch_bounds__(256, 2) dw_roll_kernel(const DwParams p, const
     wsm[cvl * WS + set * 9 + tap] = w;
   }
   __syncthreads();
+  pdl_sync();   // the taps (constants) are staged under the previous kernel's tail (common.cuh)
 
   const int xl = tid / g.cvb, cvl = tid - xl * g.cvb;
   const int x0 = (blockIdx.y * g.xb + xl) * WT;
@@ -202,9 +203,8 @@ int launch_typed(const DwParams& p, cudaStream_t s) {
   const int wt = p.gate ? 2 : 4;
   dim3 grid(cdiv(cv, g.cvb), cdiv(p.W, g.xb * wt), p.B * cdiv(p.H, g.rows));
   const size_t smem = (size_t)((p.gate ? 2 : 1) * 9 + 1) * g.cvb * sizeof(float4);
-  if (p.gate) dw_roll_kernel<TI, TO, 2, true><<<grid, 256, smem, s>>>(p, g);
-  else        dw_roll_kernel<TI, TO, 4, false><<<grid, 256, smem, s>>>(p, g);
-  IRB_LAUNCH_CHECK();
+  if (p.gate) IRB_CUDA(launch_pdl(dw_roll_kernel<TI, TO, 2, true>, grid, dim3(256), smem, s, p, g));
+  else        IRB_CUDA(launch_pdl(dw_roll_kernel<TI, TO, 4, false>, grid, dim3(256), smem, s, p, g));
   return IR_OK;
 }
 

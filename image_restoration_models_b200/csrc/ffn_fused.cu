@@ -171,6 +171,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
+  pdl_sync();   // set-up done under the previous kernel's tail; from here on global memory is ours (common.cuh)
 
   uint32_t ntl = 0;
   for (TileIter ti(p); ti.valid(); ti.next()) ++ntl;
@@ -532,8 +533,7 @@ template <int CW, int DBG = 0, bool NEXT = false>
 int launch_inst(const CUtensorMap& tA, const CUtensorMap& tY, const FusedParams& p, int grid, size_t smem, cudaStream_t s) {
   static SmemOptIn optin;
   IRB_TRY(opt_in_smem(ffn_fused_kernel<CW, DBG, NEXT>, optin));
-  ffn_fused_kernel<CW, DBG, NEXT><<<grid, NTHREADS, smem, s>>>(tA, tY, p);
-  IRB_LAUNCH_CHECK();
+  IRB_CUDA(launch_pdl(ffn_fused_kernel<CW, DBG, NEXT>, dim3(grid), dim3(NTHREADS), smem, s, tA, tY, p));
   return IR_OK;
 }
 

@@ -133,6 +133,7 @@ ffn_tail_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
+  pdl_sync();   // set-up done under the previous kernel's tail; from here on global memory is ours (common.cuh)
 
   if (warp == WARP_H) {
     // =============================== hidden / weight producer ===============================
@@ -328,8 +329,7 @@ int launch_inst(const CUtensorMap& tH, const CUtensorMap& tR, const CUtensorMap&
                 size_t smem, cudaStream_t s) {
   static SmemOptIn optin;
   IRB_TRY(opt_in_smem(ffn_tail_kernel<TH_>, optin));
-  ffn_tail_kernel<TH_><<<grid, (EPI_WARPS + Geo<TH_>::DW_WARPS + 3) * 32, smem, s>>>(tH, tR, tY, p);
-  IRB_LAUNCH_CHECK();
+  IRB_CUDA(launch_pdl(ffn_tail_kernel<TH_>, dim3(grid), dim3((EPI_WARPS + Geo<TH_>::DW_WARPS + 3) * 32), smem, s, tH, tR, tY, p));
   return IR_OK;
 }
 

@@ -366,6 +366,7 @@ __global__ void __launch_bounds__(1024) fold_kernel(const FoldParams p) {
   float* nk = nq + ch;           // [ch]
   const int tid = threadIdx.x;
   const long long pb = ((long long)b * p.heads + head) * p.nparts;
+  pdl_sync();
   // deterministic reduction of the pixel-slice partials (fixed order), 16-byte loads, 8 slices in flight per thread
   for (int e = tid * 4; e < ch * ch; e += blockDim.x * 4) {
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -455,7 +456,7 @@ int launch_fold(const FoldParams& p, cudaStream_t s) {
   ProfScope prof(TAG_FOLD, 4.0 * (double)p.B * p.C * p.C, 2.0 * (double)p.B * p.C * p.C * ch, s);
   // 1024 threads: the kernel is a chain of L2 round trips (partials -> softmax -> products) over a 48x48 .. 96x96 matrix;
   // four times the threads is a quarter of the trips per thread
-  fold_kernel<<<grid, 1024, smem, s>>>(p);
+  IRB_CUDA(launch_pdl(fold_kernel, dim3(grid), dim3(1024), smem, s, p));
   IRB_LAUNCH_CHECK();
   return IR_OK;
 }
@@ -478,6 +479,7 @@ __global__ void __launch_bounds__(256) conv3x3_small_kernel(const float* __restr
     wsm[i] = w[(long long)co * kp + k];
   }
   __syncthreads();
+  pdl_sync();   // the weights (constants) are staged under the previous kernel's tail (common.cuh)
   const int lane = threadIdx.x & 31;
   const int segs = (W + 31) >> 5;
   const long long nwarps = (long long)B * H * segs;
@@ -562,10 +564,10 @@ int launch_conv3x3_small(const float* in, int ld, int cin, const float* w, int k
   const double pix = (double)B * H * W;
   ProfScope prof(TAG_CONV3, 4.0 * pix * (cin + cout * (r ? 2.0 : 1.0)), 2.0 * 9.0 * pix * cin * cout, s);
   switch (cout) {
-    case 1: conv3x3_small_kernel<1><<<blocks, 256, smem, s>>>(in, ld, cin, w, kp, bias, B, H, W, r, sign, y); break;
-    case 2: conv3x3_small_kernel<2><<<blocks, 256, smem, s>>>(in, ld, cin, w, kp, bias, B, H, W, r, sign, y); break;
-    case 3: conv3x3_small_kernel<3><<<blocks, 256, smem, s>>>(in, ld, cin, w, kp, bias, B, H, W, r, sign, y); break;
-    default: conv3x3_small_kernel<4><<<blocks, 256, smem, s>>>(in, ld, cin, w, kp, bias, B, H, W, r, sign, y); break;
+    case 1: IRB_CUDA(launch_pdl(conv3x3_small_kernel<1>, dim3(blocks), dim3(256), smem, s, in, ld, cin, w, kp, bias, B, H, W, r, sign, y)); break;
+    case 2: IRB_CUDA(launch_pdl(conv3x3_small_kernel<2>, dim3(blocks), dim3(256), smem, s, in, ld, cin, w, kp, bias, B, H, W, r, sign, y)); break;
+    case 3: IRB_CUDA(launch_pdl(conv3x3_small_kernel<3>, dim3(blocks), dim3(256), smem, s, in, ld, cin, w, kp, bias, B, H, W, r, sign, y)); break;
+    default: IRB_CUDA(launch_pdl(conv3x3_small_kernel<4>, dim3(blocks), dim3(256), smem, s, in, ld, cin, w, kp, bias, B, H, W, r, sign, y)); break;
   }
   IRB_LAUNCH_CHECK();
   return IR_OK;
@@ -587,6 +589,7 @@ __global__ void __launch_bounds__(256) conv3x3_first_kernel(const float* __restr
     wsm[k * cout + co] = w[(long long)co * kp + k];
   }
   __syncthreads();
+  pdl_sync();   // the weights (constants) are staged under the previous kernel's tail (common.cuh)
   // grid.y walks the B*H image rows, grid.x the W * cout/4 (pixel, quad) pairs of a row: 32-bit index arithmetic only
   // (64-bit divisions per thread cost more than the convolution)
   const int q4 = cout >> 2;
@@ -628,9 +631,9 @@ int launch_conv3x3_first(const float* x_nchw, int cin, const float* w, int kp, c
   const double pix = (double)B * H * W;
   ProfScope prof(TAG_CONV3, 4.0 * pix * (cin + cout), 2.0 * 9.0 * pix * cin * cout, s);
   switch (cin) {
-    case 1: conv3x3_first_kernel<1><<<blocks, 256, smem, s>>>(x_nchw, w, kp, bias, relu, cout, B, H, W, y, ldy); break;
-    case 3: conv3x3_first_kernel<3><<<blocks, 256, smem, s>>>(x_nchw, w, kp, bias, relu, cout, B, H, W, y, ldy); break;
-    default: conv3x3_first_kernel<6><<<blocks, 256, smem, s>>>(x_nchw, w, kp, bias, relu, cout, B, H, W, y, ldy); break;
+    case 1: IRB_CUDA(launch_pdl(conv3x3_first_kernel<1>, dim3(blocks), dim3(256), smem, s, x_nchw, w, kp, bias, relu, cout, B, H, W, y, ldy)); break;
+    case 3: IRB_CUDA(launch_pdl(conv3x3_first_kernel<3>, dim3(blocks), dim3(256), smem, s, x_nchw, w, kp, bias, relu, cout, B, H, W, y, ldy)); break;
+    default: IRB_CUDA(launch_pdl(conv3x3_first_kernel<6>, dim3(blocks), dim3(256), smem, s, x_nchw, w, kp, bias, relu, cout, B, H, W, y, ldy)); break;
   }
   IRB_LAUNCH_CHECK();
   return IR_OK;
@@ -654,6 +657,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
   const int f4n = C >> 2;
+  pdl_sync();
   for (long long row = warp0; row < rows; row += nwarps) {
     float4 v[8];
     float s = 0.f;
@@ -720,6 +724,7 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(const float* __rest
     g[i] = __ldg(reinterpret_cast<const float4*>(w) + i * LPR + l);
     bb[i] = ln_mode == LN_WITHBIAS ? __ldg(reinterpret_cast<const float4*>(b) + i * LPR + l) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
+  pdl_sync();
   for (long long row0 = warp0 * RPW; row0 < rows; row0 += nwarps * RPW) {
     const long long row = row0 + r;
     const bool ok = row < rows;
@@ -769,8 +774,8 @@ static int launch_layernorm_rows(const float* x, void* y, int y_fmt, long long r
   constexpr int RPB = 8 * (32 / LPR);      // pixels per block pass
   const long long need = cdivll(rows, RPB);
   const int blocks = (int)(need < 148LL * 8 ? (need > 0 ? need : 1) : 148LL * 8);
-  if (y_half) layernorm_rows_kernel<__half, LPR, 3><<<blocks, 256, 0, s>>>(x, (__half*)y, rows, ln_mode, w, b, 0);
-  else        layernorm_rows_kernel<float, LPR, 3><<<blocks, 256, 0, s>>>(x, (float*)y, rows, ln_mode, w, b, rnd);
+  if (y_half) IRB_CUDA(launch_pdl(layernorm_rows_kernel<__half, LPR, 3>, dim3(blocks), dim3(256), 0, s, x, (__half*)y, rows, ln_mode, w, b, 0));
+  else        IRB_CUDA(launch_pdl(layernorm_rows_kernel<float, LPR, 3>, dim3(blocks), dim3(256), 0, s, x, (float*)y, rows, ln_mode, w, b, rnd));
   IRB_LAUNCH_CHECK();
   return IR_OK;
 }
@@ -794,8 +799,8 @@ int launch_layernorm(const float* x, int ldx, void* y, int ldy, int y_fmt, long 
       default: break;
     }
   }
-  if (y_half) layernorm_kernel<__half><<<blocks > 0 ? blocks : 1, 256, 0, s>>>(x, ldx, (__half*)y, ldy, rows, C, ln_mode, w, b, 0);
-  else        layernorm_kernel<float><<<blocks > 0 ? blocks : 1, 256, 0, s>>>(x, ldx, (float*)y, ldy, rows, C, ln_mode, w, b, y_fmt == 2);
+  if (y_half) IRB_CUDA(launch_pdl(layernorm_kernel<__half>, dim3(blocks > 0 ? blocks : 1), dim3(256), 0, s, x, ldx, (__half*)y, ldy, rows, C, ln_mode, w, b, 0));
+  else        IRB_CUDA(launch_pdl(layernorm_kernel<float>, dim3(blocks > 0 ? blocks : 1), dim3(256), 0, s, x, ldx, (float*)y, ldy, rows, C, ln_mode, w, b, y_fmt == 2));
   IRB_LAUNCH_CHECK();
   return IR_OK;
 }
@@ -805,6 +810,7 @@ int launch_layernorm(const float* x, int ldx, void* y, int ldy, int y_fmt, long 
 // ---------------------------------------------------------------------------------------------
 __global__ void copy_channels_kernel(const float* __restrict__ src, int lds, float* __restrict__ dst, int ldd,
                                      long long rows, int c4) {
+  pdl_sync();
   const long long total = rows * c4;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -819,7 +825,7 @@ int launch_copy_channels(const float* src, int lds, float* dst, int ldd, long lo
   const long long total = rows * (C / 4);
   const int blocks = (int)(cdivll(total, 256) < 148LL * 16 ? cdivll(total, 256) : 148LL * 16);
   ProfScope prof(TAG_COPY, 8.0 * (double)rows * C, 0.0, s);
-  copy_channels_kernel<<<blocks > 0 ? blocks : 1, 256, 0, s>>>(src, lds, dst, ldd, rows, C / 4);
+  IRB_CUDA(launch_pdl(copy_channels_kernel, dim3(blocks > 0 ? blocks : 1), dim3(256), 0, s, src, lds, dst, ldd, rows, C / 4));
   IRB_LAUNCH_CHECK();
   return IR_OK;
 }

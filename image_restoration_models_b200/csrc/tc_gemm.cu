@@ -561,6 +561,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const TcGemmParams
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = hdr->tmem_base;
+  pdl_sync();   // set-up done under the previous kernel's tail; from here on global memory is ours (common.cuh)
 
   // tile range of this CTA: contiguous; per-image weights -> the CTA stays inside image blockIdx.z
   long long t_begin, t_end;
@@ -844,8 +845,7 @@ template <typename TA, typename TOp, typename TY, int MODE>
 static int launch_one(const TcGemmParams& p, dim3 grid, size_t smem, cudaStream_t s) {
   static SmemOptIn optin;
   IRB_TRY(opt_in_smem(tc_gemm_kernel<TA, TOp, TY, MODE>, optin));
-  tc_gemm_kernel<TA, TOp, TY, MODE><<<grid, NTHREADS, smem, s>>>(p);
-  IRB_LAUNCH_CHECK();
+  IRB_CUDA(launch_pdl(tc_gemm_kernel<TA, TOp, TY, MODE>, grid, dim3(NTHREADS), smem, s, p));
   return IR_OK;
 }
 

@@ -107,6 +107,7 @@ tma_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const Conv3Params p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
+  pdl_sync();   // set-up done under the previous kernel's tail; from here on global memory is ours (common.cuh)
 
   if (warp == WARP_A) {
     // =============================== activation / weight producer ===============================
@@ -336,8 +337,7 @@ template <typename TOp>
 int launch_inst(const CUtensorMap& tA, const Conv3Params& p, dim3 grid, size_t smem, cudaStream_t s) {
   static SmemOptIn optin;
   IRB_TRY(opt_in_smem(tma_conv3_kernel<TOp>, optin));
-  tma_conv3_kernel<TOp><<<grid, NTHREADS, smem, s>>>(tA, p);
-  IRB_LAUNCH_CHECK();
+  IRB_CUDA(launch_pdl(tma_conv3_kernel<TOp>, grid, dim3(NTHREADS), smem, s, tA, p));
   return IR_OK;
 }
 

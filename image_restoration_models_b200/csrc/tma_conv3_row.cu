@@ -173,6 +173,7 @@ conv3_row_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
+  pdl_sync();   // set-up done under the previous kernel's tail; from here on global memory is ours (common.cuh)
 
   if (warp == WARP_A) {
     // =============================== row producer ===============================
@@ -404,8 +405,7 @@ template <typename TOp>
 int launch_inst(const CUtensorMap& tA, const CUtensorMap& tY, const RowParams& p, int grid, size_t smem, cudaStream_t s) {
   static SmemOptIn optin;
   IRB_TRY(opt_in_smem(conv3_row_kernel<TOp>, optin));
-  conv3_row_kernel<TOp><<<grid, NTHREADS, smem, s>>>(tA, tY, p);
-  IRB_LAUNCH_CHECK();
+  IRB_CUDA(launch_pdl(conv3_row_kernel<TOp>, dim3(grid), dim3(NTHREADS), smem, s, tA, tY, p));
   return IR_OK;
 }
 

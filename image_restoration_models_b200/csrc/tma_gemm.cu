@@ -244,6 +244,7 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
+  pdl_sync();   // set-up (incl. the constant LayerNorm vectors) done under the previous kernel's tail (common.cuh)
 
   if (warp == WARP_A) {
     // =============================== A-producer ===============================
@@ -657,8 +658,7 @@ int launch_inst(const CUtensorMap& tA, const CUtensorMap& tR, const CUtensorMap&
                 const TmaGemmParams& p, dim3 grid, size_t smem, cudaStream_t s) {
   static SmemOptIn optin;
   IRB_TRY(opt_in_smem(tma_gemm_kernel<TOp, LN, TY>, optin));
-  tma_gemm_kernel<TOp, LN, TY><<<grid, NTHREADS, smem, s>>>(tA, tR, tY, tXn, p);
-  IRB_LAUNCH_CHECK();
+  IRB_CUDA(launch_pdl(tma_gemm_kernel<TOp, LN, TY>, grid, dim3(NTHREADS), smem, s, tA, tR, tY, tXn, p));
   return IR_OK;
 }
 
