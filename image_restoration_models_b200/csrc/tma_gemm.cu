@@ -583,7 +583,13 @@ bool configure(int K, int N, bool op_half, bool ln, bool has_r, bool y_half, Tma
     } else if (has_r) {
       const int boxes = (int)(rest / BOX);
       if (boxes < 4) continue;
-      RB = std::min(MAX_RB, std::max(2, boxes / 3));
+      // the two rings split the boxes in proportion to the bytes a tile pulls through them (fp32 residual columns against
+      // operand bytes): with a third of the boxes the residual ring held ONE tile at C = 96 -- load, epilogue and store of
+      // a tile's residual ran back to back with nothing in flight behind them
+      static const bool old_split = getenv("IRB_OLD_RING_SPLIT") != nullptr;    // A/B switch for benchmarks
+      const double rb = 4.0 * nc, ab = (double)K * op_es;
+      RB = old_split ? boxes / 3 : (int)((double)boxes * rb / (rb + ab));
+      RB = std::min(MAX_RB, std::max(2, std::min(RB, boxes - 2)));
       S = std::min(MAX_S, boxes - RB);
       if (S < 2) continue;
     } else {
