@@ -16,6 +16,7 @@
 #include "tmap.cuh"
 
 #include <type_traits>
+#include <cstdlib>
 
 namespace irb {
 
@@ -25,10 +26,18 @@ using namespace sm100;
 
 constexpr int TH = 8, TW = 16, TM = TH * TW;
 constexpr int BOX = TM * 128;
+// Patch mode (tf32 operands): the (8+2) x (14+2) halo patch of a 32-channel box is loaded ONCE -- [160 px][128 B], flattened
+// with a pitch of 16 pixels -- and tap (dy, dx) is a descriptor whose start address is shifted by dy * 16 + dx rows
+// (tcgen05 swizzles on absolute address bits: tma_conv3_row.cu).  MMA row i is then patch position (i / 16, i % 16): the
+// 8 x 14 positions with i % 16 < 14 are the tile's outputs, the other 16 lanes compute values nobody stores.  Activations
+// cross L2 -> SM 1.4 times instead of 9, and the tf32 rounding pass runs once per box instead of once per (tap, box).
+constexpr int PTW = 14, PPW = 16, PPH = TH + 2;
+constexpr int PTX = PPH * PPW * 128;           // bytes one patch load delivers (160 rows)
+constexpr int PBOX = 21 * 1024;                // stage pitch: the last tap's window ends at row 2 * 16 + 2 + 127 = 161
 constexpr int EPI_WARPS = 4, XF_WARPS = 4;
 constexpr int WARP_A = 8, WARP_MMA = 9;
 constexpr int NTHREADS = 10 * 32;
-constexpr int MAX_S = 8, MAX_OP = 4, MAX_W = 4;
+constexpr int MAX_S = 8, MAX_OP = 4, MAX_W = 16;
 constexpr int HDR = 1024;
 
 struct Bars {
@@ -50,16 +59,18 @@ struct Conv3Params {
   int tiles_x, tiles_y, ntiles;
   int nacc, acc_stride, tmem_cols;
   uint32_t off_a, off_op, off_w, wstage;
+  int patch;               // 1: patch mode (see PTW)
 };
 
 struct TileIter {
-  int t, step, end, tx_n, ty_n;
-  __device__ TileIter(const Conv3Params& p) : t(blockIdx.x), step(gridDim.x), end(p.ntiles), tx_n(p.tiles_x), ty_n(p.tiles_y) {}
+  int t, step, end, tx_n, ty_n, tw;
+  __device__ TileIter(const Conv3Params& p)
+      : t(blockIdx.x), step(gridDim.x), end(p.ntiles), tx_n(p.tiles_x), ty_n(p.tiles_y), tw(p.patch ? PTW : TW) {}
   __device__ bool valid() const { return t < end; }
   __device__ void next() { t += step; }
   __device__ int img() const { return t / (tx_n * ty_n); }
   __device__ int y0() const { return ((t / tx_n) % ty_n) * TH; }
-  __device__ int x0() const { return (t % tx_n) * TW; }
+  __device__ int x0() const { return (t % tx_n) * tw; }
 };
 
 template <typename TOp>
@@ -115,6 +126,25 @@ tma_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const Conv3Params p) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
       uint32_t sa = 0, pa = 0, sw = 0, pw = 0;
       const uint32_t wbytes = (uint32_t)ncur * 128u;
+      if (!OPRING && p.patch) {
+        for (TileIter ti(p); ti.valid(); ti.next()) {
+          const int b = ti.img(), y0 = ti.y0(), x0 = ti.x0();
+          for (int cb = 0; cb < p.nkb_t; ++cb) {
+            mbar_wait(smem_u32(&bars->a_empty[sa]), pa ^ 1u);
+            const uint32_t fa = smem_u32(&bars->a_full[sa]);
+            mbar_expect_tx(fa, PTX);
+            tma_load_4d(&tmA, fa, sA + sa * PBOX, cb * 32, x0 - 1, y0 - 1, b);
+            if (++sa == (uint32_t)p.S) { sa = 0; pa ^= 1u; }
+            for (int tap = 0; tap < 9; ++tap) {
+              mbar_wait(smem_u32(&bars->w_empty[sw]), pw ^ 1u);
+              const uint32_t fb = smem_u32(&bars->w_full[sw]);
+              mbar_expect_tx(fb, wbytes);
+              bulk_load(sW + sw * p.wstage, p.w + ((size_t)(tap * p.nkb_t + cb) * p.N + n0) * 128, wbytes, fb);
+              if (++sw == (uint32_t)p.NW) { sw = 0; pw ^= 1u; }
+            }
+          }
+        }
+      } else
       for (TileIter ti(p); ti.valid(); ti.next()) {
         const int b = ti.img(), y0 = ti.y0(), x0 = ti.x0();
         for (int tap = 0; tap < 9; ++tap) {
@@ -160,6 +190,29 @@ tma_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const Conv3Params p) {
       tc_fence_after();
       const uint32_t dacc = tmem_base + slot * (uint32_t)p.acc_stride;
       uint32_t acc = 0u;
+      if (!OPRING && p.patch) {
+        for (int ob = 0; ob < nbox_t; ++ob) {
+          const int nk = ob == nbox_t - 1 ? nk_last : 4;
+          mbar_wait(smem_u32(&a_rdy[so]), po);
+          tc_fence_after();
+          const uint64_t a0 = dhi | (uint64_t)((abase + so * PBOX) >> 4);
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(smem_u32(&bars->w_full[sw]), pw);
+            tc_fence_after();
+            const uint64_t ad = a0 + (uint64_t)((((tap / 3) * PPW + tap % 3) * 128) >> 4);
+            const uint64_t wd = dhi | (uint64_t)((sW + sw * p.wstage) >> 4);
+            for (int kk = 0; kk < nk; ++kk) {
+              umma_elect<TOp>(dacc, ad + (uint64_t)(2 * kk), wd + (uint64_t)(2 * kk), idesc, acc);
+              acc = 1u;
+            }
+            umma_commit_elect(smem_u32(&bars->w_empty[sw]));
+            if (++sw == (uint32_t)p.NW) { sw = 0; pw ^= 1u; }
+          }
+          umma_commit_elect(smem_u32(&a_rel[so]));
+          if (++so == ring) { so = 0; po ^= 1u; }
+        }
+      } else
       for (int tap = 0; tap < 9; ++tap) {
         for (int ob = 0; ob < nbox_t; ++ob) {
           const int nk = ob == nbox_t - 1 ? nk_last : 4;
@@ -189,6 +242,25 @@ tma_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const Conv3Params p) {
     uint32_t sa = 0, pa = 0, so = 0, po = 0;
     for (TileIter ti(p); ti.valid(); ti.next()) {
       if constexpr (!OPRING) {
+        if (p.patch) {
+          for (int i = 0; i < p.nkb_t; ++i) {
+            mbar_wait(smem_u32(&bars->a_full[sa]), pa);
+            for (int rr = r; rr < PPH * PPW; rr += XF_WARPS * 32) {
+              const uint32_t row = sA + sa * PBOX + (uint32_t)rr * 128u, sw7 = (uint32_t)(rr & 7);
+              float4 x[8];
+#pragma unroll
+              for (int c = 0; c < 8; ++c) x[c] = lds128(row + (((uint32_t)c ^ sw7) << 4));
+#pragma unroll
+              for (int c = 0; c < 8; ++c)
+                sts128(row + (((uint32_t)c ^ sw7) << 4),
+                       make_float4(to_tf32(x[c].x), to_tf32(x[c].y), to_tf32(x[c].z), to_tf32(x[c].w)));
+            }
+            fence_async_smem();
+            mbar_arrive(smem_u32(&bars->a_ready[sa]));
+            if (++sa == (uint32_t)p.S) { sa = 0; pa ^= 1u; }
+          }
+          continue;
+        }
         for (int i = 0; i < nraw; ++i) {
           mbar_wait(smem_u32(&bars->a_full[sa]), pa);
           const uint32_t row = sA + sa * BOX + (uint32_t)r * 128u;
@@ -246,7 +318,7 @@ tma_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const Conv3Params p) {
     for (TileIter ti(p); ti.valid(); ti.next(), ++j) {
       const int b = ti.img();
       const int y = ti.y0() + 2 * q + (lane >> 4), x = ti.x0() + (lane & 15);     // TMEM lane 32q + lane == patch pixel
-      const bool live = y < p.H && x < p.W;
+      const bool live = y < p.H && x < p.W && (!p.patch || (lane & 15) < PTW);
       const uint32_t slot = p.nacc == 2 ? (j & 1u) : 0u;
       const uint32_t use = p.nacc == 2 ? (j >> 1) : j;
       mbar_wait(smem_u32(&bars->acc_full[slot]), use & 1u);
@@ -312,9 +384,12 @@ tma_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const Conv3Params p) {
   }
 }
 
-struct Conv3Cfg { int nc, nchunks, S, SOP, NW; uint32_t off_a, off_op, off_w, wstage; size_t smem; };
+struct Conv3Cfg { int nc, nchunks, S, SOP, NW, patch; uint32_t off_a, off_op, off_w, wstage; size_t smem; };
 
 bool configure(int cin, int n, bool half, Conv3Cfg& c) {
+  static const bool no_patch = getenv("IRB_NO_CONV_PATCH") != nullptr;       // A/B switch for benchmarks
+  c.patch = !half && !no_patch;
+  const size_t abox = c.patch ? PBOX : BOX;
   if (cin % 4 != 0 || cin < 4 || n % 16 != 0 || n < 16) return false;
   if (half && cin % 8 != 0) return false;
   const size_t budget = 227 * 1024 - 1024;
@@ -323,12 +398,29 @@ bool configure(int cin, int n, bool half, Conv3Cfg& c) {
   c.nchunks = (n + c.nc - 1) / c.nc;
   c.wstage = (uint32_t)((size_t)c.nc * 128 + 1023) / 1024 * 1024;
   c.NW = 3; c.SOP = half ? 2 : 0;
+  if (c.patch) {
+    // a patch box serves nine weight boxes: three or four patch stages are plenty, and the rest of shared memory goes to the
+    // weight ring -- the weight stream is latency-bound (every CTA pulls the same boxes out of L2), so bytes in flight are
+    // what counts (three 12 KB stages paced the 192 -> 96 Downsample at 0.4 us per box)
+    const size_t rest = budget - HDR;
+    int S = 4;
+    if (rest < (size_t)S * PBOX + 3 * (size_t)c.wstage) S = 3;
+    if (rest < (size_t)S * PBOX + 3 * (size_t)c.wstage) return false;
+    c.NW = (int)std::min<size_t>(MAX_W, (rest - (size_t)S * PBOX) / c.wstage);
+    c.S = S;
+    size_t off = HDR;
+    c.off_w = (uint32_t)off; off += (size_t)c.NW * c.wstage;
+    c.off_op = (uint32_t)off;
+    c.off_a = (uint32_t)off; off += (size_t)c.S * PBOX;
+    c.smem = off + 1024;
+    return true;
+  }
   size_t off = HDR;
   c.off_w = (uint32_t)off; off += (size_t)c.NW * c.wstage;
   c.off_op = (uint32_t)off; off += (size_t)c.SOP * BOX;
-  if (off + 3 * BOX > budget) return false;
-  c.S = (int)std::min<size_t>(MAX_S, (budget - off) / BOX);
-  c.off_a = (uint32_t)off; off += (size_t)c.S * BOX;
+  if (off + 3 * abox > budget) return false;
+  c.S = (int)std::min<size_t>(MAX_S, (budget - off) / abox);
+  c.off_a = (uint32_t)off; off += (size_t)c.S * abox;
   c.smem = off + 1024;
   return true;
 }
@@ -365,7 +457,7 @@ int launch_conv3_tma(const float* in, int ld_in, int cin, const void* w_packed, 
   {
     cuuint64_t d[4] = {(cuuint64_t)cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     cuuint64_t st[3] = {(cuuint64_t)ld_in * 4, (cuuint64_t)ld_in * 4 * W, (cuuint64_t)ld_in * 4 * W * H};
-    cuuint32_t box[4] = {32, TW, TH, 1};
+    cuuint32_t box[4] = {32, (cuuint32_t)(c.patch ? PPW : TW), (cuuint32_t)(c.patch ? PPH : TH), 1};
     IRB_TRY(make_tmap(&tA, in, false, 4, d, st, box, true));
   }
   Conv3Params p{};
@@ -373,7 +465,8 @@ int launch_conv3_tma(const float* in, int ld_in, int cin, const void* w_packed, 
   p.B = B; p.H = H; p.W = W; p.Cin = cin; p.N = cout_p; p.n_valid = cout_valid; p.o_mode = o_mode;
   p.nc = c.nc; p.nkb_t = (cin + 31) / 32; p.nob_t = (cin + 63) / 64;
   p.S = c.S; p.SOP = c.SOP; p.NW = c.NW;
-  p.tiles_x = cdiv(W, TW); p.tiles_y = cdiv(H, TH); p.ntiles = p.tiles_x * p.tiles_y * B;
+  p.patch = c.patch;
+  p.tiles_x = cdiv(W, c.patch ? PTW : TW); p.tiles_y = cdiv(H, TH); p.ntiles = p.tiles_x * p.tiles_y * B;
   p.acc_stride = (c.nc + 31) / 32 * 32;
   p.nacc = 2 * p.acc_stride <= 512 ? 2 : 1;
   int cols = 32; while (cols < p.nacc * p.acc_stride) cols <<= 1;

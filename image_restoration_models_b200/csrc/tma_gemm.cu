@@ -67,6 +67,7 @@ struct TmaGemmParams {
   int xn_mode;             // LnMode of the second output xn = LayerNorm(y) (fp16), 0 = none
   const float* xn_w; const float* xn_b;
   int xn_boxes;            // 64-channel boxes of an xn row (1 or 2)
+  int egroups;             // epilogue warpgroups of the xn path (2 at N = 48: see xn_epilogue)
   uint32_t off_xn;         // per-warp xn staging boxes
   int wstream;             // 1: the weight chunk does not fit next to the rings (K * nc too large): every stage carries
                            // the [nc][128 B] weight box of its K box next to the A box (no LayerNorm prologue in this mode)
@@ -177,6 +178,129 @@ __device__ __forceinline__ void ln_transform(const TmaGemmParams& p, Bars* bars,
       }
     }
     it += NKB;
+  }
+}
+
+// Residual epilogue that also emits xn = LayerNorm(y) (norm2, restormer.py:148) as the fp16 operand of the fused GDFN: the
+// thread owns a whole pixel row (<= 3 groups of 32 columns), so the row stays in registers, the statistics are two passes
+// over them, and the LayerNorm pass over HBM disappears.  NC = N as a compile-time constant (48 or 96): no predicates in the
+// statistics, four independent sums.
+// p.egroups == 2 (N = 48): TWO epilogue warpgroups -- warps 0-3 take the even tiles (accumulator slot 0), the otherwise idle
+// transform warps 4-7 the odd ones (slot 1; a warp reaches TMEM lane quarter warp % 4 either way).  At N = 48 a tile is 74 KB
+// of traffic against the same fixed chain of waits per tile, and one warpgroup could not keep up with the loads.
+template <int NC>
+__device__ __forceinline__ void xn_epilogue(const TmaGemmParams& p, Bars* bars, uint32_t tmem_base, uint32_t base, uint32_t sRO,
+                                            const float* lnv, const CUtensorMap& tmY, const CUtensorMap& tmXn, int n0, int q,
+                                            int lane, int eg) {
+  constexpr int NG = (NC + 31) / 32, NV = NC / 4, GC = 32;
+  const float inv_n = 1.0f / (float)NC;
+  const uint32_t lsw = (uint32_t)(lane & 7);
+  const uint32_t sXN = base + p.off_xn + (uint32_t)(eg * EPI_WARPS + q) * (uint32_t)p.xn_boxes * WBOX + (uint32_t)lane * 128u;
+  if (lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmY)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmXn)) : "memory");
+  }
+  const uint32_t neg = (uint32_t)p.egroups;
+  uint32_t j = 0;
+  bool have_prev = false;
+  uint32_t prev_gc = 0;
+  for (TileIter ti(p); ti.valid(); ti.next(), ++j) {
+    if (neg == 2u && (j & 1u) != (uint32_t)eg) continue;
+    const int b = ti.img(), row0 = ti.row0();
+    const uint32_t slot = j & 1u;
+    mbar_wait(smem_u32(&bars->acc_full[slot]), (j >> 1) & 1u);
+    tc_fence_after();
+    const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + slot * (uint32_t)p.acc_stride;
+    float4 xr[NG * 8];
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+      const uint32_t gc = j * (uint32_t)NG + (uint32_t)g;          // the box's position in the residual ring
+      const int col = n0 + g * GC;
+      uint32_t box;
+      if (p.has_r) {
+        const uint32_t s = gc % (uint32_t)p.RB, ph = (gc / (uint32_t)p.RB) & 1u;
+        mbar_wait(smem_u32(&bars->r_full[s]), ph);
+        box = sRO + s * BOX + (uint32_t)q * WBOX;
+      } else {
+        box = sRO + (uint32_t)((eg * EPI_WARPS + q) * 2 + (int)(gc & 1u)) * WBOX;
+        if (lane == 0) bulk_wait_read<1>();
+        __syncwarp();
+      }
+      const uint32_t myrow = box + (uint32_t)lane * 128u;
+      float v[32];
+      tmem_ld32(tacc + (uint32_t)(g * 32), v);
+      tmem_ld_wait();
+      if (g == NG - 1) { tc_fence_before(); mbar_arrive(smem_u32(&bars->acc_empty[slot])); }
+      if (p.bias) {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) v[e] += (col + e < p.N) ? __ldg(p.bias + col + e) : 0.f;
+      }
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const uint32_t a = myrow + (((uint32_t)c ^ lsw) << 4);
+        float4 o = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+        if (p.has_r) {
+          const float4 rr = lds128(a);
+          o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+        }
+        sts128(a, o);
+        xr[g * 8 + c] = o;
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_3d(&tmY, box, col, row0 + q * 32, b);
+        bulk_commit();
+        if (p.has_r && have_prev) {
+          // this warpgroup's previous box: its store (older than the one just committed) has finished reading it
+          bulk_wait_read<1>();
+          mbar_arrive(smem_u32(&bars->r_empty[prev_gc % (uint32_t)p.RB]));
+        }
+      }
+      have_prev = true; prev_gc = gc;
+    }
+    // statistics over the NC valid columns (TMEM columns past N were never written: not read here)
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) { s0 += xr[i].x; s1 += xr[i].y; s2 += xr[i].z; s3 += xr[i].w; }
+    const float mu = ((s0 + s1) + (s2 + s3)) * inv_n;
+    s0 = s1 = s2 = s3 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float d0 = xr[i].x - mu, d1 = xr[i].y - mu, d2 = xr[i].z - mu, d3 = xr[i].w - mu;
+      s0 = fmaf(d0, d0, s0); s1 = fmaf(d1, d1, s1); s2 = fmaf(d2, d2, s2); s3 = fmaf(d3, d3, s3);
+    }
+    const float rstd = 1.0f / sqrtf(((s0 + s1) + (s2 + s3)) * inv_n + 1e-5f);
+    const float sub = p.xn_mode == LN_WITHBIAS ? mu : 0.f;
+    // the previous tile's xn store has read the staging boxes (it is older than this tile's y stores)
+    if (lane == 0) bulk_wait_read<NG>();
+    __syncwarp();
+#pragma unroll
+    for (int c8 = 0; c8 < NC / 8; ++c8) {                   // 16-byte chunks of 8 fp16 channels
+      uint4 t;
+      __half2* h = reinterpret_cast<__half2*>(&t);
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const float4 x = xr[c8 * 2 + e];
+        const float4 gw = *reinterpret_cast<const float4*>(lnv + c8 * 8 + e * 4);
+        const float4 gb = *reinterpret_cast<const float4*>(lnv + NC + c8 * 8 + e * 4);
+        h[2 * e] = f2h2_sat(fmaf((x.x - sub) * rstd, gw.x, gb.x), fmaf((x.y - sub) * rstd, gw.y, gb.y));
+        h[2 * e + 1] = f2h2_sat(fmaf((x.z - sub) * rstd, gw.z, gb.z), fmaf((x.w - sub) * rstd, gw.w, gb.w));
+      }
+      sts128u(sXN + (uint32_t)(c8 >> 3) * WBOX + ((((uint32_t)c8 & 7u) ^ lsw) << 4), t);
+    }
+    fence_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      for (int xb = 0; xb < p.xn_boxes; ++xb)
+        tma_store_3d(&tmXn, sXN - (uint32_t)lane * 128u + (uint32_t)xb * WBOX, xb * 64, row0 + q * 32, b);
+      bulk_commit();
+    }
+  }
+  if (lane == 0) {
+    bulk_wait_read<0>();
+    // with two warpgroups the other one may still need ring slots behind this group's last box
+    if (p.has_r && have_prev && neg == 2u) mbar_arrive(smem_u32(&bars->r_empty[prev_gc % (uint32_t)p.RB]));
   }
 }
 
@@ -328,6 +452,13 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
   } else if (warp >= EPI_WARPS) {
     // =============================== LayerNorm transform ===============================
+    if constexpr (!LN && sizeof(TY) == 4) {
+      // no prologue to run: with two epilogue warpgroups these warps take the odd tiles of the xn path
+      if (p.xn_mode && p.egroups == 2) {
+        if (p.N == 96) xn_epilogue<96>(p, bars, tmem_base, base, sRO, lnv, tmY, tmXn, n0, warp - EPI_WARPS, lane, 1);
+        else xn_epilogue<48>(p, bars, tmem_base, base, sRO, lnv, tmY, tmXn, n0, warp - EPI_WARPS, lane, 1);
+      }
+    }
     if constexpr (LN) {
       switch (p.nkb) {
         case 1: ln_transform<TOp, 1>(p, bars, sA, sOP, lnv, tid - EPI_WARPS * 32); break;
@@ -350,104 +481,8 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         //      fused GDFN: the thread owns a whole pixel row (<= 3 groups of 32 columns), so the row stays in registers,
         //      the statistics are two passes over them, and the LayerNorm pass over HBM disappears ----
         xn_done = true;
-        const uint32_t sXN = base + p.off_xn + (uint32_t)q * (uint32_t)p.xn_boxes * WBOX + (uint32_t)lane * 128u;
-        if (lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmXn)) : "memory");
-        // NC = N as a compile-time constant (48 or 96): no predicates in the statistics, four independent sums
-        auto xn_path = [&](auto nc_tag) {
-          constexpr int NC = decltype(nc_tag)::value, NG = (NC + 31) / 32, NV = NC / 4;
-          const float inv_n = 1.0f / (float)NC;
-          for (TileIter ti(p); ti.valid(); ti.next(), ++j) {
-            const int b = ti.img(), row0 = ti.row0();
-            const uint32_t slot = j & 1u;
-            mbar_wait(smem_u32(&bars->acc_full[slot]), (j >> 1) & 1u);
-            tc_fence_after();
-            const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + slot * (uint32_t)p.acc_stride;
-            float4 xr[NG * 8];
-#pragma unroll
-            for (int g = 0; g < NG; ++g, ++gc) {
-              const int col = n0 + g * GC;
-              uint32_t box;
-              if (p.has_r) {
-                const uint32_t s = gc % (uint32_t)p.RB, ph = (gc / (uint32_t)p.RB) & 1u;
-                mbar_wait(smem_u32(&bars->r_full[s]), ph);
-                box = sRO + s * BOX + (uint32_t)q * WBOX;
-              } else {
-                box = sRO + (uint32_t)(q * 2 + (int)(gc & 1u)) * WBOX;
-                if (lane == 0) bulk_wait_read<1>();
-                __syncwarp();
-              }
-              const uint32_t myrow = box + (uint32_t)lane * 128u;
-              float v[32];
-              tmem_ld32(tacc + (uint32_t)(g * 32), v);
-              tmem_ld_wait();
-              if (g == NG - 1) { tc_fence_before(); mbar_arrive(smem_u32(&bars->acc_empty[slot])); }
-              if (p.bias) {
-#pragma unroll
-                for (int e = 0; e < 32; ++e) v[e] += (col + e < p.N) ? __ldg(p.bias + col + e) : 0.f;
-              }
-#pragma unroll
-              for (int c = 0; c < 8; ++c) {
-                const uint32_t a = myrow + (((uint32_t)c ^ lsw) << 4);
-                float4 o = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
-                if (p.has_r) {
-                  const float4 rr = lds128(a);
-                  o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
-                }
-                sts128(a, o);
-                xr[g * 8 + c] = o;
-              }
-              fence_async_smem();
-              __syncwarp();
-              if (lane == 0) {
-                tma_store_3d(&tmY, box, col, row0 + q * 32, b);
-                bulk_commit();
-                if (p.has_r && gc > 0) {
-                  bulk_wait_read<1>();
-                  mbar_arrive(smem_u32(&bars->r_empty[(gc - 1) % (uint32_t)p.RB]));
-                }
-              }
-            }
-            // statistics over the NC valid columns (TMEM columns past N were never written: not read here)
-            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-            for (int i = 0; i < NV; ++i) { s0 += xr[i].x; s1 += xr[i].y; s2 += xr[i].z; s3 += xr[i].w; }
-            const float mu = ((s0 + s1) + (s2 + s3)) * inv_n;
-            s0 = s1 = s2 = s3 = 0.f;
-#pragma unroll
-            for (int i = 0; i < NV; ++i) {
-              const float d0 = xr[i].x - mu, d1 = xr[i].y - mu, d2 = xr[i].z - mu, d3 = xr[i].w - mu;
-              s0 = fmaf(d0, d0, s0); s1 = fmaf(d1, d1, s1); s2 = fmaf(d2, d2, s2); s3 = fmaf(d3, d3, s3);
-            }
-            const float rstd = 1.0f / sqrtf(((s0 + s1) + (s2 + s3)) * inv_n + 1e-5f);
-            const float sub = p.xn_mode == LN_WITHBIAS ? mu : 0.f;
-            // the previous tile's xn store has read the staging boxes (it is older than this tile's y stores)
-            if (lane == 0) bulk_wait_read<NG>();
-            __syncwarp();
-#pragma unroll
-            for (int c8 = 0; c8 < NC / 8; ++c8) {                   // 16-byte chunks of 8 fp16 channels
-              uint4 t;
-              __half2* h = reinterpret_cast<__half2*>(&t);
-#pragma unroll
-              for (int e = 0; e < 2; ++e) {
-                const float4 x = xr[c8 * 2 + e];
-                const float4 gw = *reinterpret_cast<const float4*>(lnv + c8 * 8 + e * 4);
-                const float4 gb = *reinterpret_cast<const float4*>(lnv + NC + c8 * 8 + e * 4);
-                h[2 * e] = f2h2_sat(fmaf((x.x - sub) * rstd, gw.x, gb.x), fmaf((x.y - sub) * rstd, gw.y, gb.y));
-                h[2 * e + 1] = f2h2_sat(fmaf((x.z - sub) * rstd, gw.z, gb.z), fmaf((x.w - sub) * rstd, gw.w, gb.w));
-              }
-              sts128u(sXN + (uint32_t)(c8 >> 3) * WBOX + ((((uint32_t)c8 & 7u) ^ lsw) << 4), t);
-            }
-            fence_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-              for (int xb = 0; xb < p.xn_boxes; ++xb)
-                tma_store_3d(&tmXn, sXN - (uint32_t)lane * 128u + (uint32_t)xb * WBOX, xb * 64, row0 + q * 32, b);
-              bulk_commit();
-            }
-          }
-        };
-        if (p.N == 96) xn_path(std::integral_constant<int, 96>{});
-        else xn_path(std::integral_constant<int, 48>{});
+        if (p.N == 96) xn_epilogue<96>(p, bars, tmem_base, base, sRO, lnv, tmY, tmXn, n0, q, lane, 0);
+        else xn_epilogue<48>(p, bars, tmem_base, base, sRO, lnv, tmY, tmXn, n0, q, lane, 0);
       }
     }
     if (!xn_done)
@@ -544,7 +579,7 @@ int make_map(CUtensorMap* tm, const void* ptr, bool half, int inner, long long r
   return make_tmap(tm, ptr, half, 3, gdim, gstr, box, true);
 }
 
-struct TmaCfg { int nc, nchunks, nkb, nob, S, SOP, RB, wstream; uint32_t a_stride, off_w, off_a, off_op, off_ro, off_ln, off_xn; size_t smem; };
+struct TmaCfg { int nc, nchunks, nkb, nob, S, SOP, RB, wstream, egroups; uint32_t a_stride, off_w, off_a, off_op, off_ro, off_ln, off_xn; size_t smem; };
 
 // Shape-only feasibility + shared-memory carve-up.  ln: fused LayerNorm prologue.
 bool configure(int K, int N, bool op_half, bool ln, bool has_r, bool y_half, TmaCfg& c, bool xn = false) {
@@ -559,7 +594,9 @@ bool configure(int K, int N, bool op_half, bool ln, bool has_r, bool y_half, Tma
   const int gcs = y_half ? 64 : 32;
   // xn second output: per-warp staging boxes + the LayerNorm parameters; the row must be whole (one N-chunk, <= 3 groups)
   if (xn && (ln || y_half || (N != 48 && N != 96))) return false;
-  const size_t xn_bytes = xn ? (size_t)EPI_WARPS * ((N + 63) / 64) * WBOX + (size_t)2 * N * 4 + 16 : 0;
+  static const bool one_group = getenv("IRB_ONE_EPI_GROUP") != nullptr;       // A/B switch for benchmarks
+  c.egroups = xn && has_r && N == 48 && !one_group ? 2 : 1;
+  const size_t xn_bytes = xn ? (size_t)c.egroups * EPI_WARPS * ((N + 63) / 64) * WBOX + (size_t)2 * N * 4 + 16 : 0;
   const size_t budget = 227 * 1024 - 1024 /*alignment slack*/ - xn_bytes;
   for (int chunks = 1; chunks <= N / 16; ++chunks) {
     int nc = (N + chunks - 1) / chunks;
@@ -604,7 +641,7 @@ bool configure(int K, int N, bool op_half, bool ln, bool has_r, bool y_half, Tma
     c.off_ln = (uint32_t)off; off += lnb;
     if (xn) {
       if (chunks != 1) return false;
-      c.off_xn = (uint32_t)off; off += (size_t)EPI_WARPS * ((N + 63) / 64) * WBOX;
+      c.off_xn = (uint32_t)off; off += (size_t)c.egroups * EPI_WARPS * ((N + 63) / 64) * WBOX;
       c.off_ln = (uint32_t)off; off += (size_t)2 * N * 4 + 16;
     }
     c.smem = off + 1024;
@@ -728,7 +765,7 @@ int launch_gemm_tma(const TcGemmParams& t, cudaStream_t s) {
   p.tmem_cols = cols;
   p.off_w = c.off_w; p.off_a = c.off_a; p.off_op = c.off_op; p.off_ro = c.off_ro; p.off_ln = c.off_ln;
   p.wstream = c.wstream; p.a_stride = c.a_stride;
-  p.xn_mode = xn ? t.xn_ln_mode : 0; p.xn_w = t.xn_w; p.xn_b = t.xn_b; p.xn_boxes = (t.N + 63) / 64; p.off_xn = c.off_xn;
+  p.xn_mode = xn ? t.xn_ln_mode : 0; p.xn_w = t.xn_w; p.xn_b = t.xn_b; p.xn_boxes = (t.N + 63) / 64; p.off_xn = c.off_xn; p.egroups = xn ? c.egroups : 1;
 
   dim3 grid;
   if (p.per_image) grid = dim3(std::max(1, std::min(p.tiles_per_img, 148 / (c.nchunks * t.B))), c.nchunks, t.B);

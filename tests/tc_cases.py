@@ -177,6 +177,11 @@ TMA_CONV3_CASES = [
     (64, 64, 2, 19, 31, 0, True, True, 0),       # DnCNN body layer on the TMA kernel: plain rows, bias + ReLU, odd extent
     (64, 64, 1, 32, 32, 0, True, True, 1),
     (64, 48, 1, 16, 24, 0, True, False, 0),      # 1.5 output groups, no activation
+    # tf32 patch mode (8 x 14 output tiles cut out of one (8+2) x (14+2) patch load): widths around the multiples of 14
+    (96, 48, 1, 18, 30, 1, False, False, 0),     # three tile columns, the last two pixels wide; ragged bottom row of tiles
+    (192, 384, 1, 9, 29, 2, False, False, 0),    # odd extent, PixelShuffle, two N-chunks
+    (96, 192, 2, 17, 57, 2, False, False, 0),    # batch 2, five tile columns (the last one pixel wide)
+    (64, 64, 1, 8, 14, 0, True, True, 0),        # exactly one tile, plain rows
 ]
 
 
