@@ -467,13 +467,23 @@ int launch_fold(const FoldParams& p, cudaStream_t s) {
 // input channels (float4 each), a 3x3 register window slides along x (3 new loads per pixel), the per-pixel result
 // is warp-reduced and parked in lane (x mod 32) so the final store / residual load is one coalesced row segment.
 // ---------------------------------------------------------------------------------------------
-template <int COUT>
+// R output rows per warp: the (R + 2) x 3 register window slides along x, so every input row crosses L2 -> SM (R + 2) / R
+// times instead of 3.  The loop is a load -> FMA -> reduce chain per pixel with few warps per SM (the window is 70+
+// registers), so the bytes in flight decide its speed: every lane runs its own cp.async queue -- column x + 1 + PD is
+// requested (16 bytes per row, zero-filled outside the image: the conv's padding) into a 4-slot ring in shared memory
+// while column x + 1 is read back into the window.  A lane only ever reads what it copied itself: no barrier.
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, bool ok) {
+  const int n = ok ? 16 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
+}
+template <int COUT, int R>
 __global__ void __launch_bounds__(256) conv3x3_small_kernel(const float* __restrict__ in, int ld, int cin,
                                                             const float* __restrict__ w, int kp,
                                                             const float* __restrict__ bias, int B, int H, int W,
                                                             const float* __restrict__ r, float sign,
                                                             float* __restrict__ y) {
-  extern __shared__ float wsm[];                  // [COUT][9][cin]
+  constexpr int PD = 3, NS = 4;                   // prefetch distance (columns), ring slots
+  extern __shared__ __align__(16) float wsm[];    // [COUT][9][cin] weights, then the per-warp column rings
   for (int i = threadIdx.x; i < COUT * 9 * cin; i += 256) {
     const int co = i / (9 * cin), k = i - co * 9 * cin;
     wsm[i] = w[(long long)co * kp + k];
@@ -481,31 +491,52 @@ __global__ void __launch_bounds__(256) conv3x3_small_kernel(const float* __restr
   __syncthreads();
   pdl_sync();   // the weights (constants) are staged under the previous kernel's tail (common.cuh)
   const int lane = threadIdx.x & 31;
+  const uint32_t ring = (uint32_t)__cvta_generic_to_shared(wsm) + (uint32_t)((COUT * 9 * cin * 4 + 15) & ~15) +
+                        (uint32_t)(threadIdx.x >> 5) * (uint32_t)(NS * (R + 2) * 512) + (uint32_t)lane * 16u;
   const int segs = (W + 31) >> 5;
-  const long long nwarps = (long long)B * H * segs;
+  const int hb = (H + R - 1) / R;                 // row blocks per image
+  const long long nwarps = (long long)B * hb * segs;
   const int c4n = cin >> 2;
   for (long long wi = ((long long)blockIdx.x * 256 + threadIdx.x) >> 5; wi < nwarps; wi += ((long long)gridDim.x * 256) >> 5) {
     const int seg = (int)(wi % segs);
     const long long by = wi / segs;
-    const int yy = (int)(by % H), b = (int)(by / H);
+    const int yy = (int)(by % hb) * R, b = (int)(by / hb);
     const int x0 = seg * 32;
-    float res[COUT];
+    float res[COUT][R];
 #pragma unroll
-    for (int co = 0; co < COUT; ++co) res[co] = 0.f;
+    for (int co = 0; co < COUT; ++co)
+#pragma unroll
+      for (int rr = 0; rr < R; ++rr) res[co][rr] = 0.f;
     for (int cb = 0; cb < c4n; cb += 32) {        // channel blocks of 32 float4 (one per lane)
       const int c4 = cb + lane;
       const bool cok = c4 < c4n;
-      float4 win[3][3];                           // [row dy][col: x-1, x, x+1]
-      auto ldv = [&](int ry, int x) -> float4 {
-        const int y2 = yy + ry - 1;
-        if (!cok || y2 < 0 || y2 >= H || x < 0 || x >= W) return make_float4(0.f, 0.f, 0.f, 0.f);
-        return *reinterpret_cast<const float4*>(in + (((long long)b * H + y2) * W + x) * ld + 4 * c4);
-      };
-      // the column two steps ahead is already in flight when a pixel is computed (the loop is a load -> FMA -> reduce
-      // chain per pixel; without the extra column every step waited a full L2 round trip)
-      float4 nxt[3];
+      const float* base = in + ((long long)b * H * W) * ld + 4 * c4;
+      // column k of the segment is image column x0 - 1 + k
+      auto issue = [&](int k) {
+        const int x = x0 - 1 + k;
+        const uint32_t dst = ring + (uint32_t)((k & (NS - 1)) * (R + 2) * 512);
 #pragma unroll
-      for (int ry = 0; ry < 3; ++ry) { win[ry][1] = ldv(ry, x0 - 1); win[ry][2] = ldv(ry, x0); nxt[ry] = ldv(ry, x0 + 1); }
+        for (int ry = 0; ry < R + 2; ++ry) {
+          const int y2 = yy + ry - 1;
+          const bool ok = cok && y2 >= 0 && y2 < H && x >= 0 && x < W;
+          cp_async16_zfill(dst + (uint32_t)(ry * 512), ok ? base + ((long long)y2 * W + x) * ld : in, ok);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      };
+      float4 win[R + 2][3];                       // [input row yy - 1 + ry][col: x-1, x, x+1]
+      auto fetch = [&](int k, int col) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(PD - 1) : "memory");
+        const uint32_t src = ring + (uint32_t)((k & (NS - 1)) * (R + 2) * 512);
+#pragma unroll
+        for (int ry = 0; ry < R + 2; ++ry)
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                       : "=f"(win[ry][col].x), "=f"(win[ry][col].y), "=f"(win[ry][col].z), "=f"(win[ry][col].w)
+                       : "r"(src + (uint32_t)(ry * 512)));
+      };
+#pragma unroll
+      for (int k = 0; k < PD; ++k) issue(k);
+      fetch(0, 1); issue(PD);
+      fetch(1, 2); issue(PD + 1);
       // single-output case (gray images): the lane's 9 taps live in registers for the whole segment
       float4 kreg[COUT == 1 ? 9 : 1];
       if constexpr (COUT == 1) {
@@ -515,59 +546,88 @@ __global__ void __launch_bounds__(256) conv3x3_small_kernel(const float* __restr
       }
       for (int j = 0; j < 32 && x0 + j < W; ++j) {
 #pragma unroll
-        for (int ry = 0; ry < 3; ++ry) { win[ry][0] = win[ry][1]; win[ry][1] = win[ry][2]; win[ry][2] = nxt[ry]; nxt[ry] = ldv(ry, x0 + j + 2); }
-        float acc[COUT];
+        for (int ry = 0; ry < R + 2; ++ry) { win[ry][0] = win[ry][1]; win[ry][1] = win[ry][2]; }
+        fetch(j + 2, 2);
+        issue(j + 2 + PD);
+        float acc[COUT][R];
 #pragma unroll
-        for (int co = 0; co < COUT; ++co) acc[co] = 0.f;
+        for (int co = 0; co < COUT; ++co)
+#pragma unroll
+          for (int rr = 0; rr < R; ++rr) acc[co][rr] = 0.f;
         if (cok) {
 #pragma unroll
-          for (int ry = 0; ry < 3; ++ry)
+          for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-            for (int dx = 0; dx < 3; ++dx) {
-              const float4 v = win[ry][dx];
+            for (int dx = 0; dx < 3; ++dx)
 #pragma unroll
               for (int co = 0; co < COUT; ++co) {
                 float4 k;
-                if constexpr (COUT == 1) k = kreg[ry * 3 + dx];
-                else k = *reinterpret_cast<const float4*>(wsm + (co * 9 + ry * 3 + dx) * cin + 4 * c4);
-                acc[co] = fmaf(v.x, k.x, fmaf(v.y, k.y, fmaf(v.z, k.z, fmaf(v.w, k.w, acc[co]))));
+                if constexpr (COUT == 1) k = kreg[ky * 3 + dx];
+                else k = *reinterpret_cast<const float4*>(wsm + (co * 9 + ky * 3 + dx) * cin + 4 * c4);
+#pragma unroll
+                for (int rr = 0; rr < R; ++rr) {
+                  const float4 v = win[rr + ky][dx];
+                  acc[co][rr] = fmaf(v.x, k.x, fmaf(v.y, k.y, fmaf(v.z, k.z, fmaf(v.w, k.w, acc[co][rr]))));
+                }
               }
-            }
         }
 #pragma unroll
-        for (int co = 0; co < COUT; ++co) {
-          const float t = warp_sum(acc[co]);
-          if (lane == j) res[co] += t;
-        }
+        for (int co = 0; co < COUT; ++co)
+#pragma unroll
+          for (int rr = 0; rr < R; ++rr) {
+            const float t = warp_sum(acc[co][rr]);
+            if (lane == j) res[co][rr] += t;
+          }
       }
+      // the ring is reused by the next channel block / segment: nothing of this one may still be in flight
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     if (x0 + lane < W) {
 #pragma unroll
-      for (int co = 0; co < COUT; ++co) {
-        const long long o = (((long long)b * COUT + co) * H + yy) * W + x0 + lane;
-        float v = res[co] + (bias ? bias[co] : 0.f);
-        v *= sign;
-        if (r) v += r[o];
-        y[o] = v;
-      }
+      for (int co = 0; co < COUT; ++co)
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr) {
+          if (yy + rr >= H) continue;
+          const long long o = (((long long)b * COUT + co) * H + yy + rr) * W + x0 + lane;
+          float v = res[co][rr] + (bias ? bias[co] : 0.f);
+          v *= sign;
+          if (r) v += r[o];
+          y[o] = v;
+        }
     }
   }
+}
+
+template <int COUT, int R>
+static int launch_conv3x3_small_inst(int blocks, size_t smem, cudaStream_t s, const float* in, int ld, int cin, const float* w,
+                                     int kp, const float* bias, int B, int H, int W, const float* r, float sign, float* y) {
+  static SmemOptIn optin;
+  IRB_TRY(opt_in_smem(conv3x3_small_kernel<COUT, R>, optin, 160 * 1024));
+  IRB_CUDA(launch_pdl(conv3x3_small_kernel<COUT, R>, dim3(blocks), dim3(256), smem, s, in, ld, cin, w, kp, bias, B, H, W, r, sign, y));
+  return IR_OK;
 }
 
 int launch_conv3x3_small(const float* in, int ld, int cin, const float* w, int kp, const float* bias, int cout, int B,
                          int H, int W, const float* r, float sign, float* y, cudaStream_t s) {
   IRB_REQUIRE(cout >= 1 && cout <= 4 && cin % 4 == 0 && ld % 4 == 0, "conv3x3_small: cout in 1..4, cin % 4 == 0");
-  const size_t smem = (size_t)cout * 9 * cin * sizeof(float);
-  IRB_REQUIRE(smem <= 48 * 1024, "conv3x3_small: weights do not fit shared memory");
-  const long long nwarps = (long long)B * H * ((W + 31) / 32);
+  const size_t wbytes = ((size_t)cout * 9 * cin * sizeof(float) + 15) & ~(size_t)15;
+  IRB_REQUIRE(wbytes <= 48 * 1024, "conv3x3_small: weights do not fit shared memory");
+  // rows per warp: 4 for the single-output (gray) case, 2 otherwise (the register window is (R + 2) x 3 float4 + COUT x R sums)
+  static const bool r2 = getenv("IRB_OUTCONV_R2") != nullptr;        // A/B switch for benchmarks
+  const int R = cout == 1 && !r2 ? 4 : 2;
+  const size_t smem = wbytes + (size_t)8 * 4 * (R + 2) * 512;      // + 8 warps x 4 ring slots x (R + 2) rows x 32 lanes x 16 B
+  const long long nwarps = (long long)B * cdiv(H, R) * ((W + 31) / 32);
   const int blocks = (int)std::min<long long>(cdivll(nwarps, 8), 148LL * 32);
   const double pix = (double)B * H * W;
   ProfScope prof(TAG_CONV3, 4.0 * pix * (cin + cout * (r ? 2.0 : 1.0)), 2.0 * 9.0 * pix * cin * cout, s);
   switch (cout) {
-    case 1: IRB_CUDA(launch_pdl(conv3x3_small_kernel<1>, dim3(blocks), dim3(256), smem, s, in, ld, cin, w, kp, bias, B, H, W, r, sign, y)); break;
-    case 2: IRB_CUDA(launch_pdl(conv3x3_small_kernel<2>, dim3(blocks), dim3(256), smem, s, in, ld, cin, w, kp, bias, B, H, W, r, sign, y)); break;
-    case 3: IRB_CUDA(launch_pdl(conv3x3_small_kernel<3>, dim3(blocks), dim3(256), smem, s, in, ld, cin, w, kp, bias, B, H, W, r, sign, y)); break;
-    default: IRB_CUDA(launch_pdl(conv3x3_small_kernel<4>, dim3(blocks), dim3(256), smem, s, in, ld, cin, w, kp, bias, B, H, W, r, sign, y)); break;
+    case 1:
+      if (R == 2) IRB_TRY((launch_conv3x3_small_inst<1, 2>(blocks, smem, s, in, ld, cin, w, kp, bias, B, H, W, r, sign, y)));
+      else IRB_TRY((launch_conv3x3_small_inst<1, 4>(blocks, smem, s, in, ld, cin, w, kp, bias, B, H, W, r, sign, y)));
+      break;
+    case 2: IRB_TRY((launch_conv3x3_small_inst<2, 2>(blocks, smem, s, in, ld, cin, w, kp, bias, B, H, W, r, sign, y))); break;
+    case 3: IRB_TRY((launch_conv3x3_small_inst<3, 2>(blocks, smem, s, in, ld, cin, w, kp, bias, B, H, W, r, sign, y))); break;
+    default: IRB_TRY((launch_conv3x3_small_inst<4, 2>(blocks, smem, s, in, ld, cin, w, kp, bias, B, H, W, r, sign, y))); break;
   }
   IRB_LAUNCH_CHECK();
   return IR_OK;
@@ -596,18 +656,35 @@ __global__ void __launch_bounds__(256) conv3x3_first_kernel(const float* __restr
   const int in_row = blockIdx.x * 256 + threadIdx.x;
   if (in_row >= W * q4) return;
   const int xx = in_row / q4, q = in_row - xx * q4;
+  // a thread's column never changes: the x-validity of the taps and the tap offsets are loop invariants, and an invalid tap
+  // contributes a zero (the first build recomputed nine 64-bit addresses and eighteen bounds checks per pixel: ~250
+  // instructions per float4 stored, integer-bound at 1.6 TB/s)
+  const bool xl = xx > 0, xr = xx + 1 < W;
+  const long long plane = (long long)H * W;
+  const float4 bq = bias ? *reinterpret_cast<const float4*>(bias + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+  // gray images: the thread's nine weight quads live in registers for its whole column (per output float4 the loop is then
+  // 9 broadcast loads + 1 store; with the quads in shared memory nine more 4-wavefront LDS.128 went through the same LSU)
+  float4 wreg[CIN == 1 ? 9 : 1];
+  if constexpr (CIN == 1) {
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) wreg[tap] = *reinterpret_cast<const float4*>(wsm + tap * cout + 4 * q);
+  }
   for (int row = blockIdx.y; row < B * H; row += gridDim.y) {
     const int b = row / H, yy = row - b * H;
     const long long pix = (long long)row * W + xx;
-    float4 acc = bias ? *reinterpret_cast<const float4*>(bias + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* xc = x + ((long long)b * CIN * H + yy) * W + xx;     // channel 0, centre tap
+    const bool yu = yy > 0, yd = yy + 1 < H;
+    float4 acc = bq;
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap) {
-      const int y2 = yy + tap / 3 - 1, x2 = xx + tap % 3 - 1;
-      if (y2 < 0 || y2 >= H || x2 < 0 || x2 >= W) continue;
+      const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+      const bool ok = (dy < 0 ? yu : dy > 0 ? yd : true) && (dx < 0 ? xl : dx > 0 ? xr : true);
 #pragma unroll
       for (int c = 0; c < CIN; ++c) {
-        const float v = __ldg(x + (((long long)b * CIN + c) * H + y2) * W + x2);
-        const float4 ww = *reinterpret_cast<const float4*>(wsm + (tap * CIN + c) * cout + 4 * q);
+        const float v = ok ? __ldg(xc + c * plane + dy * W + dx) : 0.f;
+        float4 ww;
+        if constexpr (CIN == 1) ww = wreg[tap];
+        else ww = *reinterpret_cast<const float4*>(wsm + (tap * CIN + c) * cout + 4 * q);
         acc.x = fmaf(v, ww.x, acc.x); acc.y = fmaf(v, ww.y, acc.y); acc.z = fmaf(v, ww.z, acc.z); acc.w = fmaf(v, ww.w, acc.w);
       }
     }
