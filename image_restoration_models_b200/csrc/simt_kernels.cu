@@ -612,19 +612,15 @@ int launch_conv3x3_small(const float* in, int ld, int cin, const float* w, int k
   IRB_REQUIRE(cout >= 1 && cout <= 4 && cin % 4 == 0 && ld % 4 == 0, "conv3x3_small: cout in 1..4, cin % 4 == 0");
   const size_t wbytes = ((size_t)cout * 9 * cin * sizeof(float) + 15) & ~(size_t)15;
   IRB_REQUIRE(wbytes <= 48 * 1024, "conv3x3_small: weights do not fit shared memory");
-  // rows per warp: 4 for the single-output (gray) case, 2 otherwise (the register window is (R + 2) x 3 float4 + COUT x R sums)
-  static const bool r2 = getenv("IRB_OUTCONV_R2") != nullptr;        // A/B switch for benchmarks
-  const int R = cout == 1 && !r2 ? 4 : 2;
+  // two rows per warp: four (255 registers, one block per SM) measured 420-430 us against 377-386 us on the bench's output conv
+  const int R = 2;
   const size_t smem = wbytes + (size_t)8 * 4 * (R + 2) * 512;      // + 8 warps x 4 ring slots x (R + 2) rows x 32 lanes x 16 B
   const long long nwarps = (long long)B * cdiv(H, R) * ((W + 31) / 32);
   const int blocks = (int)std::min<long long>(cdivll(nwarps, 8), 148LL * 32);
   const double pix = (double)B * H * W;
   ProfScope prof(TAG_CONV3, 4.0 * pix * (cin + cout * (r ? 2.0 : 1.0)), 2.0 * 9.0 * pix * cin * cout, s);
   switch (cout) {
-    case 1:
-      if (R == 2) IRB_TRY((launch_conv3x3_small_inst<1, 2>(blocks, smem, s, in, ld, cin, w, kp, bias, B, H, W, r, sign, y)));
-      else IRB_TRY((launch_conv3x3_small_inst<1, 4>(blocks, smem, s, in, ld, cin, w, kp, bias, B, H, W, r, sign, y)));
-      break;
+    case 1: IRB_TRY((launch_conv3x3_small_inst<1, 2>(blocks, smem, s, in, ld, cin, w, kp, bias, B, H, W, r, sign, y))); break;
     case 2: IRB_TRY((launch_conv3x3_small_inst<2, 2>(blocks, smem, s, in, ld, cin, w, kp, bias, B, H, W, r, sign, y))); break;
     case 3: IRB_TRY((launch_conv3x3_small_inst<3, 2>(blocks, smem, s, in, ld, cin, w, kp, bias, B, H, W, r, sign, y))); break;
     default: IRB_TRY((launch_conv3x3_small_inst<4, 2>(blocks, smem, s, in, ld, cin, w, kp, bias, B, H, W, r, sign, y))); break;
