@@ -461,7 +461,9 @@ def main():
             except Exception:
                 pass
         # the largest family that IS bound by HBM, same definition of achieved / peak
-        rest = [r for r in rows if r["name"] != "gdfn_fused" and r["bytes"] > 0]
+        # (a family whose FP32-pipe or tensor fraction exceeds its HBM fraction is not HBM-bound: the fused front is skipped)
+        rest = [r for r, k in zip(rows, kernels) if r["name"] != "gdfn_fused" and r["bytes"] > 0 and
+                k["hbm_frac"] >= max(k.get("fp32_pipe_frac", 0.0), k["tensor_frac"])]
         if rest:
             h = rest[0]
             h_ms = h["ms"] / h["launches"]

@@ -24,6 +24,7 @@ timeout 600 python scripts/bench_latency.py > $OUT/latency_$TAG.json 2> $OUT/lat
 echo "latency exit $?" | tee -a $OUT/status_$TAG.txt
 NCU_K="ffn_fused|attn_fused" NCU_CS=96 NCU_MODES=0 bash scripts/ncu_blocks.sh $TAG > $OUT/ncu_blocks_$TAG.log 2>&1
 python scripts/summarize_ncu_full.py $OUT/ncu_raw_$TAG.csv $OUT/ncu_summary_$TAG.csv | tee -a $OUT/status_$TAG.txt
+cp $OUT/ncu_raw_$TAG.csv $OUT/ncu_raw_keep_$TAG.csv 2>/dev/null
 timeout 900 python scripts/bench_configs.py --steps 5 > $OUT/configs_$TAG.log 2>&1
 echo "configs exit $?" | tee -a $OUT/status_$TAG.txt; cp $OUT/configs.json $OUT/configs_$TAG.json 2>/dev/null
 cat $OUT/status_$TAG.txt
