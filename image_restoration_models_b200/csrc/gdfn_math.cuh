@@ -51,22 +51,45 @@ __device__ __forceinline__ f2_t gelu_gate2(f2_t x, f2_t gate) {
 // gelu(x) * gate with ONE special-function instruction per element.  For a = |x| the tail of the Gaussian is
 // erfc(a / sqrt 2) = 2^(-Q(a)) with Q smooth and Q(0) = 0, and
 //     gelu(x) = max(x, 0) - |x| * 0.5 erfc(|x| / sqrt 2) = max(x, 0) - a * 2^(-(Q(a) + 1))
-// (x > 0: x - 0.5 x erfc; x <= 0: 0.5 x erfc).  Q is a degree-6 polynomial without constant term: six packed FMAs (the last
+// (x > 0: x - 0.5 x erfc; x <= 0: 0.5 x erfc).  Q is a polynomial without constant term: one packed FMA per degree (the last
 // one adds the 1 that halves the result), one MUFU.EX2, no reciprocal, no select.  The error of the polynomial is weighted by
 // erfc itself, i.e. it vanishes where gelu is large.  Fit: scripts/fit_gelu_exp2.py (weighted minimax on [0, 6], |x| clamped
-// to 6 where erfc < 2e-9): max |gelu error| 3.1e-7 in fp32 arithmetic, the rounding level of the subtraction itself.  The A&S
-// form above costs two MUFU per element (rcp + ex2) and four more packed operations.
+// to 6 where erfc < 2e-9).  max |gelu error| in fp32 arithmetic: degree 6 3.1e-7 (the rounding level of the subtraction
+// itself), degree 5 7.1e-7, degree 4 8.7e-6.  The result is rounded to a 16-bit tensor-core operand right away (2^-11
+// relative), so degree 4 would be fifty times below what the consumer can see -- but measured on B200 it buys nothing (fused
+// GDFN C = 96 0.765 ms against 0.751-0.753 ms, C = 48 0.403 against 0.412 ms: the gate's FMAs are not on the critical path
+// of the lock-step phases), so the library keeps degree 6; IRB_GELU_DEG = 4 / 5 select the shorter ones.  The A&S form above
+// costs two MUFU per element (rcp + ex2) and four more packed operations.
+#ifndef IRB_GELU_DEG
+#define IRB_GELU_DEG 6
+#endif
 __device__ __forceinline__ f2_t gelu_gate2e(f2_t x, f2_t gate) {
+#if IRB_GELU_DEG == 6
   const f2_t C6 = pack2(-2.992467082811e-05f, -2.992467082811e-05f), C5 = pack2(7.398781788458e-04f, 7.398781788458e-04f),
              C4 = pack2(-7.977474556594e-03f, -7.977474556594e-03f), C3 = pack2(5.323820251441e-02f, 5.323820251441e-02f),
-             C2 = pack2(4.589156769318e-01f, 4.589156769318e-01f), C1 = pack2(1.151147084379f, 1.151147084379f),
-             ONE = pack2(1.0f, 1.0f), NEG1 = pack2(-1.0f, -1.0f);
+             C2 = pack2(4.589156769318e-01f, 4.589156769318e-01f), C1 = pack2(1.151147084379f, 1.151147084379f);
+#elif IRB_GELU_DEG == 5
+  const f2_t C5 = pack2(4.88102132e-04f, 4.88102132e-04f), C4 = pack2(-7.19871846e-03f, -7.19871846e-03f),
+             C3 = pack2(5.21466320e-02f, 5.21466320e-02f), C2 = pack2(4.59595844e-01f, 4.59595844e-01f),
+             C1 = pack2(1.15100054f, 1.15100054f);
+#else
+  const f2_t C4 = pack2(-4.16167e-03f, -4.16167e-03f), C3 = pack2(4.573546e-02f, 4.573546e-02f),
+             C2 = pack2(4.6493045e-01f, 4.6493045e-01f), C1 = pack2(1.14956698f, 1.14956698f);
+#endif
+  const f2_t ONE = pack2(1.0f, 1.0f), NEG1 = pack2(-1.0f, -1.0f);
   float xx, xy;
   unpack2(x, xx, xy);
   const f2_t a = pack2(fminf(fabsf(xx), 6.0f), fminf(fabsf(xy), 6.0f));
+#if IRB_GELU_DEG == 6
   f2_t q = fma2(C6, a, C5);
   q = fma2(q, a, C4);
   q = fma2(q, a, C3);
+#elif IRB_GELU_DEG == 5
+  f2_t q = fma2(C5, a, C4);
+  q = fma2(q, a, C3);
+#else
+  f2_t q = fma2(C4, a, C3);
+#endif
   q = fma2(q, a, C2);
   q = fma2(q, a, C1);
   q = fma2(q, a, ONE);                                          // Q(a) + 1
