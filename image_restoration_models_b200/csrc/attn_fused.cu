@@ -47,6 +47,7 @@
 #include "tmap.cuh"
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <type_traits>
 
@@ -70,6 +71,7 @@ constexpr int NTHREADS = (WARP_PROD + 1) * 32;
 constexpr int D1_COLS = AROWS;                 // accumulator columns per group
 constexpr int ND = 2;                          // group accumulators in TMEM
 constexpr int S_COL0 = ND * D1_COLS;           // the Gram accumulator (<= 96 columns)
+constexpr int W_COL0 = S_COL0 + 96;            // the depthwise taps: 9 columns per group, lane = channel (<= 27 of the 32 spare columns)
 constexpr int TMEM_COLS = 512;
 #ifndef IRB_PROD_POLL_NS
 #define IRB_PROD_POLL_NS 200
@@ -268,7 +270,24 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const FusedFrontParam
     // =============================== depthwise 3x3 from tensor memory -> X tile (q, k) / global (v) ===============================
     const int q = warp & 3, h = warp >> 2;
     const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(8 * h);
+    // The nine taps of every unit this lane quarter will ever read, parked in the spare TENSOR-MEMORY columns with
+    // lane = channel: the kernel's shared memory leaves the L1 no room, and a tap fetch from L2 in front of every group sat
+    // on the critical path of the lock-step phases (clock64 instrumentation: ~700 cycles per group outside the waits and the
+    // units).  Both warps of a quarter store the same values; each reads them back behind its own tcgen05.wait::st.
+    const uint32_t wlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)W_COL0;
+#pragma unroll
+    for (int g = 0; g < G::NG; ++g) {
+      const int u = g < G::NG - 1 ? 4 * g + q : G::NUNITS - 1;
+      uint32_t r[9];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) r[t] = __float_as_uint(__ldg(p.dw + (size_t)(u * 9 + t) * UC + lane));
+      tmem_st8(wlane + (uint32_t)(9 * g), r);
+      tmem_st1(wlane + (uint32_t)(9 * g + 8), r[8]);
+    }
+    tmem_st_wait();
     uint32_t gg = 0, j = 0;
+    long long t_wait[3] = {0, 0, 0}, t_unit[3] = {0, 0, 0}, t_xw = 0, t_all = 0, t_arr = 0, t_pre = 0, t_mark = 0;   // DBG & 64: where a depthwise warp's time goes
+    if (DBG & 64) t_all = clock64();
     for (TileIter ti(p); ti.valid(); ti.next(), ++j) {
       const int y0 = ti.y0(), x0 = ti.x0();
       const int vy = min(TH, p.H - y0), vx = max(0, min(8, p.W - (x0 + 8 * h)));   // valid output rows / columns of this half
@@ -283,83 +302,114 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const FusedFrontParam
         const int ch = u * UC + lane;                        // this thread's qkv channel
         f2_t w[9];
         if (active) {
+          uint32_t r[9];
+          tmem_ld8(wlane + (uint32_t)(9 * grp), r);
+          tmem_ld1(wlane + (uint32_t)(9 * grp + 8), r[8]);
+          tmem_ld_wait9(r);
 #pragma unroll
-          for (int t = 0; t < 9; ++t) {
-            const float f = __ldg(p.dw + (size_t)(u * 9 + t) * UC + lane);
-            w[t] = dwt::pack2(f, f);
-          }
+          for (int t = 0; t < 9; ++t) w[t] = dwt::pack2u(r[t], r[t]);
         }
         const uint32_t sd = gg & 1u;
+        long long tw0 = 0;
+        if (DBG & 64) { tw0 = clock64(); if (t_mark) t_pre += tw0 - t_mark; }
         mbar_wait_spin(smem_u32(&bars->d1_full[sd]), (gg >> 1) & 1u);
         tc_fence_after();
+        if (DBG & 64) { const long long t1 = clock64(); t_wait[grp] += t1 - tw0; tw0 = t1; }
         if (active) {
           const uint32_t taddr = tlane + sd * D1_COLS;
-          if (u * UC < 2 * CW) {
-            // ---- q | k unit: row `ch` of the X tile, 8 fp16 pixels per output row; squared norms ----
-            f2_t n = dwt::pack2(0.f, 0.f);
-            const uint32_t xrow = sX + (uint32_t)ch * 128u + (uint32_t)(h << 4), sw = ((uint32_t)ch & 7u) << 4;
-            dwt::unit(taddr, w, [&](int oy, const f2_t (&acc)[4]) {
-              if (oy == 0 && xwait) { mbar_wait_spin(smem_u32(&bars->x_empty), (j & 1u) ^ 1u); xwait = false; }
-              if (DBG & 32) { n = dwt::add2(n, dwt::add2(dwt::add2(acc[0], acc[1]), dwt::add2(acc[2], acc[3]))); return; }
-              float a[8];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) dwt::unpack2(acc[e], a[2 * e], a[2 * e + 1]);
-              if (partial) {
-                // output pixels past the right / bottom image edge still see taps from inside the image: they must not
-                // reach the Gram or the norms
-#pragma unroll
-                for (int e = 0; e < 8; ++e) if (oy >= vy || e >= vx) a[e] = 0.f;
-              }
-              const __half2 h0 = f2h2_sat(a[0], a[1]), h1 = f2h2_sat(a[2], a[3]), h2 = f2h2_sat(a[4], a[5]), h3 = f2h2_sat(a[6], a[7]);
-              // pixel (oy, 8h + e) of the tile: X box oy / 4, 16-byte chunk (oy % 4) * 2 + h of the channel's 128-byte row
-              sts128u((xrow + (uint32_t)(oy >> 2) * xbox + (uint32_t)((oy & 3) << 5)) ^ sw,
-                      make_uint4(h2_bits(h0), h2_bits(h1), h2_bits(h2), h2_bits(h3)));
-              // the norms take the unrounded fp32 values: against the fp16 operands the Gram sees, each term differs by a
-              // mean-zero rounding error of 2^-11, which averages out over the H * W pixels of the sum
-              n = dwt::fma2(dwt::pack2(a[0], a[1]), dwt::pack2(a[0], a[1]), n);
-              n = dwt::fma2(dwt::pack2(a[2], a[3]), dwt::pack2(a[2], a[3]), n);
-              n = dwt::fma2(dwt::pack2(a[4], a[5]), dwt::pack2(a[4], a[5]), n);
-              n = dwt::fma2(dwt::pack2(a[6], a[7]), dwt::pack2(a[6], a[7]), n);
-            });
-            float n0, n1;
-            dwt::unpack2(n, n0, n1);
-            red[h * (2 * CW) + ch] += n0 + n1;               // this thread is the only writer of the slot
-          } else {
-            // ---- v unit: fp16 straight to global memory, a warp writes 64 contiguous bytes per pixel ----
-            const bool chv = ch < 3 * CW;                    // C = 48: the last unit is half padding
-            unsigned short* vrow = reinterpret_cast<unsigned short*>(p.v) +
-                                   (((long long)b * p.H + y0) * p.W + x0 + 8 * h) * CW + (ch - 2 * CW);
-            const long long rs = (long long)p.W * CW;
-            f2_t dummy = dwt::pack2(0.f, 0.f);
-            dwt::unit(taddr, w, [&](int oy, const f2_t (&acc)[4]) {
-              if (DBG & 16) { dummy = dwt::add2(dummy, dwt::add2(dwt::add2(acc[0], acc[1]), dwt::add2(acc[2], acc[3]))); return; }
-              if (chv && oy < vy) {
-                unsigned short* dst = vrow + oy * rs;
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  float lo, hi;
-                  dwt::unpack2(acc[e], lo, hi);
-                  const uint32_t bits = h2_bits(f2h2_sat(lo, hi));
-                  if (!partial || 2 * e < vx) dst[(2 * e) * CW] = (unsigned short)(bits & 0xffffu);
-                  if (!partial || 2 * e + 1 < vx) dst[(2 * e + 1) * CW] = (unsigned short)(bits >> 16);
+          // PARTIAL (compile time): tiles that cross the right / bottom image edge mask their outputs; every other tile
+          // runs the variant without a single predicate or select (the masks and the per-store address arithmetic were as
+          // many integer instructions as the v unit has FFMA2 -- and IMAD shares the FMA pipe)
+          auto run_unit = [&](auto partial_tag) {
+            constexpr bool PARTIAL = decltype(partial_tag)::value;
+            if (u * UC < 2 * CW) {
+              // ---- q | k unit: row `ch` of the X tile, 8 fp16 pixels per output row; squared norms ----
+              f2_t n = dwt::pack2(0.f, 0.f);
+              const uint32_t xrow = sX + (uint32_t)ch * 128u + (uint32_t)(h << 4), sw = ((uint32_t)ch & 7u) << 4;
+              const uint32_t xr0 = xrow ^ sw, xr1 = (xrow + xbox) ^ sw;      // X boxes of output rows 0-3 / 4-7 (xbox is a multiple of 1024)
+              dwt::unit(taddr, w, [&](int oy, const f2_t (&acc)[4]) {
+                if (oy == 0 && xwait) {
+                  long long tx0 = 0;
+                  if (DBG & 64) tx0 = clock64();
+                  mbar_wait_spin(smem_u32(&bars->x_empty), (j & 1u) ^ 1u); xwait = false;
+                  if (DBG & 64) t_xw += clock64() - tx0;
                 }
-              }
-            });
-            if (DBG & 16) { float d0, d1; dwt::unpack2(dummy, d0, d1); if (d0 + d1 == 123.456f) red[0] = d0; }
-          }
+                if (DBG & 32) { n = dwt::add2(n, dwt::add2(dwt::add2(acc[0], acc[1]), dwt::add2(acc[2], acc[3]))); return; }
+                float a[8];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) dwt::unpack2(acc[e], a[2 * e], a[2 * e + 1]);
+                if (PARTIAL) {
+                  // output pixels past the right / bottom image edge still see taps from inside the image: they must not
+                  // reach the Gram or the norms
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) if (oy >= vy || e >= vx) a[e] = 0.f;
+                }
+                const __half2 h0 = f2h2_sat(a[0], a[1]), h1 = f2h2_sat(a[2], a[3]), h2 = f2h2_sat(a[4], a[5]), h3 = f2h2_sat(a[6], a[7]);
+                // pixel (oy, 8h + e) of the tile: X box oy / 4, 16-byte chunk (oy % 4) * 2 + h of the channel's 128-byte row
+                // (the chunk bits (oy & 3) << 5 and h << 4 never carry into the swizzle's bits, so they XOR in as a constant)
+                sts128u((oy < 4 ? xr0 : xr1) ^ (uint32_t)((oy & 3) << 5),
+                        make_uint4(h2_bits(h0), h2_bits(h1), h2_bits(h2), h2_bits(h3)));
+                // the norms take the unrounded fp32 values: against the fp16 operands the Gram sees, each term differs by a
+                // mean-zero rounding error of 2^-11, which averages out over the H * W pixels of the sum
+                if (PARTIAL) {
+                  n = dwt::fma2(dwt::pack2(a[0], a[1]), dwt::pack2(a[0], a[1]), n);
+                  n = dwt::fma2(dwt::pack2(a[2], a[3]), dwt::pack2(a[2], a[3]), n);
+                  n = dwt::fma2(dwt::pack2(a[4], a[5]), dwt::pack2(a[4], a[5]), n);
+                  n = dwt::fma2(dwt::pack2(a[6], a[7]), dwt::pack2(a[6], a[7]), n);
+                } else {
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) n = dwt::fma2(acc[e], acc[e], n);
+                }
+              });
+              float n0, n1;
+              dwt::unpack2(n, n0, n1);
+              red[h * (2 * CW) + ch] += n0 + n1;               // this thread is the only writer of the slot
+            } else {
+              // ---- v unit: fp16 straight to global memory, a warp writes 64 contiguous bytes per pixel ----
+              const bool chv = ch < 3 * CW;                    // C = 48: the last unit is half padding
+              unsigned short* dst = reinterpret_cast<unsigned short*>(p.v) +
+                                    (((long long)b * p.H + y0) * p.W + x0 + 8 * h) * CW + (ch - 2 * CW);
+              const long long rs = (long long)p.W * CW;
+              f2_t dummy = dwt::pack2(0.f, 0.f);
+              dwt::unit(taddr, w, [&](int oy, const f2_t (&acc)[4]) {
+                if (DBG & 16) { dummy = dwt::add2(dummy, dwt::add2(dwt::add2(acc[0], acc[1]), dwt::add2(acc[2], acc[3]))); return; }
+                if (chv && (!PARTIAL || oy < vy)) {
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    float lo, hi;
+                    dwt::unpack2(acc[e], lo, hi);
+                    const uint32_t bits = h2_bits(f2h2_sat(lo, hi));
+                    // the pixel offsets (2e) * CW are immediates; the row pointer advances once per output row
+                    if (!PARTIAL || 2 * e < vx) dst[(2 * e) * CW] = (unsigned short)(bits & 0xffffu);
+                    if (!PARTIAL || 2 * e + 1 < vx) dst[(2 * e + 1) * CW] = (unsigned short)(bits >> 16);
+                  }
+                }
+                dst += rs;
+              });
+              if (DBG & 16) { float d0, d1; dwt::unpack2(dummy, d0, d1); if (d0 + d1 == 123.456f) red[0] = d0; }
+            }
+          };
+          if (partial) run_unit(std::true_type{});
+          else run_unit(std::false_type{});
         }
+        if (DBG & 64) { t_mark = clock64(); t_unit[grp] += t_mark - tw0; }
         // the group's accumulator is free again
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&bars->d1_empty[sd]));
         if (grp == G::NG - 2) {
           // every q | k unit lives in the full groups: the X tile is complete, the Gram can go (the lone v unit is still ahead)
-          fence_async_smem();
+          if (!(DBG & 128)) fence_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&bars->x_ready));
         }
+        if (DBG & 64) { const long long t1 = clock64(); t_arr += t1 - t_mark; t_mark = t1; }
       }
     }
+    if ((DBG & 64) && lane == 0 && blockIdx.x == 1 && blockIdx.y == 0)
+      printf("af-dbg warp %d tiles %u total %lld | wait g0 %lld g1 %lld g2 %lld | unit g0 %lld g1 %lld g2 %lld | xwait %lld\n", warp, j,
+             clock64() - t_all, t_wait[0], t_wait[1], t_wait[2], t_unit[0], t_unit[1], t_unit[2], t_xw);
+    if ((DBG & 64) && lane == 0 && blockIdx.x == 1 && blockIdx.y == 0) printf("af-dbg2 warp %d arrive %lld pre %lld\n", warp, t_arr, t_pre);
     // ---- squared-norm partials: the two column halves of every q | k channel ----
     asm volatile("bar.sync 1, %0;" ::"n"(DW_WARPS * 32) : "memory");
     if (tid < 2 * CW) {
@@ -495,6 +545,9 @@ int launch_attn_fused(const AttnFusedArgs& a, cudaStream_t s) {
       case 32: return launch_inst<96, 32>(tA, p, grid, smem, s);
       case 48: return launch_inst<96, 48>(tA, p, grid, smem, s);
       case 56: return launch_inst<96, 56>(tA, p, grid, smem, s);
+      case 64: return launch_inst<96, 64>(tA, p, grid, smem, s);
+      case 128: return launch_inst<96, 128>(tA, p, grid, smem, s);
+      case 192: return launch_inst<96, 192>(tA, p, grid, smem, s);
       default: break;
     }
   }

@@ -11,6 +11,7 @@
 #include "common.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace irb {
 
@@ -357,41 +358,84 @@ int launch_gram_ref(const GramParams& p, cudaStream_t s) {
 //   W_eff[b][n][h*ch + j] = sum_i W_proj[n][h*ch + i] * softmax_j(S[i][j] / (|q_i| |k_j|) * T_h)
 // grid (heads, B); dynamic smem: ch*ch + 2*ch floats
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) fold_kernel(const FoldParams p) {
+__global__ void __launch_bounds__(1024) fold_kernel(const FoldParams p, const int PG) {
   extern __shared__ float sm[];
   const int head = blockIdx.x, b = blockIdx.y;
   const int ch = p.C / p.heads;
-  float* A = sm;                 // [ch][ch]
-  float* nq = sm + ch * ch;      // [ch]
-  float* nk = nq + ch;           // [ch]
+  const int NE = (ch * ch) >> 2;                 // float4 elements of the Gram
+  float* A = sm;                                 // [PG][ch][ch]: slab 0 becomes the reduced Gram / the softmax
+  float* nq = sm + PG * ch * ch;                 // [ch]
+  float* nk = nq + ch;                           // [ch]
+  float* wsm = nk + ch;                          // [rows_per][ch]: this CTA's slice of W_proj
   const int tid = threadIdx.x;
   const long long pb = ((long long)b * p.heads + head) * p.nparts;
-  pdl_sync();
-  // deterministic reduction of the pixel-slice partials (fixed order), 16-byte loads, 8 slices in flight per thread
-  for (int e = tid * 4; e < ch * ch; e += blockDim.x * 4) {
-    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float* src = p.s_part + pb * ch * ch + e;
-    int part = 0;
-    for (; part + 8 <= p.nparts; part += 8) {
-      float4 t[8];
+  const int rows_per = (p.C + gridDim.z - 1) / gridDim.z;
+  const int n_lo = blockIdx.z * rows_per, n_hi = min(p.C, n_lo + rows_per);
+  const int nw = max(0, n_hi - n_lo) * ch;
+  // W_proj is a constant: its slice is requested before the wait on the producing kernel and parked in registers until the
+  // reduction's loads are out (the kernel is a chain of L2 round trips: every load that can be is issued up front)
+  constexpr int WR = 4;
+  float wreg[WR];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) t[u] = __ldg(reinterpret_cast<const float4*>(src + (long long)(part + u) * ch * ch));
-#pragma unroll
-      for (int u = 0; u < 8; ++u) { s.x += t[u].x; s.y += t[u].y; s.z += t[u].z; s.w += t[u].w; }
-    }
-    for (; part < p.nparts; ++part) {
-      const float4 t = __ldg(reinterpret_cast<const float4*>(src + (long long)part * ch * ch));
-      s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
-    }
-    *reinterpret_cast<float4*>(A + e) = s;
+  for (int u = 0; u < WR; ++u) {
+    const int e = tid + u * 1024;
+    wreg[u] = e < nw ? __ldg(p.w_proj + (long long)(n_lo + e / ch) * p.C + head * ch + e % ch) : 0.f;
   }
-  for (int e = tid; e < 2 * ch; e += blockDim.x) {
+  pdl_sync();
+  // deterministic reduction of the pixel-slice partials: the parts are dealt round-robin to PG groups of threads (fixed
+  // order inside a group, groups summed in order below), so that a thread's dependent L2 round trips are nparts / PG / 4
+  const float4* sp4 = reinterpret_cast<const float4*>(p.s_part + pb * ch * ch);
+  for (int idx = tid; idx < NE * PG; idx += 1024) {
+    const int pg = idx / NE, e4 = idx - pg * NE;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4* src = sp4 + e4;
+    int part = pg;
+    for (; part + 3 * PG < p.nparts; part += 4 * PG) {
+      float4 t[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) t[u] = __ldg(src + (long long)(part + u * PG) * NE);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { s.x += t[u].x; s.y += t[u].y; s.z += t[u].z; s.w += t[u].w; }
+    }
+    {
+      float4 t[3];
+#pragma unroll
+      for (int u = 0; u < 3; ++u)
+        t[u] = part + u * PG < p.nparts ? __ldg(src + (long long)(part + u * PG) * NE) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < 3; ++u) { s.x += t[u].x; s.y += t[u].y; s.z += t[u].z; s.w += t[u].w; }
+    }
+    reinterpret_cast<float4*>(A)[idx] = s;
+  }
+  // squared norms: eight lanes per entry, each a fixed subset of the parts, then a fixed shuffle tree
+  // (16 * ch entries-lanes: whole warps enter every iteration)
+  for (int idx = tid; idx < 16 * ch; idx += 1024) {
+    const int e = idx >> 3, l = idx & 7;
     float s = 0.f;
-    for (int part = 0; part < p.nparts; ++part) s += p.n_part[(pb + part) * 2 * ch + e];
+    for (int part = l; part < p.nparts; part += 8) s += __ldg(p.n_part + (pb + part) * 2 * ch + e);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
     // F.normalize: x / max(||x||_2, 1e-12)
-    nq[e] = 1.0f / fmaxf(sqrtf(s), 1e-12f);
+    if (l == 0) nq[e] = 1.0f / fmaxf(sqrtf(s), 1e-12f);
+  }
+#pragma unroll
+  for (int u = 0; u < WR; ++u) {
+    const int e = tid + u * 1024;
+    if (e < nw) wsm[e] = wreg[u];
   }
   __syncthreads();
+  if (PG > 1) {
+    for (int e4 = tid; e4 < NE; e4 += 1024) {
+      float4 s = reinterpret_cast<const float4*>(A)[e4];
+      for (int g = 1; g < PG; ++g) {
+        const float4 t = reinterpret_cast<const float4*>(A)[g * NE + e4];
+        s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+      }
+      reinterpret_cast<float4*>(A)[e4] = s;
+    }
+    __syncthreads();
+  }
   const float temp = p.temperature[head];
   const int warp = tid >> 5, lane = tid & 31, nwarp = blockDim.x >> 5;
   for (int i = warp; i < ch; i += nwarp) {
@@ -416,13 +460,18 @@ __global__ void __launch_bounds__(1024) fold_kernel(const FoldParams p) {
   __syncthreads();
   // this CTA's slice of the output rows (grid.z row blocks share the softmax work, split the C x ch products)
   float* we = p.w_eff + (long long)b * p.w_eff_bstride;
-  const int rows_per = (p.C + gridDim.z - 1) / gridDim.z;
-  const int n_lo = blockIdx.z * rows_per, n_hi = min(p.C, n_lo + rows_per);
+  const bool w_staged = nw <= WR * 1024;
   for (int e = n_lo * ch + tid; e < n_hi * ch; e += blockDim.x) {
     const int n = e / ch, j = e - n * ch;
-    const float* wrow = p.w_proj + (long long)n * p.C + head * ch;
     float s = 0.f;
-    for (int i = 0; i < ch; ++i) s = fmaf(wrow[i], A[i * ch + j], s);
+    if (w_staged) {
+      const float* wrow = wsm + (n - n_lo) * ch;
+#pragma unroll 8
+      for (int i = 0; i < ch; ++i) s = fmaf(wrow[i], A[i * ch + j], s);
+    } else {
+      const float* wrow = p.w_proj + (long long)n * p.C + head * ch;
+      for (int i = 0; i < ch; ++i) s = fmaf(wrow[i], A[i * ch + j], s);
+    }
     const int k = head * ch + j;
     if (p.fmt == 1) {
       uint32_t u;
@@ -446,17 +495,23 @@ __global__ void __launch_bounds__(1024) fold_kernel(const FoldParams p) {
 
 int launch_fold(const FoldParams& p, cudaStream_t s) {
   const int ch = p.C / p.heads;
-  const size_t smem = (size_t)(ch * ch + 2 * ch) * sizeof(float);
-  IRB_REQUIRE(smem <= 48 * 1024 + 0u || ch <= 128, "fold: head dim too large");
-  if (smem > 48 * 1024) IRB_CUDA(cudaFuncSetAttribute(fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  IRB_REQUIRE(p.C % p.heads == 0 && ch % 4 == 0 && ch <= 128, "fold: head dim must be a multiple of 4, <= 128");
   // the C x ch products are split over grid.z row blocks so that about two waves of CTAs share them (every block
   // repeats the cheap partial reduction and softmax of its head)
   const int zb = std::max(1, std::min(8, cdiv(2 * 148, p.heads * p.B)));
+  const int rows_per = cdiv(p.C, zb);
+  // part groups: enough (element, group) pairs to give each of the 1024 threads a few independent load chains
+  static const bool pg1 = getenv("IRB_FOLD_PG1") != nullptr;      // A/B switch for benchmarks
+  const int PG = pg1 ? 1 : std::max(1, std::min(4, p.nparts / 2));
+  const size_t smem = (size_t)(PG * ch * ch + 2 * ch + std::min(rows_per * ch, 4 * 1024)) * sizeof(float);
+  IRB_REQUIRE(smem <= 200 * 1024, "fold: head dim too large");
+  static SmemOptIn optin;
+  IRB_TRY(opt_in_smem(fold_kernel, optin));
   dim3 grid(p.heads, p.B, zb);
   ProfScope prof(TAG_FOLD, 4.0 * (double)p.B * p.C * p.C, 2.0 * (double)p.B * p.C * p.C * ch, s);
   // 1024 threads: the kernel is a chain of L2 round trips (partials -> softmax -> products) over a 48x48 .. 96x96 matrix;
   // four times the threads is a quarter of the trips per thread
-  IRB_CUDA(launch_pdl(fold_kernel, dim3(grid), dim3(1024), smem, s, p));
+  IRB_CUDA(launch_pdl(fold_kernel, dim3(grid), dim3(1024), smem, s, p, PG));
   IRB_LAUNCH_CHECK();
   return IR_OK;
 }

@@ -115,6 +115,10 @@ if "--blocks" in sys.argv:
     for mode, nm in ((0, "fp32"), (1, "half")):
         for Cc, heads in ((48, 1), (96, 1)):
             print(json.dumps({"block": f"C{Cc}h{heads}", "mode": nm, "kernels": run_block(Cc, heads, 8, 512, 512, mode)}))
+        if "--levels" in sys.argv:
+            # the lower-resolution levels of the bench workload (8 x 512 x 512 input)
+            for Cc, heads, hw in ((96, 2, 256), (192, 4, 128), (384, 8, 64)):
+                print(json.dumps({"block": f"C{Cc}h{heads}@{hw}", "mode": nm, "kernels": run_block(Cc, heads, 8, hw, hw, mode)}))
 
 if __name__ == "__main__" and "--blocks" not in sys.argv:
     main()
