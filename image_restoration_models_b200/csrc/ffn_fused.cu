@@ -61,6 +61,8 @@ constexpr int NTHREADS = (WARP_PROD + 1) * 32;
 constexpr int D1_COLS = AROWS;                 // accumulator A at column 0, B at 192
 constexpr int D2_COL0 = 2 * D1_COLS;           // D2[128 px][C] at column 384
 constexpr int TMEM_COLS = 512;
+constexpr int W_COL0 = D2_COL0 + 96;           // depthwise taps, lane = hidden channel: 9 columns per (chunk, x1 | x2) set
+constexpr int W_SETS = (TMEM_COLS - W_COL0) / 9;   // three sets fit the 32 spare columns
 #ifndef IRB_PROD_POLL_NS
 #define IRB_PROD_POLL_NS 200
 #endif
@@ -323,6 +325,38 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int e = 0; e < 8; ++e) xo[e] = opbase + (((c16 ^ (uint32_t)e) << 4) + (uint32_t)e * 128u);
     const uint32_t lsw = (uint32_t)(lane & 7);
     if (warp == 0 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmY)) : "memory");
+    // The taps this thread's channel needs in every phase, parked in the spare tensor-memory columns (lane = channel): a tap
+    // fetch through the L1 this kernel's shared memory leaves no room for sat in front of every lock-step phase.  Three of
+    // the 2 NC sets fit: all of them at C = 48.  C = 96 (four sets) keeps the global loads -- three sets from tensor memory and
+    // one from global memory measured SLOWER than four from global memory (0.81 against 0.75 ms; two code paths in the phase).
+    const uint32_t wlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)W_COL0;
+    auto tap_ptr = [&](int set) {     // set = 2 * chunk + (0: x1, 1: x2); layout [64-channel chunk][x1 | x2][9][64]
+      return p.dw + ((size_t)(((set >> 1) * 2 + (lc >> 6)) * 2 + (set & 1)) * 9) * 64 + (lc & 63);
+    };
+#pragma unroll
+    constexpr bool W_TMEM = 2 * NC <= W_SETS;
+    for (int set = 0; W_TMEM && set < 2 * NC; ++set) {
+      uint32_t r[9];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) r[t] = __float_as_uint(__ldg(tap_ptr(set) + t * 64));
+      tmem_st8(wlane + (uint32_t)(9 * set), r);
+      tmem_st1(wlane + (uint32_t)(9 * set + 8), r[8]);
+    }
+    if (W_TMEM) tmem_st_wait();
+    auto load_taps = [&](int set, f2_t (&w)[9]) {
+      if (W_TMEM) {
+        uint32_t r[9];
+        tmem_ld8(wlane + (uint32_t)(9 * set), r);
+        tmem_ld1(wlane + (uint32_t)(9 * set + 8), r[8]);
+        tmem_ld_wait9(r);
+#pragma unroll
+        for (int t = 0; t < 9; ++t) w[t] = dwt::pack2u(r[t], r[t]);
+      } else {
+        const float* taps = tap_ptr(set);
+#pragma unroll
+        for (int t = 0; t < 9; ++t) { const float f = __ldg(taps + t * 64); w[t] = gdfn::pack2(f, f); }
+      }
+    };
 
     // D2 of tile j -> staging -> x += : lanes = the 32 pixels of tile rows 2q, 2q+1; this warp's 32-channel groups
     auto epilogue = [&](uint32_t j, int b, int y0, int x0) {
@@ -426,13 +460,11 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll 1
       for (int c = 0; c < NC; ++c, ++cc) {
         const uint32_t ph = cc & 1u;
-        const float* taps = p.dw + ((size_t)((c * 2 + (lc >> 6)) * 2) * 9) * 64 + (lc & 63);   // [64-chunk][set][9][64]
         f2_t r1[8][4];
         // ---- phase 1: depthwise taps of x1 (accumulator A) into registers ----
         {
           f2_t w[9];
-#pragma unroll
-          for (int t = 0; t < 9; ++t) { const float f = __ldg(taps + t * 64); w[t] = gdfn::pack2(f, f); }
+          load_taps(2 * c, w);
           mbar_wait_spin(smem_u32(&bars->d1_full[0]), ph);
           tc_fence_after();
           if (!(DBG & 2)) {
@@ -456,8 +488,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // ---- phase 2: depthwise taps of x2 (accumulator B), gate, fp16 operand rows ----
         {
           f2_t w[9];
-#pragma unroll
-          for (int t = 0; t < 9; ++t) { const float f = __ldg(taps + (9 + t) * 64); w[t] = gdfn::pack2(f, f); }
+          load_taps(2 * c + 1, w);
           mbar_wait_spin(smem_u32(&bars->d1_full[1]), ph);
           tc_fence_after();
           mbar_wait_spin(smem_u32(&bars->op_empty), ph ^ 1u);     // MMA2 of the previous chunk has read the operand boxes
