@@ -132,7 +132,10 @@ attn_front_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
   float* red = reinterpret_cast<float*>(gbase + p.off_red);
   const uint32_t xbox = (uint32_t)p.xrows * 128u;      // bytes of one X box
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // the warp index through a warp reduction lives in a UNIFORM register: the role branches become uniform branches and the
+  // code under them uses the uniform datapath (memory descriptors, TMEM / barrier addresses) without one R2UR per use
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = (int)__reduce_or_sync(0xffffffffu, (unsigned)(tid >> 5));
   const int b = blockIdx.y, part = blockIdx.x, grp = blockIdx.z;
   const int nchunk = p.nqk + p.nv;
 

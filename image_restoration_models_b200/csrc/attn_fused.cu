@@ -151,7 +151,10 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const FusedFrontParam
   float* red = reinterpret_cast<float*>(gbase + p.off_red);    // [2 column halves][2C] squared-norm partials
   const uint32_t xbox = (uint32_t)p.xrows * 128u;
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // the warp index through a warp reduction: its result lives in a UNIFORM register, so the role branches below are uniform
+  // branches and the code under them may use the uniform datapath (memory descriptors, TMEM addresses) without R2UR
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = (int)__reduce_or_sync(0xffffffffu, (unsigned)(tid >> 5));
   const int b = blockIdx.y, part = blockIdx.x;
 
   if (tid == 0) {

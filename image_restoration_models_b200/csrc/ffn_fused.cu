@@ -141,7 +141,10 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t sA = base + p.off_a, sWin = base + p.off_win, sWout = base + p.off_wout, sOP = base + p.off_op,
                  sStg = base + p.off_stg;
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // the warp index through a warp reduction lives in a UNIFORM register: the role branches become uniform branches and the
+  // code under them uses the uniform datapath (memory descriptors, TMEM / barrier addresses) without one R2UR per use
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = (int)__reduce_or_sync(0xffffffffu, (unsigned)(tid >> 5));
 
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) {

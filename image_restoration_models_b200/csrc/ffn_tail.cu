@@ -101,7 +101,10 @@ ffn_tail_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__
   const uint32_t sST = base + p.off_stage, sOP = base + p.off_op, sR = base + p.off_r;
   const uint32_t wbytes = (uint32_t)p.C * 128u, dwbytes = 2u * 9u * KC * 4u;
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // the warp index through a warp reduction lives in a UNIFORM register: the role branches become uniform branches and the
+  // code under them uses the uniform datapath (memory descriptors, TMEM / barrier addresses) without one R2UR per use
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = (int)__reduce_or_sync(0xffffffffu, (unsigned)(tid >> 5));
 
   if (tid == 0) {
     for (int s = 0; s < NST; ++s) {

@@ -372,15 +372,9 @@ __global__ void __launch_bounds__(1024) fold_kernel(const FoldParams p, const in
   const int rows_per = (p.C + gridDim.z - 1) / gridDim.z;
   const int n_lo = blockIdx.z * rows_per, n_hi = min(p.C, n_lo + rows_per);
   const int nw = max(0, n_hi - n_lo) * ch;
-  // W_proj is a constant: its slice is requested before the wait on the producing kernel and parked in registers until the
-  // reduction's loads are out (the kernel is a chain of L2 round trips: every load that can be is issued up front)
-  constexpr int WR = 4;
-  float wreg[WR];
-#pragma unroll
-  for (int u = 0; u < WR; ++u) {
-    const int e = tid + u * 1024;
-    wreg[u] = e < nw ? __ldg(p.w_proj + (long long)(n_lo + e / ch) * p.C + head * ch + e % ch) : 0.f;
-  }
+  // W_proj is a constant: this CTA's slice goes to shared memory before the wait on the producing kernel (the kernel is a
+  // chain of L2 round trips; with the slice in shared memory the product loop below has none)
+  for (int e = tid; e < nw; e += 1024) wsm[e] = __ldg(p.w_proj + (long long)(n_lo + e / ch) * p.C + head * ch + e % ch);
   pdl_sync();
   // deterministic reduction of the pixel-slice partials: the parts are dealt round-robin to PG groups of threads (fixed
   // order inside a group, groups summed in order below), so that a thread's dependent L2 round trips are nparts / PG / 4
@@ -419,11 +413,6 @@ __global__ void __launch_bounds__(1024) fold_kernel(const FoldParams p, const in
     // F.normalize: x / max(||x||_2, 1e-12)
     if (l == 0) nq[e] = 1.0f / fmaxf(sqrtf(s), 1e-12f);
   }
-#pragma unroll
-  for (int u = 0; u < WR; ++u) {
-    const int e = tid + u * 1024;
-    if (e < nw) wsm[e] = wreg[u];
-  }
   __syncthreads();
   if (PG > 1) {
     for (int e4 = tid; e4 < NE; e4 += 1024) {
@@ -460,18 +449,12 @@ __global__ void __launch_bounds__(1024) fold_kernel(const FoldParams p, const in
   __syncthreads();
   // this CTA's slice of the output rows (grid.z row blocks share the softmax work, split the C x ch products)
   float* we = p.w_eff + (long long)b * p.w_eff_bstride;
-  const bool w_staged = nw <= WR * 1024;
   for (int e = n_lo * ch + tid; e < n_hi * ch; e += blockDim.x) {
     const int n = e / ch, j = e - n * ch;
     float s = 0.f;
-    if (w_staged) {
-      const float* wrow = wsm + (n - n_lo) * ch;
+    const float* wrow = wsm + (n - n_lo) * ch;
 #pragma unroll 8
-      for (int i = 0; i < ch; ++i) s = fmaf(wrow[i], A[i * ch + j], s);
-    } else {
-      const float* wrow = p.w_proj + (long long)n * p.C + head * ch;
-      for (int i = 0; i < ch; ++i) s = fmaf(wrow[i], A[i * ch + j], s);
-    }
+    for (int i = 0; i < ch; ++i) s = fmaf(wrow[i], A[i * ch + j], s);
     const int k = head * ch + j;
     if (p.fmt == 1) {
       uint32_t u;
@@ -496,14 +479,17 @@ __global__ void __launch_bounds__(1024) fold_kernel(const FoldParams p, const in
 int launch_fold(const FoldParams& p, cudaStream_t s) {
   const int ch = p.C / p.heads;
   IRB_REQUIRE(p.C % p.heads == 0 && ch % 4 == 0 && ch <= 128, "fold: head dim must be a multiple of 4, <= 128");
-  // the C x ch products are split over grid.z row blocks so that about two waves of CTAs share them (every block
-  // repeats the cheap partial reduction and softmax of its head)
-  const int zb = std::max(1, std::min(8, cdiv(2 * 148, p.heads * p.B)));
+  // the C x ch products are split over grid.z row blocks so that ONE wave of CTAs shares them (every block repeats the
+  // partial reduction and softmax of its head: with 32 .. 64 (image, head) pairs at the low-resolution levels a second
+  // wave only re-reads the partials -- measured 18.7 -> 16.8 us at C = 192, 37.9 -> 29.7 us at C = 384)
+  static const int zb_env = getenv("IRB_FOLD_ZB") ? atoi(getenv("IRB_FOLD_ZB")) : 0;      // A/B switches for benchmarks
+  static const int pg_env = getenv("IRB_FOLD_PG") ? atoi(getenv("IRB_FOLD_PG")) : 0;
+  const int zb = zb_env > 0 ? std::min(zb_env, p.C) : std::max(1, std::min(8, 148 / std::max(1, p.heads * p.B)));
   const int rows_per = cdiv(p.C, zb);
-  // part groups: enough (element, group) pairs to give each of the 1024 threads a few independent load chains
-  static const bool pg1 = getenv("IRB_FOLD_PG1") != nullptr;      // A/B switch for benchmarks
-  const int PG = pg1 ? 1 : std::max(1, std::min(4, p.nparts / 2));
-  const size_t smem = (size_t)(PG * ch * ch + 2 * ch + std::min(rows_per * ch, 4 * 1024)) * sizeof(float);
+  // part groups (PG > 1: the parts dealt to PG groups of threads, more independent load chains per thread; measured no
+  // faster at C = 48 / 96 and slower at the low-resolution levels: one group)
+  const int PG = pg_env > 0 ? std::max(1, std::min(pg_env, p.nparts)) : 1;
+  const size_t smem = (size_t)(PG * ch * ch + 2 * ch + rows_per * ch) * sizeof(float);
   IRB_REQUIRE(smem <= 200 * 1024, "fold: head dim too large");
   static SmemOptIn optin;
   IRB_TRY(opt_in_smem(fold_kernel, optin));

@@ -81,7 +81,10 @@ tma_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const Conv3Params p) {
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   Bars* bars = reinterpret_cast<Bars*>(smem_raw + (base - smem_u32(smem_raw)));
   const uint32_t sA = base + p.off_a, sOP = base + p.off_op, sW = base + p.off_w;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // the warp index through a warp reduction lives in a UNIFORM register: the role branches become uniform branches and the
+  // code under them uses the uniform datapath (memory descriptors, TMEM / barrier addresses) without one R2UR per use
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = (int)__reduce_or_sync(0xffffffffu, (unsigned)(tid >> 5));
   const int n0 = blockIdx.y * p.nc;
   const int ncur = min(p.nc, p.N - n0);
   const int nraw = 9 * p.nkb_t;                      // raw boxes per tile

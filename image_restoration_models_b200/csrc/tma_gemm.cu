@@ -320,7 +320,10 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const uint32_t sW = base + p.off_w, sA = base + p.off_a, sOP = base + p.off_op, sRO = base + p.off_ro;
   float* lnv = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw)) + p.off_ln);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // the warp index through a warp reduction lives in a UNIFORM register: the role branches become uniform branches and the
+  // code under them uses the uniform datapath (memory descriptors, TMEM / barrier addresses) without one R2UR per use
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = (int)__reduce_or_sync(0xffffffffu, (unsigned)(tid >> 5));
   const int n0 = (p.split > 0 ? ((int)blockIdx.x >= p.split ? 1 : 0) : (int)blockIdx.y) * p.nc;
   const int ncur = min(p.nc, p.N - n0);
 
