@@ -10,6 +10,7 @@
 //   * consecutive lanes own consecutive channel vectors of the same pixels -> fully coalesced 512-byte segments;
 //   * the 3x3 weights of the block's channel slice live in shared memory.
 #include "common.cuh"
+#include "gdfn_math.cuh"
 
 #include <type_traits>
 
@@ -110,7 +111,6 @@ __global__ void __launch_bounds__(256, 2) dw_roll_kernel(const DwParams p, const
     coff[i] = min(max(x, 0), p.W - 1) * p.ldi;
   }
   const long long in_pitch = (long long)p.W * p.ldi, out_pitch = (long long)p.W * p.ldo;
-  const TI* rowp = in + ((long long)b * p.H + (y0 - 1)) * in_pitch + c;
   TO* orow = out + ((long long)b * p.H + (y0 - 1)) * out_pitch + (long long)x0 * p.ldo + c;
 
   float4 bias[NS];
@@ -129,22 +129,34 @@ __global__ void __launch_bounds__(256, 2) dw_roll_kernel(const DwParams p, const
   // One step consumes input row yy.  The three accumulator rows rotate roles; the rotation is resolved at compile
   // time (K = step index mod 3: row (K+0)%3 completes output yy-1, (K+1)%3 is output yy, (K+2)%3 is output yy+1),
   // so no register moves are needed between rows.
+  // The raw vectors of row yy+1 are requested BEFORE row yy's taps run (ncu: 32 % of the warp samples of the gated
+  // kernel sat on the first conversion of a freshly loaded vector -- with 16 warps per SM and ~200 instructions per row
+  // nothing else covered the load latency).  Rows outside the image are fetched from a clamped address and ignored.
+  const TI* imgp = in + (long long)b * p.H * in_pitch + c;
+  typename Raw4<TI>::type raw[NS][WT + 2];
+  auto fetch = [&](int yy) {
+    const TI* rp = imgp + (long long)min(max(yy, 0), p.H - 1) * in_pitch;
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+#pragma unroll
+      for (int i = 0; i < WT + 2; ++i) raw[s][i] = ldraw<TI>(rp + coff[i] + s * p.gate_off);
+  };
+  // (fp16 rows only: the fp32 vectors of two rows in flight do not fit the 128 registers of two resident blocks)
+  constexpr bool PREFETCH = std::is_same<TI, __half>::value;
+  if (PREFETCH) fetch(y0 - 1);
   auto step = [&](auto kc, int yy) {
     constexpr int K = decltype(kc)::value;
+    if (!PREFETCH) fetch(yy);
+    float4 v[NS][WT + 2];
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+#pragma unroll
+      for (int i = 0; i < WT + 2; ++i) {
+        const float4 t = cvt4(raw[s][i]);
+        v[s][i] = cmask[i] ? t : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    if (PREFETCH && yy < y1) fetch(yy + 1);  // the next step's row (the band ends with row y1)
     if (yy >= 0 && yy < p.H) {
-      typename Raw4<TI>::type raw[NS][WT + 2];
-#pragma unroll
-      for (int s = 0; s < NS; ++s)
-#pragma unroll
-        for (int i = 0; i < WT + 2; ++i) raw[s][i] = ldraw<TI>(rowp + coff[i] + s * p.gate_off);
-      float4 v[NS][WT + 2];
-#pragma unroll
-      for (int s = 0; s < NS; ++s)
-#pragma unroll
-        for (int i = 0; i < WT + 2; ++i) {
-          const float4 t = cvt4(raw[s][i]);
-          v[s][i] = cmask[i] ? t : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
       // input row yy feeds output rows yy-1 (tap row 2), yy (tap row 1), yy+1 (tap row 0)
 #pragma unroll
       for (int s = 0; s < NS; ++s)
@@ -165,8 +177,11 @@ __global__ void __launch_bounds__(256, 2) dw_roll_kernel(const DwParams p, const
           float4 o = acc[0][K % 3][i];
           if (GATE) {
             const float4 gt = acc[NS - 1][K % 3][i];
-            o.x = gelu_erf(o.x) * gt.x; o.y = gelu_erf(o.y) * gt.y;
-            o.z = gelu_erf(o.z) * gt.z; o.w = gelu_erf(o.w) * gt.w;
+            // gelu(x1) * x2 on packed pairs, one MUFU per element (gdfn_math.cuh; max error 3.1e-7)
+            const gdfn::f2_t g0 = gdfn::gelu_gate2e(gdfn::pack2(o.x, o.y), gdfn::pack2(gt.x, gt.y));
+            const gdfn::f2_t g1 = gdfn::gelu_gate2e(gdfn::pack2(o.z, o.w), gdfn::pack2(gt.z, gt.w));
+            gdfn::unpack2(g0, o.x, o.y);
+            gdfn::unpack2(g1, o.z, o.w);
           }
           if (std::is_same<TO, float>::value && p.round_tf32) { o.x = rna_tf32(o.x); o.y = rna_tf32(o.y); o.z = rna_tf32(o.z); o.w = rna_tf32(o.w); }
           st4<TO>(o_ + (long long)i * p.ldo, o);
@@ -177,7 +192,6 @@ __global__ void __launch_bounds__(256, 2) dw_roll_kernel(const DwParams p, const
     for (int s = 0; s < NS; ++s)
 #pragma unroll
       for (int i = 0; i < WT; ++i) acc[s][K % 3][i] = bias[s];      // becomes output row yy+2
-    rowp += in_pitch;
     orow += out_pitch;
   };
   for (int yy = y0 - 1; yy <= y1; yy += 3) {

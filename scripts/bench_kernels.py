@@ -103,12 +103,14 @@ if "--ncu" in sys.argv:
     Bn = 2
     modes = [int(m) for m in os.environ.get("NCU_MODES", "0,1").split(",")]
     cs = [int(c) for c in os.environ.get("NCU_CS", "48,96,192").split(",")]
+    # pixel counts of the bench workload's levels (8 x 512 x 512 input): C = 192 -> 131 k pixels, C = 384 -> 32 k pixels
+    side = {48: 512, 96: 512, 192: 256, 384: 128}
     for mode in modes:
-        for Cc, heads in ((48, 1), (96, 1), (192, 4)):
+        for Cc, heads in ((48, 1), (96, 1), (192, 4), (384, 8)):
             if Cc not in cs:
                 continue
             lib = _native.lib()
-            run_block(Cc, heads, Bn, 512 if Cc < 192 else 256, 512 if Cc < 192 else 256, mode, ncu=True)
+            run_block(Cc, heads, Bn, side[Cc], side[Cc], mode, ncu=True)
     sys.exit(0)
 
 if "--blocks" in sys.argv:
