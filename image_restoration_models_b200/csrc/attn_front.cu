@@ -21,6 +21,16 @@
 
 #include <type_traits>
 
+// Barrier waits of the depthwise warps and of the MMA issuer.  -DIRB_TAIL_SPIN: spinning / short-poll waits as in the fused
+// kernels (a wait with a suspend-time hint that outlasts the hardware window wakes up late); default: suspend-hint waits.
+#ifdef IRB_TAIL_SPIN
+#define IRB_DW_WAIT(bar, ph) sm100::mbar_wait_spin(bar, ph)
+#define IRB_MMA_WAIT(bar, ph) sm100::mbar_wait_poll<32>(bar, ph)
+#else
+#define IRB_DW_WAIT(bar, ph) sm100::mbar_wait(bar, ph)
+#define IRB_MMA_WAIT(bar, ph) sm100::mbar_wait(bar, ph)
+#endif
+
 namespace irb {
 
 namespace {
@@ -194,7 +204,7 @@ attn_front_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
     const uint32_t idesc = make_idesc<TH_>(p.C);
     uint32_t j = 0;
     for (TileIter ti(p); ti.valid(); ti.next(), ++j) {
-      mbar_wait(smem_u32(&bars->x_ready), j & 1u);
+      IRB_MMA_WAIT(smem_u32(&bars->x_ready), j & 1u);
       tc_fence_after();
       {
 #pragma unroll
@@ -233,10 +243,10 @@ attn_front_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
 #pragma unroll
         for (int ox = 0; ox < BW; ++ox) okp[oy][ox] = (y0 + BH * by + oy < p.H) && (x0 + BW * bx + ox < p.W);
       // the MMA of the previous tile has read the X tile (it ran while this CTA produced that tile's v chunks)
-      mbar_wait(smem_u32(&bars->x_empty), (j & 1u) ^ 1u);
+      IRB_DW_WAIT(smem_u32(&bars->x_empty), (j & 1u) ^ 1u);
 #pragma unroll
       for (int ch = 0; ch < NQK; ++ch) {
-        mbar_wait(smem_u32(&bars->h_full[s]), ph);
+        IRB_DW_WAIT(smem_u32(&bars->h_full[s]), ph);
         const uint32_t st = sST + s * p.stage_bytes;
         f2_t acc[BH][BW];
         dw_chunk<TH_>(st + win0, st + HPIX * PXB + (uint32_t)cp * 8u, acc);
@@ -293,7 +303,7 @@ attn_front_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
       // ---- v chunks: each warp stages its own 2 x 8 pixel region ([pixel][channel]) and stores it with its own
       //      bulk-tensor copy: no block-wide barrier on the path ----
       for (int ch = 0; ch < p.nv; ++ch, ++vc) {
-        mbar_wait(smem_u32(&bars->h_full[s]), ph);
+        IRB_DW_WAIT(smem_u32(&bars->h_full[s]), ph);
         const uint32_t st = sST + s * p.stage_bytes;
         f2_t acc[BH][BW];
         dw_chunk<TH_>(st + win0, st + HPIX * PXB + (uint32_t)cp * 8u, acc);

@@ -336,8 +336,8 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     auto tap_ptr = [&](int set) {     // set = 2 * chunk + (0: x1, 1: x2); layout [64-channel chunk][x1 | x2][9][64]
       return p.dw + ((size_t)(((set >> 1) * 2 + (lc >> 6)) * 2 + (set & 1)) * 9) * 64 + (lc & 63);
     };
-#pragma unroll
     constexpr bool W_TMEM = 2 * NC <= W_SETS;
+#pragma unroll
     for (int set = 0; W_TMEM && set < 2 * NC; ++set) {
       uint32_t r[9];
 #pragma unroll

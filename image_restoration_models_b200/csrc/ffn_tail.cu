@@ -23,6 +23,16 @@
 
 #include <type_traits>
 
+// Barrier waits of the depthwise warps and of the MMA issuer.  -DIRB_TAIL_SPIN: spinning / short-poll waits as in the fused
+// kernels (a wait with a suspend-time hint that outlasts the hardware window wakes up late); default: suspend-hint waits.
+#ifdef IRB_TAIL_SPIN
+#define IRB_DW_WAIT(bar, ph) sm100::mbar_wait_spin(bar, ph)
+#define IRB_MMA_WAIT(bar, ph) sm100::mbar_wait_poll<32>(bar, ph)
+#else
+#define IRB_DW_WAIT(bar, ph) sm100::mbar_wait(bar, ph)
+#define IRB_MMA_WAIT(bar, ph) sm100::mbar_wait(bar, ph)
+#endif
+
 namespace irb {
 
 namespace {
@@ -182,12 +192,12 @@ ffn_tail_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__
     for (TileIter ti(p); ti.valid(); ti.next(), ++j) {
       const uint32_t slot = p.nacc == 2 ? (j & 1u) : 0u;
       const uint32_t use = p.nacc == 2 ? (j >> 1) : j;
-      mbar_wait(smem_u32(&bars->acc_empty[slot]), (use & 1u) ^ 1u);
+      IRB_MMA_WAIT(smem_u32(&bars->acc_empty[slot]), (use & 1u) ^ 1u);
       tc_fence_after();
       for (int ch = 0; ch < p.nchunk; ++ch, ++it) {
         const uint32_t s = it % NST, o = it % NOP;
-        mbar_wait(smem_u32(&bars->h_full[s]), (it / NST) & 1u);          // the chunk's W_out rows (already there)
-        mbar_wait(smem_u32(&bars->op_ready[o]), (it / NOP) & 1u);
+        IRB_MMA_WAIT(smem_u32(&bars->h_full[s]), (it / NST) & 1u);          // the chunk's W_out rows (already there)
+        IRB_MMA_WAIT(smem_u32(&bars->op_ready[o]), (it / NOP) & 1u);
         tc_fence_after();
         {
           const uint32_t a_addr = sOP + o * OPBOX;
@@ -214,7 +224,7 @@ ffn_tail_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__
     for (TileIter ti(p); ti.valid(); ti.next()) {
       for (int ch = 0; ch < p.nchunk; ++ch, ++it) {
         const uint32_t s = it % NST, o = it % NOP;
-        mbar_wait(smem_u32(&bars->h_full[s]), (it / NST) & 1u);
+        IRB_DW_WAIT(smem_u32(&bars->h_full[s]), (it / NST) & 1u);
         const uint32_t st = sST + s * p.stage_bytes;
         const uint32_t dws = st + 2 * HBOX + wbytes + (uint32_t)cp * 8u;
         f2_t acc[2][BH][BW];
@@ -247,7 +257,7 @@ ffn_tail_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__
         // the patch (and the taps) are consumed: release the stage as far as this warp is concerned
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&bars->h_empty[s]));
-        mbar_wait(smem_u32(&bars->op_empty[o]), ((it / NOP) & 1u) ^ 1u);
+        IRB_DW_WAIT(smem_u32(&bars->op_empty[o]), ((it / NOP) & 1u) ^ 1u);
         const uint32_t ob = sOP + o * OPBOX;
 #pragma unroll
         for (int oy = 0; oy < BH; ++oy)
