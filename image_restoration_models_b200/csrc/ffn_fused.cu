@@ -331,7 +331,8 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // The taps this thread's channel needs in every phase, parked in the spare tensor-memory columns (lane = channel): a tap
     // fetch through the L1 this kernel's shared memory leaves no room for sat in front of every lock-step phase.  Three of
     // the 2 NC sets fit: all of them at C = 48.  C = 96 (four sets) keeps the global loads -- three sets from tensor memory and
-    // one from global memory measured SLOWER than four from global memory (0.81 against 0.75 ms; two code paths in the phase).
+    // one from global memory measured SLOWER than four from global memory (0.81 against 0.75 ms), and eight taps of every set in
+    // tensor memory with the ninth in a register no faster (0.74 against 0.73 ms): at C = 96 the tap fetch is not what a phase waits for.
     const uint32_t wlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)W_COL0;
     auto tap_ptr = [&](int set) {     // set = 2 * chunk + (0: x1, 1: x2); layout [64-channel chunk][x1 | x2][9][64]
       return p.dw + ((size_t)(((set >> 1) * 2 + (lc >> 6)) * 2 + (set & 1)) * 9) * 64 + (lc & 63);
