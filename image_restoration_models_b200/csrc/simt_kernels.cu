@@ -673,13 +673,16 @@ int launch_conv3x3_small(const float* in, int ld, int cin, const float* w, int k
 // ---------------------------------------------------------------------------------------------
 // First 3x3 convolution of a network (patch_embed restormer.py:160-165, DnCNN head network_dncnn.py:63): an NCHW image
 // with 1-8 channels -> channels-last [pixel][cout] (+ bias, ReLU).  Pure store bandwidth (48-64 floats out per 1-6 in):
-// cout/4 consecutive threads own one pixel and write one float4 each, so a warp's store is one contiguous segment;
-// the 9*cin inputs of a pixel are broadcast loads shared by its threads and by the neighbouring pixels through L1.
+// cout/4 consecutive threads own one pixel and write one float4 each, so a warp's store is one contiguous segment.
+// A thread walks DOWN a band of rows with its 3x3 input window in registers: per output float4 it issues three loads (the
+// window's new row; neighbouring threads share them through L1), 36 FMAs per input channel and one store.  (The previous
+// version re-read all nine taps with nine predicates and nine 64-bit addresses per output -- ncu: issue-bound, ~150
+// instructions per float4 stored, 1.6 TB/s.)
 // ---------------------------------------------------------------------------------------------
 template <int CIN>
 __global__ void __launch_bounds__(256) conv3x3_first_kernel(const float* __restrict__ x, const float* __restrict__ w, int kp,
                                                             const float* __restrict__ bias, int relu, int cout, int B, int H,
-                                                            int W, float* __restrict__ y, int ldy) {
+                                                            int W, float* __restrict__ y, int ldy, int band) {
   extern __shared__ float wsm[];                  // [9*CIN][cout] (transposed: a thread's 4 outputs are one float4)
   for (int i = threadIdx.x; i < cout * 9 * CIN; i += 256) {
     const int co = i / (9 * CIN), k = i - co * 9 * CIN;      // k = tap * CIN + c (PackMat kind 1 order)
@@ -687,38 +690,49 @@ __global__ void __launch_bounds__(256) conv3x3_first_kernel(const float* __restr
   }
   __syncthreads();
   pdl_sync();   // the weights (constants) are staged under the previous kernel's tail (common.cuh)
-  // grid.y walks the B*H image rows, grid.x the W * cout/4 (pixel, quad) pairs of a row: 32-bit index arithmetic only
-  // (64-bit divisions per thread cost more than the convolution)
+  // grid.x walks the W * cout/4 (pixel, quad) pairs of a row, grid.y the (image, row band) pairs
   const int q4 = cout >> 2;
   const int in_row = blockIdx.x * 256 + threadIdx.x;
   if (in_row >= W * q4) return;
   const int xx = in_row / q4, q = in_row - xx * q4;
-  // a thread's column never changes: the x-validity of the taps and the tap offsets are loop invariants, and an invalid tap
-  // contributes a zero (the first build recomputed nine 64-bit addresses and eighteen bounds checks per pixel: ~250
-  // instructions per float4 stored, integer-bound at 1.6 TB/s)
+  const int nbands = (H + band - 1) / band;
+  const int b = blockIdx.y / nbands, y0 = (blockIdx.y - b * nbands) * band, y1 = min(H, y0 + band);
+  // a thread's column never changes: the x-validity of the taps and the (clamped) column offsets are loop invariants
   const bool xl = xx > 0, xr = xx + 1 < W;
+  const int cl = xl ? -1 : 0, cr = xr ? 1 : 0;
   const long long plane = (long long)H * W;
+  const float* xc = x + (long long)b * CIN * plane + xx;              // channel 0, row 0, this column
   const float4 bq = bias ? *reinterpret_cast<const float4*>(bias + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
-  // gray images: the thread's nine weight quads live in registers for its whole column (per output float4 the loop is then
-  // 9 broadcast loads + 1 store; with the quads in shared memory nine more 4-wavefront LDS.128 went through the same LSU)
+  // gray images: the thread's nine weight quads live in registers for its whole band
   float4 wreg[CIN == 1 ? 9 : 1];
   if constexpr (CIN == 1) {
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap) wreg[tap] = *reinterpret_cast<const float4*>(wsm + tap * cout + 4 * q);
   }
-  for (int row = blockIdx.y; row < B * H; row += gridDim.y) {
-    const int b = row / H, yy = row - b * H;
-    const long long pix = (long long)row * W + xx;
-    const float* xc = x + ((long long)b * CIN * H + yy) * W + xx;     // channel 0, centre tap
-    const bool yu = yy > 0, yd = yy + 1 < H;
+  // one row of the window: columns xx-1, xx, xx+1 of every input channel; zeros outside the image (the loads themselves
+  // are unconditional, from clamped addresses)
+  auto load_row = [&](int yy, float (&v)[CIN][3]) {
+    const bool ok = yy >= 0 && yy < H;
+    const float* rp = xc + (long long)min(max(yy, 0), H - 1) * W;
+#pragma unroll
+    for (int c = 0; c < CIN; ++c) {
+      const float l = __ldg(rp + c * plane + cl), m = __ldg(rp + c * plane), r = __ldg(rp + c * plane + cr);
+      v[c][0] = (ok && xl) ? l : 0.f; v[c][1] = ok ? m : 0.f; v[c][2] = (ok && xr) ? r : 0.f;
+    }
+  };
+  float win[3][CIN][3];
+  load_row(y0 - 1, win[0]);
+  load_row(y0, win[1]);
+  float* yp = y + (((long long)b * H + y0) * W + xx) * ldy + 4 * q;
+  const long long ystep = (long long)W * ldy;
+  for (int yy = y0; yy < y1; ++yy) {
+    load_row(yy + 1, win[2]);
     float4 acc = bq;
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap) {
-      const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-      const bool ok = (dy < 0 ? yu : dy > 0 ? yd : true) && (dx < 0 ? xl : dx > 0 ? xr : true);
 #pragma unroll
       for (int c = 0; c < CIN; ++c) {
-        const float v = ok ? __ldg(xc + c * plane + dy * W + dx) : 0.f;
+        const float v = win[tap / 3][c][tap % 3];
         float4 ww;
         if constexpr (CIN == 1) ww = wreg[tap];
         else ww = *reinterpret_cast<const float4*>(wsm + (tap * CIN + c) * cout + 4 * q);
@@ -726,7 +740,12 @@ __global__ void __launch_bounds__(256) conv3x3_first_kernel(const float* __restr
       }
     }
     if (relu) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
-    *reinterpret_cast<float4*>(y + pix * ldy + 4 * q) = acc;
+    *reinterpret_cast<float4*>(yp) = acc;
+    yp += ystep;
+#pragma unroll
+    for (int c = 0; c < CIN; ++c)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { win[0][c][k] = win[1][c][k]; win[1][c][k] = win[2][c][k]; }
   }
 }
 
@@ -738,16 +757,20 @@ int launch_conv3x3_first(const float* x_nchw, int cin, const float* w, int kp, c
                          int H, int W, float* y, int ldy, cudaStream_t s) {
   IRB_REQUIRE(conv3x3_first_supported(cin, cout) && ldy % 4 == 0, "conv3x3_first: unsupported shape");
   IRB_REQUIRE((long long)B * H < (1LL << 31), "conv3x3_first: too many image rows");
-  // ~8 resident blocks per SM in total; each walks many image rows, so the per-block weight staging is amortised
+  // row bands of 16 (the window's two halo rows cost 12 % more loads); shorter bands when the image alone would not give
+  // every SM about four blocks (the batch-1 latency path)
   const int gx = cdiv(W * (cout / 4), 256);
-  const dim3 blocks(gx, (unsigned)std::max<long long>(1, std::min<long long>((long long)B * H, cdiv(148 * 8, gx))));
+  int band = 16;
+  while (band > 4 && (long long)gx * B * cdiv(H, band) < 4 * 148) band >>= 1;
+  IRB_REQUIRE((long long)B * cdiv(H, band) <= 65535, "conv3x3_first: too many row bands for one launch");
+  const dim3 blocks(gx, (unsigned)(B * cdiv(H, band)));
   const size_t smem = (size_t)cout * 9 * cin * sizeof(float);
   const double pix = (double)B * H * W;
   ProfScope prof(TAG_CONV3, 4.0 * pix * (cin + cout), 2.0 * 9.0 * pix * cin * cout, s);
   switch (cin) {
-    case 1: IRB_CUDA(launch_pdl(conv3x3_first_kernel<1>, dim3(blocks), dim3(256), smem, s, x_nchw, w, kp, bias, relu, cout, B, H, W, y, ldy)); break;
-    case 3: IRB_CUDA(launch_pdl(conv3x3_first_kernel<3>, dim3(blocks), dim3(256), smem, s, x_nchw, w, kp, bias, relu, cout, B, H, W, y, ldy)); break;
-    default: IRB_CUDA(launch_pdl(conv3x3_first_kernel<6>, dim3(blocks), dim3(256), smem, s, x_nchw, w, kp, bias, relu, cout, B, H, W, y, ldy)); break;
+    case 1: IRB_CUDA(launch_pdl(conv3x3_first_kernel<1>, dim3(blocks), dim3(256), smem, s, x_nchw, w, kp, bias, relu, cout, B, H, W, y, ldy, band)); break;
+    case 3: IRB_CUDA(launch_pdl(conv3x3_first_kernel<3>, dim3(blocks), dim3(256), smem, s, x_nchw, w, kp, bias, relu, cout, B, H, W, y, ldy, band)); break;
+    default: IRB_CUDA(launch_pdl(conv3x3_first_kernel<6>, dim3(blocks), dim3(256), smem, s, x_nchw, w, kp, bias, relu, cout, B, H, W, y, ldy, band)); break;
   }
   IRB_LAUNCH_CHECK();
   return IR_OK;
