@@ -598,7 +598,8 @@ bool configure(int K, int N, bool op_half, bool ln, bool has_r, bool y_half, Tma
   // xn second output: per-warp staging boxes + the LayerNorm parameters; the row must be whole (one N-chunk, <= 3 groups)
   if (xn && (ln || y_half || (N != 48 && N != 96))) return false;
   static const bool one_group = getenv("IRB_ONE_EPI_GROUP") != nullptr;       // A/B switch for benchmarks
-  c.egroups = xn && has_r && N == 48 && !one_group ? 2 : 1;
+  static const bool two96 = getenv("IRB_TWO_EPI_GROUPS_96") != nullptr;     // A/B switch: two epilogue warpgroups at N = 96 too
+  c.egroups = xn && has_r && (N == 48 || (N == 96 && two96)) && !one_group ? 2 : 1;
   const size_t xn_bytes = xn ? (size_t)c.egroups * EPI_WARPS * ((N + 63) / 64) * WBOX + (size_t)2 * N * 4 + 16 : 0;
   const size_t budget = 227 * 1024 - 1024 /*alignment slack*/ - xn_bytes;
   for (int chunks = 1; chunks <= N / 16; ++chunks) {
