@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(256, 2) dw_roll_kernel(const DwParams p, const
           float4 o = acc[0][K % 3][i];
           if (GATE) {
             const float4 gt = acc[NS - 1][K % 3][i];
-            // gelu(x1) * x2 on packed pairs, one MUFU per element (gdfn_math.cuh; max error 3.1e-7)
+            // gelu(x1) * x2 on packed pairs, one MUFU per element (gdfn_math.cuh; max error 7.1e-7)
             const gdfn::f2_t g0 = gdfn::gelu_gate2e(gdfn::pack2(o.x, o.y), gdfn::pack2(gt.x, gt.y));
             const gdfn::f2_t g1 = gdfn::gelu_gate2e(gdfn::pack2(o.z, o.w), gdfn::pack2(gt.z, gt.w));
             gdfn::unpack2(g0, o.x, o.y);

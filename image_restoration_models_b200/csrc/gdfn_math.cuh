@@ -56,12 +56,14 @@ __device__ __forceinline__ f2_t gelu_gate2(f2_t x, f2_t gate) {
 // erfc itself, i.e. it vanishes where gelu is large.  Fit: scripts/fit_gelu_exp2.py (weighted minimax on [0, 6], |x| clamped
 // to 6 where erfc < 2e-9).  max |gelu error| in fp32 arithmetic: degree 6 3.1e-7 (the rounding level of the subtraction
 // itself), degree 5 7.1e-7, degree 4 8.7e-6.  The result is rounded to a 16-bit tensor-core operand right away (2^-11
-// relative), so degree 4 would be fifty times below what the consumer can see -- but measured on B200 it buys nothing (fused
-// GDFN C = 96 0.765 ms against 0.751-0.753 ms, C = 48 0.403 against 0.412 ms: the gate's FMAs are not on the critical path
-// of the lock-step phases), so the library keeps degree 6; IRB_GELU_DEG = 4 / 5 select the shorter ones.  The A&S form above
-// costs two MUFU per element (rcp + ex2) and four more packed operations.
+// relative), so degree 5 is three orders of magnitude below what the consumer can see.  Measured on B200: with the first
+// TMEM-direct kernels the degree bought nothing (fused GDFN C = 96 0.765 ms against 0.751-0.753 ms: the gate's FMAs were not
+// on the critical path of the lock-step phases); after the depthwise warps' instruction diet degree 5 is 1-2 % faster than
+// degree 6 (C = 96 0.713 against 0.721 ms, C = 48 0.360 against 0.367 ms, A/B on one box), so the library uses degree 5;
+// IRB_GELU_DEG = 4 / 6 select the others.  The A&S form above costs two MUFU per element (rcp + ex2) and four more packed
+// operations.
 #ifndef IRB_GELU_DEG
-#define IRB_GELU_DEG 6
+#define IRB_GELU_DEG 5
 #endif
 __device__ __forceinline__ f2_t gelu_gate2e(f2_t x, f2_t gate) {
 #if IRB_GELU_DEG == 6
